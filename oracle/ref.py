@@ -1,0 +1,274 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of oracle/_ref/libgraspit_ref.so.
+
+The library is the reference's own GraspitCollision backend compiled verbatim (see
+oracle/Makefile, oracle/ref_driver.cpp).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / ``--impl reference`` legs may import this module; the product path
+(graspit_b200/, include/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libgraspit_ref.so")
+
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(f"oracle library missing: {LIB_PATH} (run `make -C oracle` where /root/reference exists)")
+        L = C.CDLL(LIB_PATH)
+        L.ref_create.restype = C.c_void_p
+        L.ref_destroy.argtypes = [C.c_void_p]
+        L.ref_add_body.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        L.ref_clone_body.argtypes = [C.c_void_p, C.c_int]
+        L.ref_remove_body.argtypes = [C.c_void_p, C.c_int]
+        L.ref_set_transform.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_activate_body.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_activate_pair.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.ref_is_active.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_all_collisions.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.c_int]
+        L.ref_body_distance.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_body_distance.restype = C.c_double
+        L.ref_point_distance.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_point_distance.restype = C.c_double
+        L.ref_contact.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_int]
+        L.ref_contact_raw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
+        L.ref_all_contacts.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int),
+                                       C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double), C.c_int]
+        L.ref_region.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
+                                 C.POINTER(C.c_double), C.c_int]
+        L.ref_bounding_volumes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int]
+        L.ref_collide_pair_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.ref_distance_pair_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.ref_distance_pair_stats.restype = C.c_double
+        L.ref_point_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ref_point_stats.restype = C.c_double
+        for name in ("ref_transf_compose",):
+            getattr(L, name).argtypes = [C.POINTER(C.c_double)] * 5
+        L.ref_transf_inverse.argtypes = [C.POINTER(C.c_double)] * 3
+        L.ref_transf_apply.argtypes = [C.POINTER(C.c_double)] * 4
+        L.ref_transf_rotate.argtypes = [C.POINTER(C.c_double)] * 4
+        L.ref_transf_axis_angle.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_transf_jacobian.argtypes = [C.POINTER(C.c_double)] * 3
+        L.ref_quat_roundtrip.argtypes = [C.POINTER(C.c_double)] * 3
+        L.ref_eval_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,
+                                     C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_ubyte),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_hardware_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _d(x, n=None):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+    if n is not None:
+        assert a.size == n, (a.size, n)
+    return a
+
+
+class RefWorld:
+    """One reference ``GraspitCollision`` instance with integer body ids."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.ref_create())
+
+    def close(self):
+        if self.h:
+            self.L.ref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- bodies -----------------------------------------------------------------------
+    def add_body(self, tris) -> int:
+        t = _d(np.asarray(tris, dtype=np.float64))
+        assert t.size % 9 == 0
+        bid = self.L.ref_add_body(self.h, _dp(t), t.size // 9)
+        if bid < 0:
+            raise RuntimeError("ref_add_body failed")
+        return bid
+
+    def clone_body(self, original: int) -> int:
+        return self.L.ref_clone_body(self.h, original)
+
+    def remove_body(self, bid: int):
+        self.L.ref_remove_body(self.h, bid)
+
+    def set_transform(self, bid: int, q_wxyz, t):
+        q = _d(q_wxyz, 4); tt = _d(t, 3)
+        self.L.ref_set_transform(self.h, bid, _dp(q), _dp(tt))
+
+    def activate_body(self, bid, active):
+        self.L.ref_activate_body(self.h, bid, int(bool(active)))
+
+    def activate_pair(self, a, b, active):
+        self.L.ref_activate_pair(self.h, a, b, int(bool(active)))
+
+    def is_active(self, a, b=-1) -> bool:
+        return bool(self.L.ref_is_active(self.h, a, b))
+
+    # --- queries ----------------------------------------------------------------------
+    def all_collisions(self, fast=False, interest: Optional[Sequence[int]] = None, cap=4096):
+        il = np.ascontiguousarray(np.asarray(interest if interest is not None else [], dtype=np.int32))
+        out = np.zeros(2 * cap, dtype=np.int32)
+        n = self.L.ref_all_collisions(self.h, int(fast), _ip(il) if interest is not None else None, il.size,
+                                      _ip(out), cap)
+        pairs = [tuple(sorted((int(out[2 * i]), int(out[2 * i + 1])))) for i in range(0 if fast else min(n, cap))]
+        return n, pairs
+
+    def body_distance(self, a, b):
+        p1 = np.zeros(3); p2 = np.zeros(3)
+        d = self.L.ref_body_distance(self.h, a, b, _dp(p1), _dp(p2))
+        return d, p1, p2
+
+    def point_distance(self, body, p):
+        pp = _d(p, 3); cp = np.zeros(3); cn = np.zeros(3)
+        d = self.L.ref_point_distance(self.h, body, _dp(pp), _dp(cp), _dp(cn))
+        return d, cp, cn
+
+    def contact(self, a, b, thr, cap=8192):
+        out = np.zeros(13 * cap)
+        n = self.L.ref_contact(self.h, a, b, float(thr), _dp(out), cap)
+        return out[: 13 * min(n, cap)].reshape(-1, 13).copy()
+
+    def contact_raw(self, a, b, thr, cap=65536):
+        out = np.zeros(13 * cap)
+        st = np.zeros(3, dtype=np.int32)
+        n = self.L.ref_contact_raw(self.h, a, b, float(thr), _dp(out), cap, _ip(st))
+        return out[: 13 * min(n, cap)].reshape(-1, 13).copy(), st
+
+    def all_contacts(self, thr, interest: Optional[Sequence[int]] = None, cap_pairs=1024, cap_contacts=65536):
+        il = np.ascontiguousarray(np.asarray(interest if interest is not None else [], dtype=np.int32))
+        pid = np.zeros(2 * cap_pairs, dtype=np.int32); cnt = np.zeros(cap_pairs, dtype=np.int32)
+        out = np.zeros(13 * cap_contacts)
+        n = self.L.ref_all_contacts(self.h, float(thr), _ip(il) if interest is not None else None, il.size,
+                                    _ip(pid), _ip(cnt), cap_pairs, _dp(out), cap_contacts)
+        res, k = [], 0
+        for i in range(n):
+            c = int(cnt[i])
+            res.append(((int(pid[2 * i]), int(pid[2 * i + 1])), out[13 * k: 13 * (k + c)].reshape(-1, 13).copy()))
+            k += c
+        return res
+
+    def region(self, body, p, n, radius, cap=65536):
+        pp = _d(p, 3); nn = _d(n, 3); out = np.zeros(3 * cap)
+        k = self.L.ref_region(self.h, body, _dp(pp), _dp(nn), float(radius), _dp(out), cap)
+        return out[: 3 * min(k, cap)].reshape(-1, 3).copy()
+
+    def bounding_volumes(self, body, depth, cap=1 << 16):
+        out = np.zeros(10 * cap)
+        k = self.L.ref_bounding_volumes(self.h, body, depth, _dp(out), cap)
+        return out[: 10 * min(k, cap)].reshape(-1, 10).copy()
+
+    def collide_pair_stats(self, a, b):
+        st = np.zeros(3, dtype=np.int32)
+        r = self.L.ref_collide_pair_stats(self.h, a, b, _ip(st))
+        return bool(r), st
+
+    def distance_pair_stats(self, a, b):
+        st = np.zeros(3, dtype=np.int32)
+        d = self.L.ref_distance_pair_stats(self.h, a, b, _ip(st))
+        return d, st
+
+    def point_stats(self, body, p):
+        st = np.zeros(3, dtype=np.int32); pp = _d(p, 3)
+        d = self.L.ref_point_stats(self.h, body, _dp(pp), _ip(st))
+        return d, st
+
+
+# --- transf helpers (pin the shim against test/transform_tests.cpp, test/eigen_tests.cpp) ---
+
+def transf_compose(a, b):
+    qa, ta = _d(a[0], 4), _d(a[1], 3); qb, tb = _d(b[0], 4), _d(b[1], 3)
+    out = np.zeros(7)
+    lib().ref_transf_compose(_dp(qa), _dp(ta), _dp(qb), _dp(tb), _dp(out))
+    return out[:4].copy(), out[4:].copy()
+
+
+def transf_inverse(a):
+    q, t = _d(a[0], 4), _d(a[1], 3); out = np.zeros(7)
+    lib().ref_transf_inverse(_dp(q), _dp(t), _dp(out))
+    return out[:4].copy(), out[4:].copy()
+
+
+def transf_apply(a, p):
+    q, t, pp = _d(a[0], 4), _d(a[1], 3), _d(p, 3); out = np.zeros(3)
+    lib().ref_transf_apply(_dp(q), _dp(t), _dp(pp), _dp(out))
+    return out
+
+
+def transf_rotate(a, v):
+    q, t, vv = _d(a[0], 4), _d(a[1], 3), _d(v, 3); out = np.zeros(3)
+    lib().ref_transf_rotate(_dp(q), _dp(t), _dp(vv), _dp(out))
+    return out
+
+
+def transf_axis_angle(angle, axis):
+    ax = _d(axis, 3); out = np.zeros(7)
+    lib().ref_transf_axis_angle(float(angle), _dp(ax), _dp(out))
+    return out[:4].copy(), out[4:].copy()
+
+
+def transf_jacobian(a):
+    q, t = _d(a[0], 4), _d(a[1], 3); out = np.zeros(36)
+    lib().ref_transf_jacobian(_dp(q), _dp(t), _dp(out))
+    return out
+
+
+def quat_roundtrip(q):
+    qq = _d(q, 4); m = np.zeros(9); qo = np.zeros(4)
+    lib().ref_quat_roundtrip(_dp(qq), _dp(m), _dp(qo))
+    return m.reshape(3, 3), qo
+
+
+def eval_batch(worlds: Sequence[RefWorld], hand_ids, object_id, tf7, vc_link, vc_loc, vc_normal, mode=0,
+               want_dist=False):
+    """Reference per-pose loop (legal + CONTACT_ENERGY) over precomputed link poses.
+
+    tf7: (npose, nhand, 7) doubles.  Returns (legal uint8[npose], energy f64[npose], link_dist or None)."""
+    L = lib()
+    tf7 = np.ascontiguousarray(tf7, dtype=np.float64)
+    npose, nhand = tf7.shape[0], tf7.shape[1]
+    hid = np.ascontiguousarray(hand_ids, dtype=np.int32)
+    assert hid.size == nhand
+    vl = np.ascontiguousarray(vc_link, dtype=np.int32)
+    vloc = np.ascontiguousarray(vc_loc, dtype=np.float64)
+    vn = np.ascontiguousarray(vc_normal, dtype=np.float64)
+    legal = np.zeros(npose, dtype=np.uint8)
+    energy = np.zeros(npose, dtype=np.float64)
+    dist = np.zeros((npose, nhand), dtype=np.float64) if want_dist else None
+    arr = (C.c_void_p * len(worlds))(*[w.h for w in worlds])
+    L.ref_eval_batch(arr, len(worlds), npose, nhand, _ip(hid), int(object_id), _dp(tf7), vl.size, _ip(vl),
+                     _dp(vloc), _dp(vn), int(mode), int(bool(want_dist)),
+                     legal.ctypes.data_as(C.POINTER(C.c_ubyte)), _dp(energy), _dp(dist) if want_dist else None)
+    return legal, energy, dist
+
+
+def hardware_threads() -> int:
+    return int(lib().ref_hardware_threads())
