@@ -1,0 +1,54 @@
+"""Builds graspit_b200/libb2c.so (the CUDA engine + C ABI) in-tree with nvcc for sm_100a."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libb2c.so")
+SOURCES = ["api.cu", "kernels.cu", "bvh.cpp", "contacts_host.cpp"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xcompiler", "-O3"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b2c.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    env = dict(os.environ)
+    # the image exports CXX=/opt/gcc/bin/g++ whose static libstdc++ misbehaves in dlopen()ed libraries
+    ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    objs = []
+    for s in SOURCES:
+        o = os.path.join(objdir, os.path.splitext(s)[0] + ".o")
+        cmd = [_nvcc(), "-ccbin", ccbin, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
+            print(" ".join(cmd))
+        subprocess.check_call(cmd, env=env)
+        objs.append(o)
+    cmd = [_nvcc(), "-ccbin", ccbin, "-shared", "-o", LIB, *objs, "-lcudart"]
+    subprocess.check_call(cmd, env=env)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,887 @@
+// C ABI of the engine (include/b2c.h): context, geometry registry, pair activation, robots,
+// single-pose CollisionInterface queries and the batched FK -> legal -> energy evaluation.
+// Host-side bookkeeping mirrors GraspitCollision (src/Collision/Graspit/graspitCollision.cpp):
+// body <-> model map, disabled-pair set, active-pair enumeration (:55-100).
+#include "../../include/b2c.h"
+#include "b2c_internal.h"
+#include "contacts_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+using namespace b2c;
+
+namespace {
+
+struct MeshHost {
+  bool alive = false;
+  int ntri = 0;
+  std::vector<float> tri9;        // kept for the host-side OBB hierarchy / region / contact post-processing
+  std::vector<Node> nodes;
+  Node *d_nodes = nullptr;
+  Tri *d_tris = nullptr;
+  int depth = 0;
+  float extent = 0.f;
+  ObbTree *obb = nullptr;         // lazily built reference-style hierarchy (getBoundingVolumes)
+};
+
+struct BodyHost {
+  bool alive = false;
+  int mesh = -1;
+  bool active = true;
+  Qt tf;
+};
+
+struct RobotHost {
+  b2c_robot_desc d;
+  std::vector<double> dof_min, dof_max, eg, eg_origin, eg_norm;
+  std::vector<b2c_chain_desc> chains;
+  std::vector<b2c_joint_desc> joints;
+  std::vector<int> link_body, link_last_joint;
+  std::vector<b2c_vcontact_desc> vcs;
+};
+
+template <typename T> struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 4 + 16;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Plan {
+  bool valid = false;
+  int robot = -1, object = -1;
+  std::vector<int> robots;          // robot ids in FK order (root first)
+  std::vector<int> slots;           // robot body ids, slot order
+  std::vector<int> ebodies;         // eval bodies: slots, then static bodies
+  std::vector<int2> pairs;          // eval-body indices
+  std::vector<int2> pair_ids;       // body ids
+  int object_e = -1;
+  int ndof_total = 0;
+  int nvc = 0;
+  int nhand = 0;                    // bodies of the root robot only (LIVE contacts / link_dist)
+  // device copies
+  DevBuf<FkRobot> d_robots; DevBuf<FkChain> d_chains; DevBuf<FkJoint> d_joints; DevBuf<FkLink> d_links;
+  DevBuf<double> d_eg; DevBuf<int> d_body_mesh; DevBuf<int2> d_pairs; DevBuf<VcDev> d_vcs; DevBuf<int2> d_queries;
+  DevBuf<Xf> d_static;
+  FkProgram prog;
+  void release() {
+    d_robots.release(); d_chains.release(); d_joints.release(); d_links.release(); d_eg.release();
+    d_body_mesh.release(); d_pairs.release(); d_vcs.release(); d_queries.release(); d_static.release();
+    valid = false;
+  }
+};
+
+} // namespace
+
+struct b2c_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  int sm_count = 148;
+  std::vector<MeshHost> meshes;
+  std::vector<BodyHost> bodies;
+  std::set<std::pair<int, int>> disabled;
+  std::vector<RobotHost> robots;
+  bool meshes_dirty = true;
+  DevBuf<MeshDev> d_meshes;
+  std::map<std::pair<int, int>, Plan *> plans;
+  // scratch
+  DevBuf<float> d_states; DevBuf<Xf> d_fk; DevBuf<double> d_fkqt; DevBuf<uint8_t> d_legal; DevBuf<float> d_energy;
+  DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
+  DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc;
+  unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int eval_warps_per_block = 8;
+  int eval_blocks_per_sm = 0;      // 0 = derive from shared memory
+};
+
+namespace {
+
+int fail(b2c_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return fail(ctx, B2C_ECUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+bool body_ok(const b2c_ctx *c, int b) { return b >= 0 && b < (int)c->bodies.size() && c->bodies[b].alive; }
+bool mesh_ok(const b2c_ctx *c, int m) { return m >= 0 && m < (int)c->meshes.size() && c->meshes[m].alive; }
+
+Qt make_qt(const double *q, const double *t) {
+  Qt r; r.w = q[0]; r.x = q[1]; r.y = q[2]; r.z = q[3]; r.tx = t[0]; r.ty = t[1]; r.tz = t[2];
+  q_normalize(r);
+  return r;
+}
+Xf qt_to_xf(const Qt &q) { Xf x; q_to_xf(q, reinterpret_cast<double *>(&x)); return x; }
+
+void invalidate_plans(b2c_ctx *c) {
+  for (auto &kv : c->plans) { kv.second->release(); delete kv.second; }
+  c->plans.clear();
+}
+
+int sync_meshes(b2c_ctx *ctx) {
+  if (!ctx->meshes_dirty) return B2C_OK;
+  std::vector<MeshDev> md(ctx->meshes.size());
+  for (size_t i = 0; i < ctx->meshes.size(); i++) {
+    const MeshHost &m = ctx->meshes[i];
+    md[i].nodes = m.d_nodes; md[i].tris = m.d_tris;
+    md[i].nnodes = (int)m.nodes.size(); md[i].ntri = m.ntri;
+    md[i].extent = m.extent; md[i].depth = m.depth;
+  }
+  CU(ctx->d_meshes.reserve(md.size() + 1));
+  if (!md.empty()) CU(cudaMemcpyAsync(ctx->d_meshes.p, md.data(), md.size() * sizeof(MeshDev), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->meshes_dirty = false;
+  return B2C_OK;
+}
+
+bool pair_active(const b2c_ctx *c, int a, int b) {
+  if (a == b) return false;
+  if (!c->bodies[a].active || !c->bodies[b].active) return false;
+  return c->disabled.find({std::min(a, b), std::max(a, b)}) == c->disabled.end();
+}
+
+// GraspitCollision::getActivePairs (graspitCollision.cpp:55-100): both active, not disabled, at least
+// one body in the interest list (NULL = all).  The reference orders pairs by model pointer; we order
+// by body id, and callers compare as sets.
+void active_pairs(const b2c_ctx *c, const std::set<int> *interest, std::vector<std::pair<int, int>> &out) {
+  out.clear();
+  int n = (int)c->bodies.size();
+  for (int a = 0; a < n; a++) {
+    if (!c->bodies[a].alive || !c->bodies[a].active) continue;
+    bool ia = !interest || interest->count(a);
+    for (int b = a + 1; b < n; b++) {
+      if (!c->bodies[b].alive || !c->bodies[b].active) continue;
+      if (!ia && !interest->count(b)) continue;
+      if (c->disabled.count({a, b})) continue;
+      out.push_back({a, b});
+    }
+  }
+}
+
+int ensure_scratch(b2c_ctx *ctx) {
+  CU(ctx->d_counters.reserve(8));
+  CU(ctx->d_stats.reserve(8));
+  CU(ctx->d_ambig.reserve(1 << 20));
+  return B2C_OK;
+}
+
+// launch geometry of the evaluation kernel for a given per-warp shared-memory need
+void eval_launch_shape(const b2c_ctx *c, size_t warp_bytes, int work, int &blocks, int &wpb, size_t &smem) {
+  wpb = c->eval_warps_per_block;
+  const size_t limit = 200 * 1024;
+  while (wpb > 1 && warp_bytes * wpb > limit) wpb >>= 1;
+  smem = warp_bytes * wpb;
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(limit / smem, 64 / wpb));
+  if (c->eval_blocks_per_sm > 0) per_sm = std::min(per_sm, c->eval_blocks_per_sm);
+  blocks = c->sm_count * per_sm;
+  int need = (work + wpb - 1) / wpb;
+  if (blocks > need) blocks = std::max(1, need);
+}
+
+// Run the collision traversal over explicit static bodies (single-pose CollisionInterface queries).
+int run_static_collisions(b2c_ctx *ctx, const std::vector<std::pair<int, int>> &pairs, bool all_mode,
+                          std::vector<unsigned long long> &mask, int &legal) {
+  legal = 1;
+  mask.assign((pairs.size() + 63) / 64 + 1, 0ull);
+  if (pairs.empty()) return B2C_OK;
+  int rc = sync_meshes(ctx); if (rc) return rc;
+  rc = ensure_scratch(ctx); if (rc) return rc;
+  std::map<int, int> eidx;
+  std::vector<int> ebodies;
+  std::vector<int2> epairs;
+  for (auto &pr : pairs) {
+    for (int b : {pr.first, pr.second})
+      if (!eidx.count(b)) { eidx[b] = (int)ebodies.size(); ebodies.push_back(b); }
+    epairs.push_back(make_int2(eidx[pr.first], eidx[pr.second]));
+  }
+  int nb = (int)ebodies.size(), np = (int)epairs.size();
+  std::vector<Xf> sx(nb);
+  std::vector<int> bm(nb);
+  for (int i = 0; i < nb; i++) { sx[i] = qt_to_xf(ctx->bodies[ebodies[i]].tf); bm[i] = ctx->bodies[ebodies[i]].mesh; }
+  int mw = (np + 63) / 64;
+  size_t bytes_x = sizeof(Xf) * nb, bytes_p = sizeof(int2) * np, bytes_m = sizeof(int) * nb;
+  CU(ctx->d_misc.reserve((bytes_x + 7) / 8 + 8));
+  CU(ctx->d_imisc.reserve(bytes_p / 4 + bytes_m / 4 + 16));
+  CU(ctx->d_mask.reserve(mw + 1));
+  CU(ctx->d_legal.reserve(16));
+  int2 *d_pairs = reinterpret_cast<int2 *>(ctx->d_imisc.p);
+  int *d_bm = ctx->d_imisc.p + 2 * np;
+  CU(cudaMemcpyAsync(ctx->d_misc.p, sx.data(), bytes_x, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_pairs, epairs.data(), bytes_p, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_bm, bm.data(), bytes_m, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_mask.p, 0, (mw + 1) * 8, ctx->stream));
+  EvalParams ep;
+  memset(&ep, 0, sizeof ep);
+  ep.npose = 1; ep.nrb = 0; ep.nb = nb; ep.npairs = np; ep.nvc = 0; ep.object = -1;
+  ep.mode_all = all_mode ? 1 : 0; ep.do_energy = 0; ep.mask_words = mw;
+  ep.stack_phys = std::max(256, np + 96); ep.stack_cap = ep.stack_phys - 64;
+  ep.fk = nullptr; ep.static_xf = reinterpret_cast<const Xf *>(ctx->d_misc.p);
+  ep.body_mesh = d_bm; ep.meshes = ctx->d_meshes.p; ep.pairs = d_pairs; ep.vcs = nullptr;
+  ep.legal = ctx->d_legal.p; ep.energy = nullptr; ep.pair_mask = ctx->d_mask.p;
+  ep.pose_counter = ctx->d_counters.p; ep.ambig = ctx->d_ambig.p; ep.ambig_count = ctx->d_counters.p + 1;
+  ep.ambig_cap = (int)ctx->d_ambig.cap; ep.stats = nullptr;
+  size_t wb = eval_warp_smem_bytes(nb, np, mw, ep.stack_phys);
+  if (wb > 200 * 1024) return fail(ctx, B2C_ECAPACITY, "too many bodies/pairs for one query (%d bodies, %d pairs)", nb, np);
+  CU(launch_eval(ep, 1, 1, wb, ctx->stream)); ctx->launches++;
+  RecheckParams rp;
+  memset(&rp, 0, sizeof rp);
+  rp.ambig = ctx->d_ambig.p; rp.ambig_count = ctx->d_counters.p + 1; rp.ambig_cap = (int)ctx->d_ambig.cap;
+  rp.nrb = 0; rp.nb = nb; rp.fk = nullptr; rp.static_xf = ep.static_xf; rp.body_mesh = d_bm; rp.meshes = ctx->d_meshes.p;
+  rp.pairs = d_pairs; rp.legal = ctx->d_legal.p; rp.energy = nullptr; rp.pair_mask = ctx->d_mask.p; rp.mask_words = mw;
+  CU(launch_recheck(rp, ctx->stream)); ctx->launches++;
+  uint8_t lg = 1;
+  CU(cudaMemcpyAsync(&lg, ctx->d_legal.p, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(mask.data(), ctx->d_mask.p, mw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  legal = lg;
+  return B2C_OK;
+}
+
+// body-body distance over explicit static bodies; one warp per query
+int run_static_distance(b2c_ctx *ctx, int a, int b, double *dist, double pa[3], double pb[3]) {
+  int rc = sync_meshes(ctx); if (rc) return rc;
+  rc = ensure_scratch(ctx); if (rc) return rc;
+  Xf sx[2] = {qt_to_xf(ctx->bodies[a].tf), qt_to_xf(ctx->bodies[b].tf)};
+  int bm[2] = {ctx->bodies[a].mesh, ctx->bodies[b].mesh};
+  int2 q = make_int2(0, 1);
+  CU(ctx->d_misc.reserve(2 * 12 + 8));
+  CU(ctx->d_imisc.reserve(16));
+  CU(ctx->d_dist.reserve(4));
+  CU(ctx->d_pts.reserve(8));
+  int2 *d_q = reinterpret_cast<int2 *>(ctx->d_imisc.p);
+  int *d_bm = ctx->d_imisc.p + 2;
+  CU(cudaMemcpyAsync(ctx->d_misc.p, sx, sizeof sx, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_q, &q, sizeof q, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_bm, bm, sizeof bm, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(int), ctx->stream));
+  DistParams dp;
+  memset(&dp, 0, sizeof dp);
+  dp.npose = 1; dp.nrb = 0; dp.nb = 2; dp.nq = 1; dp.queries = d_q; dp.fk = nullptr;
+  dp.static_xf = reinterpret_cast<const Xf *>(ctx->d_misc.p); dp.body_mesh = d_bm; dp.meshes = ctx->d_meshes.p;
+  dp.legal = nullptr; dp.dist = ctx->d_dist.p; dp.pts = ctx->d_pts.p; dp.work_counter = ctx->d_counters.p;
+  dp.ambig = ctx->d_ambig.p; dp.ambig_count = ctx->d_counters.p + 1; dp.ambig_cap = (int)ctx->d_ambig.cap; dp.stats = nullptr;
+  CU(launch_dist(dp, 1, ctx->stream)); ctx->launches++;
+  RecheckParams rp;
+  memset(&rp, 0, sizeof rp);
+  rp.ambig = ctx->d_ambig.p; rp.ambig_count = ctx->d_counters.p + 1; rp.ambig_cap = (int)ctx->d_ambig.cap;
+  rp.nrb = 0; rp.nb = 2; rp.static_xf = dp.static_xf; rp.body_mesh = d_bm; rp.meshes = ctx->d_meshes.p; rp.pairs = d_q;
+  rp.dist = ctx->d_dist.p; rp.pts = ctx->d_pts.p; rp.nq = 1;
+  CU(launch_recheck(rp, ctx->stream)); ctx->launches++;
+  float d = 0.f;
+  double pts[6];
+  CU(cudaMemcpyAsync(&d, ctx->d_dist.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(pts, ctx->d_pts.p, sizeof pts, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *dist = d;
+  for (int k = 0; k < 3; k++) { pa[k] = pts[k]; pb[k] = pts[3 + k]; }
+  if (d >= 0.f) {
+    // report the distance from the fp64 closest points (the fp32 value only steered the search)
+    d3 wa = q_rot(ctx->bodies[a].tf, mk<double>(pa[0], pa[1], pa[2]));
+    d3 wb = q_rot(ctx->bodies[b].tf, mk<double>(pb[0], pb[1], pb[2]));
+    d3 dv = mk<double>(wa.x + ctx->bodies[a].tf.tx - wb.x - ctx->bodies[b].tf.tx,
+                       wa.y + ctx->bodies[a].tf.ty - wb.y - ctx->bodies[b].tf.ty,
+                       wa.z + ctx->bodies[a].tf.tz - wb.z - ctx->bodies[b].tf.tz);
+    *dist = std::sqrt(dot(dv, dv));
+  }
+  return B2C_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+extern "C" {
+
+int b2c_create(int device, b2c_ctx **out) {
+  if (!out) return B2C_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return B2C_ENODEVICE;
+  b2c_ctx *ctx = new b2c_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return B2C_ENODEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return B2C_OK;
+}
+
+void b2c_destroy(b2c_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  invalidate_plans(ctx);
+  for (auto &m : ctx->meshes) {
+    if (m.d_nodes) cudaFree(m.d_nodes);
+    if (m.d_tris) cudaFree(m.d_tris);
+    if (m.obb) obb_tree_free(m.obb);
+  }
+  ctx->d_meshes.release(); ctx->d_states.release(); ctx->d_fk.release(); ctx->d_fkqt.release(); ctx->d_legal.release();
+  ctx->d_energy.release(); ctx->d_mask.release(); ctx->d_ambig.release(); ctx->d_counters.release(); ctx->d_stats.release();
+  ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *b2c_last_error(const b2c_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void *b2c_stream(const b2c_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int b2c_device(const b2c_ctx *ctx) { return ctx ? ctx->device : -1; }
+long long b2c_launch_count(const b2c_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- geometry ------------------------------------------------------------------------------------
+int b2c_mesh_create(b2c_ctx *ctx, const float *tri9, int ntri, int *mesh_id) {
+  if (!ctx || !mesh_id || ntri < 0 || (ntri > 0 && !tri9)) return fail(ctx, B2C_EINVAL, "mesh_create: bad arguments");
+  if (ntri >= (1 << 23)) return fail(ctx, B2C_ECAPACITY, "mesh_create: %d triangles exceed the 2^23 per-mesh limit", ntri);
+  cudaSetDevice(ctx->device);
+  MeshHost m;
+  m.alive = true;
+  m.ntri = ntri;
+  m.tri9.assign(tri9, tri9 + 9 * (size_t)ntri);
+  build_bvh(m.tri9.data(), ntri, m.nodes, &m.depth);
+  const Node &r = m.nodes[0];
+  m.extent = ntri > 0 ? std::fabs(r.cx) + std::fabs(r.cy) + std::fabs(r.cz) + r.hx + r.hy + r.hz : 0.f;
+  std::vector<Tri> tris(std::max(ntri, 1));
+  for (int i = 0; i < ntri; i++)
+    for (int v = 0; v < 3; v++)
+      tris[i].v[v] = make_float4(tri9[9 * (size_t)i + 3 * v], tri9[9 * (size_t)i + 3 * v + 1], tri9[9 * (size_t)i + 3 * v + 2], 0.f);
+  CU(cudaMalloc(&m.d_nodes, m.nodes.size() * sizeof(Node)));
+  CU(cudaMalloc(&m.d_tris, tris.size() * sizeof(Tri)));
+  CU(cudaMemcpy(m.d_nodes, m.nodes.data(), m.nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(m.d_tris, tris.data(), tris.size() * sizeof(Tri), cudaMemcpyHostToDevice));
+  ctx->meshes.push_back(std::move(m));
+  ctx->meshes_dirty = true;
+  *mesh_id = (int)ctx->meshes.size() - 1;
+  return B2C_OK;
+}
+
+int b2c_mesh_destroy(b2c_ctx *ctx, int mesh_id) {
+  if (!ctx || !mesh_ok(ctx, mesh_id)) return fail(ctx, B2C_EINVAL, "mesh_destroy: unknown mesh %d", mesh_id);
+  for (auto &b : ctx->bodies)
+    if (b.alive && b.mesh == mesh_id) return fail(ctx, B2C_EINVAL, "mesh_destroy: mesh %d still used by a body", mesh_id);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  MeshHost &m = ctx->meshes[mesh_id];
+  cudaFree(m.d_nodes); cudaFree(m.d_tris);
+  if (m.obb) obb_tree_free(m.obb);
+  m = MeshHost();
+  ctx->meshes_dirty = true;
+  return B2C_OK;
+}
+
+int b2c_body_create(b2c_ctx *ctx, int mesh_id, int *body_id) {
+  if (!ctx || !body_id || !mesh_ok(ctx, mesh_id)) return fail(ctx, B2C_EINVAL, "body_create: unknown mesh %d", mesh_id);
+  BodyHost b;
+  b.alive = true; b.mesh = mesh_id; b.active = true; b.tf = q_identity();
+  ctx->bodies.push_back(b);
+  *body_id = (int)ctx->bodies.size() - 1;
+  invalidate_plans(ctx);
+  return B2C_OK;
+}
+
+int b2c_body_set_mesh(b2c_ctx *ctx, int body_id, int mesh_id) {
+  if (!ctx || !body_ok(ctx, body_id) || !mesh_ok(ctx, mesh_id)) return fail(ctx, B2C_EINVAL, "body_set_mesh: unknown body/mesh");
+  ctx->bodies[body_id].mesh = mesh_id;
+  invalidate_plans(ctx);
+  return B2C_OK;
+}
+
+int b2c_body_remove(b2c_ctx *ctx, int body_id) {
+  if (!ctx || !body_ok(ctx, body_id)) return fail(ctx, B2C_EINVAL, "body_remove: unknown body %d", body_id);
+  ctx->bodies[body_id].alive = false;
+  for (auto it = ctx->disabled.begin(); it != ctx->disabled.end();)
+    if (it->first == body_id || it->second == body_id) it = ctx->disabled.erase(it); else ++it;
+  invalidate_plans(ctx);
+  return B2C_OK;
+}
+
+int b2c_body_set_transform(b2c_ctx *ctx, int body_id, const double q[4], const double t[3]) {
+  if (!ctx || !body_ok(ctx, body_id) || !q || !t) return fail(ctx, B2C_EINVAL, "set_transform: unknown body %d", body_id);
+  ctx->bodies[body_id].tf = make_qt(q, t);
+  return B2C_OK;
+}
+
+int b2c_body_get_transform(b2c_ctx *ctx, int body_id, double q[4], double t[3]) {
+  if (!ctx || !body_ok(ctx, body_id) || !q || !t) return fail(ctx, B2C_EINVAL, "get_transform: unknown body %d", body_id);
+  const Qt &f = ctx->bodies[body_id].tf;
+  q[0] = f.w; q[1] = f.x; q[2] = f.y; q[3] = f.z; t[0] = f.tx; t[1] = f.ty; t[2] = f.tz;
+  return B2C_OK;
+}
+
+int b2c_body_set_active(b2c_ctx *ctx, int body_id, int active) {
+  if (!ctx || !body_ok(ctx, body_id)) return fail(ctx, B2C_EINVAL, "set_active: unknown body %d", body_id);
+  ctx->bodies[body_id].active = active != 0;
+  invalidate_plans(ctx);
+  return B2C_OK;
+}
+
+int b2c_pair_set_active(b2c_ctx *ctx, int a, int b, int active) {
+  if (!ctx || !body_ok(ctx, a) || !body_ok(ctx, b)) return fail(ctx, B2C_EINVAL, "pair_set_active: unknown body");
+  if (a == b) {   // reference: "insertion collision pair is actually one body" -> toggles the body
+    ctx->bodies[a].active = active != 0;
+  } else {
+    std::pair<int, int> k(std::min(a, b), std::max(a, b));
+    if (active) ctx->disabled.erase(k); else ctx->disabled.insert(k);
+  }
+  invalidate_plans(ctx);
+  return B2C_OK;
+}
+
+int b2c_pair_is_active(b2c_ctx *ctx, int a, int b, int *active) {
+  if (!ctx || !active || !body_ok(ctx, a)) return fail(ctx, B2C_EINVAL, "pair_is_active: unknown body");
+  if (b < 0 || a == b) { *active = ctx->bodies[a].active ? 1 : 0; return B2C_OK; }
+  if (!body_ok(ctx, b)) return fail(ctx, B2C_EINVAL, "pair_is_active: unknown body");
+  *active = pair_active(ctx, a, b) ? 1 : 0;
+  return B2C_OK;
+}
+
+// ---- single-pose queries ---------------------------------------------------------------------------
+int b2c_all_collisions(b2c_ctx *ctx, int fast, const int *interest, int ninterest, int *pairs_out, int cap, int *ncolliding) {
+  if (!ctx || !ncolliding) return fail(ctx, B2C_EINVAL, "all_collisions: bad arguments");
+  cudaSetDevice(ctx->device);
+  std::set<int> il;
+  if (interest) for (int i = 0; i < ninterest; i++) if (body_ok(ctx, interest[i])) il.insert(interest[i]);
+  std::vector<std::pair<int, int>> pairs;
+  active_pairs(ctx, interest ? &il : nullptr, pairs);
+  std::vector<unsigned long long> mask;
+  int legal = 1;
+  int rc = run_static_collisions(ctx, pairs, !fast, mask, legal);
+  if (rc) return rc;
+  if (fast) { *ncolliding = legal ? 0 : 1; return B2C_OK; }
+  int n = 0;
+  for (size_t i = 0; i < pairs.size(); i++)
+    if ((mask[i >> 6] >> (i & 63)) & 1ull) {
+      if (pairs_out && n < cap) { pairs_out[2 * n] = pairs[i].first; pairs_out[2 * n + 1] = pairs[i].second; }
+      n++;
+    }
+  *ncolliding = n;
+  return B2C_OK;
+}
+
+int b2c_body_distance(b2c_ctx *ctx, int a, int b, double *dist, double p1[3], double p2[3], double p1l[3], double p2l[3]) {
+  if (!ctx || !dist) return fail(ctx, B2C_EINVAL, "body_distance: bad arguments");
+  if (!body_ok(ctx, a) || !body_ok(ctx, b)) { *dist = 0.0; return fail(ctx, B2C_EINVAL, "body_distance: model not found"); }
+  cudaSetDevice(ctx->device);
+  double pa[3], pb[3];
+  int rc = run_static_distance(ctx, a, b, dist, pa, pb);
+  if (rc) return rc;
+  if (p1l) for (int k = 0; k < 3; k++) p1l[k] = pa[k];
+  if (p2l) for (int k = 0; k < 3; k++) p2l[k] = pb[k];
+  // reference quirk: the already-local points are pushed through the inverse body transforms once more
+  // (graspitCollision.cpp:473-475)
+  if (p1) { Qt inv = q_inverse(ctx->bodies[a].tf); d3 r = q_rot(inv, mk<double>(pa[0], pa[1], pa[2])); p1[0] = r.x + inv.tx; p1[1] = r.y + inv.ty; p1[2] = r.z + inv.tz; }
+  if (p2) { Qt inv = q_inverse(ctx->bodies[b].tf); d3 r = q_rot(inv, mk<double>(pb[0], pb[1], pb[2])); p2[0] = r.x + inv.tx; p2[1] = r.y + inv.ty; p2[2] = r.z + inv.tz; }
+  return B2C_OK;
+}
+
+int b2c_point_distance(b2c_ctx *ctx, int body, const double point[3], double *dist, double closest[3], double normal[3]) {
+  if (!ctx || !dist || !point) return fail(ctx, B2C_EINVAL, "point_distance: bad arguments");
+  if (!body_ok(ctx, body)) { *dist = 0.0; return fail(ctx, B2C_EINVAL, "point_distance: model not found"); }
+  cudaSetDevice(ctx->device);
+  int rc = sync_meshes(ctx); if (rc) return rc;
+  CU(ctx->d_misc.reserve(12 + 3 + 7 + 8));
+  Xf x = qt_to_xf(ctx->bodies[body].tf);
+  double *d_x = ctx->d_misc.p, *d_p = d_x + 12, *d_o = d_p + 4;
+  CU(cudaMemcpyAsync(d_x, &x, sizeof x, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_p, point, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  PointParams pp;
+  pp.n = 1; pp.points = d_p; pp.body_xf = reinterpret_cast<const Xf *>(d_x);
+  const MeshHost &m = ctx->meshes[ctx->bodies[body].mesh];
+  pp.mesh.nodes = m.d_nodes; pp.mesh.tris = m.d_tris; pp.mesh.nnodes = (int)m.nodes.size(); pp.mesh.ntri = m.ntri;
+  pp.mesh.extent = m.extent; pp.mesh.depth = m.depth;
+  pp.out = d_o;
+  CU(launch_point(pp, ctx->stream)); ctx->launches++;
+  double o[7];
+  CU(cudaMemcpyAsync(o, d_o, sizeof o, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *dist = o[0];
+  if (closest) for (int k = 0; k < 3; k++) closest[k] = o[1 + k];
+  if (normal) for (int k = 0; k < 3; k++) normal[k] = o[4 + k];
+  return B2C_OK;
+}
+
+int b2c_bounding_volumes(b2c_ctx *ctx, int body, int depth, b2c_obb *out, int cap, int *nboxes) {
+  if (!ctx || !nboxes) return fail(ctx, B2C_EINVAL, "bounding_volumes: bad arguments");
+  if (!body_ok(ctx, body)) { *nboxes = 0; return fail(ctx, B2C_EINVAL, "bounding_volumes: model not found"); }
+  MeshHost &m = ctx->meshes[ctx->bodies[body].mesh];
+  if (!m.obb) m.obb = obb_tree_build(m.tri9.data(), m.ntri);
+  std::vector<ObbBox> boxes;
+  obb_tree_level(m.obb, depth, boxes);
+  *nboxes = (int)boxes.size();
+  for (int i = 0; i < (int)boxes.size() && i < cap && out; i++) {
+    for (int k = 0; k < 3; k++) { out[i].t[k] = boxes[i].t[k]; out[i].half[k] = boxes[i].half[k]; }
+    for (int k = 0; k < 4; k++) out[i].q_wxyz[k] = boxes[i].q[k];
+  }
+  return B2C_OK;
+}
+
+// ---- robots ----------------------------------------------------------------------------------------
+int b2c_robot_define(b2c_ctx *ctx, const b2c_robot_desc *d, int *robot_id) {
+  if (!ctx || !d || !robot_id) return fail(ctx, B2C_EINVAL, "robot_define: bad arguments");
+  if (!body_ok(ctx, d->base_body)) return fail(ctx, B2C_EINVAL, "robot_define: unknown base body %d", d->base_body);
+  if (d->ndof > FK_MAX_DOF_HOST) return fail(ctx, B2C_ECAPACITY, "robot_define: more than %d DOFs", FK_MAX_DOF_HOST);
+  RobotHost r;
+  r.d = *d;
+  r.dof_min.assign(d->dof_min, d->dof_min + d->ndof);
+  r.dof_max.assign(d->dof_max, d->dof_max + d->ndof);
+  r.chains.assign(d->chains, d->chains + d->nchains);
+  r.joints.assign(d->joints, d->joints + d->njoints);
+  r.link_body.assign(d->link_body, d->link_body + d->nlinks);
+  r.link_last_joint.assign(d->link_last_joint, d->link_last_joint + d->nlinks);
+  for (int b : r.link_body) if (!body_ok(ctx, b)) return fail(ctx, B2C_EINVAL, "robot_define: unknown link body %d", b);
+  if (d->neg > 0 && d->eg) {
+    r.eg.assign(d->eg, d->eg + (size_t)d->neg * d->ndof);
+    r.eg_origin.assign(d->eg_origin, d->eg_origin + d->ndof);
+    r.eg_norm.assign(d->eg_norm, d->eg_norm + d->ndof);
+  } else {
+    r.d.neg = 0;
+  }
+  if (d->nvcontacts > 0) r.vcs.assign(d->vcontacts, d->vcontacts + d->nvcontacts);
+  if (d->parent_robot >= (int)ctx->robots.size()) return fail(ctx, B2C_EINVAL, "robot_define: parent robot %d not defined yet", d->parent_robot);
+  ctx->robots.push_back(std::move(r));
+  *robot_id = (int)ctx->robots.size() - 1;
+  invalidate_plans(ctx);
+  return B2C_OK;
+}
+
+} // extern "C"
+
+namespace {
+
+void collect_robots(const b2c_ctx *c, int root, std::vector<int> &order) {
+  order.push_back(root);
+  for (int r = 0; r < (int)c->robots.size(); r++)
+    if (c->robots[r].d.parent_robot == root) collect_robots(c, r, order);
+}
+
+// bodies of one robot in World::findVirtualContacts order: links chain-major, base, mount
+void robot_own_bodies(const RobotHost &r, std::vector<int> &out) {
+  for (int b : r.link_body) out.push_back(b);
+  out.push_back(r.d.base_body);
+  if (r.d.mount_body >= 0) out.push_back(r.d.mount_body);
+}
+
+int build_plan(b2c_ctx *ctx, int robot, int object, Plan **out) {
+  auto key = std::make_pair(robot, object);
+  auto it = ctx->plans.find(key);
+  if (it != ctx->plans.end() && it->second->valid) { *out = it->second; return B2C_OK; }
+  Plan *P = new Plan();
+  P->robot = robot; P->object = object;
+  collect_robots(ctx, robot, P->robots);
+  std::map<int, int> slot_of;
+  for (size_t i = 0; i < P->robots.size(); i++) {
+    std::vector<int> own;
+    robot_own_bodies(ctx->robots[P->robots[i]], own);
+    if (i == 0) P->nhand = (int)own.size();
+    for (int b : own) { slot_of[b] = (int)P->slots.size(); P->slots.push_back(b); }
+  }
+  // FK program
+  std::vector<FkRobot> fr; std::vector<FkChain> fc; std::vector<FkJoint> fj; std::vector<FkLink> fl; std::vector<double> eg;
+  int dof_ofs = 0;
+  std::map<int, int> prog_index;
+  for (size_t i = 0; i < P->robots.size(); i++) {
+    const RobotHost &r = ctx->robots[P->robots[i]];
+    prog_index[P->robots[i]] = (int)i;
+    FkRobot R;
+    memset(&R, 0, sizeof R);
+    R.base_slot = slot_of[r.d.base_body];
+    R.mount_slot = r.d.mount_body >= 0 ? slot_of[r.d.mount_body] : -1;
+    R.parent = -1; R.parent_last_slot = -1; R.parent_offset = q_identity();
+    if (i > 0) {
+      const RobotHost &pr = ctx->robots[r.d.parent_robot];
+      R.parent = prog_index[r.d.parent_robot];
+      const b2c_chain_desc &pc = pr.chains[r.d.parent_chain];
+      R.parent_last_slot = slot_of[pr.link_body[pc.first_link + pc.nlinks - 1]];
+      R.parent_offset = make_qt(r.d.parent_offset_q, r.d.parent_offset_t);
+    }
+    R.dof_ofs = dof_ofs; R.ndof = r.d.ndof;
+    R.first_chain = (int)fc.size(); R.nchains = r.d.nchains;
+    R.approach_inv = q_inverse(make_qt(r.d.approach_q, r.d.approach_t));
+    R.neg = r.d.neg;
+    R.eg_ofs = (int)eg.size();
+    if (r.d.neg > 0) {
+      eg.insert(eg.end(), r.eg.begin(), r.eg.end());
+      eg.insert(eg.end(), r.eg_origin.begin(), r.eg_origin.end());
+      eg.insert(eg.end(), r.eg_norm.begin(), r.eg_norm.end());
+      eg.insert(eg.end(), r.dof_min.begin(), r.dof_min.end());
+      eg.insert(eg.end(), r.dof_max.begin(), r.dof_max.end());
+    }
+    for (int ci = 0; ci < r.d.nchains; ci++) {
+      const b2c_chain_desc &c = r.chains[ci];
+      FkChain C;
+      C.tran = make_qt(c.tran_q, c.tran_t);
+      C.first_joint = (int)fj.size(); C.njoints = c.njoints;
+      C.first_link = (int)fl.size(); C.nlinks = c.nlinks;
+      for (int j = 0; j < c.njoints; j++) {
+        const b2c_joint_desc &jd = r.joints[c.first_joint + j];
+        FkJoint J;
+        J.dof = dof_ofs + jd.dof; J.revolute = jd.revolute; J.ratio = jd.ratio; J.theta = jd.theta; J.d = jd.d;
+        Qt tr3 = q_identity(); tr3.tx = jd.a;
+        J.tr4tr3 = q_compose(tr3, q_axis_angle(jd.alpha, 1.0, 0.0, 0.0));
+        fj.push_back(J);
+      }
+      for (int l = 0; l < c.nlinks; l++) {
+        FkLink L;
+        L.out_slot = slot_of[r.link_body[c.first_link + l]];
+        L.last_joint = r.link_last_joint[c.first_link + l];
+        fl.push_back(L);
+      }
+      fc.push_back(C);
+    }
+    dof_ofs += r.d.ndof;
+    fr.push_back(R);
+  }
+  P->ndof_total = dof_ofs;
+  if (dof_ofs > FK_MAX_DOF_HOST) { delete P; return fail(ctx, B2C_ECAPACITY, "more than %d DOFs in the robot tree", FK_MAX_DOF_HOST); }
+
+  // eval bodies and pairs: every active pair touching a robot body (World::noCollision interest list,
+  // src/world.cpp:1491-1503)
+  P->ebodies = P->slots;
+  std::map<int, int> eidx;
+  for (size_t i = 0; i < P->slots.size(); i++) eidx[P->slots[i]] = (int)i;
+  std::set<int> interest(P->slots.begin(), P->slots.end());
+  std::vector<std::pair<int, int>> ap;
+  active_pairs(ctx, &interest, ap);
+  auto eb = [&](int b) {
+    auto f = eidx.find(b);
+    if (f != eidx.end()) return f->second;
+    eidx[b] = (int)P->ebodies.size();
+    P->ebodies.push_back(b);
+    return eidx[b];
+  };
+  for (auto &pr : ap) {
+    P->pairs.push_back(make_int2(eb(pr.first), eb(pr.second)));
+    P->pair_ids.push_back(make_int2(pr.first, pr.second));
+  }
+  P->object_e = object >= 0 ? eb(object) : -1;
+  // virtual contacts of the root robot (Grasp::collectVirtualContacts order is irrelevant to the mean)
+  std::vector<VcDev> vcs;
+  for (auto &v : ctx->robots[robot].vcs) {
+    VcDev d;
+    memset(&d, 0, sizeof d);
+    auto f = eidx.find(v.body);
+    if (f == eidx.end()) continue;
+    d.body = f->second;
+    for (int k = 0; k < 3; k++) { d.loc[k] = v.loc[k]; d.normal[k] = v.normal[k]; }
+    vcs.push_back(d);
+  }
+  P->nvc = (int)vcs.size();
+  std::vector<int> bm(P->ebodies.size());
+  for (size_t i = 0; i < bm.size(); i++) bm[i] = ctx->bodies[P->ebodies[i]].mesh;
+  std::vector<int2> queries;
+  if (P->object_e >= 0) for (int i = 0; i < P->nhand; i++) queries.push_back(make_int2(i, P->object_e));
+
+#define UP(buf, vec)                                                                                        \
+  do {                                                                                                      \
+    if (P->buf.reserve((vec).size() + 1) != cudaSuccess) { delete P; return fail(ctx, B2C_ECUDA, "plan upload: cudaMalloc failed"); } \
+    if (!(vec).empty() && cudaMemcpy(P->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice) != cudaSuccess) { \
+      delete P; return fail(ctx, B2C_ECUDA, "plan upload: cudaMemcpy failed"); }                            \
+  } while (0)
+  UP(d_robots, fr); UP(d_chains, fc); UP(d_joints, fj); UP(d_links, fl); UP(d_eg, eg);
+  UP(d_body_mesh, bm); UP(d_pairs, P->pairs); UP(d_vcs, vcs); UP(d_queries, queries);
+#undef UP
+  if (P->d_static.reserve(P->ebodies.size() - P->slots.size() + 1) != cudaSuccess) { delete P; return fail(ctx, B2C_ECUDA, "plan upload: cudaMalloc failed"); }
+  P->prog.robots = P->d_robots.p; P->prog.chains = P->d_chains.p; P->prog.joints = P->d_joints.p; P->prog.links = P->d_links.p;
+  P->prog.egdata = P->d_eg.p; P->prog.nrobots = (int)fr.size(); P->prog.nslots = (int)P->slots.size(); P->prog.ndof_total = dof_ofs;
+  P->valid = true;
+  ctx->plans[key] = P;
+  *out = P;
+  return B2C_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int b2c_robot_bodies(b2c_ctx *ctx, int robot, int *bodies, int cap, int *nbodies) {
+  if (!ctx || !nbodies || robot < 0 || robot >= (int)ctx->robots.size()) return fail(ctx, B2C_EINVAL, "robot_bodies: unknown robot");
+  cudaSetDevice(ctx->device);
+  Plan *P;
+  int rc = build_plan(ctx, robot, -1, &P);
+  if (rc) return rc;
+  *nbodies = (int)P->slots.size();
+  for (int i = 0; i < (int)P->slots.size() && i < cap && bodies; i++) bodies[i] = P->slots[i];
+  return B2C_OK;
+}
+
+int b2c_robot_pairs(b2c_ctx *ctx, int robot, int *pairs, int cap, int *npairs) {
+  if (!ctx || !npairs || robot < 0 || robot >= (int)ctx->robots.size()) return fail(ctx, B2C_EINVAL, "robot_pairs: unknown robot");
+  cudaSetDevice(ctx->device);
+  Plan *P;
+  int rc = build_plan(ctx, robot, -1, &P);
+  if (rc) return rc;
+  *npairs = (int)P->pair_ids.size();
+  for (int i = 0; i < (int)P->pair_ids.size() && i < cap && pairs; i++) { pairs[2 * i] = P->pair_ids[i].x; pairs[2 * i + 1] = P->pair_ids[i].y; }
+  return B2C_OK;
+}
+
+int b2c_last_stats(b2c_ctx *ctx, unsigned long long stats[8]) {
+  if (!ctx || !stats) return B2C_EINVAL;
+  for (int i = 0; i < 8; i++) stats[i] = ctx->last_stats[i];
+  return B2C_OK;
+}
+
+int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
+  if (!ctx || !a) return fail(ctx, B2C_EINVAL, "eval_batch: null arguments");
+  if (a->robot < 0 || a->robot >= (int)ctx->robots.size()) return fail(ctx, B2C_EINVAL, "eval_batch: unknown robot %d", a->robot);
+  if (a->object >= 0 && !body_ok(ctx, a->object)) return fail(ctx, B2C_EINVAL, "eval_batch: unknown object body %d", a->object);
+  if (a->npose < 0 || !a->states) return fail(ctx, B2C_EINVAL, "eval_batch: bad pose batch");
+  if (a->npose == 0) return B2C_OK;
+  cudaSetDevice(ctx->device);
+  int rc = sync_meshes(ctx); if (rc) return rc;
+  rc = ensure_scratch(ctx); if (rc) return rc;
+  Plan *P;
+  rc = build_plan(ctx, a->robot, a->object, &P); if (rc) return rc;
+  const RobotHost &root = ctx->robots[a->robot];
+  const int npose = a->npose;
+  const bool dev = (a->flags & B2C_EVAL_DEVICE_PTRS) != 0;
+  const bool live = (a->flags & B2C_EVAL_LIVE) != 0;
+  const bool want_mask = (a->flags & B2C_EVAL_PAIRMASK) != 0 && a->pair_mask;
+  const bool want_dist = (a->flags & B2C_EVAL_LINKDIST) != 0 && a->link_dist;
+  int min_stride = a->input_mode == B2C_INPUT_RAW ? 7 + P->ndof_total : 6 + root.d.neg;
+  if (a->stride < min_stride) return fail(ctx, B2C_EINVAL, "eval_batch: stride %d < %d", a->stride, min_stride);
+  if (a->input_mode == B2C_INPUT_AA_EIGEN && root.d.neg <= 0) return fail(ctx, B2C_EINVAL, "eval_batch: robot has no eigengrasps");
+  if ((live || want_dist) && a->object < 0) return fail(ctx, B2C_EINVAL, "eval_batch: LIVE / LINKDIST need an object");
+  const int nrb = (int)P->slots.size(), nb = (int)P->ebodies.size(), np = (int)P->pairs.size();
+  const int mw = std::max(1, (np + 63) / 64);
+
+  // inputs
+  const float *d_states = a->states;
+  if (!dev) {
+    CU(ctx->d_states.reserve((size_t)npose * a->stride));
+    CU(cudaMemcpyAsync(ctx->d_states.p, a->states, (size_t)npose * a->stride * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    d_states = ctx->d_states.p;
+  }
+  CU(ctx->d_fk.reserve((size_t)npose * nrb));
+  const bool want_tf = a->body_tf != nullptr;
+  if (want_tf && !dev) CU(ctx->d_fkqt.reserve((size_t)npose * nrb * 7));
+  uint8_t *d_legal = dev && a->legal ? a->legal : nullptr;
+  float *d_energy = dev && a->energy ? a->energy : nullptr;
+  unsigned long long *d_mask = dev && want_mask ? (unsigned long long *)a->pair_mask : nullptr;
+  if (!d_legal) { CU(ctx->d_legal.reserve(npose)); d_legal = ctx->d_legal.p; }
+  if (!d_energy) { CU(ctx->d_energy.reserve(npose)); d_energy = ctx->d_energy.p; }
+  if (want_mask && !d_mask) { CU(ctx->d_mask.reserve((size_t)npose * mw)); d_mask = ctx->d_mask.p; }
+  // static transforms
+  std::vector<Xf> sx(nb - nrb);
+  for (int i = nrb; i < nb; i++) sx[i - nrb] = qt_to_xf(ctx->bodies[P->ebodies[i]].tf);
+  if (!sx.empty()) CU(cudaMemcpyAsync(P->d_static.p, sx.data(), sx.size() * sizeof(Xf), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_stats.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+
+  // K1
+  FkParams fp;
+  memset(&fp, 0, sizeof fp);
+  fp.prog = P->prog; fp.npose = npose; fp.input_mode = a->input_mode; fp.stride = a->stride; fp.states = d_states;
+  fp.ref = make_qt(a->ref_q, a->ref_t);
+  fp.out = ctx->d_fk.p;
+  fp.out_qt = want_tf ? (dev ? a->body_tf : ctx->d_fkqt.p) : nullptr;
+  CU(launch_fk(fp, ctx->stream)); ctx->launches++;
+
+  // K3 (+K5+K8 when PRESET)
+  EvalParams ep;
+  memset(&ep, 0, sizeof ep);
+  ep.npose = npose; ep.nrb = nrb; ep.nb = nb; ep.npairs = np; ep.nvc = P->nvc; ep.object = P->object_e;
+  ep.mode_all = want_mask ? 1 : 0;
+  ep.do_energy = (!live && a->object >= 0 && P->nvc > 0) ? 1 : 0;
+  ep.mask_words = mw;
+  ep.stack_phys = std::max(256, np + 96); ep.stack_cap = ep.stack_phys - 64;
+  ep.fk = ctx->d_fk.p; ep.static_xf = P->d_static.p; ep.body_mesh = P->d_body_mesh.p; ep.meshes = ctx->d_meshes.p;
+  ep.pairs = P->d_pairs.p; ep.vcs = P->d_vcs.p; ep.legal = d_legal; ep.energy = d_energy; ep.pair_mask = d_mask;
+  ep.pose_counter = ctx->d_counters.p; ep.ambig = ctx->d_ambig.p; ep.ambig_count = ctx->d_counters.p + 1;
+  ep.ambig_cap = (int)ctx->d_ambig.cap; ep.stats = ctx->d_stats.p;
+  size_t wb = eval_warp_smem_bytes(nb, np, mw, ep.stack_phys);
+  if (wb > 200 * 1024) return fail(ctx, B2C_ECAPACITY, "eval_batch: %d bodies / %d pairs exceed the per-warp shared memory", nb, np);
+  int blocks, wpb; size_t smem;
+  eval_launch_shape(ctx, wb, npose, blocks, wpb, smem);
+  CU(launch_eval(ep, blocks, wpb, smem, ctx->stream)); ctx->launches++;
+  RecheckParams rp;
+  memset(&rp, 0, sizeof rp);
+  rp.ambig = ctx->d_ambig.p; rp.ambig_count = ctx->d_counters.p + 1; rp.ambig_cap = (int)ctx->d_ambig.cap;
+  rp.nrb = nrb; rp.nb = nb; rp.fk = ctx->d_fk.p; rp.static_xf = P->d_static.p; rp.body_mesh = P->d_body_mesh.p;
+  rp.meshes = ctx->d_meshes.p; rp.pairs = P->d_pairs.p; rp.legal = d_legal; rp.energy = d_energy; rp.pair_mask = d_mask;
+  rp.mask_words = mw; rp.stats = ctx->d_stats.p;
+  CU(launch_recheck(rp, ctx->stream)); ctx->launches++;
+
+  // K4 (+ LIVE energy)
+  float *d_dist = nullptr;
+  const int nq = P->nhand;
+  if (live || want_dist) {
+    CU(ctx->d_dist.reserve((size_t)npose * nq));
+    CU(ctx->d_pts.reserve((size_t)npose * nq * 6));
+    d_dist = dev && want_dist ? a->link_dist : ctx->d_dist.p;
+    DistParams dp;
+    memset(&dp, 0, sizeof dp);
+    dp.npose = npose; dp.nrb = nrb; dp.nb = nb; dp.nq = nq; dp.queries = P->d_queries.p; dp.fk = ctx->d_fk.p;
+    dp.static_xf = P->d_static.p; dp.body_mesh = P->d_body_mesh.p; dp.meshes = ctx->d_meshes.p;
+    dp.legal = want_dist ? nullptr : d_legal;       // LIVE alone only needs legal poses
+    dp.dist = d_dist; dp.pts = ctx->d_pts.p; dp.work_counter = ctx->d_counters.p + 2;
+    dp.ambig = ctx->d_ambig.p; dp.ambig_count = ctx->d_counters.p + 3; dp.ambig_cap = (int)ctx->d_ambig.cap; dp.stats = ctx->d_stats.p;
+    int dblocks = std::min(ctx->sm_count * 4, (npose * nq + 7) / 8);
+    CU(launch_dist(dp, std::max(1, dblocks), ctx->stream)); ctx->launches++;
+    RecheckParams rd;
+    memset(&rd, 0, sizeof rd);
+    rd.ambig = ctx->d_ambig.p; rd.ambig_count = ctx->d_counters.p + 3; rd.ambig_cap = (int)ctx->d_ambig.cap;
+    rd.nrb = nrb; rd.nb = nb; rd.fk = ctx->d_fk.p; rd.static_xf = P->d_static.p; rd.body_mesh = P->d_body_mesh.p;
+    rd.meshes = ctx->d_meshes.p; rd.pairs = P->d_queries.p; rd.dist = d_dist; rd.pts = ctx->d_pts.p; rd.nq = nq; rd.stats = ctx->d_stats.p;
+    CU(launch_recheck(rd, ctx->stream)); ctx->launches++;
+    if (live) {
+      LiveParams lp;
+      memset(&lp, 0, sizeof lp);
+      lp.npose = npose; lp.nrb = nrb; lp.nb = nb; lp.nq = nq; lp.object = P->object_e; lp.fk = ctx->d_fk.p;
+      lp.static_xf = P->d_static.p; lp.body_mesh = P->d_body_mesh.p; lp.meshes = ctx->d_meshes.p;
+      lp.dist = d_dist; lp.pts = ctx->d_pts.p; lp.legal = d_legal; lp.energy = d_energy; lp.stats = ctx->d_stats.p;
+      CU(launch_live(lp, ctx->stream)); ctx->launches++;
+    }
+  }
+
+  // outputs
+  if (!dev) {
+    if (a->legal) CU(cudaMemcpyAsync(a->legal, d_legal, npose, cudaMemcpyDeviceToHost, ctx->stream));
+    if (a->energy) CU(cudaMemcpyAsync(a->energy, d_energy, (size_t)npose * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_mask) CU(cudaMemcpyAsync(a->pair_mask, d_mask, (size_t)npose * mw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_dist) CU(cudaMemcpyAsync(a->link_dist, d_dist, (size_t)npose * nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_tf) CU(cudaMemcpyAsync(a->body_tf, ctx->d_fkqt.p, (size_t)npose * nrb * 7 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaMemcpyAsync(ctx->last_stats, ctx->d_stats.p, sizeof ctx->last_stats, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!dev) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    int amb[4];
+    CU(cudaMemcpy(amb, ctx->d_counters.p, sizeof amb, cudaMemcpyDeviceToHost));
+    if (amb[1] > (int)ctx->d_ambig.cap || amb[3] > (int)ctx->d_ambig.cap)
+      return fail(ctx, B2C_ECAPACITY, "eval_batch: recheck queue overflow (%d entries)", std::max(amb[1], amb[3]));
+  }
+  return B2C_OK;
+}
+
+} // extern "C"
+
+// ---- contacts / region (K6, K7) ------------------------------------------------------------------
+#include "contacts_api.inc"

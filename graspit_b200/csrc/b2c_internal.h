@@ -1,0 +1,207 @@
+// Internal data layouts shared by the host (api.cu, bvh.cpp) and the kernels (kernels.cu).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "geom.cuh"
+#include "bvh.h"
+
+namespace b2c {
+
+// triangle: three float4 (x,y,z,0), 48 B, 16-B aligned
+struct Tri {
+  float4 v[3];
+};
+
+struct MeshDev {
+  const Node *nodes;
+  const Tri *tris;
+  int nnodes;
+  int ntri;
+  float extent;      // |root centre|_1 + |root half|_1 : coordinate scale of the mesh
+  int depth;
+};
+
+// ---- forward-kinematics program ----------------------------------------
+struct FkJoint {
+  int dof;           // index into the pose's DOF vector (robot dof offset already added)
+  int revolute;
+  double ratio, theta, d;
+  Qt tr4tr3;         // TRANSLATION(a,0,0) % AXIS_ANGLE_ROTATION(alpha, x)   (joint.cpp:68-88)
+};
+struct FkChain {
+  Qt tran;
+  int first_joint, njoints;
+  int first_link, nlinks;
+};
+struct FkLink {
+  int out_slot;      // slot in the per-pose output
+  int last_joint;    // chain-local joint index after which the link pose is read
+};
+struct FkRobot {
+  int base_slot, mount_slot;
+  int parent;            // index into the program's robot list, -1 for the root
+  int parent_last_slot;  // output slot of the parent chain's last link
+  Qt parent_offset;
+  int dof_ofs, ndof;
+  int first_chain, nchains;
+  Qt approach_inv;
+  int neg;
+  int eg_ofs;            // offset into eg arrays: eg[neg*ndof], origin[ndof], norm[ndof], min[ndof], max[ndof]
+};
+struct FkProgram {
+  const FkRobot *robots;
+  const FkChain *chains;
+  const FkJoint *joints;
+  const FkLink *links;
+  const double *egdata;
+  int nrobots;
+  int nslots;
+  int ndof_total;
+};
+
+// ---- batched evaluation plan ---------------------------------------------------------------------
+struct VcDev {
+  int body;            // eval-body index
+  int pad;
+  double loc[3];
+  double normal[3];
+};
+
+struct Ambig {         // triangle pair whose fp32 SAT was too close to call
+  int pose, pair, tri_a, tri_b;
+};
+
+struct EvalParams {
+  int npose;
+  int nrb;             // robot bodies: transforms come from fk[pose][0..nrb)
+  int nb;              // all eval bodies (robot bodies first, then static bodies)
+  int npairs;
+  int nvc;
+  int object;          // eval-body index of the target object, -1 if none
+  int mode_all;        // 1: evaluate every pair (ALL_COLLISIONS mask); 0: stop at the first hit
+  int do_energy;       // 1: CONTACT_PRESET energy fused behind the legality test
+  int mask_words;      // 64-bit words per pose in pair_mask
+  int stage_nodes;     // top-of-tree nodes of the object mesh staged in shared memory (0 = off)
+  int stack_cap;       // logical / physical entries of the per-warp work stack
+  int stack_phys;
+  const Xf *fk;
+  const Xf *static_xf;     // [nb - nrb]
+  const int *body_mesh;    // [nb]
+  const MeshDev *meshes;
+  const int2 *pairs;       // [npairs] eval-body indices
+  const VcDev *vcs;
+  uint8_t *legal;
+  float *energy;
+  unsigned long long *pair_mask;
+  int *pose_counter;
+  Ambig *ambig;
+  int *ambig_count;
+  int ambig_cap;
+  unsigned long long *stats;   // [8]: box tests, tri-pair tests, point-box, point-tri, ambiguous, ...
+};
+
+// LIVE contacts / generic point-energy input: per pose, per contact: world location + world normal
+struct LiveContact {
+  double loc[3];
+  double cn[3];
+};
+
+struct DistParams {
+  int npose;
+  int nrb, nb;
+  int nq;                  // distance queries per pose
+  const int2 *queries;     // [nq] (eval body a, eval body b)
+  const Xf *fk;
+  const Xf *static_xf;
+  const int *body_mesh;
+  const MeshDev *meshes;
+  const uint8_t *legal;    // optional: skip poses with legal == 0
+  float *dist;             // [npose][nq]  (-1 = interpenetration)
+  double *pts;             // optional [npose][nq][6]: closest points, each in its own body frame
+  int *work_counter;
+  Ambig *ambig;
+  int *ambig_count;
+  int ambig_cap;
+  unsigned long long *stats;
+};
+
+enum { STAT_BOX = 0, STAT_TRI = 1, STAT_PBOX = 2, STAT_PTRI = 3, STAT_AMBIG = 4, STAT_DBOX = 5, STAT_DTRI = 6, STAT_HITFIX = 7 };
+
+// per-warp shared-memory budget of the evaluation kernel
+constexpr int STACK_CAP = 192;     // logical capacity (entries popped per step are limited to the room left)
+constexpr int STACK_PHYS = 256;    // physical entries: + combined tree depth of slack
+constexpr int LEAFQ_CAP = 96;
+
+struct FkParams {
+  FkProgram prog;
+  int npose;
+  int input_mode;          // B2C_INPUT_RAW = 0, B2C_INPUT_AA_EIGEN = 1
+  int stride;
+  const float *states;
+  Qt ref;                  // mRefTran for AA_EIGEN
+  Xf *out;                 // [npose][nslots]
+  double *out_qt;          // optional [npose][nslots][7]
+};
+
+struct RecheckParams {
+  const Ambig *ambig;
+  const int *ambig_count;
+  int ambig_cap;
+  int nrb, nb;
+  const Xf *fk;
+  const Xf *static_xf;
+  const int *body_mesh;
+  const MeshDev *meshes;
+  const int2 *pairs;          // pair index -> (eval body a, eval body b)
+  uint8_t *legal;
+  float *energy;
+  unsigned long long *pair_mask;
+  int mask_words;
+  float *dist;                // distance mode: dist[pose * nq + pair] = -1
+  double *pts;
+  int nq;
+  unsigned long long *stats;
+};
+
+struct PointParams {
+  int n;
+  const double *points;     // [n][3] world
+  const Xf *body_xf;        // [1]
+  MeshDev mesh;
+  double *out;              // [n][7]: dist, closest(3, world), normal(3) = unit(point -> closest)
+};
+
+struct LiveParams {
+  int npose;
+  int nrb, nb;
+  int nq;                   // queries per pose == hand bodies, query i = (hand body i, object)
+  int object;
+  const Xf *fk;
+  const Xf *static_xf;
+  const int *body_mesh;
+  const MeshDev *meshes;
+  const float *dist;        // [npose][nq]
+  const double *pts;        // [npose][nq][6]
+  const uint8_t *legal;
+  float *energy;
+  unsigned long long *stats;
+};
+
+__host__ __device__ inline size_t eval_warp_smem_bytes(int nb, int npairs, int mask_words, int stack_phys) {
+  size_t b = (size_t)nb * 96 + (size_t)npairs * sizeof(PairXf) + (size_t)stack_phys * 8 + (size_t)LEAFQ_CAP * 8 +
+             (size_t)mask_words * 8;
+  return (b + 15) & ~(size_t)15;
+}
+
+constexpr int DSTACK_CAP = 448, DSTACK_PHYS = 512, DLEAF_CAP = 96;
+constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 2 * 96 + 96 + 32;
+
+// launchers (kernels.cu)
+cudaError_t launch_fk(const FkParams &p, cudaStream_t s);
+cudaError_t launch_eval(const EvalParams &p, int blocks, int warps_per_block, size_t smem, cudaStream_t s);
+cudaError_t launch_recheck(const RecheckParams &p, cudaStream_t s);
+cudaError_t launch_point(const PointParams &p, cudaStream_t s);
+cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s);
+cudaError_t launch_live(const LiveParams &p, cudaStream_t s);
+
+} // namespace b2c

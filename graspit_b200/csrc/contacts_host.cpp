@@ -1,0 +1,448 @@
+// Host-side, non-throughput parts of the CollisionInterface surface (see contacts_host.h).
+#include "contacts_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <list>
+
+namespace b2c {
+
+namespace {
+
+struct P3 {
+  double x, y, z;
+};
+inline P3 operator+(P3 a, P3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline P3 operator-(P3 a, P3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline P3 operator*(double s, P3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline double dotp(P3 a, P3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline P3 crossp(P3 a, P3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline double normp(P3 a) { return std::sqrt(dotp(a, a)); }
+inline P3 unitp(P3 a) {
+  double n2 = dotp(a, a);
+  if (n2 > 0.0) { double n = std::sqrt(n2); return {a.x / n, a.y / n, a.z / n}; }
+  return a;
+}
+inline double comp(const P3 &a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+struct M3 {
+  double m[3][3];
+  P3 col(int c) const { return {m[0][c], m[1][c], m[2][c]}; }
+  void setcol(int c, P3 v) { m[0][c] = v.x; m[1][c] = v.y; m[2][c] = v.z; }
+  P3 mul(P3 v) const {
+    return {m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z, m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z,
+            m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z};
+  }
+};
+inline M3 matmul(const M3 &a, const M3 &b) {
+  M3 r;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+      for (int k = 0; k < 3; k++) s += a.m[i][k] * b.m[k][j];
+      r.m[i][j] = s;
+    }
+  return r;
+}
+
+// rotation matrix of the unit quaternion for an axis/angle rotation (transf::AXIS_ANGLE_ROTATION)
+M3 axis_angle_matrix(double angle, P3 axis) {
+  axis = unitp(axis);
+  double s = std::sin(0.5 * angle), w = std::cos(0.5 * angle);
+  double x = s * axis.x, y = s * axis.y, z = s * axis.z;
+  double n = std::sqrt(w * w + x * x + y * y + z * z);
+  w /= n; x /= n; y /= n; z /= n;
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y,
+               tzz = tz * z;
+  M3 r;
+  r.m[0][0] = 1 - (tyy + tzz); r.m[0][1] = txy - twz; r.m[0][2] = txz + twy;
+  r.m[1][0] = txy + twz; r.m[1][1] = 1 - (txx + tzz); r.m[1][2] = tyz - twx;
+  r.m[2][0] = txz - twy; r.m[2][1] = tyz + twx; r.m[2][2] = 1 - (txx + tyy);
+  return r;
+}
+
+// rotation matrix -> unit quaternion (wxyz), trace-branch algorithm (what transf::set(mat3) gets from Eigen)
+void matrix_to_quat(const M3 &R, double q[4]) {
+  double t = R.m[0][0] + R.m[1][1] + R.m[2][2];
+  double c[4];   // x y z w
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    c[3] = 0.5 * t;
+    t = 0.5 / t;
+    c[0] = (R.m[2][1] - R.m[1][2]) * t;
+    c[1] = (R.m[0][2] - R.m[2][0]) * t;
+    c[2] = (R.m[1][0] - R.m[0][1]) * t;
+  } else {
+    int i = 0;
+    if (R.m[1][1] > R.m[0][0]) i = 1;
+    if (R.m[2][2] > R.m[i][i]) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(R.m[i][i] - R.m[j][j] - R.m[k][k] + 1.0);
+    c[i] = 0.5 * t;
+    t = 0.5 / t;
+    c[3] = (R.m[k][j] - R.m[j][k]) * t;
+    c[j] = (R.m[j][i] + R.m[i][j]) * t;
+    c[k] = (R.m[k][i] + R.m[i][k]) * t;
+  }
+  double n = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2] + c[3] * c[3]);
+  q[0] = c[3] / n; q[1] = c[0] / n; q[2] = c[1] / n; q[3] = c[2] / n;
+}
+
+// Classic cyclic-by-largest-element Jacobi eigen-solver for a symmetric 3x3 (Golub & Van Loan 8.4),
+// with the reference's stopping rule: at most 50 rotations, stop once the off-diagonal norm no longer
+// decreases after the third rotation (collisionModel.cpp:612-679); Schur rotation skipped when the
+// pivot is below 1e-4 (:585-602).
+void jacobi3(double a[3][3], double v[3][3]) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) v[i][j] = (i == j) ? 1.0 : 0.0;
+  double prevoff = std::numeric_limits<double>::max();
+  for (int n = 0; n < 50; n++) {
+    int p = 0, q = 1;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        if (i == j) continue;
+        if (std::fabs(a[i][j]) > std::fabs(a[p][q])) { p = i; q = j; }
+      }
+    double c = 1.0, s = 0.0;
+    if (std::fabs(a[p][q]) > 0.0001f) {
+      double r = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+      double t = (r >= 0.0) ? 1.0 / (r + std::sqrt(1.0 + r * r)) : -1.0 / (-r + std::sqrt(1.0 + r * r));
+      c = 1.0 / std::sqrt(1.0 + t * t);
+      s = t * c;
+    }
+    double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    J[p][p] = c; J[p][q] = s; J[q][p] = -s; J[q][q] = c;
+    double t1[3][3], t2[3][3];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        t1[i][j] = 0.0;
+        for (int k = 0; k < 3; k++) t1[i][j] += v[i][k] * J[k][j];
+      }
+    std::memcpy(v, t1, sizeof t1);
+    // a = (J^T a) J
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        t2[i][j] = 0.0;
+        for (int k = 0; k < 3; k++) t2[i][j] += J[k][i] * a[k][j];
+      }
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        t1[i][j] = 0.0;
+        for (int k = 0; k < 3; k++) t1[i][j] += t2[i][k] * J[k][j];
+      }
+    std::memcpy(a, t1, sizeof t1);
+    double off = 0.0;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        if (i != j) off += a[i][j] * a[i][j];
+    if (n > 2 && off >= prevoff) return;
+    prevoff = off;
+  }
+}
+
+struct TriD {
+  P3 v[3];
+};
+
+const double kPad = 1.0e-2;   // Leaf::TOLERANCE
+
+struct ObbNode {
+  M3 R;
+  P3 center;
+  P3 half;
+  int child[2] = {-1, -1};
+};
+
+} // namespace
+
+struct ObbTree {
+  std::vector<ObbNode> nodes;
+};
+
+namespace {
+
+void fit_obb(const std::vector<TriD> &tris, const std::vector<int> &idx, ObbNode &out) {
+  // area-weighted covariance (collisionModel.cpp:134-166)
+  double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  double total = 0.0;
+  P3 wm = {0, 0, 0};
+  for (int t : idx) {
+    const TriD &T = tris[t];
+    P3 m = (1.0 / 3.0) * (T.v[0] + T.v[1] + T.v[2]);
+    double area = 0.5 * normp(crossp(T.v[1] - T.v[0], T.v[2] - T.v[0]));
+    total += area;
+    wm = wm + area * m;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        cov[i][j] += (area / 12.0) * (9 * comp(m, i) * comp(m, j) + comp(T.v[0], i) * comp(T.v[0], j) +
+                                      comp(T.v[1], i) * comp(T.v[1], j) + comp(T.v[2], i) * comp(T.v[2], j));
+  }
+  wm = (1.0 / total) * wm;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) cov[i][j] = (1.0 / total) * cov[i][j] - comp(wm, i) * comp(wm, j);
+  double v[3][3];
+  jacobi3(cov, v);
+  // order the axes by eigenvalue with the reference's swap sequence (collisionModel.cpp:179-188)
+  int first = 0, second = 1, third = 2;
+  if (cov[1][1] > cov[0][0]) std::swap(first, second);
+  if (cov[2][2] > cov[first][first]) std::swap(first, third);
+  if (cov[third][third] > cov[second][second]) std::swap(second, third);
+  P3 xA = {v[0][first], v[1][first], v[2][first]};
+  P3 yA = {v[0][second], v[1][second], v[2][second]};
+  P3 zA = crossp(unitp(xA), unitp(yA));
+  yA = crossp(zA, unitp(xA));
+  xA = crossp(yA, zA);
+  M3 R;
+  R.setcol(0, xA); R.setcol(1, yA); R.setcol(2, zA);
+  // extents along the axes, padded (collisionModel.cpp:82-131)
+  double mx[3] = {-1.0e10, -1.0e10, -1.0e10}, mn[3] = {1.0e10, 1.0e10, 1.0e10};
+  for (int t : idx)
+    for (int k = 0; k < 3; k++) {
+      const P3 &p = tris[t].v[k];
+      double d[3] = {dotp(p, xA), dotp(p, yA), dotp(p, zA)};
+      for (int a = 0; a < 3; a++) {
+        if (d[a] + kPad > mx[a]) mx[a] = d[a] + kPad;
+        if (d[a] - kPad < mn[a]) mn[a] = d[a] - kPad;
+      }
+    }
+  double h[3];
+  for (int a = 0; a < 3; a++) h[a] = 0.5 * (mx[a] - mn[a]);
+  P3 c = {mn[0] + h[0], mn[1] + h[1], mn[2] + h[2]};
+  c = R.mul(c);
+  for (int a = 0; a < 3; a++)
+    if (h[a] < kPad) h[a] = kPad;
+  // x axis := direction of largest extent (collisionModel.cpp:211-229)
+  int big = 0;
+  if (h[1] > h[0]) big = 1;
+  if (h[2] > h[big]) big = 2;
+  P3 hv = {h[0], h[1], h[2]};
+  if (big != 0) {
+    M3 rot = axis_angle_matrix(M_PI / 2.0, big == 1 ? P3{0, 0, 1} : P3{0, 1, 0});
+    hv = rot.mul(hv);
+    hv = {std::fabs(hv.x), std::fabs(hv.y), std::fabs(hv.z)};
+    R = matmul(R, rot);
+  }
+  out.R = R;
+  out.center = c;
+  out.half = hv;
+}
+
+void split_node(ObbTree &T, const std::vector<TriD> &tris, int node, std::vector<int> idx) {
+  if ((int)idx.size() <= 1) return;
+  ObbNode nd = T.nodes[node];
+  P3 xA = nd.R.col(0), yA = nd.R.col(1), zA = nd.R.col(2);
+  if (nd.half.y > nd.half.x + 1.0e-5) { std::swap(xA, yA); yA = -1.0 * yA; }
+  if (nd.half.z > nd.half.y && nd.half.z > nd.half.x + 1.0e-5) { std::swap(xA, zA); zA = -1.0 * zA; }
+  // split plane at the mean vertex (collisionModel.cpp:46-60,284)
+  P3 mean = {0, 0, 0};
+  for (int t : idx) { mean = mean + tris[t].v[0]; mean = mean + tris[t].v[1]; mean = mean + tris[t].v[2]; }
+  mean = (1.0 / (3.0 * (int)idx.size())) * mean;
+  double sep = dotp(mean, xA);
+  std::vector<int> c1, c2;
+  auto balanced = [&](double s) {
+    c1.clear(); c2.clear();
+    for (int t : idx) {
+      P3 med = {0, 0, 0};
+      med = med + tris[t].v[0]; med = med + tris[t].v[1]; med = med + tris[t].v[2];
+      med = (1.0 / 3.0) * med;
+      if (dotp(med, xA) < s) c1.push_back(t); else c2.push_back(t);
+    }
+  };
+  balanced(sep);
+  if (c1.empty() || c2.empty()) {
+    // median of the centroid projections (collisionModel.cpp:62-80)
+    std::vector<double> pr;
+    for (int t : idx) {
+      P3 m = tris[t].v[0] + tris[t].v[1] + tris[t].v[2];
+      m = (1.0 / 3.0) * m;
+      pr.push_back(dotp(m, xA));
+    }
+    double med = pr.front();
+    if (pr.size() > 1) {
+      std::nth_element(pr.begin(), pr.begin() + pr.size() / 2, pr.end());
+      med = pr[pr.size() / 2];
+    }
+    balanced(med);
+  }
+  if (c1.empty() || c2.empty()) {
+    c1.clear(); c2.clear();
+    bool one = true;
+    for (int t : idx) { (one ? c1 : c2).push_back(t); one = !one; }
+  }
+  int a = (int)T.nodes.size();
+  T.nodes.emplace_back();
+  T.nodes.emplace_back();
+  fit_obb(tris, c1, T.nodes[a]);
+  fit_obb(tris, c2, T.nodes[a + 1]);
+  T.nodes[node].child[0] = a;
+  T.nodes[node].child[1] = a + 1;
+  split_node(T, tris, a, std::move(c1));
+  split_node(T, tris, a + 1, std::move(c2));
+}
+
+void level_rec(const ObbTree &T, int node, int cur, int want, std::vector<ObbBox> &out) {
+  const ObbNode &n = T.nodes[node];
+  bool leaf = n.child[0] < 0;
+  if (cur == want || leaf) {
+    ObbBox b;
+    b.t[0] = n.center.x; b.t[1] = n.center.y; b.t[2] = n.center.z;
+    b.half[0] = n.half.x; b.half[1] = n.half.y; b.half[2] = n.half.z;
+    matrix_to_quat(n.R, b.q);
+    out.push_back(b);
+  }
+  if (!leaf && cur < want) {
+    level_rec(T, n.child[0], cur + 1, want, out);
+    level_rec(T, n.child[1], cur + 1, want, out);
+  }
+}
+
+} // namespace
+
+ObbTree *obb_tree_build(const float *tri9, int ntri) {
+  ObbTree *T = new ObbTree();
+  std::vector<TriD> tris(ntri);
+  for (int i = 0; i < ntri; i++)
+    for (int k = 0; k < 3; k++)
+      tris[i].v[k] = {(double)tri9[9 * (size_t)i + 3 * k], (double)tri9[9 * (size_t)i + 3 * k + 1], (double)tri9[9 * (size_t)i + 3 * k + 2]};
+  std::vector<int> idx(ntri);
+  for (int i = 0; i < ntri; i++) idx[i] = i;
+  T->nodes.reserve(2 * (size_t)std::max(ntri, 1));
+  T->nodes.emplace_back();
+  if (ntri > 0) {
+    fit_obb(tris, idx, T->nodes[0]);
+    split_node(*T, tris, 0, idx);
+  } else {
+    ObbNode &n = T->nodes[0];
+    n.R = M3{{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}};
+    n.center = {0, 0, 0};
+    n.half = {kPad, kPad, kPad};
+  }
+  return T;
+}
+
+void obb_tree_free(ObbTree *t) { delete t; }
+
+void obb_tree_level(const ObbTree *t, int depth, std::vector<ObbBox> &out) {
+  out.clear();
+  if (!t || t->nodes.empty()) return;
+  level_rec(*t, 0, 0, depth, out);
+}
+
+// -------------------------------------------------------------------------------------------------
+// contact post-processing
+// -------------------------------------------------------------------------------------------------
+static inline double d2(const double a[3], const double b[3]) {
+  double s = 0.0;
+  for (int k = 0; k < 3; k++) s += (a[k] - b[k]) * (a[k] - b[k]);
+  return s;
+}
+
+void remove_contact_duplicates(std::vector<b2c_contact> &c, double thr) {
+  const double t2 = thr * thr;
+  size_t i = 0;
+  while (i < c.size()) {
+    bool remove_me = false;
+    size_t j = i + 1;
+    while (j < c.size()) {
+      if (d2(c[j].b1_pos, c[i].b1_pos) > t2 || d2(c[j].b2_pos, c[i].b2_pos) > t2) {
+        j++;
+      } else if (c[i].distSq < c[j].distSq) {
+        c.erase(c.begin() + j);
+      } else {
+        remove_me = true;
+        break;
+      }
+    }
+    if (remove_me) c.erase(c.begin() + i); else i++;
+  }
+}
+
+namespace {
+
+// strict 2-D convex hull (collinear points are not vertices), indices into pts
+std::vector<int> hull2d(const std::vector<std::pair<double, double>> &pts) {
+  int n = (int)pts.size();
+  std::vector<int> order(n);
+  for (int i = 0; i < n; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return pts[a] < pts[b]; });
+  auto cr = [&](int o, int a, int b) {
+    return (pts[a].first - pts[o].first) * (pts[b].second - pts[o].second) -
+           (pts[a].second - pts[o].second) * (pts[b].first - pts[o].first);
+  };
+  std::vector<int> h(2 * n);
+  int k = 0;
+  for (int i = 0; i < n; i++) {
+    while (k >= 2 && cr(h[k - 2], h[k - 1], order[i]) <= 0) k--;
+    h[k++] = order[i];
+  }
+  for (int i = n - 2, t = k + 1; i >= 0; i--) {
+    while (k >= t && cr(h[k - 2], h[k - 1], order[i]) <= 0) k--;
+    h[k++] = order[i];
+  }
+  h.resize(k > 1 ? k - 1 : k);
+  return h;
+}
+
+void perimeter(std::vector<b2c_contact> &set) {
+  if (set.size() < 2) return;
+  const double resabs = 1.0e-1;
+  auto P = [&](size_t i) { return P3{set[i].b1_pos[0], set[i].b1_pos[1], set[i].b1_pos[2]}; };
+  size_t e1 = 0, e2 = 1, cp = 0;
+  P3 curr = {0, 0, 0}, test = {0, 0, 0};
+  for (cp = 0; cp < set.size(); cp++) {
+    curr = P(e2) - P(e1);
+    test = P(cp) - P(e1);
+    if (normp(crossp(test, curr)) > resabs) break;
+    double dt = dotp(test, curr);
+    if (dt < 0) e1 = cp;
+    if (dt > dotp(curr, curr)) e2 = cp;
+  }
+  if (cp == set.size()) {
+    std::vector<b2c_contact> tmp = {set[e1], set[e2]};
+    set = tmp;
+    return;
+  }
+  P3 normal = unitp(crossp(test, curr));
+  P3 axis1 = unitp(test);
+  P3 axis2 = crossp(normal, axis1);
+  std::vector<std::pair<double, double>> pts;
+  for (size_t i = 0; i < set.size(); i++) pts.push_back({dotp(P(i), axis1), dotp(P(i), axis2)});
+  std::vector<int> h = hull2d(pts);
+  std::vector<b2c_contact> tmp;
+  for (int i : h) tmp.push_back(set[i]);
+  set = tmp;
+}
+
+} // namespace
+
+void compact_contact_set(std::vector<b2c_contact> &contacts) {
+  if (contacts.size() < 2) return;
+  const double NORMAL_TOL = 1e-3, DIST_TOL = 1.0e-1;
+  std::list<std::vector<b2c_contact>> groups;
+  for (auto &c : contacts) {
+    auto sp = groups.begin();
+    for (; sp != groups.end(); ++sp) {
+      const b2c_contact &f = sp->front();
+      double d = f.b1_normal[0] * c.b1_normal[0] + f.b1_normal[1] * c.b1_normal[1] + f.b1_normal[2] * c.b1_normal[2];
+      if (d > 1.0 - NORMAL_TOL) break;
+    }
+    if (sp == groups.end()) {
+      groups.push_back({c});
+    } else {
+      bool dup = false;
+      for (auto &o : *sp)
+        if (d2(o.b1_pos, c.b1_pos) < DIST_TOL) { dup = true; break; }
+      if (!dup) sp->push_back(c);
+    }
+  }
+  contacts.clear();
+  for (auto &g : groups) {
+    if (g.size() > 1) perimeter(g);
+    for (auto &c : g) contacts.push_back(c);
+  }
+}
+
+} // namespace b2c

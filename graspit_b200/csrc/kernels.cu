@@ -1,0 +1,787 @@
+// CUDA kernels of the B200 collision engine (sm_100a).
+//
+//   fk_kernel        K1  search state -> hand pose -> per-link transforms          (thread / pose)
+//   eval_kernel      K3+K5+K8  legality (all active pairs) fused with CONTACT_ENERGY (warp / pose)
+//   recheck_kernel   fp64 re-decision of triangle pairs the fp32 SAT could not call
+//   point_kernel     K5 stand-alone closest point queries                            (thread / query)
+//   dist_kernel      K4 body-body minimum distance                                   (warp / query)
+//   live_kernel      CONTACT_LIVE virtual contacts + energy                          (thread / pose,link)
+//
+// See DESIGN.md for the data layout and the roofline that bounds each kernel.
+#include "b2c_internal.h"
+
+namespace b2c {
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ Node load_node(const Node *nodes, int i) {
+  const float4 *p = reinterpret_cast<const float4 *>(nodes + i);
+  float4 a = __ldg(p), b = __ldg(p + 1);
+  Node n;
+  n.cx = a.x; n.cy = a.y; n.cz = a.z; n.hx = a.w;
+  n.hy = b.x; n.hz = b.y; n.child = __float_as_int(b.z); n.tri = __float_as_int(b.w);
+  return n;
+}
+__device__ __forceinline__ void node_ch(const Node &n, float *c, float *h) {
+  c[0] = n.cx; c[1] = n.cy; c[2] = n.cz; h[0] = n.hx; h[1] = n.hy; h[2] = n.hz;
+}
+__device__ __forceinline__ d3 tri_vertex(const Tri *tris, int t, int k) {
+  float4 v = __ldg(&tris[t].v[k]);
+  return mk<double>((double)v.x, (double)v.y, (double)v.z);
+}
+
+__device__ __forceinline__ unsigned long long pack_entry(int pair, int a, int b) {
+  return ((unsigned long long)(unsigned)pair << 48) | ((unsigned long long)(unsigned)a << 24) | (unsigned long long)(unsigned)b;
+}
+
+// ============================================================================================
+// K1: forward kinematics.  One thread per pose, fp64 quaternion algebra in the reference's
+// composition order (KinematicChain::fwdKinematics, src/kinematicChain.cpp:543-560;
+// DHTransform::getTran, include/graspit/joint.h:126-130; HandObjectState::execute,
+// src/EGPlanner/searchState.cpp:515-527; PositionStateAA::getCoreTran, searchStateImpl.cpp:156-168;
+// EigenGraspInterface::toDOFSpace, src/eigenGrasp.cpp:638-646; Robot::checkSetDOFVals, robot.h:698-709).
+// ============================================================================================
+
+#define FK_MAX_DOF 32
+
+__global__ void __launch_bounds__(128) fk_kernel(FkParams p) {
+  int pose = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pose >= p.npose) return;
+  const float *s = p.states + (size_t)pose * p.stride;
+  const FkProgram &g = p.prog;
+  double dof[FK_MAX_DOF];
+  Qt base;
+  if (p.input_mode == 0) {
+    base.w = s[0]; base.x = s[1]; base.y = s[2]; base.z = s[3];
+    base.tx = s[4]; base.ty = s[5]; base.tz = s[6];
+    q_normalize(base);
+    for (int d = 0; d < g.ndof_total && d < FK_MAX_DOF; d++) dof[d] = (double)s[7 + d];
+  } else {
+    const FkRobot &r0 = g.robots[0];
+    double tx = s[0], ty = s[1], tz = s[2], th = s[3], ph = s[4], al = s[5];
+    double sth, cth, sph, cph;
+    sincos(th, &sth, &cth);
+    sincos(ph, &sph, &cph);
+    Qt tr = q_identity(); tr.tx = tx; tr.ty = ty; tr.tz = tz;
+    Qt core = q_compose(tr, q_axis_angle(al, sth * cph, sth * sph, cth));
+    core = q_compose(core, r0.approach_inv);
+    base = q_compose(p.ref, core);
+    const double *eg = g.egdata + r0.eg_ofs;
+    const double *origin = eg + r0.neg * r0.ndof, *norm = origin + r0.ndof, *mn = norm + r0.ndof, *mx = mn + r0.ndof;
+    for (int d = 0; d < r0.ndof && d < FK_MAX_DOF; d++) {
+      double x = 0.0;
+      for (int e = 0; e < r0.neg; e++) x += eg[e * r0.ndof + d] * (double)s[6 + e];
+      double v = x * norm[d] + origin[d];
+      v = v > mx[d] ? mx[d] : (v < mn[d] ? mn[d] : v);
+      dof[d] = v;
+    }
+    for (int d = r0.ndof; d < g.ndof_total && d < FK_MAX_DOF; d++) dof[d] = 0.0;
+  }
+  Xf *out = p.out + (size_t)pose * g.nslots;
+  double *oq = p.out_qt ? p.out_qt + (size_t)pose * g.nslots * 7 : nullptr;
+  auto emit = [&](int slot, const Qt &t) {
+    if (slot < 0) return;
+    q_to_xf(t, reinterpret_cast<double *>(&out[slot]));
+    if (oq) {
+      double *o = oq + slot * 7;
+      o[0] = t.w; o[1] = t.x; o[2] = t.y; o[3] = t.z; o[4] = t.tx; o[5] = t.ty; o[6] = t.tz;
+    }
+  };
+  // last-link transforms of chains that carry an attached robot are re-read from this small table
+  Qt lastlink[4];
+  for (int ri = 0; ri < g.nrobots; ri++) {
+    const FkRobot &r = g.robots[ri];
+    Qt rb = base;
+    if (r.parent >= 0) rb = q_compose(lastlink[ri & 3], r.parent_offset);
+    emit(r.base_slot, rb);
+    emit(r.mount_slot, rb);
+    for (int ci = 0; ci < r.nchains; ci++) {
+      const FkChain &c = g.chains[r.first_chain + ci];
+      Qt total = q_compose(rb, c.tran);
+      int l = 0;
+      for (int j = 0; j < c.njoints; j++) {
+        const FkJoint &jd = g.joints[c.first_joint + j];
+        double val = dof[jd.dof] * jd.ratio;
+        double theta = jd.revolute ? val + jd.theta : jd.theta;
+        double dd = jd.revolute ? jd.d : val + jd.d;
+        Qt tz = q_identity(); tz.tz = dd;
+        Qt jt = q_compose(q_compose(q_axis_angle(theta, 0.0, 0.0, 1.0), tz), jd.tr4tr3);
+        total = q_compose(total, jt);
+        if (l < c.nlinks && g.links[c.first_link + l].last_joint == j) {
+          emit(g.links[c.first_link + l].out_slot, total);
+          l++;
+        }
+      }
+      // children attached to this chain's end: remember the last link pose for them
+      for (int rj = ri + 1; rj < g.nrobots; rj++)
+        if (g.robots[rj].parent == ri && g.robots[rj].parent_last_slot == g.links[c.first_link + c.nlinks - 1].out_slot)
+          lastlink[rj & 3] = total;
+    }
+  }
+}
+
+// ============================================================================================
+// closest point on a mesh to a query point (object frame).  Per-lane depth-first, nearer child
+// first; boxes cull in fp32 (they are padded at build time), leaves are re-centred on the query
+// in fp64 before the fp32 closestPtTriangle so the returned vector carries fp32 *relative* accuracy.
+// Must agree with ClosestPtCallback (collisionAlgorithms_inl.h:210-238, collisionAlgorithms.h:220-242).
+// ============================================================================================
+__device__ __forceinline__ float closest_point_query(const MeshDev &m, d3 q, f3 &bestv, int &best_tri,
+                                                     unsigned &n_box, unsigned &n_tri) {
+  const Node *nodes = m.nodes;
+  f3 qf = tof(q);
+  float best = 1.0e30f;
+  bestv = mk<float>(0.f, 0.f, 0.f);
+  best_tri = -1;
+  int stk_n[40];
+  float stk_d[40];
+  int sp = 0;
+  int cur = 0;
+  float curd = 0.f;
+  while (true) {
+    if (curd <= best) {
+      Node n = load_node(nodes, cur);
+      if (n.child < 0) {
+        n_tri++;
+        d3 a = tri_vertex(m.tris, n.tri, 0) - q, b = tri_vertex(m.tris, n.tri, 1) - q, c = tri_vertex(m.tris, n.tri, 2) - q;
+        f3 v = closest_pt_triangle<float>(tof(a), tof(b), tof(c), mk<float>(0.f, 0.f, 0.f));
+        float d2 = dot(v, v);
+        if (d2 < best) { best = d2; bestv = v; best_tri = n.tri; }
+      } else {
+        Node c0 = load_node(nodes, n.child), c1 = load_node(nodes, n.child + 1);
+        float cc[3], hh[3];
+        node_ch(c0, cc, hh); float d0 = point_box_dist2(cc, hh, qf);
+        node_ch(c1, cc, hh); float d1 = point_box_dist2(cc, hh, qf);
+        n_box += 2;
+        int near = n.child, far = n.child + 1;
+        if (d1 < d0) { near = n.child + 1; far = n.child; float t = d0; d0 = d1; d1 = t; }
+        if (d1 <= best && sp < 40) { stk_n[sp] = far; stk_d[sp] = d1; sp++; }
+        if (d0 <= best) { cur = near; curd = d0; continue; }
+      }
+    }
+    if (sp == 0) break;
+    sp--;
+    cur = stk_n[sp]; curd = stk_d[sp];
+  }
+  return best;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// ContactEnergy::energy (src/EGPlanner/energy/contactEnergy.cpp:9-55) for one contact: world contact
+// location p and world normal cn -> |v| + 50 (1 - cn . v/|v|), v = closest object point - p.
+__device__ __forceinline__ float contact_term(const MeshDev &mo, const double *XO, d3 pw, d3 cnw,
+                                              unsigned &n_box, unsigned &n_tri) {
+  d3 q = xf_apply_inv(XO, pw);
+  f3 cnl = tof(xf_rot_t(XO, cnw));
+  f3 v; int bt;
+  float d2 = closest_point_query(mo, q, v, bt, n_box, n_tri);
+  float dist = sqrtf(d2);
+  float inv = d2 > 0.f ? 1.0f / dist : 0.f;
+  float c = (cnl.x * v.x + cnl.y * v.y + cnl.z * v.z) * inv;
+  return dist + (1.0f - c) * 50.0f;
+}
+
+// ============================================================================================
+// K3 + K5 + K8: one warp evaluates one pose.
+//   phase 1  load the pose's body transforms, build the fp32 relative transform of every active
+//            pair (lanes = pairs) and test the root boxes
+//   phase 2  warp-cooperative traversal of ALL surviving pairs through one shared work stack:
+//            each lane pops one (pair, nodeA, nodeB) entry, tests the two children of the larger
+//            node against the other node, and the survivors are compacted back with ballot/popc;
+//            leaf-leaf entries go to a separate queue that is drained 32 triangle pairs at a time
+//   phase 3  if no pair collides: lanes = virtual contacts, closest point on the object, energy
+//            reduction with shuffles
+// Replaces GraspitCollision::allCollisions (graspitCollision.cpp:332-363) + recursion/CollisionCallback
+// (collisionAlgorithms.cpp:42-147, collisionAlgorithms_inl.h:50-81) and ContactEnergy::energy.
+// ============================================================================================
+struct WarpSmem {
+  double *bodyxf;                // [nb][12]
+  PairXf *pxf;                   // [npairs]
+  unsigned long long *stack;     // [STACK_PHYS]
+  unsigned long long *leafq;     // [LEAFQ_CAP]
+  unsigned *mask;                // [mask_words * 2]
+};
+
+
+__device__ __forceinline__ void make_pair_xf(const double *XA, const double *XB, float extA, float extB, PairXf &o) {
+  // A <- B : R = Ra^T Rb, t = Ra^T (tb - ta), fp64 then rounded
+  double r[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) r[3 * i + j] = XA[0 + i] * XB[0 + j] + XA[3 + i] * XB[3 + j] + XA[6 + i] * XB[6 + j];
+  d3 dt = mk<double>(XB[9] - XA[9], XB[10] - XA[10], XB[11] - XA[11]);
+  d3 t = xf_rot_t(XA, dt);
+#pragma unroll
+  for (int i = 0; i < 9; i++) { o.r[i] = (float)r[i]; o.ar[i] = fabsf((float)r[i]) + 1.0e-6f; }
+  o.t[0] = (float)t.x; o.t[1] = (float)t.y; o.t[2] = (float)t.z;
+  o.eps = 1.0e-6f * (fabsf(o.t[0]) + fabsf(o.t[1]) + fabsf(o.t[2]) + extA + extB) + 1.0e-5f;
+  o.pad[0] = o.pad[1] = 0.f;
+}
+
+// triangle pair (tri_a of body A, tri_b of body B) -> TT_SEP / TT_HIT / TT_AMBIG.
+// Triangle A is moved into B's frame in fp64 (reference: t1.applyTransform(mTran1To2),
+// collisionAlgorithms_inl.h:58-60) and everything is re-centred on its first vertex before rounding.
+__device__ __forceinline__ int leaf_pair_test(const MeshDev &ma, const MeshDev &mb, const double *XA, const double *XB,
+                                              int ta, int tb) {
+  d3 a1 = tri_vertex(ma.tris, ta, 0), a2 = tri_vertex(ma.tris, ta, 1), a3 = tri_vertex(ma.tris, ta, 2);
+  d3 b1 = tri_vertex(mb.tris, tb, 0), b2 = tri_vertex(mb.tris, tb, 1), b3 = tri_vertex(mb.tris, tb, 2);
+  d3 P1 = xf_apply_inv(XB, xf_apply(XA, a1));
+  d3 E1 = xf_rot_t(XB, xf_rot(XA, a2 - a1));
+  d3 E2 = xf_rot_t(XB, xf_rot(XA, a3 - a2));
+  f3 e1 = tof(E1), e2 = tof(E2);
+  f3 p2 = e1, p3 = tof(E1 + E2);
+  f3 q1 = tof(b1 - P1), q2 = tof(b2 - P1), q3 = tof(b3 - P1);
+  f3 f1 = tof(b2 - b1), f2 = tof(b3 - b2);
+  return tri_tri_filter(p2, p3, e1, e2, q1, q2, q3, f1, f2);
+}
+
+__global__ void __launch_bounds__(256) eval_kernel(EvalParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const size_t wbytes = eval_warp_smem_bytes(p.nb, p.npairs, p.mask_words, p.stack_phys);
+  unsigned char *base = smem_raw + (size_t)warp * wbytes;
+  WarpSmem S;
+  S.bodyxf = reinterpret_cast<double *>(base);
+  S.pxf = reinterpret_cast<PairXf *>(base + (size_t)p.nb * 96);
+  S.stack = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(S.pxf) + (size_t)p.npairs * sizeof(PairXf));
+  S.leafq = S.stack + p.stack_phys;
+  S.mask = reinterpret_cast<unsigned *>(S.leafq + LEAFQ_CAP);
+
+  unsigned n_box = 0, n_tri = 0, n_pbox = 0, n_ptri = 0, n_amb = 0;
+
+  // static bodies never change: load once per warp
+  for (int i = p.nrb * 12 + lane; i < p.nb * 12; i += 32)
+    S.bodyxf[i] = reinterpret_cast<const double *>(p.static_xf)[i - p.nrb * 12];
+
+  while (true) {
+    int pose = 0;
+    if (lane == 0) pose = atomicAdd(p.pose_counter, 1);
+    pose = __shfl_sync(FULL, pose, 0);
+    if (pose >= p.npose) break;
+
+    // ---- phase 1 ----
+    {
+      const double *src = reinterpret_cast<const double *>(p.fk + (size_t)pose * p.nrb);
+      for (int i = lane; i < p.nrb * 12; i += 32) S.bodyxf[i] = src[i];
+      for (int i = lane; i < p.mask_words * 2; i += 32) S.mask[i] = 0u;
+    }
+    __syncwarp();
+    int sp = 0, lq = 0;
+    bool collided = false;
+    for (int pbase = 0; pbase < p.npairs; pbase += 32) {
+      int pi = pbase + lane;
+      bool ov = false;
+      if (pi < p.npairs) {
+        int2 ab = __ldg(&p.pairs[pi]);
+        const MeshDev &ma = p.meshes[__ldg(&p.body_mesh[ab.x])];
+        const MeshDev &mb = p.meshes[__ldg(&p.body_mesh[ab.y])];
+        PairXf x;
+        make_pair_xf(S.bodyxf + 12 * ab.x, S.bodyxf + 12 * ab.y, ma.extent, mb.extent, x);
+        S.pxf[pi] = x;
+        Node ra = load_node(ma.nodes, 0), rb = load_node(mb.nodes, 0);
+        float ca[3], ha[3], cb[3], hb[3];
+        node_ch(ra, ca, ha); node_ch(rb, cb, hb);
+        ov = box_overlap(ca, ha, cb, hb, x);
+        n_box++;
+      }
+      unsigned m = __ballot_sync(FULL, ov);
+      if (ov) S.stack[sp + __popc(m & lt_mask)] = pack_entry(pi, 0, 0);
+      sp += __popc(m);
+    }
+    __syncwarp();
+
+    // ---- phase 2 ----
+    while (true) {
+      if (lq >= 32 || (sp == 0 && lq > 0)) {
+        int n = lq < 32 ? lq : 32;
+        int res = TT_SEP;
+        int pair = 0, ta = 0, tb = 0;
+        if (lane < n) {
+          unsigned long long e = S.leafq[lq - n + lane];
+          pair = (int)(e >> 48); ta = (int)((e >> 24) & 0xffffffu); tb = (int)(e & 0xffffffu);
+          bool skip = p.mode_all && ((S.mask[pair >> 5] >> (pair & 31)) & 1u);
+          if (!skip) {
+            int2 ab = __ldg(&p.pairs[pair]);
+            res = leaf_pair_test(p.meshes[__ldg(&p.body_mesh[ab.x])], p.meshes[__ldg(&p.body_mesh[ab.y])],
+                                 S.bodyxf + 12 * ab.x, S.bodyxf + 12 * ab.y, ta, tb);
+            n_tri++;
+          }
+        }
+        lq -= n;
+        if (res == TT_HIT) atomicOr(&S.mask[pair >> 5], 1u << (pair & 31));
+        if (res == TT_AMBIG) {
+          n_amb++;
+          int slot = atomicAdd(p.ambig_count, 1);
+          if (slot < p.ambig_cap) { Ambig a; a.pose = pose; a.pair = pair; a.tri_a = ta; a.tri_b = tb; p.ambig[slot] = a; }
+        }
+        bool any = __any_sync(FULL, res == TT_HIT);
+        __syncwarp();
+        if (any) { collided = true; if (!p.mode_all) break; }
+        continue;
+      }
+      if (sp == 0) break;
+      int room = p.stack_cap - sp;
+      int k = sp < 32 ? sp : 32;
+      if (k > room) k = room > 1 ? room : 1;
+      bool have = lane < k;
+      unsigned long long e = have ? S.stack[sp - 1 - lane] : 0ull;
+      sp -= k;
+      __syncwarp();
+      bool push0 = false, push1 = false, leaf0 = false, leaf1 = false;
+      unsigned long long c0 = 0ull, c1 = 0ull;
+      if (have) {
+        int pair = (int)(e >> 48), na = (int)((e >> 24) & 0xffffffu), nb = (int)(e & 0xffffffu);
+        bool skip = p.mode_all && ((S.mask[pair >> 5] >> (pair & 31)) & 1u);
+        if (!skip) {
+          int2 ab = __ldg(&p.pairs[pair]);
+          const MeshDev &ma = p.meshes[__ldg(&p.body_mesh[ab.x])];
+          const MeshDev &mb = p.meshes[__ldg(&p.body_mesh[ab.y])];
+          Node a = load_node(ma.nodes, na), b = load_node(mb.nodes, nb);
+          bool la = a.child < 0, lb = b.child < 0;
+          if (la && lb) {
+            push0 = leaf0 = true;
+            c0 = pack_entry(pair, a.tri, b.tri);
+          } else {
+            const PairXf &x = S.pxf[pair];
+            bool splitA = lb || (!la && (a.hx * a.hy * a.hz > b.hx * b.hy * b.hz));
+            float ca[3], ha[3], cb[3], hb[3];
+            if (splitA) {
+              Node a0 = load_node(ma.nodes, a.child), a1 = load_node(ma.nodes, a.child + 1);
+              node_ch(b, cb, hb);
+              node_ch(a0, ca, ha); push0 = box_overlap(ca, ha, cb, hb, x);
+              node_ch(a1, ca, ha); push1 = box_overlap(ca, ha, cb, hb, x);
+              leaf0 = push0 && lb && a0.child < 0;
+              leaf1 = push1 && lb && a1.child < 0;
+              c0 = leaf0 ? pack_entry(pair, a0.tri, b.tri) : pack_entry(pair, a.child, nb);
+              c1 = leaf1 ? pack_entry(pair, a1.tri, b.tri) : pack_entry(pair, a.child + 1, nb);
+            } else {
+              Node b0 = load_node(mb.nodes, b.child), b1 = load_node(mb.nodes, b.child + 1);
+              node_ch(a, ca, ha);
+              node_ch(b0, cb, hb); push0 = box_overlap(ca, ha, cb, hb, x);
+              node_ch(b1, cb, hb); push1 = box_overlap(ca, ha, cb, hb, x);
+              leaf0 = push0 && la && b0.child < 0;
+              leaf1 = push1 && la && b1.child < 0;
+              c0 = leaf0 ? pack_entry(pair, a.tri, b0.tri) : pack_entry(pair, na, b.child);
+              c1 = leaf1 ? pack_entry(pair, a.tri, b1.tri) : pack_entry(pair, na, b.child + 1);
+            }
+            n_box += 2;
+          }
+        }
+      }
+      unsigned s0 = __ballot_sync(FULL, push0 && !leaf0), s1 = __ballot_sync(FULL, push1 && !leaf1);
+      unsigned l0 = __ballot_sync(FULL, push0 && leaf0), l1 = __ballot_sync(FULL, push1 && leaf1);
+      if (push0 && !leaf0) S.stack[sp + __popc(s0 & lt_mask)] = c0;
+      if (push1 && !leaf1) S.stack[sp + __popc(s0) + __popc(s1 & lt_mask)] = c1;
+      sp += __popc(s0) + __popc(s1);
+      if (push0 && leaf0) S.leafq[lq + __popc(l0 & lt_mask)] = c0;
+      if (push1 && leaf1) S.leafq[lq + __popc(l0) + __popc(l1 & lt_mask)] = c1;
+      lq += __popc(l0) + __popc(l1);
+      __syncwarp();
+    }
+    __syncwarp();
+
+    // ---- results of the legality test ----
+    if (p.pair_mask && lane < p.mask_words)
+      p.pair_mask[(size_t)pose * p.mask_words + lane] =
+          (unsigned long long)S.mask[2 * lane] | ((unsigned long long)S.mask[2 * lane + 1] << 32);
+
+    // ---- phase 3: CONTACT_PRESET energy ----
+    float energy = 0.f;
+    if (p.do_energy && !collided && p.object >= 0 && p.nvc > 0) {
+      const MeshDev &mo = p.meshes[__ldg(&p.body_mesh[p.object])];
+      const double *XO = S.bodyxf + 12 * p.object;
+      float total = 0.f;
+      for (int cbase = 0; cbase < p.nvc; cbase += 32) {
+        int c = cbase + lane;
+        float term = 0.f;
+        if (c < p.nvc) {
+          const VcDev &vc = p.vcs[c];
+          const double *XL = S.bodyxf + 12 * vc.body;
+          d3 pw = xf_apply(XL, mk<double>(vc.loc[0], vc.loc[1], vc.loc[2]));
+          d3 cnw = xf_rot(XL, mk<double>(vc.normal[0], vc.normal[1], vc.normal[2]));
+          term = contact_term(mo, XO, pw, cnw, n_pbox, n_ptri);
+        }
+        total += warp_sum(term);
+      }
+      energy = total / (float)p.nvc;
+    }
+    if (lane == 0) {
+      if (p.legal) p.legal[pose] = collided ? 0 : 1;
+      if (p.energy) p.energy[pose] = energy;
+    }
+    __syncwarp();
+  }
+
+  if (p.stats) {
+    unsigned long long v;
+    v = n_box; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_BOX], v);
+    v = n_tri; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_TRI], v);
+    v = n_pbox; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PBOX], v);
+    v = n_ptri; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PTRI], v);
+    v = n_amb; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_AMBIG], v);
+  }
+}
+
+// ============================================================================================
+// fp64 re-decision of ambiguous triangle pairs (reference arithmetic, see tri_tri_intersect_exact).
+// A confirmed intersection clears legal/energy, sets the pair bit, and (distance queries) forces -1.
+// ============================================================================================
+
+__device__ __forceinline__ const double *body_xf_ptr(const Xf *fk, const Xf *static_xf, int nrb, int pose, int body) {
+  return body < nrb ? reinterpret_cast<const double *>(fk + (size_t)pose * nrb + body)
+                    : reinterpret_cast<const double *>(static_xf + (body - nrb));
+}
+
+__global__ void recheck_kernel(RecheckParams p) {
+  int n = *p.ambig_count;
+  if (n > p.ambig_cap) n = p.ambig_cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Ambig a = p.ambig[i];
+    int2 ab = p.pairs[a.pair];
+    const double *XA = body_xf_ptr(p.fk, p.static_xf, p.nrb, a.pose, ab.x);
+    const double *XB = body_xf_ptr(p.fk, p.static_xf, p.nrb, a.pose, ab.y);
+    const MeshDev &ma = p.meshes[p.body_mesh[ab.x]];
+    const MeshDev &mb = p.meshes[p.body_mesh[ab.y]];
+    d3 a1 = xf_apply_inv(XB, xf_apply(XA, tri_vertex(ma.tris, a.tri_a, 0)));
+    d3 a2 = xf_apply_inv(XB, xf_apply(XA, tri_vertex(ma.tris, a.tri_a, 1)));
+    d3 a3 = xf_apply_inv(XB, xf_apply(XA, tri_vertex(ma.tris, a.tri_a, 2)));
+    d3 b1 = tri_vertex(mb.tris, a.tri_b, 0), b2 = tri_vertex(mb.tris, a.tri_b, 1), b3 = tri_vertex(mb.tris, a.tri_b, 2);
+    if (tri_tri_intersect_exact(a1, a2, a3, b1, b2, b3)) {
+      if (p.legal) p.legal[a.pose] = 0;
+      if (p.energy) p.energy[a.pose] = 0.f;
+      if (p.pair_mask) atomicOr(&p.pair_mask[(size_t)a.pose * p.mask_words + (a.pair >> 6)], 1ull << (a.pair & 63));
+      if (p.dist) {
+        p.dist[(size_t)a.pose * p.nq + a.pair] = -1.f;
+        if (p.pts) for (int k = 0; k < 6; k++) p.pts[((size_t)a.pose * p.nq + a.pair) * 6 + k] = 0.0;
+      }
+      if (p.stats) atomicAdd(&p.stats[STAT_HITFIX], 1ull);
+    }
+  }
+}
+
+// ============================================================================================
+// K5 stand-alone: closest point from world points to one body.  One thread per query.
+// pointToBodyDistance (graspitCollision.cpp:435-456).
+// ============================================================================================
+
+__global__ void point_kernel(PointParams p) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const double *X = reinterpret_cast<const double *>(p.body_xf);
+  d3 pw = mk<double>(p.points[3 * i], p.points[3 * i + 1], p.points[3 * i + 2]);
+  d3 q = xf_apply_inv(X, pw);
+  f3 v; int bt; unsigned nb = 0, nt = 0;
+  float d2 = closest_point_query(p.mesh, q, v, bt, nb, nt);
+  // refine the winning triangle in fp64 so the returned coordinates carry fp64 accuracy
+  d3 cl = q;
+  double dist = 0.0;
+  if (bt >= 0) {
+    d3 a = tri_vertex(p.mesh.tris, bt, 0), b = tri_vertex(p.mesh.tris, bt, 1), c = tri_vertex(p.mesh.tris, bt, 2);
+    cl = closest_pt_triangle<double>(a, b, c, q);
+    d3 dv = cl - q;
+    dist = sqrt(dot(dv, dv));
+  }
+  (void)d2;
+  d3 cw = xf_apply(X, cl);
+  d3 nv = cw - pw;
+  double nn = sqrt(dot(nv, nv));
+  if (nn > 0.0) nv = nv * (1.0 / nn);
+  double *o = p.out + 7 * i;
+  o[0] = dist; o[1] = cw.x; o[2] = cw.y; o[3] = cw.z; o[4] = nv.x; o[5] = nv.y; o[6] = nv.z;
+}
+
+// ============================================================================================
+// K4: body-body minimum distance.  One warp per (pose, query).  Same cooperative work stack as the
+// collision traversal, but every entry carries a lower bound and the warp shares the best distance
+// found so far: entries whose bound exceeds it are dropped when popped.  Children are pushed far
+// first, near last, so the top of the stack is the most promising region (the reference descends
+// the nearer child first, collisionAlgorithms.cpp:98-101).
+// Agrees with DistanceCallback (collisionAlgorithms_inl.h:168-204, collisionAlgorithms.h:187-210):
+// -1 as soon as any triangle pair intersects, else the minimum over triangleTriangleDistanceSq.
+// ============================================================================================
+__device__ __forceinline__ unsigned long long pack_dist_entry(float lb, int a, int b) {
+  // 16-bit truncated (rounded toward zero => still a lower bound) float | nodeA:24 | nodeB:24
+  unsigned hb = __float_as_uint(lb) >> 16;
+  return ((unsigned long long)hb << 48) | ((unsigned long long)(unsigned)a << 24) | (unsigned long long)(unsigned)b;
+}
+__device__ __forceinline__ float entry_lb(unsigned long long e) { return __uint_as_float(((unsigned)(e >> 48)) << 16); }
+
+
+__global__ void __launch_bounds__(256) dist_kernel(DistParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned char *base = smem_raw + (size_t)warp * DIST_WARP_SMEM;
+  unsigned long long *stack = reinterpret_cast<unsigned long long *>(base);
+  unsigned long long *leafq = stack + DSTACK_PHYS;
+  double *XA = reinterpret_cast<double *>(leafq + DLEAF_CAP);
+  double *XB = XA + 12;
+  PairXf *xp = reinterpret_cast<PairXf *>(XB + 12);
+  unsigned n_box = 0, n_tri = 0;
+  const int total = p.npose * p.nq;
+
+  while (true) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(p.work_counter, 1);
+    w = __shfl_sync(FULL, w, 0);
+    if (w >= total) break;
+    int pose = w / p.nq, qi = w - pose * p.nq;
+    if (p.legal && !p.legal[pose]) {
+      if (lane == 0) { p.dist[w] = -1.f; if (p.pts) for (int k = 0; k < 6; k++) p.pts[(size_t)w * 6 + k] = 0.0; }
+      continue;
+    }
+    int2 ab = __ldg(&p.queries[qi]);
+    const MeshDev &ma = p.meshes[__ldg(&p.body_mesh[ab.x])];
+    const MeshDev &mb = p.meshes[__ldg(&p.body_mesh[ab.y])];
+    {
+      const double *sa = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, ab.x);
+      const double *sb = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, ab.y);
+      if (lane < 12) XA[lane] = sa[lane];
+      else if (lane < 24) XB[lane - 12] = sb[lane - 12];
+    }
+    __syncwarp();
+    if (lane == 0) { PairXf x; make_pair_xf(XA, XB, ma.extent, mb.extent, x); *xp = x; }
+    __syncwarp();
+    const PairXf x = *xp;
+
+    float best = 3.0e38f;          // squared distance, warp-uniform
+    d3 bpa = mk<double>(0, 0, 0), bpb = mk<double>(0, 0, 0);   // valid on every lane after each leaf batch
+    bool hit = false;
+    int sp = 0, lq = 0;
+    if (lane == 0) stack[0] = pack_dist_entry(0.f, 0, 0);
+    sp = 1;
+    __syncwarp();
+
+    while (true) {
+      if (lq >= 32 || (sp == 0 && lq > 0)) {
+        int n = lq < 32 ? lq : 32;
+        float d2 = 3.0e38f;
+        int res = TT_SEP;
+        int ta = 0, tb = 0;
+        d3 P1 = mk<double>(0, 0, 0);
+        f3 pa = mk<float>(0, 0, 0), pb = pa;
+        if (lane < n) {
+          unsigned long long e = leafq[lq - n + lane];
+          ta = (int)((e >> 24) & 0xffffffu); tb = (int)(e & 0xffffffu);
+          if (entry_lb(e) <= best) {
+            n_tri++;
+            d3 a1 = tri_vertex(ma.tris, ta, 0), a2 = tri_vertex(ma.tris, ta, 1), a3 = tri_vertex(ma.tris, ta, 2);
+            d3 b1 = tri_vertex(mb.tris, tb, 0), b2 = tri_vertex(mb.tris, tb, 1), b3 = tri_vertex(mb.tris, tb, 2);
+            P1 = xf_apply_inv(XB, xf_apply(XA, a1));
+            d3 E1 = xf_rot_t(XB, xf_rot(XA, a2 - a1));
+            d3 E2 = xf_rot_t(XB, xf_rot(XA, a3 - a2));
+            f3 e1 = tof(E1), e2 = tof(E2);
+            f3 p2 = e1, p3 = tof(E1 + E2);
+            f3 q1 = tof(b1 - P1), q2 = tof(b2 - P1), q3 = tof(b3 - P1);
+            res = tri_tri_filter(p2, p3, e1, e2, q1, q2, q3, tof(b2 - b1), tof(b3 - b2));
+            if (res != TT_HIT) d2 = tri_tri_dist2<float>(mk<float>(0, 0, 0), p2, p3, q1, q2, q3, pa, pb);
+          }
+        }
+        lq -= n;
+        if (res == TT_AMBIG) {
+          int slot = atomicAdd(p.ambig_count, 1);
+          if (slot < p.ambig_cap) { Ambig a; a.pose = pose; a.pair = qi; a.tri_a = ta; a.tri_b = tb; p.ambig[slot] = a; }
+        }
+        if (__any_sync(FULL, res == TT_HIT)) { hit = true; break; }
+        // warp arg-min
+        float m = d2;
+        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, o));
+        if (m < best) {
+          unsigned who = __ballot_sync(FULL, d2 == m);
+          int src = __ffs(who) - 1;
+          best = m;
+          // closest points in B's frame, fp64: re-centred fp32 result + fp64 origin
+          d3 PA = mk<double>(P1.x + (double)pa.x, P1.y + (double)pa.y, P1.z + (double)pa.z);
+          d3 PB = mk<double>(P1.x + (double)pb.x, P1.y + (double)pb.y, P1.z + (double)pb.z);
+          bpa.x = __shfl_sync(FULL, PA.x, src); bpa.y = __shfl_sync(FULL, PA.y, src); bpa.z = __shfl_sync(FULL, PA.z, src);
+          bpb.x = __shfl_sync(FULL, PB.x, src); bpb.y = __shfl_sync(FULL, PB.y, src); bpb.z = __shfl_sync(FULL, PB.z, src);
+        }
+        __syncwarp();
+        continue;
+      }
+      if (sp == 0) break;
+      int room = DSTACK_CAP - sp;
+      int k = sp < 32 ? sp : 32;
+      if (k > room) k = room > 1 ? room : 1;
+      bool have = lane < k;
+      unsigned long long e = have ? stack[sp - 1 - lane] : 0ull;
+      sp -= k;
+      __syncwarp();
+      bool pn = false, pf = false, ln = false, lf = false;      // near / far child: push?, leaf pair?
+      unsigned long long cn = 0ull, cf = 0ull;
+      if (have && entry_lb(e) <= best) {
+        int na = (int)((e >> 24) & 0xffffffu), nb = (int)(e & 0xffffffu);
+        Node a = load_node(ma.nodes, na), b = load_node(mb.nodes, nb);
+        bool la = a.child < 0, lb = b.child < 0;
+        if (la && lb) {
+          pn = ln = true;
+          cn = pack_dist_entry(entry_lb(e), a.tri, b.tri);
+        } else {
+          bool splitA = lb || (!la && (a.hx * a.hy * a.hz > b.hx * b.hy * b.hz));
+          float ca[3], ha[3], cb[3], hb[3];
+          float d0, d1;
+          int i0a, i0b, i1a, i1b;
+          bool lf0, lf1;
+          if (splitA) {
+            Node a0 = load_node(ma.nodes, a.child), a1 = load_node(ma.nodes, a.child + 1);
+            node_ch(b, cb, hb);
+            node_ch(a0, ca, ha); d0 = box_dist_lb(ca, ha, cb, hb, x);
+            node_ch(a1, ca, ha); d1 = box_dist_lb(ca, ha, cb, hb, x);
+            lf0 = lb && a0.child < 0; lf1 = lb && a1.child < 0;
+            i0a = lf0 ? a0.tri : a.child; i0b = lf0 ? b.tri : nb;
+            i1a = lf1 ? a1.tri : a.child + 1; i1b = lf1 ? b.tri : nb;
+          } else {
+            Node b0 = load_node(mb.nodes, b.child), b1 = load_node(mb.nodes, b.child + 1);
+            node_ch(a, ca, ha);
+            node_ch(b0, cb, hb); d0 = box_dist_lb(ca, ha, cb, hb, x);
+            node_ch(b1, cb, hb); d1 = box_dist_lb(ca, ha, cb, hb, x);
+            lf0 = la && b0.child < 0; lf1 = la && b1.child < 0;
+            i0a = lf0 ? a.tri : na; i0b = lf0 ? b0.tri : b.child;
+            i1a = lf1 ? a.tri : na; i1b = lf1 ? b1.tri : b.child + 1;
+          }
+          n_box += 2;
+          bool swap = d1 < d0;
+          float dn = swap ? d1 : d0, df = swap ? d0 : d1;
+          pn = dn <= best; pf = df <= best;
+          ln = swap ? lf1 : lf0; lf = swap ? lf0 : lf1;
+          cn = pack_dist_entry(dn, swap ? i1a : i0a, swap ? i1b : i0b);
+          cf = pack_dist_entry(df, swap ? i0a : i1a, swap ? i0b : i1b);
+        }
+      }
+      // far children first (deeper in the stack), near children on top
+      unsigned sF = __ballot_sync(FULL, pf && !lf), sN = __ballot_sync(FULL, pn && !ln);
+      unsigned qF = __ballot_sync(FULL, pf && lf), qN = __ballot_sync(FULL, pn && ln);
+      if (pf && !lf) stack[sp + __popc(sF & lt_mask)] = cf;
+      if (pn && !ln) stack[sp + __popc(sF) + __popc(sN & lt_mask)] = cn;
+      sp += __popc(sF) + __popc(sN);
+      if (pf && lf) leafq[lq + __popc(qF & lt_mask)] = cf;
+      if (pn && ln) leafq[lq + __popc(qF) + __popc(qN & lt_mask)] = cn;
+      lq += __popc(qF) + __popc(qN);
+      __syncwarp();
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (hit) {
+        p.dist[w] = -1.f;
+        if (p.pts) for (int k = 0; k < 6; k++) p.pts[(size_t)w * 6 + k] = 0.0;
+      } else {
+        p.dist[w] = sqrtf(best);
+        if (p.pts) {
+          // bpa/bpb are in B's frame: p1 -> A's frame, p2 stays in B's frame
+          d3 pa_local = xf_apply_inv(XA, xf_apply(XB, bpa));
+          double *o = p.pts + (size_t)w * 6;
+          o[0] = pa_local.x; o[1] = pa_local.y; o[2] = pa_local.z;
+          o[3] = bpb.x; o[4] = bpb.y; o[5] = bpb.z;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (p.stats) {
+    unsigned long long v;
+    v = n_box; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_DBOX], v);
+    v = n_tri; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_DTRI], v);
+  }
+}
+
+// ============================================================================================
+// CONTACT_LIVE energy.  Per pose, per hand body: virtual contact rebuilt from the body-body closest
+// points exactly as the reference does -- including its frame quirks:
+//   bodyToBodyDistance returns p1 = T_link^-1 * mP1, p2 = T_obj^-1 * mP2 with mP1/mP2 already local
+//   (graspitCollision.cpp:473-475); World::findVirtualContact (world.cpp:1641-1651) then forms
+//   n = normalize(T_link p1 - T_obj p2) = normalize(mP1 - mP2), the contact location is T_link p1 = mP1
+//   read as a world point, and the virtual contact's world normal is -n (virtualContact.cpp:92).
+// One warp per pose, lanes = hand bodies.
+// ============================================================================================
+
+__global__ void __launch_bounds__(256) live_kernel(LiveParams p) {
+  const int lane = threadIdx.x & 31;
+  int pose = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (pose >= p.npose) return;
+  if (p.legal && !p.legal[pose]) { if (lane == 0) p.energy[pose] = 0.f; return; }
+  const MeshDev &mo = p.meshes[p.body_mesh[p.object]];
+  const double *XO = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, p.object);
+  unsigned nbx = 0, ntr = 0;
+  float total = 0.f;
+  for (int base = 0; base < p.nq; base += 32) {
+    int i = base + lane;
+    float term = 0.f;
+    if (i < p.nq) {
+      const double *o = p.pts + ((size_t)pose * p.nq + i) * 6;
+      d3 mP1 = mk<double>(o[0], o[1], o[2]), mP2 = mk<double>(o[3], o[4], o[5]);
+      d3 n = mP1 - mP2;
+      double nn = sqrt(dot(n, n));
+      if (nn > 0.0) n = n * (1.0 / nn);
+      d3 cnw = mk<double>(-n.x, -n.y, -n.z);
+      term = contact_term(mo, XO, mP1, cnw, nbx, ntr);
+    }
+    total += warp_sum(term);
+  }
+  if (lane == 0) p.energy[pose] = total / (float)p.nq;
+  if (p.stats) {
+    unsigned long long v;
+    v = nbx; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PBOX], v);
+    v = ntr; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PTRI], v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-callable launchers (api.cu)
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_fk(const FkParams &p, cudaStream_t s) {
+  if (p.npose <= 0) return cudaSuccess;
+  fk_kernel<<<(p.npose + 127) / 128, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_eval(const EvalParams &p, int blocks, int warps_per_block, size_t smem, cudaStream_t s) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  eval_kernel<<<blocks, warps_per_block * 32, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_recheck(const RecheckParams &p, cudaStream_t s) {
+  recheck_kernel<<<64, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_point(const PointParams &p, cudaStream_t s) {
+  if (p.n <= 0) return cudaSuccess;
+  point_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s) {
+  static bool configured = false;
+  size_t smem = (size_t)8 * DIST_WARP_SMEM;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dist_kernel<<<blocks, 256, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_live(const LiveParams &p, cudaStream_t s) {
+  if (p.npose <= 0) return cudaSuccess;
+  int threads = 256;
+  long long total = (long long)p.npose * 32;
+  live_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+} // namespace b2c

@@ -1,0 +1,462 @@
+"""Python host mirror of the reference's ``CollisionInterface`` over the C ABI (``include/b2c.h``).
+
+Method names and argument meaning follow ``include/graspit/Collision/collisionInterface.h:44-185``
+(``addBody``, ``setBodyTransform``, ``activatePair``, ``allCollisions``, ``bodyToBodyDistance``,
+``pointToBodyDistance``, ``contact``, ``allContacts``, ``bodyRegion``, ``getBoundingVolumes``) so that
+the parity tests read like the reference's own ``test/graspit_collision_tests.cpp``; the batched
+``eval_batch`` replaces the ``SearchEnergy::analyzeState`` loop.  Everything here is plumbing: the
+work happens in ``libb2c.so`` (CUDA, sm_100a).  There is no CPU path -- if the library or a CUDA
+device is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2c.so")
+
+B2C_INPUT_RAW, B2C_INPUT_AA_EIGEN = 0, 1
+B2C_EVAL_PRESET, B2C_EVAL_LIVE, B2C_EVAL_PAIRMASK, B2C_EVAL_LINKDIST, B2C_EVAL_DEVICE_PTRS = 0, 1, 2, 4, 8
+FAST_COLLISION, ALL_COLLISIONS = 0, 1
+
+EXPORTS = [
+    "b2c_create", "b2c_destroy", "b2c_last_error", "b2c_stream", "b2c_device", "b2c_launch_count",
+    "b2c_mesh_create", "b2c_mesh_destroy", "b2c_body_create", "b2c_body_set_mesh", "b2c_body_remove",
+    "b2c_body_set_transform", "b2c_body_get_transform", "b2c_body_set_active", "b2c_pair_set_active",
+    "b2c_pair_is_active", "b2c_all_collisions", "b2c_body_distance", "b2c_point_distance", "b2c_contacts",
+    "b2c_all_contacts", "b2c_region", "b2c_bounding_volumes", "b2c_robot_define", "b2c_eval_batch",
+    "b2c_robot_bodies", "b2c_robot_pairs", "b2c_last_stats",
+]
+
+
+class B2CError(RuntimeError):
+    pass
+
+
+class Contact(C.Structure):
+    _fields_ = [("b1_pos", C.c_double * 3), ("b2_pos", C.c_double * 3), ("b1_normal", C.c_double * 3),
+                ("b2_normal", C.c_double * 3), ("distSq", C.c_double)]
+
+
+class Obb(C.Structure):
+    _fields_ = [("t", C.c_double * 3), ("q_wxyz", C.c_double * 4), ("half", C.c_double * 3)]
+
+
+class JointDesc(C.Structure):
+    _fields_ = [("dof", C.c_int), ("revolute", C.c_int), ("ratio", C.c_double), ("theta", C.c_double),
+                ("d", C.c_double), ("a", C.c_double), ("alpha", C.c_double)]
+
+
+class ChainDesc(C.Structure):
+    _fields_ = [("tran_q", C.c_double * 4), ("tran_t", C.c_double * 3), ("first_joint", C.c_int),
+                ("njoints", C.c_int), ("first_link", C.c_int), ("nlinks", C.c_int)]
+
+
+class VContactDesc(C.Structure):
+    _fields_ = [("body", C.c_int), ("loc", C.c_double * 3), ("normal", C.c_double * 3)]
+
+
+class RobotDescC(C.Structure):
+    _fields_ = [("base_body", C.c_int), ("mount_body", C.c_int), ("ndof", C.c_int),
+                ("dof_min", C.POINTER(C.c_double)), ("dof_max", C.POINTER(C.c_double)),
+                ("nchains", C.c_int), ("chains", C.POINTER(ChainDesc)),
+                ("njoints", C.c_int), ("joints", C.POINTER(JointDesc)),
+                ("nlinks", C.c_int), ("link_body", C.POINTER(C.c_int)), ("link_last_joint", C.POINTER(C.c_int)),
+                ("parent_robot", C.c_int), ("parent_chain", C.c_int),
+                ("parent_offset_q", C.c_double * 4), ("parent_offset_t", C.c_double * 3),
+                ("approach_q", C.c_double * 4), ("approach_t", C.c_double * 3),
+                ("neg", C.c_int), ("eg", C.POINTER(C.c_double)),
+                ("eg_origin", C.POINTER(C.c_double)), ("eg_norm", C.POINTER(C.c_double)),
+                ("nvcontacts", C.c_int), ("vcontacts", C.POINTER(VContactDesc))]
+
+
+class EvalArgs(C.Structure):
+    _fields_ = [("robot", C.c_int), ("object", C.c_int), ("npose", C.c_int), ("input_mode", C.c_int),
+                ("states", C.c_void_p), ("stride", C.c_int),
+                ("ref_q", C.c_double * 4), ("ref_t", C.c_double * 3), ("flags", C.c_int),
+                ("legal", C.c_void_p), ("energy", C.c_void_p), ("pair_mask", C.c_void_p),
+                ("link_dist", C.c_void_p), ("body_tf", C.c_void_p)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libb2c.so and declare prototypes.  Raises if the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B2CError(f"CUDA extension missing: {LIB_PATH}. Build it with `python -m graspit_b200.build` "
+                       "(there is no CPU fallback).")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, dp, ip = C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.b2c_create.argtypes = [ci, C.POINTER(vp)]
+    L.b2c_destroy.argtypes = [vp]; L.b2c_destroy.restype = None
+    L.b2c_last_error.argtypes = [vp]; L.b2c_last_error.restype = C.c_char_p
+    L.b2c_stream.argtypes = [vp]; L.b2c_stream.restype = vp
+    L.b2c_device.argtypes = [vp]
+    L.b2c_launch_count.argtypes = [vp]; L.b2c_launch_count.restype = C.c_longlong
+    L.b2c_mesh_create.argtypes = [vp, C.POINTER(C.c_float), ci, ip]
+    L.b2c_mesh_destroy.argtypes = [vp, ci]
+    L.b2c_body_create.argtypes = [vp, ci, ip]
+    L.b2c_body_set_mesh.argtypes = [vp, ci, ci]
+    L.b2c_body_remove.argtypes = [vp, ci]
+    L.b2c_body_set_transform.argtypes = [vp, ci, dp, dp]
+    L.b2c_body_get_transform.argtypes = [vp, ci, dp, dp]
+    L.b2c_body_set_active.argtypes = [vp, ci, ci]
+    L.b2c_pair_set_active.argtypes = [vp, ci, ci, ci]
+    L.b2c_pair_is_active.argtypes = [vp, ci, ci, ip]
+    L.b2c_all_collisions.argtypes = [vp, ci, ip, ci, ip, ci, ip]
+    L.b2c_body_distance.argtypes = [vp, ci, ci, dp, dp, dp, dp, dp]
+    L.b2c_point_distance.argtypes = [vp, ci, dp, dp, dp, dp]
+    L.b2c_contacts.argtypes = [vp, ci, ci, C.c_double, ci, C.POINTER(Contact), ci, ip]
+    L.b2c_all_contacts.argtypes = [vp, C.c_double, ip, ci, ip, ip, ci, ip, C.POINTER(Contact), ci, ip]
+    L.b2c_region.argtypes = [vp, ci, dp, dp, C.c_double, dp, ci, ip]
+    L.b2c_bounding_volumes.argtypes = [vp, ci, ci, C.POINTER(Obb), ci, ip]
+    L.b2c_robot_define.argtypes = [vp, C.POINTER(RobotDescC), ip]
+    L.b2c_eval_batch.argtypes = [vp, C.POINTER(EvalArgs)]
+    L.b2c_robot_bodies.argtypes = [vp, ci, ip, ci, ip]
+    L.b2c_robot_pairs.argtypes = [vp, ci, ip, ci, ip]
+    L.b2c_last_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    _lib = L
+    return L
+
+
+def _d(x, n=None):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} values, got {a.size}")
+    return a
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _contacts_to_array(buf, n):
+    out = np.zeros((n, 13))
+    for i in range(n):
+        c = buf[i]
+        out[i, 0:3] = c.b1_pos[:]; out[i, 3:6] = c.b2_pos[:]
+        out[i, 6:9] = c.b1_normal[:]; out[i, 9:12] = c.b2_normal[:]; out[i, 12] = c.distSq
+    return out
+
+
+class Engine:
+    """One collision context on one CUDA device (one instance per World, like the reference)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.b2c_create(int(device), C.byref(h))
+        if rc != 0 or not h:
+            raise B2CError(f"b2c_create(device={device}) failed with code {rc}: no usable CUDA device "
+                           "(the engine has no CPU path)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b2c_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, soft=False):
+        if rc != 0 and not soft:
+            raise B2CError(f"b2c error {rc}: {self.L.b2c_last_error(self.h).decode()}")
+        return rc
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.b2c_launch_count(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.b2c_stream(self.h) or 0)
+
+    # ---- addBody / cloneBody / removeBody / updateBodyGeometry ---------------------------------
+    def create_mesh(self, tris) -> int:
+        t = np.ascontiguousarray(np.asarray(tris, dtype=np.float32).reshape(-1, 9))
+        mid = C.c_int(-1)
+        self._ck(self.L.b2c_mesh_create(self.h, t.ctypes.data_as(C.POINTER(C.c_float)), t.shape[0], C.byref(mid)))
+        return mid.value
+
+    def add_body(self, tris=None, mesh: Optional[int] = None) -> int:
+        """addBody: register geometry (or reuse ``mesh``) and return the body id."""
+        if mesh is None:
+            mesh = self.create_mesh(tris)
+        bid = C.c_int(-1)
+        self._ck(self.L.b2c_body_create(self.h, mesh, C.byref(bid)))
+        self._mesh_of = getattr(self, "_mesh_of", {})
+        self._mesh_of[bid.value] = mesh
+        return bid.value
+
+    def clone_body(self, original: int) -> int:
+        """cloneBody: a second body sharing the original's collision geometry."""
+        return self.add_body(mesh=self._mesh_of[original])
+
+    def update_body_geometry(self, body: int, tris):
+        mesh = self.create_mesh(tris)
+        self._ck(self.L.b2c_body_set_mesh(self.h, body, mesh))
+        self._mesh_of[body] = mesh
+
+    def remove_body(self, body: int):
+        self._ck(self.L.b2c_body_remove(self.h, body))
+
+    # ---- setBodyTransform / activation -----------------------------------------------------------
+    def set_body_transform(self, body: int, q_wxyz, t):
+        q, tt = _d(q_wxyz, 4), _d(t, 3)
+        self._ck(self.L.b2c_body_set_transform(self.h, body, _dp(q), _dp(tt)))
+
+    def get_body_transform(self, body: int):
+        q, t = np.zeros(4), np.zeros(3)
+        self._ck(self.L.b2c_body_get_transform(self.h, body, _dp(q), _dp(t)))
+        return q, t
+
+    def activate_body(self, body: int, active: bool):
+        self._ck(self.L.b2c_body_set_active(self.h, body, int(bool(active))))
+
+    def activate_pair(self, a: int, b: int, active: bool):
+        self._ck(self.L.b2c_pair_set_active(self.h, a, b, int(bool(active))))
+
+    def is_active(self, a: int, b: int = -1) -> bool:
+        out = C.c_int(0)
+        rc = self.L.b2c_pair_is_active(self.h, a, b, C.byref(out))
+        return bool(out.value) if rc == 0 else False
+
+    # ---- queries ---------------------------------------------------------------------------------
+    def all_collisions(self, detection=ALL_COLLISIONS, interest: Optional[Sequence[int]] = None, cap=4096):
+        """allCollisions -> (count, [(a,b), ...]); the report is empty for FAST_COLLISION."""
+        il = np.ascontiguousarray(np.asarray(interest if interest is not None else [], dtype=np.int32))
+        out = np.zeros(2 * cap, dtype=np.int32)
+        n = C.c_int(0)
+        self._ck(self.L.b2c_all_collisions(self.h, int(detection == FAST_COLLISION),
+                                           _ip(il) if interest is not None else None, il.size, _ip(out), cap, C.byref(n)))
+        pairs = [] if detection == FAST_COLLISION else [
+            (int(out[2 * i]), int(out[2 * i + 1])) for i in range(min(n.value, cap))]
+        return n.value, pairs
+
+    def body_to_body_distance(self, a: int, b: int, local=False):
+        """bodyToBodyDistance -> (dist, p1, p2) in the reference's output convention
+        (``local=True``: plain closest points in each body's frame)."""
+        d = C.c_double(0.0)
+        p1, p2, l1, l2 = np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3)
+        rc = self.L.b2c_body_distance(self.h, a, b, C.byref(d), _dp(p1), _dp(p2), _dp(l1), _dp(l2))
+        if rc == -1:
+            return 0.0, p1, p2      # reference: unknown body -> returns 0
+        self._ck(rc)
+        return (d.value, l1, l2) if local else (d.value, p1, p2)
+
+    def point_to_body_distance(self, body: int, point):
+        """pointToBodyDistance -> (dist, closestPoint, closestNormal), world frame."""
+        d = C.c_double(0.0)
+        p = _d(point, 3); cp, cn = np.zeros(3), np.zeros(3)
+        rc = self.L.b2c_point_distance(self.h, body, _dp(p), C.byref(d), _dp(cp), _dp(cn))
+        if rc == -1:
+            return 0.0, cp, cn
+        self._ck(rc)
+        return d.value, cp, cn
+
+    def contact(self, a: int, b: int, threshold: float, raw=False, cap=65536):
+        buf = (Contact * cap)()
+        n = C.c_int(0)
+        self._ck(self.L.b2c_contacts(self.h, a, b, float(threshold), int(raw), buf, cap, C.byref(n)))
+        return _contacts_to_array(buf, min(n.value, cap))
+
+    def all_contacts(self, threshold: float, interest: Optional[Sequence[int]] = None, cap_pairs=1024,
+                     cap_contacts=65536):
+        il = np.ascontiguousarray(np.asarray(interest if interest is not None else [], dtype=np.int32))
+        pid = np.zeros(2 * cap_pairs, dtype=np.int32); cnt = np.zeros(cap_pairs, dtype=np.int32)
+        buf = (Contact * cap_contacts)()
+        npairs, nc = C.c_int(0), C.c_int(0)
+        self._ck(self.L.b2c_all_contacts(self.h, float(threshold), _ip(il) if interest is not None else None,
+                                         il.size, _ip(pid), _ip(cnt), cap_pairs, C.byref(npairs), buf, cap_contacts,
+                                         C.byref(nc)))
+        allc = _contacts_to_array(buf, min(nc.value, cap_contacts))
+        res, k = [], 0
+        for i in range(min(npairs.value, cap_pairs)):
+            c = int(cnt[i])
+            res.append(((int(pid[2 * i]), int(pid[2 * i + 1])), allc[k:k + c]))
+            k += c
+        return res
+
+    def body_region(self, body: int, point, normal, radius: float, cap=1 << 18):
+        p, nn = _d(point, 3), _d(normal, 3)
+        out = np.zeros(3 * cap)
+        n = C.c_int(0)
+        self._ck(self.L.b2c_region(self.h, body, _dp(p), _dp(nn), float(radius), _dp(out), cap, C.byref(n)))
+        return out[: 3 * min(n.value, cap)].reshape(-1, 3).copy()
+
+    def get_bounding_volumes(self, body: int, depth: int, cap=1 << 16):
+        buf = (Obb * cap)()
+        n = C.c_int(0)
+        self._ck(self.L.b2c_bounding_volumes(self.h, body, depth, buf, cap, C.byref(n)))
+        out = np.zeros((min(n.value, cap), 10))
+        for i in range(out.shape[0]):
+            out[i, 0:3] = buf[i].t[:]; out[i, 3:7] = buf[i].q_wxyz[:]; out[i, 7:10] = buf[i].half[:]
+        return out
+
+    # ---- robots and batched evaluation ----------------------------------------------------------
+    def define_robot(self, robot, body_ids: dict, parent_robot_id: int = -1, parent_offset=None) -> int:
+        """Register a robot description (``formats.xmlmodel.RobotDesc``).  ``body_ids`` maps scene body
+        indices to engine body ids."""
+        joints, chains, link_body, link_last = [], [], [], []
+        for c in robot.chains:
+            cd = ChainDesc()
+            cd.tran_q[:] = list(c.tran[0]); cd.tran_t[:] = list(c.tran[1])
+            cd.first_joint, cd.njoints = len(joints), len(c.joints)
+            cd.first_link, cd.nlinks = len(link_body), len(c.link_bodies)
+            for j in c.joints:
+                jd = JointDesc(j.dof, int(j.revolute), j.ratio, j.theta, j.d, j.a, j.alpha)
+                joints.append(jd)
+            link_body += [body_ids[b] for b in c.link_bodies]
+            link_last += list(c.last_joint)
+            chains.append(cd)
+        d = RobotDescC()
+        keep = []
+        d.base_body = body_ids[robot.base_body]
+        d.mount_body = body_ids[robot.mount_body] if robot.mount_body >= 0 else -1
+        d.ndof = robot.n_dof
+        dmin, dmax = _d(robot.dof_min), _d(robot.dof_max)
+        keep += [dmin, dmax]
+        d.dof_min, d.dof_max = _dp(dmin), _dp(dmax)
+        ch = (ChainDesc * len(chains))(*chains); jt = (JointDesc * max(1, len(joints)))(*joints)
+        lb = np.ascontiguousarray(link_body, dtype=np.int32); ll = np.ascontiguousarray(link_last, dtype=np.int32)
+        keep += [ch, jt, lb, ll]
+        d.nchains, d.chains = len(chains), ch
+        d.njoints, d.joints = len(joints), jt
+        d.nlinks, d.link_body, d.link_last_joint = len(link_body), _ip(lb), _ip(ll)
+        d.parent_robot, d.parent_chain = parent_robot_id, max(robot.parent_chain, 0)
+        off = parent_offset if parent_offset is not None else (np.array([1.0, 0, 0, 0]), np.zeros(3))
+        d.parent_offset_q[:] = list(off[0]); d.parent_offset_t[:] = list(off[1])
+        d.approach_q[:] = list(robot.approach[0]); d.approach_t[:] = list(robot.approach[1])
+        if robot.eg is not None:
+            eg, eo, en = _d(robot.eg), _d(robot.eg_origin), _d(robot.eg_norm)
+            keep += [eg, eo, en]
+            d.neg, d.eg, d.eg_origin, d.eg_norm = robot.eg.shape[0], _dp(eg), _dp(eo), _dp(en)
+        else:
+            d.neg = 0
+        vcs = []
+        for v in robot.vcontacts:
+            vd = VContactDesc()
+            vd.body = body_ids[v.body]
+            vd.loc[:] = list(v.loc); vd.normal[:] = list(v.normal)
+            vcs.append(vd)
+        vc = (VContactDesc * max(1, len(vcs)))(*vcs)
+        keep.append(vc)
+        d.nvcontacts, d.vcontacts = len(vcs), vc
+        rid = C.c_int(-1)
+        self._ck(self.L.b2c_robot_define(self.h, C.byref(d), C.byref(rid)))
+        return rid.value
+
+    def robot_bodies(self, robot: int) -> List[int]:
+        out = np.zeros(256, dtype=np.int32); n = C.c_int(0)
+        self._ck(self.L.b2c_robot_bodies(self.h, robot, _ip(out), 256, C.byref(n)))
+        return [int(v) for v in out[: n.value]]
+
+    def robot_pairs(self, robot: int) -> List[Tuple[int, int]]:
+        out = np.zeros(2 * 65536, dtype=np.int32); n = C.c_int(0)
+        self._ck(self.L.b2c_robot_pairs(self.h, robot, _ip(out), 65536, C.byref(n)))
+        return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(n.value)]
+
+    def last_stats(self) -> dict:
+        st = (C.c_ulonglong * 8)()
+        self.L.b2c_last_stats(self.h, st)
+        names = ["box_tests", "tri_tests", "point_box_tests", "point_tri_tests", "ambiguous", "dist_box_tests",
+                 "dist_tri_tests", "recheck_hits"]
+        return {k: int(st[i]) for i, k in enumerate(names)}
+
+    def eval_batch(self, robot: int, obj: int, states, input_mode=B2C_INPUT_RAW, ref_tran=None, live=False,
+                   pair_mask=False, link_dist=False, body_tf=False):
+        """Host-buffer batched evaluation.  states: (npose, stride) float32.
+        Returns dict(legal, energy[, pair_mask, link_dist, body_tf])."""
+        st = np.ascontiguousarray(states, dtype=np.float32)
+        npose, stride = st.shape
+        a = EvalArgs()
+        a.robot, a.object, a.npose, a.input_mode = robot, obj, npose, input_mode
+        a.states, a.stride = st.ctypes.data, stride
+        rq, rt = ref_tran if ref_tran is not None else (np.array([1.0, 0, 0, 0]), np.zeros(3))
+        a.ref_q[:] = list(rq); a.ref_t[:] = list(rt)
+        flags = (B2C_EVAL_LIVE if live else 0) | (B2C_EVAL_PAIRMASK if pair_mask else 0) | (B2C_EVAL_LINKDIST if link_dist else 0)
+        a.flags = flags
+        legal = np.zeros(npose, dtype=np.uint8); energy = np.zeros(npose, dtype=np.float32)
+        a.legal, a.energy = legal.ctypes.data, energy.ctypes.data
+        res = {"legal": legal, "energy": energy}
+        nb = len(self.robot_bodies(robot))
+        if pair_mask:
+            mw = max(1, (len(self.robot_pairs(robot)) + 63) // 64)
+            pm = np.zeros((npose, mw), dtype=np.uint64)
+            a.pair_mask = pm.ctypes.data
+            res["pair_mask"] = pm
+        if link_dist:
+            nh = self._root_bodies(robot)
+            ld = np.zeros((npose, nh), dtype=np.float32)
+            a.link_dist = ld.ctypes.data
+            res["link_dist"] = ld
+        if body_tf:
+            bt = np.zeros((npose, nb, 7), dtype=np.float64)
+            a.body_tf = bt.ctypes.data
+            res["body_tf"] = bt
+        self._ck(self.L.b2c_eval_batch(self.h, C.byref(a)))
+        return res
+
+    def _root_bodies(self, robot: int) -> int:
+        return getattr(self, "_nroot", {}).get(robot, len(self.robot_bodies(robot)))
+
+    def eval_batch_device(self, robot: int, obj: int, states_ptr: int, npose: int, stride: int, legal_ptr: int,
+                          energy_ptr: int, input_mode=B2C_INPUT_RAW, ref_tran=None, live=False):
+        """Device-pointer variant: inputs/outputs already resident in HBM; asynchronous on ``stream``."""
+        a = EvalArgs()
+        a.robot, a.object, a.npose, a.input_mode = robot, obj, npose, input_mode
+        a.states, a.stride = states_ptr, stride
+        rq, rt = ref_tran if ref_tran is not None else (np.array([1.0, 0, 0, 0]), np.zeros(3))
+        a.ref_q[:] = list(rq); a.ref_t[:] = list(rt)
+        a.flags = B2C_EVAL_DEVICE_PTRS | (B2C_EVAL_LIVE if live else 0)
+        a.legal, a.energy = legal_ptr, energy_ptr
+        self._ck(self.L.b2c_eval_batch(self.h, C.byref(a)))
+
+
+class SceneBinding:
+    """A ``formats.xmlmodel.Scene`` loaded into an :class:`Engine`: bodies, transforms, the file-defined
+    disabled pairs, the pairs found touching at load, and the robots."""
+
+    def __init__(self, engine: Engine, scene, apply_touching=True):
+        self.engine = engine
+        self.scene = scene
+        self.body_ids = {}
+        for i, b in enumerate(scene.bodies):
+            self.body_ids[i] = engine.add_body(b.tris)
+            q, t = scene.body_tran[i]
+            engine.set_body_transform(self.body_ids[i], q, t)
+        for (a, b) in scene.disabled_pairs:
+            engine.activate_pair(self.body_ids[a], self.body_ids[b], False)
+        if apply_touching:
+            for (a, b) in scene.touching_pairs:
+                engine.activate_pair(self.body_ids[a], self.body_ids[b], False)
+        self.robot_ids = {}
+        engine._nroot = getattr(engine, "_nroot", {})
+        for ri, r in enumerate(scene.robots):
+            off = None
+            parent_id = -1
+            if r.parent >= 0:
+                parent_id = self.robot_ids[r.parent]
+                for (child, o) in scene.robots[r.parent].chains[r.parent_chain].children:
+                    if child == ri:
+                        off = o
+            rid = engine.define_robot(r, self.body_ids, parent_id, off)
+            self.robot_ids[ri] = rid
+            engine._nroot[rid] = len(r.body_list())

@@ -1,0 +1,229 @@
+/*
+ * b2c.h -- C ABI of the B200-native batched collision / proximity / contact engine.
+ *
+ * This is the drop-in boundary: every entry point replaces one
+ * virtual of GraspIt!'s `class CollisionInterface`
+ * (reference include/graspit/Collision/collisionInterface.h:44-185) or one step of the
+ * `SearchEnergy::analyzeState` caller loop (reference src/EGPlanner/energy/searchEnergy.cpp:148-188),
+ * and is what `B200Collision : public CollisionInterface` (graspit_b200/host/b200Collision.h,
+ * INTEGRATION.md) binds inside GraspIt!.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - units: millimetres, radians; transforms are world-from-body, quaternion (w,x,y,z) + translation
+ *   - every function returns 0 on success and a negative B2C_E* code on failure, never throws and
+ *     never takes ownership of caller memory; b2c_last_error() describes the last failure
+ *   - one context = one CUDA device + stream; calls on a context must be serialised by the caller
+ *     (the reference keeps one CollisionInterface per World the same way)
+ *   - there is NO CPU fallback: if no CUDA device is usable, b2c_create() fails
+ */
+#ifndef B2C_H
+#define B2C_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2c_ctx b2c_ctx;
+
+enum {
+  B2C_OK = 0,
+  B2C_EINVAL = -1,     /* bad argument / unknown id (reference: DBGA("GCOL: model not found")) */
+  B2C_ECUDA = -2,      /* CUDA runtime failure (see b2c_last_error) */
+  B2C_ECAPACITY = -3,  /* caller buffer or internal work queue too small */
+  B2C_ENODEVICE = -4   /* no usable CUDA device: the engine has no CPU path */
+};
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+int b2c_create(int device, b2c_ctx **out);
+void b2c_destroy(b2c_ctx *ctx);
+const char *b2c_last_error(const b2c_ctx *ctx);
+/* CUDA stream the context launches on (cudaStream_t as void*), and the device ordinal */
+void *b2c_stream(const b2c_ctx *ctx);
+int b2c_device(const b2c_ctx *ctx);
+/* number of kernel launches issued by this context so far (bench.py "gpu_launches") */
+long long b2c_launch_count(const b2c_ctx *ctx);
+
+/* ---- geometry: replaces addBody / updateBodyGeometry / cloneBody / removeBody ---------------
+ * collisionInterface.h:102-114, reference graspitCollision.cpp:200-305.  A mesh is an immutable
+ * triangle soup + its BVH in device memory; a body is (mesh, transform, active flag).  Cloning a
+ * body = creating a second body on the same mesh (reference CollisionModel::cloneModel,
+ * collisionModel.cpp:466-474).  tri9: ntri x 9 floats (v1 v2 v3) -- the fp32 vertex values GraspIt!
+ * obtains from Coin (reference src/body.cpp:1225-1249). */
+int b2c_mesh_create(b2c_ctx *ctx, const float *tri9, int ntri, int *mesh_id);
+int b2c_mesh_destroy(b2c_ctx *ctx, int mesh_id);
+int b2c_body_create(b2c_ctx *ctx, int mesh_id, int *body_id);
+int b2c_body_set_mesh(b2c_ctx *ctx, int body_id, int mesh_id);   /* updateBodyGeometry */
+int b2c_body_remove(b2c_ctx *ctx, int body_id);
+
+/* setBodyTransform (collisionInterface.h:116, graspitCollision.cpp:307-316) */
+int b2c_body_set_transform(b2c_ctx *ctx, int body_id, const double q_wxyz[4], const double t[3]);
+int b2c_body_get_transform(b2c_ctx *ctx, int body_id, double q_wxyz[4], double t[3]);
+
+/* activateBody / activatePair / isActive (collisionInterface.h:123-131, graspitCollision.cpp:102-198).
+ * b == -1 in b2c_pair_is_active asks about body a alone. */
+int b2c_body_set_active(b2c_ctx *ctx, int body_id, int active);
+int b2c_pair_set_active(b2c_ctx *ctx, int a, int b, int active);
+int b2c_pair_is_active(b2c_ctx *ctx, int a, int b, int *active);
+
+/* ---- single-pose queries at the bodies' current transforms -------------------------------- */
+
+/* allCollisions (collisionInterface.h:141, graspitCollision.cpp:332-363).  interest == NULL means
+ * all active pairs.  fast != 0 = FAST_COLLISION: *ncolliding is 0 or 1 and pairs_out is untouched.
+ * Otherwise pairs_out receives (a,b) body ids, a < b, for up to cap colliding pairs. */
+int b2c_all_collisions(b2c_ctx *ctx, int fast, const int *interest, int ninterest,
+                       int *pairs_out, int cap, int *ncolliding);
+
+/* bodyToBodyDistance (collisionInterface.h:161, graspitCollision.cpp:458-477): -1 when the bodies
+ * interpenetrate.  p1/p2 reproduce the reference's output convention exactly, including its second
+ * application of the inverse body transform; p1_local/p2_local (may be NULL)
+ * receive the plain closest points in each body's own frame. */
+int b2c_body_distance(b2c_ctx *ctx, int a, int b, double *dist, double p1[3], double p2[3],
+                      double p1_local[3], double p2_local[3]);
+
+/* pointToBodyDistance (collisionInterface.h:156, graspitCollision.cpp:435-456): world point in,
+ * world closest point and unit vector point->closest out. */
+int b2c_point_distance(b2c_ctx *ctx, int body, const double point[3], double *dist,
+                       double closest[3], double normal[3]);
+
+typedef struct b2c_contact {
+  double b1_pos[3];     /* body-1 frame */
+  double b2_pos[3];     /* body-2 frame */
+  double b1_normal[3];  /* body-1 frame, points from body 2 into body 1 */
+  double b2_normal[3];  /* body-2 frame */
+  double distSq;        /* reference's mixed-frame value (collisionAlgorithms_inl.h:129-132) */
+} b2c_contact;
+
+/* contact (collisionInterface.h:149, graspitCollision.cpp:407-433) with the reference's duplicate
+ * removal (3 mm) and perimeter compaction; raw != 0 returns the unprocessed candidate list. */
+int b2c_contacts(b2c_ctx *ctx, int a, int b, double threshold, int raw,
+                 b2c_contact *out, int cap, int *ncontacts);
+
+/* allContacts (collisionInterface.h:146, graspitCollision.cpp:365-405): pair_ids gets (a,b) per
+ * contacting pair, counts the contacts per pair, out the contacts of all pairs back to back. */
+int b2c_all_contacts(b2c_ctx *ctx, double threshold, const int *interest, int ninterest,
+                     int *pair_ids, int *counts, int cap_pairs, int *npairs,
+                     b2c_contact *out, int cap_contacts, int *ncontacts);
+
+/* bodyRegion (collisionInterface.h:171, graspitCollision.cpp:479-496): vertices (body frame) of all
+ * triangles within radius of point whose normal does not oppose `normal`; the reference point itself
+ * is appended last, as the reference does. */
+int b2c_region(b2c_ctx *ctx, int body, const double point[3], const double normal[3], double radius,
+               double *out_xyz, int cap, int *npoints);
+
+typedef struct b2c_obb {
+  double t[3];
+  double q_wxyz[4];
+  double half[3];
+} b2c_obb;
+
+/* getBoundingVolumes (collisionInterface.h:175, graspitCollision.cpp:499-509): the reference-style
+ * oriented-box hierarchy (PCA fit, mean-vertex split) at `depth`, for display and for the reference's
+ * own unit test; independent of the device BVH used for queries. */
+int b2c_bounding_volumes(b2c_ctx *ctx, int body, int depth, b2c_obb *out, int cap, int *nboxes);
+
+/* ---- batched pose evaluation: FK -> legal -> proximity -> CONTACT_ENERGY --------------------
+ * Replaces, for whole batches of candidate states, the loop
+ *   HandObjectState::execute -> Robot::setTran / forceDOFVals -> KinematicChain::fwdKinematics
+ *   SearchEnergy::legal -> World::noCollision(hand) -> allCollisions(FAST, NULL, &handBodies)
+ *   ContactEnergy::energy -> [World::findVirtualContacts] -> VirtualContact::getObjectDistanceAndNormal
+ * (reference searchState.cpp:515-527, kinematicChain.cpp:543-560, searchEnergy.cpp:104-188,
+ *  contactEnergy.cpp:9-55, world.cpp:1478-1508,1618-1651). */
+
+typedef struct b2c_joint_desc {
+  int dof;            /* index into the robot's DOF vector */
+  int revolute;       /* 1 revolute, 0 prismatic */
+  double ratio;       /* coupling ratio: joint = ratio * dof */
+  double theta;       /* DH theta at joint value 0 (revolute: the offset c) */
+  double d;           /* DH d at joint value 0 (prismatic: the offset c) */
+  double a;
+  double alpha;
+} b2c_joint_desc;
+
+typedef struct b2c_chain_desc {
+  double tran_q[4], tran_t[3];   /* chain base w.r.t. robot base */
+  int first_joint, njoints;      /* range in the joints array */
+  int first_link, nlinks;        /* range in the link arrays */
+} b2c_chain_desc;
+
+typedef struct b2c_vcontact_desc {
+  int body;                      /* body id the contact is attached to */
+  double loc[3];                 /* body frame */
+  double normal[3];              /* body frame */
+} b2c_vcontact_desc;
+
+typedef struct b2c_robot_desc {
+  int base_body;                 /* body id of the palm / base link */
+  int mount_body;                /* body id of the mount piece or -1 */
+  int ndof;
+  const double *dof_min, *dof_max;         /* [ndof] */
+  int nchains;
+  const b2c_chain_desc *chains;
+  int njoints;
+  const b2c_joint_desc *joints;
+  int nlinks;
+  const int *link_body;          /* [nlinks] body id per link, chain-major */
+  const int *link_last_joint;    /* [nlinks] joint (chain-local) after which the link pose is read */
+  int parent_robot;              /* robot id this one is attached to, or -1 */
+  int parent_chain;
+  double parent_offset_q[4], parent_offset_t[3];   /* child base w.r.t. parent chain end */
+  /* search-state mapping (B2C_INPUT_AA_EIGEN) */
+  double approach_q[4], approach_t[3];     /* Robot::getApproachTran */
+  int neg;                                 /* number of eigengrasps */
+  const double *eg;                        /* [neg x ndof] normalised eigengrasp directions */
+  const double *eg_origin, *eg_norm;       /* [ndof] */
+  int nvcontacts;
+  const b2c_vcontact_desc *vcontacts;      /* CONTACT_PRESET virtual contacts */
+} b2c_robot_desc;
+
+int b2c_robot_define(b2c_ctx *ctx, const b2c_robot_desc *desc, int *robot_id);
+
+enum {
+  B2C_INPUT_RAW = 0,       /* per pose: base (qw qx qy qz tx ty tz) + ndof DOF values (root robot first,
+                              then attached robots' DOFs in robot id order); stride = 7 + total dofs */
+  B2C_INPUT_AA_EIGEN = 1   /* per pose: Tx Ty Tz theta phi alpha + neg eigengrasp amplitudes
+                              (SPACE_AXIS_ANGLE + POSE_EIGEN, searchStateImpl.cpp:83-95,156-168) */
+};
+
+enum {
+  B2C_EVAL_PRESET = 0,       /* CONTACT_PRESET: file-defined virtual contacts */
+  B2C_EVAL_LIVE = 1,         /* CONTACT_LIVE: one virtual contact per link from bodyToBodyDistance */
+  B2C_EVAL_PAIRMASK = 2,     /* also evaluate ALL_COLLISIONS and return the colliding-pair bitmask */
+  B2C_EVAL_LINKDIST = 4,     /* also return bodyToBodyDistance(link, object) per hand body */
+  B2C_EVAL_DEVICE_PTRS = 8   /* states/outputs are device pointers (already resident in HBM) */
+};
+
+typedef struct b2c_eval_args {
+  int robot;                 /* root robot (hand, or arm with the hand attached) */
+  int object;                /* body id of the target object (energy / distances); -1 = legality only */
+  int npose;
+  int input_mode;
+  const float *states;       /* npose x stride floats */
+  int stride;
+  double ref_q[4], ref_t[3]; /* B2C_INPUT_AA_EIGEN: mRefTran (normally the object pose) */
+  int flags;
+  uint8_t *legal;            /* [npose] 1 = no collision among pairs touching the robot */
+  float *energy;             /* [npose] CONTACT_ENERGY; 0 when illegal */
+  uint64_t *pair_mask;       /* [npose x mask_words] bit i = i-th active pair collides (B2C_EVAL_PAIRMASK) */
+  float *link_dist;          /* [npose x nbodies] (B2C_EVAL_LINKDIST), robot body order of b2c_robot_bodies */
+  double *body_tf;           /* optional [npose x nbodies x 7]: FK result (q wxyz, t), host or device */
+} b2c_eval_args;
+
+int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *args);
+
+/* bodies moved by a robot (and robots attached to it) in the order used by link_dist / body_tf:
+ * finger links chain-major, then the base, then the mount piece (World::findVirtualContacts order,
+ * reference world.cpp:1623-1639), children appended after their parent. */
+int b2c_robot_bodies(b2c_ctx *ctx, int robot, int *bodies, int cap, int *nbodies);
+/* the active pairs (a,b) that a batched evaluation of `robot` tests, in pair_mask bit order */
+int b2c_robot_pairs(b2c_ctx *ctx, int robot, int *pairs, int cap, int *npairs);
+
+/* per-context counters of the last batched evaluation: box tests, triangle-pair tests,
+ * point-triangle tests, fp64 rechecks (explanatory L2-level traffic) */
+int b2c_last_stats(b2c_ctx *ctx, unsigned long long stats[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2C_H */
