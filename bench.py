@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Headline benchmark: hand-pose evaluations / second (FK + collision legality + CONTACT_ENERGY).
+
+Workload (BASELINE.json configs[1]): Barrett hand vs mug (worlds/plannerMug.xml),
+65 536 candidate planner states per step per GPU in the planner's own parameterisation (SPACE_AXIS_ANGLE
+position + POSE_EIGEN posture = 8 fp32 variables), CONTACT_PRESET energy (19 virtual contacts).  One step =
+one pass of the hot path over one batch.  States are synthetic: half uniform in the planner's search box,
+half within 150 mm of the object (the config-1 strata), eigengrasp amplitudes uniform in [-4, 4].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode preset|live] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU); poses shard across ranks with no data-path collective, and
+each step ends with the small NCCL all-gather of every rank's best (state || energy) rows that the planner's
+best-list merge needs.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hand-pose evals/sec (collision+contact+energy)"
+UNIT = "poses/s"
+BEST_LIST_SIZE = 20          # SimAnnPlanner BEST_LIST_SIZE, reference src/EGPlanner/simAnnPlanner.cpp:36
+ALGO_BYTES_EVAL_PER_POSE = 9 * 96 + 1 + 4     # eval kernel: 9 link transforms (12 fp64) in, legal + energy out
+ALGO_BYTES_STEP_PER_POSE = 8 * 4 + 1 + 4 + 2 * 9 * 96   # whole step: states in, legal+energy out, transforms written+read
+
+
+def sample_states(scene, n, seed):
+    """(n, 8) float32 planner states: Tx Ty Tz theta phi alpha + 2 eigengrasp amplitudes."""
+    from tests.common import sample_aa_states
+    pos, _ = sample_aa_states(scene, n, seed=seed)
+    rng = np.random.default_rng(seed + 7919)
+    neg = scene.robots[0].eg.shape[0]
+    amps = rng.uniform(-4.0, 4.0, size=(n, neg)).astype(np.float32)
+    return np.ascontiguousarray(np.concatenate([pos, amps], 1).astype(np.float32))
+
+
+def states_to_raw(scene, states):
+    """oracle-side state -> (base, dofs) mapping (fp64 on the widened fp32 states)"""
+    from oracle.port import fk as ofk
+    from tests.common import object_body
+    r = scene.robots[0]
+    s = states.astype(np.float64)
+    base = ofk.aa_state_to_base(r, scene.body_tran[object_body(scene)], s[:, :6])
+    dofs = ofk.eigen_to_dof(r, s[:, 6:])
+    return np.concatenate([base[0], base[1], dofs], 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference(scene, states, mode, threads):
+    """Time the reference's own CPU implementation (oracle/_ref) on `states`; returns poses/s."""
+    from tests.common import OracleScene, object_body
+    raw = states_to_raw(scene, states)
+    osc = OracleScene(scene, nthreads=threads)
+    obj = object_body(scene)
+    order, tf7 = osc.link_poses(0, raw)           # FK precomputed: excluded from the CPU time (flatters the CPU)
+    from oracle import ref
+    r = scene.robots[0]
+    hand_ids = [osc.ids[b] for b in order]
+    vc_link = [order.index(v.body) for v in r.vcontacts]
+    vc_loc = np.array([v.loc for v in r.vcontacts]).reshape(-1, 3)
+    vc_n = np.array([v.normal for v in r.vcontacts]).reshape(-1, 3)
+    ref.eval_batch(osc.worlds, hand_ids, osc.ids[obj], tf7[: max(64, len(tf7) // 8)], vc_link, vc_loc, vc_n, mode=mode)   # warm-up
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ref.eval_batch(osc.worlds, hand_ids, osc.ids[obj], tf7, vc_link, vc_loc, vc_n, mode=mode)
+        best = min(best, time.perf_counter() - t0)
+    return len(tf7) / best, best
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from graspit_b200.formats.scenepack import load_pack
+    from oracle import ref
+    scene = load_pack("barrett_mug")
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgraspit_ref.so missing"}))
+        return
+    threads = max(1, ref.hardware_threads())
+    mode = 1 if args.mode == "live" else 0
+    sample = args.cpu_sample if mode == 0 else max(256, args.cpu_sample // 8)
+    from tests.common import OracleScene, object_body
+    osc = OracleScene(scene, nthreads=threads)
+    obj = object_body(scene)
+    r = scene.robots[0]
+    times = []
+    for step in range(args.warmup + args.steps):
+        st = sample_states(scene, sample, 1234 + step)
+        raw = states_to_raw(scene, st)
+        order, tf7 = osc.link_poses(0, raw)
+        hand_ids = [osc.ids[b] for b in order]
+        vc_link = [order.index(v.body) for v in r.vcontacts]
+        vc_loc = np.array([v.loc for v in r.vcontacts]).reshape(-1, 3)
+        vc_n = np.array([v.normal for v in r.vcontacts]).reshape(-1, 3)
+        t0 = time.perf_counter()
+        ref.eval_batch(osc.worlds, hand_ids, osc.ids[obj], tf7, vc_link, vc_loc, vc_n, mode=mode)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.poses),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": f"{sample} poses per step of the same workload (reference GraspitCollision compiled "
+                                       "verbatim, -O3, one instance per thread; FK precomputed outside the timed call)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, poses):
+    return {"workload": "Barrett hand vs mug (worlds/plannerMug.xml), EGPlanner CONTACT_ENERGY "
+                        f"{'CONTACT_LIVE' if args.mode == 'live' else 'CONTACT_PRESET'}, {poses} planner states per step per GPU "
+                        "(SPACE_AXIS_ANGLE + POSE_EIGEN, 8 fp32 variables; 50% planner-box / 50% within 150 mm strata)",
+            "poses_per_step_per_gpu": poses, "mode": args.mode,
+            "l2": "flushed between timed steps (256 MiB write); per-step inputs 2 MiB"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="preset", choices=["preset", "live"])
+    ap.add_argument("--poses", type=int, default=65536)
+    ap.add_argument("--cpu-sample", type=int, default=8192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from graspit_b200.engine import B2C_INPUT_AA_EIGEN, Engine, SceneBinding
+    from graspit_b200.formats.scenepack import load_pack
+    from tests.common import object_body
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    scene = load_pack("barrett_mug")
+    obj = object_body(scene)
+    eng = Engine(local_rank)
+    sb = SceneBinding(eng, scene)
+    rid, oid = sb.robot_ids[0], sb.body_ids[obj]
+    ref_tran = scene.body_tran[obj]
+    live = args.mode == "live"
+    npose, K, W = args.poses, args.steps, args.warmup
+    nvar = 6 + scene.robots[0].eg.shape[0]
+
+    # synthetic states: a distinct batch per step, distinct per rank
+    host_batches = [sample_states(scene, npose, 1234 + 1000 * rank + s) for s in range(K + W)]
+    pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
+    dev_batches = [p.to(dev, non_blocking=True) for p in pinned]
+    legal_d = torch.zeros(npose, dtype=torch.uint8, device=dev)
+    energy_d = torch.zeros(npose, dtype=torch.float32, device=dev)
+    legal_h = torch.zeros(npose, dtype=torch.uint8).pin_memory()
+    energy_h = torch.zeros(npose, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(world * BEST_LIST_SIZE, nvar + 1, dtype=torch.float32, device=dev) if world > 1 else None
+    # one explicit stream for torch ops, the engine's kernels and the timing events
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_profiling(True)
+
+    def step_device(i):
+        st = dev_batches[i]
+        eng.eval_batch_device(rid, oid, st.data_ptr(), npose, nvar, legal_d.data_ptr(), energy_d.data_ptr(),
+                              input_mode=B2C_INPUT_AA_EIGEN, ref_tran=ref_tran, live=live)
+        if world > 1:
+            # per-rank best list (state || energy) -> all ranks; illegal states never enter the list
+            e = torch.where(legal_d.bool(), energy_d, torch.full_like(energy_d, 3.0e38))
+            val, idx = torch.topk(e, BEST_LIST_SIZE, largest=False)
+            mine = torch.cat([st[idx], val[:, None]], 1).contiguous()
+            dist.all_gather_into_tensor(gathered, mine)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step_device(i)
+    sync_all()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kernel_ms = []
+    sync_all()
+    for s in range(K):
+        flush.fill_(s & 0xff)                      # L2 flush, outside the event bracket
+        ev[s][0].record(stream)
+        step_device(W + s)
+        ev[s][1].record(stream)
+        kernel_ms.append(eng.last_kernel_ms())     # synchronises; after the bracket
+    sync_all()
+    launches = eng.launch_count - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    stats = eng.last_stats()
+
+    # end to end through the C ABI with host buffers (pinned), H2D + kernels + D2H inside the timed region
+    eng.set_profiling(False)
+    from graspit_b200.engine import EvalArgs, B2C_EVAL_LIVE
+    import ctypes as C
+
+    def step_host(i):
+        a = EvalArgs()
+        a.robot, a.object, a.npose, a.input_mode = rid, oid, npose, B2C_INPUT_AA_EIGEN
+        a.states, a.stride = pinned[i].data_ptr(), nvar
+        a.ref_q[:] = list(ref_tran[0]); a.ref_t[:] = list(ref_tran[1])
+        a.flags = B2C_EVAL_LIVE if live else 0
+        a.legal, a.energy = legal_h.data_ptr(), energy_h.data_ptr()
+        eng._ck(eng.L.b2c_eval_batch(eng.h, C.byref(a)))
+
+    for i in range(W):
+        step_host(i)
+    sync_all()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for s in range(K):
+        flush.fill_(s & 0xff)
+        ev2[s][0].record(stream)
+        step_host(W + s)
+        ev2[s][1].record(stream)
+    sync_all()
+    e2e_ms = float(sum(a.elapsed_time(b) for a, b in ev2))
+    clocks = sampler.stop()
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / K
+    value = world * npose / (ms_per_step / 1e3)
+    e2e_value = world * npose / (e2e_ms / K / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        dom = "dist" if live else "eval"
+        dom_ms = float(np.mean([k[dom] for k in kernel_ms]))
+        algo_bytes = (ALGO_BYTES_EVAL_PER_POSE if not live else 9 * (2 * 96 + 4 + 48)) * npose
+        achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(args, npose),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": npose * nvar * 4,
+                        "d2h_bytes_per_step": npose * 5, "ms_per_step": e2e_ms / K},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                             "kernel_ms_all": {k: float(np.mean([x[k] for x in kernel_ms])) for k in kernel_ms[0]},
+                             "note": "working set is L2-resident by design: compulsory HBM traffic only (SURVEY.md 8(d)); "
+                                     "traversal work per step: " + json.dumps(stats)},
+                }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import ref
+                threads = max(1, ref.hardware_threads())
+                sample = args.cpu_sample if not live else max(256, args.cpu_sample // 8)
+                v, secs = cpu_reference(scene, host_batches[W][:sample], 1 if live else 0, threads)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
+                                        "sample": f"first {sample} poses of the first timed batch, best of 3 ({secs:.2f} s); reference "
+                                                  "GraspitCollision compiled verbatim (-O3), one instance per thread, FK precomputed"}
+            except Exception as ex:   # the oracle is a checker, never a dependency of the measurement
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

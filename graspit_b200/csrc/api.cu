@@ -109,6 +109,10 @@ struct b2c_ctx {
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int eval_warps_per_block = 8;
   int eval_blocks_per_sm = 0;      // 0 = derive from shared memory
+  cudaStream_t own_stream = nullptr;
+  bool profiling = false;
+  cudaEvent_t ev[16] = {};
+  bool ev_used[8] = {};
 };
 
 namespace {
@@ -331,7 +335,40 @@ int b2c_create(int device, b2c_ctx **out) {
   }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  ctx->own_stream = ctx->stream;
   *out = ctx;
+  return B2C_OK;
+}
+
+int b2c_set_stream(b2c_ctx *ctx, void *stream) {
+  if (!ctx) return B2C_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+  return B2C_OK;
+}
+
+int b2c_set_profiling(b2c_ctx *ctx, int enabled) {
+  if (!ctx) return B2C_EINVAL;
+  cudaSetDevice(ctx->device);
+  if (enabled && !ctx->ev[0])
+    for (int i = 0; i < 16; i++)
+      if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) return fail(ctx, B2C_ECUDA, "cudaEventCreate failed");
+  ctx->profiling = enabled != 0;
+  return B2C_OK;
+}
+
+int b2c_last_kernel_ms(b2c_ctx *ctx, float ms[8]) {
+  if (!ctx || !ms) return B2C_EINVAL;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < 8; i++) ms[i] = 0.f;
+  if (!ctx->ev[0]) return B2C_OK;
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 8; i++)
+    if (ctx->ev_used[i]) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, ctx->ev[2 * i], ctx->ev[2 * i + 1]) == cudaSuccess) ms[i] = t;
+    }
   return B2C_OK;
 }
 
@@ -348,7 +385,8 @@ void b2c_destroy(b2c_ctx *ctx) {
   ctx->d_meshes.release(); ctx->d_states.release(); ctx->d_fk.release(); ctx->d_fkqt.release(); ctx->d_legal.release();
   ctx->d_energy.release(); ctx->d_mask.release(); ctx->d_ambig.release(); ctx->d_counters.release(); ctx->d_stats.release();
   ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release();
-  cudaStreamDestroy(ctx->stream);
+  for (int i = 0; i < 16; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 
@@ -762,6 +800,9 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   rc = build_plan(ctx, a->robot, a->object, &P); if (rc) return rc;
   const RobotHost &root = ctx->robots[a->robot];
   const int npose = a->npose;
+#define PROF_BEGIN(i) do { if (ctx->profiling) { cudaEventRecord(ctx->ev[2 * (i)], ctx->stream); ctx->ev_used[i] = true; } } while (0)
+#define PROF_END(i) do { if (ctx->profiling) cudaEventRecord(ctx->ev[2 * (i) + 1], ctx->stream); } while (0)
+  for (int i = 0; i < 8; i++) ctx->ev_used[i] = false;
   const bool dev = (a->flags & B2C_EVAL_DEVICE_PTRS) != 0;
   const bool live = (a->flags & B2C_EVAL_LIVE) != 0;
   const bool want_mask = (a->flags & B2C_EVAL_PAIRMASK) != 0 && a->pair_mask;
@@ -803,7 +844,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   fp.ref = make_qt(a->ref_q, a->ref_t);
   fp.out = ctx->d_fk.p;
   fp.out_qt = want_tf ? (dev ? a->body_tf : ctx->d_fkqt.p) : nullptr;
-  CU(launch_fk(fp, ctx->stream)); ctx->launches++;
+  PROF_BEGIN(0); CU(launch_fk(fp, ctx->stream)); ctx->launches++; PROF_END(0);
 
   // K3 (+K5+K8 when PRESET)
   EvalParams ep;
@@ -821,14 +862,14 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   if (wb > 200 * 1024) return fail(ctx, B2C_ECAPACITY, "eval_batch: %d bodies / %d pairs exceed the per-warp shared memory", nb, np);
   int blocks, wpb; size_t smem;
   eval_launch_shape(ctx, wb, npose, blocks, wpb, smem);
-  CU(launch_eval(ep, blocks, wpb, smem, ctx->stream)); ctx->launches++;
+  PROF_BEGIN(1); CU(launch_eval(ep, blocks, wpb, smem, ctx->stream)); ctx->launches++; PROF_END(1);
   RecheckParams rp;
   memset(&rp, 0, sizeof rp);
   rp.ambig = ctx->d_ambig.p; rp.ambig_count = ctx->d_counters.p + 1; rp.ambig_cap = (int)ctx->d_ambig.cap;
   rp.nrb = nrb; rp.nb = nb; rp.fk = ctx->d_fk.p; rp.static_xf = P->d_static.p; rp.body_mesh = P->d_body_mesh.p;
   rp.meshes = ctx->d_meshes.p; rp.pairs = P->d_pairs.p; rp.legal = d_legal; rp.energy = d_energy; rp.pair_mask = d_mask;
   rp.mask_words = mw; rp.stats = ctx->d_stats.p;
-  CU(launch_recheck(rp, ctx->stream)); ctx->launches++;
+  PROF_BEGIN(2); CU(launch_recheck(rp, ctx->stream)); ctx->launches++; PROF_END(2);
 
   // K4 (+ LIVE energy)
   float *d_dist = nullptr;
@@ -845,7 +886,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
     dp.dist = d_dist; dp.pts = ctx->d_pts.p; dp.work_counter = ctx->d_counters.p + 2;
     dp.ambig = ctx->d_ambig.p; dp.ambig_count = ctx->d_counters.p + 3; dp.ambig_cap = (int)ctx->d_ambig.cap; dp.stats = ctx->d_stats.p;
     int dblocks = std::min(ctx->sm_count * 4, (npose * nq + 7) / 8);
-    CU(launch_dist(dp, std::max(1, dblocks), ctx->stream)); ctx->launches++;
+    PROF_BEGIN(3); CU(launch_dist(dp, std::max(1, dblocks), ctx->stream)); ctx->launches++; PROF_END(3);
     RecheckParams rd;
     memset(&rd, 0, sizeof rd);
     rd.ambig = ctx->d_ambig.p; rd.ambig_count = ctx->d_counters.p + 3; rd.ambig_cap = (int)ctx->d_ambig.cap;
@@ -858,7 +899,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
       lp.npose = npose; lp.nrb = nrb; lp.nb = nb; lp.nq = nq; lp.object = P->object_e; lp.fk = ctx->d_fk.p;
       lp.static_xf = P->d_static.p; lp.body_mesh = P->d_body_mesh.p; lp.meshes = ctx->d_meshes.p;
       lp.dist = d_dist; lp.pts = ctx->d_pts.p; lp.legal = d_legal; lp.energy = d_energy; lp.stats = ctx->d_stats.p;
-      CU(launch_live(lp, ctx->stream)); ctx->launches++;
+      PROF_BEGIN(4); CU(launch_live(lp, ctx->stream)); ctx->launches++; PROF_END(4);
     }
   }
 

@@ -362,24 +362,34 @@ void remove_contact_duplicates(std::vector<b2c_contact> &c, double thr) {
 
 namespace {
 
-// strict 2-D convex hull (collinear points are not vertices), indices into pts
+// 2-D convex hull vertices, indices into pts.  The reference asks qhull for the hull of the projected
+// contacts (collisionInterface.cpp:165-219, options "qhull n Pp"); qhull's default facet merging drops
+// points that sit on a hull edge to within its round-off bound (qh_distround, a few hundred ulps of the
+// largest coordinate), so a point is a vertex here only if it sticks out of the line through its hull
+// neighbours by more than that bound.
 std::vector<int> hull2d(const std::vector<std::pair<double, double>> &pts) {
   int n = (int)pts.size();
   std::vector<int> order(n);
   for (int i = 0; i < n; i++) order[i] = i;
   std::sort(order.begin(), order.end(), [&](int a, int b) { return pts[a] < pts[b]; });
-  auto cr = [&](int o, int a, int b) {
-    return (pts[a].first - pts[o].first) * (pts[b].second - pts[o].second) -
-           (pts[a].second - pts[o].second) * (pts[b].first - pts[o].first);
+  double maxabs = 0.0;
+  for (auto &p : pts) maxabs = std::max(maxabs, std::max(std::fabs(p.first), std::fabs(p.second)));
+  const double tol = 256.0 * std::numeric_limits<double>::epsilon() * std::max(maxabs, 1.0);
+  // true if `a` does not stick out to the right of the directed line o -> b by more than tol
+  auto drop = [&](int o, int a, int b) {
+    double bx = pts[b].first - pts[o].first, by = pts[b].second - pts[o].second;
+    double cr = (pts[a].first - pts[o].first) * by - (pts[a].second - pts[o].second) * bx;   // > 0: a right of o->b
+    double len = std::sqrt(bx * bx + by * by);
+    return cr <= tol * len;
   };
   std::vector<int> h(2 * n);
   int k = 0;
   for (int i = 0; i < n; i++) {
-    while (k >= 2 && cr(h[k - 2], h[k - 1], order[i]) <= 0) k--;
+    while (k >= 2 && drop(h[k - 2], h[k - 1], order[i])) k--;
     h[k++] = order[i];
   }
   for (int i = n - 2, t = k + 1; i >= 0; i--) {
-    while (k >= t && cr(h[k - 2], h[k - 1], order[i]) <= 0) k--;
+    while (k >= t && drop(h[k - 2], h[k - 1], order[i])) k--;
     h[k++] = order[i];
   }
   h.resize(k > 1 ? k - 1 : k);

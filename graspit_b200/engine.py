@@ -25,11 +25,12 @@ FAST_COLLISION, ALL_COLLISIONS = 0, 1
 
 EXPORTS = [
     "b2c_create", "b2c_destroy", "b2c_last_error", "b2c_stream", "b2c_device", "b2c_launch_count",
+    "b2c_set_stream", "b2c_set_profiling", "b2c_last_kernel_ms",
     "b2c_mesh_create", "b2c_mesh_destroy", "b2c_body_create", "b2c_body_set_mesh", "b2c_body_remove",
     "b2c_body_set_transform", "b2c_body_get_transform", "b2c_body_set_active", "b2c_pair_set_active",
     "b2c_pair_is_active", "b2c_all_collisions", "b2c_body_distance", "b2c_point_distance", "b2c_contacts",
     "b2c_all_contacts", "b2c_region", "b2c_bounding_volumes", "b2c_robot_define", "b2c_eval_batch",
-    "b2c_robot_bodies", "b2c_robot_pairs", "b2c_last_stats",
+    "b2c_robot_bodies", "b2c_robot_pairs", "b2c_last_stats", "b2c_obb_hierarchy", "b2c_contacts_postprocess",
 ]
 
 
@@ -101,6 +102,9 @@ def load_library():
     L.b2c_stream.argtypes = [vp]; L.b2c_stream.restype = vp
     L.b2c_device.argtypes = [vp]
     L.b2c_launch_count.argtypes = [vp]; L.b2c_launch_count.restype = C.c_longlong
+    L.b2c_set_stream.argtypes = [vp, vp]
+    L.b2c_set_profiling.argtypes = [vp, ci]
+    L.b2c_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.b2c_mesh_create.argtypes = [vp, C.POINTER(C.c_float), ci, ip]
     L.b2c_mesh_destroy.argtypes = [vp, ci]
     L.b2c_body_create.argtypes = [vp, ci, ip]
@@ -123,6 +127,8 @@ def load_library():
     L.b2c_robot_bodies.argtypes = [vp, ci, ip, ci, ip]
     L.b2c_robot_pairs.argtypes = [vp, ci, ip, ci, ip]
     L.b2c_last_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    L.b2c_obb_hierarchy.argtypes = [C.POINTER(C.c_float), ci, ci, C.POINTER(Obb), ci, ip]
+    L.b2c_contacts_postprocess.argtypes = [C.POINTER(Contact), ip, C.c_double, ci]
     _lib = L
     return L
 
@@ -149,6 +155,37 @@ def _contacts_to_array(buf, n):
         out[i, 0:3] = c.b1_pos[:]; out[i, 3:6] = c.b2_pos[:]
         out[i, 6:9] = c.b1_normal[:]; out[i, 9:12] = c.b2_normal[:]; out[i, 12] = c.distSq
     return out
+
+
+def obb_hierarchy(tris, depth: int, cap=1 << 16):
+    """Host-only: the reference-style oriented-box hierarchy of a triangle soup at ``depth`` -> (n,10) rows
+    (t, q wxyz, half).  What getBoundingVolumes serves."""
+    L = load_library()
+    t = np.ascontiguousarray(np.asarray(tris, dtype=np.float32).reshape(-1, 9))
+    buf = (Obb * cap)()
+    n = C.c_int(0)
+    rc = L.b2c_obb_hierarchy(t.ctypes.data_as(C.POINTER(C.c_float)), t.shape[0], depth, buf, cap, C.byref(n))
+    if rc != 0:
+        raise B2CError(f"b2c_obb_hierarchy failed: {rc}")
+    out = np.zeros((min(n.value, cap), 10))
+    for i in range(out.shape[0]):
+        out[i, 0:3] = buf[i].t[:]; out[i, 3:7] = buf[i].q_wxyz[:]; out[i, 7:10] = buf[i].half[:]
+    return out
+
+
+def contacts_postprocess(contacts, duplicate_threshold=3.0, compact=True):
+    """Host-only: removeContactDuplicates + compactContactSet on an (n,13) contact array."""
+    L = load_library()
+    c = np.asarray(contacts, dtype=np.float64).reshape(-1, 13)
+    n = C.c_int(c.shape[0])
+    buf = (Contact * max(1, c.shape[0]))()
+    for i in range(c.shape[0]):
+        buf[i].b1_pos[:] = list(c[i, 0:3]); buf[i].b2_pos[:] = list(c[i, 3:6])
+        buf[i].b1_normal[:] = list(c[i, 6:9]); buf[i].b2_normal[:] = list(c[i, 9:12]); buf[i].distSq = c[i, 12]
+    rc = L.b2c_contacts_postprocess(buf, C.byref(n), float(duplicate_threshold), int(compact))
+    if rc != 0:
+        raise B2CError(f"b2c_contacts_postprocess failed: {rc}")
+    return _contacts_to_array(buf, n.value)
 
 
 class Engine:
@@ -187,6 +224,18 @@ class Engine:
     @property
     def stream(self) -> int:
         return int(self.L.b2c_stream(self.h) or 0)
+
+    def set_stream(self, cuda_stream: int):
+        """launch on a caller-owned CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``)"""
+        self._ck(self.L.b2c_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def set_profiling(self, on: bool):
+        self._ck(self.L.b2c_set_profiling(self.h, int(bool(on))))
+
+    def last_kernel_ms(self) -> dict:
+        ms = (C.c_float * 8)()
+        self._ck(self.L.b2c_last_kernel_ms(self.h, ms))
+        return {"fk": ms[0], "eval": ms[1], "recheck": ms[2], "dist": ms[3], "live": ms[4]}
 
     # ---- addBody / cloneBody / removeBody / updateBodyGeometry ---------------------------------
     def create_mesh(self, tris) -> int:

@@ -44,6 +44,14 @@ void *b2c_stream(const b2c_ctx *ctx);
 int b2c_device(const b2c_ctx *ctx);
 /* number of kernel launches issued by this context so far (bench.py "gpu_launches") */
 long long b2c_launch_count(const b2c_ctx *ctx);
+/* launch on a caller-owned stream (cudaStream_t as void*; NULL restores the context's own stream), so
+ * that callers who own device buffers (e.g. torch tensors) can order work and time it with their events */
+int b2c_set_stream(b2c_ctx *ctx, void *stream);
+/* per-kernel CUDA-event timing of the batched evaluation: when enabled, b2c_eval_batch brackets each kernel
+ * with events on the launching stream; b2c_last_kernel_ms (which synchronises) returns the durations of the
+ * last evaluation in ms: [0] fk, [1] eval (legal+energy), [2] recheck, [3] distance, [4] live energy, [5..7] 0 */
+int b2c_set_profiling(b2c_ctx *ctx, int enabled);
+int b2c_last_kernel_ms(b2c_ctx *ctx, float ms[8]);
 
 /* ---- geometry: replaces addBody / updateBodyGeometry / cloneBody / removeBody ---------------
  * collisionInterface.h:102-114, reference graspitCollision.cpp:200-305.  A mesh is an immutable
@@ -122,6 +130,12 @@ typedef struct b2c_obb {
  * oriented-box hierarchy (PCA fit, mean-vertex split) at `depth`, for display and for the reference's
  * own unit test; independent of the device BVH used for queries. */
 int b2c_bounding_volumes(b2c_ctx *ctx, int body, int depth, b2c_obb *out, int cap, int *nboxes);
+
+/* Context-free host utilities (no CUDA): the reference-style box hierarchy of a triangle soup, and the
+ * reference's contact-set post-processing (removeContactDuplicates at `duplicate_threshold`, then
+ * compactContactSet; collisionInterface.cpp:74-287) applied in place; *n is updated. */
+int b2c_obb_hierarchy(const float *tri9, int ntri, int depth, b2c_obb *out, int cap, int *nboxes);
+int b2c_contacts_postprocess(b2c_contact *contacts, int *n, double duplicate_threshold, int compact);
 
 /* ---- batched pose evaluation: FK -> legal -> proximity -> CONTACT_ENERGY --------------------
  * Replaces, for whole batches of candidate states, the loop
