@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -105,7 +106,8 @@ struct b2c_ctx {
   // scratch
   DevBuf<float> d_states; DevBuf<Xf> d_fk; DevBuf<double> d_fkqt; DevBuf<uint8_t> d_legal; DevBuf<float> d_energy;
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
-  DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc;
+  DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
+  int stage_nodes = 511;           // object-tree nodes staged in shared memory by the energy kernel
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int eval_warps_per_block = 8;
   int eval_blocks_per_sm = 0;      // 0 = derive from shared memory
@@ -191,6 +193,8 @@ int ensure_scratch(b2c_ctx *ctx) {
   CU(ctx->d_counters.reserve(8));
   CU(ctx->d_stats.reserve(8));
   CU(ctx->d_ambig.reserve(1 << 20));
+  CU(ctx->d_near_dir.reserve(1 << 16));
+  CU(ctx->d_near_ent.reserve(1 << 20));
   return B2C_OK;
 }
 
@@ -290,7 +294,9 @@ int run_static_distance(b2c_ctx *ctx, int a, int b, double *dist, double pa[3], 
   dp.static_xf = reinterpret_cast<const Xf *>(ctx->d_misc.p); dp.body_mesh = d_bm; dp.meshes = ctx->d_meshes.p;
   dp.legal = nullptr; dp.dist = ctx->d_dist.p; dp.pts = ctx->d_pts.p; dp.work_counter = ctx->d_counters.p;
   dp.ambig = ctx->d_ambig.p; dp.ambig_count = ctx->d_counters.p + 1; dp.ambig_cap = (int)ctx->d_ambig.cap; dp.stats = nullptr;
-  CU(launch_dist(dp, 1, ctx->stream)); ctx->launches++;
+  dp.near_dir = ctx->d_near_dir.p; dp.near_ent = ctx->d_near_ent.p; dp.near_count = ctx->d_counters.p + 5;
+  dp.near_cap_dir = 1 << 16; dp.near_cap_ent = 1 << 20;
+  CU(launch_dist(dp, 1, ctx->stream)); ctx->launches += 2;
   RecheckParams rp;
   memset(&rp, 0, sizeof rp);
   rp.ambig = ctx->d_ambig.p; rp.ambig_count = ctx->d_counters.p + 1; rp.ambig_cap = (int)ctx->d_ambig.cap;
@@ -335,6 +341,8 @@ int b2c_create(int device, b2c_ctx **out) {
   }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (const char *e = getenv("B2C_STAGE_NODES")) ctx->stage_nodes = std::max(0, atoi(e));
+  if (const char *e = getenv("B2C_EVAL_WARPS")) ctx->eval_warps_per_block = std::max(1, std::min(32, atoi(e)));
   ctx->own_stream = ctx->stream;
   *out = ctx;
   return B2C_OK;
@@ -384,7 +392,7 @@ void b2c_destroy(b2c_ctx *ctx) {
   }
   ctx->d_meshes.release(); ctx->d_states.release(); ctx->d_fk.release(); ctx->d_fkqt.release(); ctx->d_legal.release();
   ctx->d_energy.release(); ctx->d_mask.release(); ctx->d_ambig.release(); ctx->d_counters.release(); ctx->d_stats.release();
-  ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release();
+  ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release(); ctx->d_legal_list.release(); ctx->d_terms.release(); ctx->d_near_dir.release(); ctx->d_near_ent.release();
   for (int i = 0; i < 16; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -851,13 +859,18 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   memset(&ep, 0, sizeof ep);
   ep.npose = npose; ep.nrb = nrb; ep.nb = nb; ep.npairs = np; ep.nvc = P->nvc; ep.object = P->object_e;
   ep.mode_all = want_mask ? 1 : 0;
-  ep.do_energy = (!live && a->object >= 0 && P->nvc > 0) ? 1 : 0;
+  ep.do_energy = 0;   // energy runs in its own kernel on the compacted list of legal poses
   ep.mask_words = mw;
   ep.stack_phys = std::max(256, np + 96); ep.stack_cap = ep.stack_phys - 64;
   ep.fk = ctx->d_fk.p; ep.static_xf = P->d_static.p; ep.body_mesh = P->d_body_mesh.p; ep.meshes = ctx->d_meshes.p;
   ep.pairs = P->d_pairs.p; ep.vcs = P->d_vcs.p; ep.legal = d_legal; ep.energy = d_energy; ep.pair_mask = d_mask;
   ep.pose_counter = ctx->d_counters.p; ep.ambig = ctx->d_ambig.p; ep.ambig_count = ctx->d_counters.p + 1;
   ep.ambig_cap = (int)ctx->d_ambig.cap; ep.stats = ctx->d_stats.p;
+  const bool want_energy = a->object >= 0 && (live || P->nvc > 0);
+  if (want_energy) {
+    CU(ctx->d_legal_list.reserve(npose));
+    ep.legal_list = ctx->d_legal_list.p; ep.legal_count = ctx->d_counters.p + 4;
+  }
   size_t wb = eval_warp_smem_bytes(nb, np, mw, ep.stack_phys);
   if (wb > 200 * 1024) return fail(ctx, B2C_ECAPACITY, "eval_batch: %d bodies / %d pairs exceed the per-warp shared memory", nb, np);
   int blocks, wpb; size_t smem;
@@ -870,6 +883,30 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   rp.meshes = ctx->d_meshes.p; rp.pairs = P->d_pairs.p; rp.legal = d_legal; rp.energy = d_energy; rp.pair_mask = d_mask;
   rp.mask_words = mw; rp.stats = ctx->d_stats.p;
   PROF_BEGIN(2); CU(launch_recheck(rp, ctx->stream)); ctx->launches++; PROF_END(2);
+
+  // K5 + K8: CONTACT_ENERGY over the compacted legal poses
+  EnergyParams gp;
+  memset(&gp, 0, sizeof gp);
+  gp.npose = npose; gp.nrb = nrb; gp.nb = nb; gp.nvc = P->nvc; gp.nq = P->nhand; gp.object = P->object_e;
+  gp.stage_nodes = ctx->stage_nodes;
+  gp.fk = ctx->d_fk.p; gp.static_xf = P->d_static.p; gp.body_mesh = P->d_body_mesh.p; gp.meshes = ctx->d_meshes.p;
+  gp.vcs = P->d_vcs.p; gp.legal = d_legal; gp.legal_list = ctx->d_legal_list.p; gp.legal_count = ctx->d_counters.p + 4;
+  gp.energy = d_energy; gp.stats = ctx->d_stats.p;
+  auto energy_blocks = [&](int contacts) {
+    size_t smem = energy_block_smem_bytes(gp.stage_nodes);
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / smem));
+    long long groups = ((long long)npose * contacts + 255) / 256;
+    return (int)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * per_sm, groups));
+  };
+  if (want_energy) {
+    CU(ctx->d_terms.reserve((size_t)npose * std::max(P->nvc, P->nhand) + 32));
+    gp.terms = ctx->d_terms.p;
+  }
+  if (want_energy && !live) {
+    if (P->nvc > 256) return fail(ctx, B2C_ECAPACITY, "eval_batch: more than 256 virtual contacts");
+    gp.live = 0;
+    PROF_BEGIN(4); CU(launch_energy(gp, energy_blocks(P->nvc), ctx->stream)); ctx->launches += 2; PROF_END(4);
+  }
 
   // K4 (+ LIVE energy)
   float *d_dist = nullptr;
@@ -885,6 +922,11 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
     dp.legal = want_dist ? nullptr : d_legal;       // LIVE alone only needs legal poses
     dp.dist = d_dist; dp.pts = ctx->d_pts.p; dp.work_counter = ctx->d_counters.p + 2;
     dp.ambig = ctx->d_ambig.p; dp.ambig_count = ctx->d_counters.p + 3; dp.ambig_cap = (int)ctx->d_ambig.cap; dp.stats = ctx->d_stats.p;
+    if (want_dist) {   // distances handed to the caller get the fp64 pass for tiny values
+      dp.near_dir = ctx->d_near_dir.p; dp.near_ent = ctx->d_near_ent.p; dp.near_count = ctx->d_counters.p + 5;
+      dp.near_cap_dir = 1 << 16; dp.near_cap_ent = 1 << 20;
+      ctx->launches++;
+    }
     int dblocks = std::min(ctx->sm_count * 4, (npose * nq + 7) / 8);
     PROF_BEGIN(3); CU(launch_dist(dp, std::max(1, dblocks), ctx->stream)); ctx->launches++; PROF_END(3);
     RecheckParams rd;
@@ -894,12 +936,8 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
     rd.meshes = ctx->d_meshes.p; rd.pairs = P->d_queries.p; rd.dist = d_dist; rd.pts = ctx->d_pts.p; rd.nq = nq; rd.stats = ctx->d_stats.p;
     CU(launch_recheck(rd, ctx->stream)); ctx->launches++;
     if (live) {
-      LiveParams lp;
-      memset(&lp, 0, sizeof lp);
-      lp.npose = npose; lp.nrb = nrb; lp.nb = nb; lp.nq = nq; lp.object = P->object_e; lp.fk = ctx->d_fk.p;
-      lp.static_xf = P->d_static.p; lp.body_mesh = P->d_body_mesh.p; lp.meshes = ctx->d_meshes.p;
-      lp.dist = d_dist; lp.pts = ctx->d_pts.p; lp.legal = d_legal; lp.energy = d_energy; lp.stats = ctx->d_stats.p;
-      PROF_BEGIN(4); CU(launch_live(lp, ctx->stream)); ctx->launches++; PROF_END(4);
+      gp.live = 1; gp.pts = ctx->d_pts.p;
+      PROF_BEGIN(4); CU(launch_energy(gp, energy_blocks(nq), ctx->stream)); ctx->launches += 2; PROF_END(4);
     }
   }
 

@@ -94,6 +94,8 @@ struct EvalParams {
   float *energy;
   unsigned long long *pair_mask;
   int *pose_counter;
+  int *legal_list;         // poses without a collision, in completion order (for the energy kernel)
+  int *legal_count;
   Ambig *ambig;
   int *ambig_count;
   int ambig_cap;
@@ -122,6 +124,11 @@ struct DistParams {
   Ambig *ambig;
   int *ambig_count;
   int ambig_cap;
+  // optional fp64 refinement of tiny distances: segment directory (query, offset, count) + triangle pairs
+  int4 *near_dir;
+  int2 *near_ent;
+  int *near_count;         // [0] segments, [1] entries
+  int near_cap_dir, near_cap_ent;
   unsigned long long *stats;
 };
 
@@ -171,19 +178,25 @@ struct PointParams {
   double *out;              // [n][7]: dist, closest(3, world), normal(3) = unit(point -> closest)
 };
 
-struct LiveParams {
+struct EnergyParams {
   int npose;
   int nrb, nb;
-  int nq;                   // queries per pose == hand bodies, query i = (hand body i, object)
+  int nvc;                  // PRESET contacts per pose
+  int nq;                   // LIVE contacts per pose (= hand bodies; query i = (hand body i, object))
   int object;
+  int live;
+  int stage_nodes;          // top-of-tree nodes of the object staged in shared memory by TMA (0 = off)
   const Xf *fk;
   const Xf *static_xf;
   const int *body_mesh;
   const MeshDev *meshes;
-  const float *dist;        // [npose][nq]
-  const double *pts;        // [npose][nq][6]
+  const VcDev *vcs;
+  const double *pts;        // LIVE: [npose][nq][6] closest points from the distance kernel
   const uint8_t *legal;
+  const int *legal_list;    // optional compact list of legal poses (+ its device-side count)
+  const int *legal_count;
   float *energy;
+  float *terms;             // [legal poses x contacts] per-contact energy terms (scratch)
   unsigned long long *stats;
 };
 
@@ -194,7 +207,8 @@ __host__ __device__ inline size_t eval_warp_smem_bytes(int nb, int npairs, int m
 }
 
 constexpr int DSTACK_CAP = 448, DSTACK_PHYS = 512, DLEAF_CAP = 96;
-constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 2 * 96 + 96 + 32;
+constexpr int DNEAR_CAP = 64;
+constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 2 * 96 + 96 + DNEAR_CAP * 8 + 32;
 
 // launchers (kernels.cu)
 cudaError_t launch_fk(const FkParams &p, cudaStream_t s);
@@ -202,6 +216,7 @@ cudaError_t launch_eval(const EvalParams &p, int blocks, int warps_per_block, si
 cudaError_t launch_recheck(const RecheckParams &p, cudaStream_t s);
 cudaError_t launch_point(const PointParams &p, cudaStream_t s);
 cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s);
-cudaError_t launch_live(const LiveParams &p, cudaStream_t s);
+cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s);
+size_t energy_block_smem_bytes(int stage_nodes);
 
 } // namespace b2c

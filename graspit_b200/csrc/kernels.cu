@@ -1,11 +1,11 @@
 // CUDA kernels of the B200 collision engine (sm_100a).
 //
 //   fk_kernel        K1  search state -> hand pose -> per-link transforms          (thread / pose)
-//   eval_kernel      K3+K5+K8  legality (all active pairs) fused with CONTACT_ENERGY (warp / pose)
+//   eval_kernel      K3  legality over all active pairs, cooperative work stack      (warp / pose)
 //   recheck_kernel   fp64 re-decision of triangle pairs the fp32 SAT could not call
 //   point_kernel     K5 stand-alone closest point queries                            (thread / query)
 //   dist_kernel      K4 body-body minimum distance                                   (warp / query)
-//   live_kernel      CONTACT_LIVE virtual contacts + energy                          (thread / pose,link)
+//   energy_kernel    K5+K8 CONTACT_ENERGY, PRESET or LIVE contacts, TMA-staged tree top (thread / pose,contact)
 //
 // See DESIGN.md for the data layout and the roofline that bounds each kernel.
 #include "b2c_internal.h"
@@ -126,42 +126,100 @@ __global__ void __launch_bounds__(128) fk_kernel(FkParams p) {
 // in fp64 before the fp32 closestPtTriangle so the returned vector carries fp32 *relative* accuracy.
 // Must agree with ClosestPtCallback (collisionAlgorithms_inl.h:210-238, collisionAlgorithms.h:220-242).
 // ============================================================================================
-__device__ __forceinline__ float closest_point_query(const MeshDev &m, d3 q, f3 &bestv, int &best_tri,
-                                                     unsigned &n_box, unsigned &n_tri) {
+// out-of-line fp64 helpers: keep their register needs out of the hot fp32 paths
+__device__ __noinline__ d3 closest_pt_triangle_d(d3 a, d3 b, d3 c) {
+  return closest_pt_triangle<double>(a, b, c, mk<double>(0.0, 0.0, 0.0));
+}
+__device__ __noinline__ double tri_tri_dist2_d(d3 a1, d3 a2, d3 a3, d3 b1, d3 b2, d3 b3, d3 *pa, d3 *pb) {
+  d3 x, y;
+  double d = tri_tri_dist2<double>(a1, a2, a3, b1, b2, b3, x, y);
+  *pa = x; *pb = y;
+  return d;
+}
+
+// node fetch: the first `ntop` nodes (top levels, breadth-first prefix) may live in shared memory
+__device__ __forceinline__ Node fetch_node(const Node *nodes, const Node *top, int ntop, int i) {
+  if (i < ntop) {
+    const float4 *p = reinterpret_cast<const float4 *>(top + i);
+    float4 a = p[0], b = p[1];
+    Node n;
+    n.cx = a.x; n.cy = a.y; n.cz = a.z; n.hx = a.w;
+    n.hy = b.x; n.hz = b.y; n.child = __float_as_int(b.z); n.tri = __float_as_int(b.w);
+    return n;
+  }
+  return load_node(nodes, i);
+}
+
+// ============================================================================================
+// closest point on a mesh to a query point (object frame).  Per-lane depth-first, nearer child
+// first, "while-while" form: a lane descends inner nodes until it holds a leaf, then all lanes of the
+// warp that hold a leaf run the triangle test together.  Boxes cull in fp32 (they are padded at
+// build time); a leaf is re-centred on the query in fp64 before the fp32 closestPtTriangle, so the
+// returned vector carries fp32 *relative* accuracy; when the winning distance is tiny against the
+// triangle's extent the winner is redone in fp64.
+// Must agree with ClosestPtCallback (collisionAlgorithms_inl.h:210-238, collisionAlgorithms.h:220-242).
+// ============================================================================================
+#define CPQ_STACK 40
+__device__ __forceinline__ float closest_point_query(const MeshDev &m, const Node *top, int ntop, d3 q, f3 &bestv,
+                                                     int &best_tri, unsigned &n_box, unsigned &n_tri) {
   const Node *nodes = m.nodes;
-  f3 qf = tof(q);
-  float best = 1.0e30f;
+  const f3 qf = tof(q);
+  float best = 1.0e30f, best_sc = 0.f;
   bestv = mk<float>(0.f, 0.f, 0.f);
   best_tri = -1;
-  int stk_n[40];
-  float stk_d[40];
+  int stk_n[CPQ_STACK];
+  float stk_d[CPQ_STACK];
   int sp = 0;
-  int cur = 0;
+  int cur = 0;          // node to visit, -1 = none
   float curd = 0.f;
   while (true) {
-    if (curd <= best) {
-      Node n = load_node(nodes, cur);
-      if (n.child < 0) {
-        n_tri++;
-        d3 a = tri_vertex(m.tris, n.tri, 0) - q, b = tri_vertex(m.tris, n.tri, 1) - q, c = tri_vertex(m.tris, n.tri, 2) - q;
-        f3 v = closest_pt_triangle<float>(tof(a), tof(b), tof(c), mk<float>(0.f, 0.f, 0.f));
-        float d2 = dot(v, v);
-        if (d2 < best) { best = d2; bestv = v; best_tri = n.tri; }
+    int leaf = -1;
+    // ---- descend until this lane holds a leaf or runs out of work
+    while (cur >= 0) {
+      if (curd <= best) {
+        Node n = fetch_node(nodes, top, ntop, cur);
+        if (n.child < 0) {
+          leaf = n.tri;
+          cur = -1;
+        } else {
+          Node c0 = fetch_node(nodes, top, ntop, n.child), c1 = fetch_node(nodes, top, ntop, n.child + 1);
+          float cc[3], hh[3];
+          node_ch(c0, cc, hh); float d0 = point_box_dist2(cc, hh, qf);
+          node_ch(c1, cc, hh); float d1 = point_box_dist2(cc, hh, qf);
+          n_box += 2;
+          int near = n.child, far = n.child + 1;
+          if (d1 < d0) { near = n.child + 1; far = n.child; float t = d0; d0 = d1; d1 = t; }
+          if (d1 <= best && sp < CPQ_STACK) { stk_n[sp] = far; stk_d[sp] = d1; sp++; }
+          if (d0 <= best) { cur = near; curd = d0; continue; }
+          cur = -1;
+        }
       } else {
-        Node c0 = load_node(nodes, n.child), c1 = load_node(nodes, n.child + 1);
-        float cc[3], hh[3];
-        node_ch(c0, cc, hh); float d0 = point_box_dist2(cc, hh, qf);
-        node_ch(c1, cc, hh); float d1 = point_box_dist2(cc, hh, qf);
-        n_box += 2;
-        int near = n.child, far = n.child + 1;
-        if (d1 < d0) { near = n.child + 1; far = n.child; float t = d0; d0 = d1; d1 = t; }
-        if (d1 <= best && sp < 40) { stk_n[sp] = far; stk_d[sp] = d1; sp++; }
-        if (d0 <= best) { cur = near; curd = d0; continue; }
+        cur = -1;
       }
+      if (cur < 0 && leaf < 0 && sp > 0) { sp--; cur = stk_n[sp]; curd = stk_d[sp]; }
     }
-    if (sp == 0) break;
-    sp--;
-    cur = stk_n[sp]; curd = stk_d[sp];
+    // ---- triangle test for every lane that holds a leaf
+    if (leaf >= 0) {
+      n_tri++;
+      d3 a = tri_vertex(m.tris, leaf, 0) - q, b = tri_vertex(m.tris, leaf, 1) - q, c = tri_vertex(m.tris, leaf, 2) - q;
+      f3 af = tof(a), bf = tof(b), cf = tof(c);
+      f3 v = closest_pt_triangle<float>(af, bf, cf, mk<float>(0.f, 0.f, 0.f));
+      float d2 = dot(v, v);
+      if (d2 < best) {
+        best = d2; bestv = v; best_tri = leaf;
+        best_sc = fmaxf(fmaxf(fmaxf(fabsf(af.x), fabsf(af.y)), fmaxf(fabsf(af.z), fabsf(bf.x))),
+                        fmaxf(fmaxf(fabsf(bf.y), fabsf(bf.z)), fmaxf(fabsf(cf.x), fmaxf(fabsf(cf.y), fabsf(cf.z)))));
+      }
+      if (sp > 0) { sp--; cur = stk_n[sp]; curd = stk_d[sp]; }
+    }
+    if (cur < 0) break;
+  }
+  // fp32 loses relative accuracy once the distance is small against the triangle's own extent
+  if (best_tri >= 0 && best < 1.0e-4f * best_sc * best_sc) {
+    d3 a = tri_vertex(m.tris, best_tri, 0) - q, b = tri_vertex(m.tris, best_tri, 1) - q, c = tri_vertex(m.tris, best_tri, 2) - q;
+    d3 v64 = closest_pt_triangle_d(a, b, c);
+    bestv = tof(v64);
+    best = (float)dot(v64, v64);
   }
   return best;
 }
@@ -173,12 +231,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ContactEnergy::energy (src/EGPlanner/energy/contactEnergy.cpp:9-55) for one contact: world contact
 // location p and world normal cn -> |v| + 50 (1 - cn . v/|v|), v = closest object point - p.
-__device__ __forceinline__ float contact_term(const MeshDev &mo, const double *XO, d3 pw, d3 cnw,
+__device__ __forceinline__ float contact_term(const MeshDev &mo, const Node *top, int ntop, const double *XO, d3 pw, d3 cnw,
                                               unsigned &n_box, unsigned &n_tri) {
   d3 q = xf_apply_inv(XO, pw);
   f3 cnl = tof(xf_rot_t(XO, cnw));
   f3 v; int bt;
-  float d2 = closest_point_query(mo, q, v, bt, n_box, n_tri);
+  float d2 = closest_point_query(mo, top, ntop, q, v, bt, n_box, n_tri);
   float dist = sqrtf(d2);
   float inv = d2 > 0.f ? 1.0f / dist : 0.f;
   float c = (cnl.x * v.x + cnl.y * v.y + cnl.z * v.z) * inv;
@@ -193,8 +251,7 @@ __device__ __forceinline__ float contact_term(const MeshDev &mo, const double *X
 //            each lane pops one (pair, nodeA, nodeB) entry, tests the two children of the larger
 //            node against the other node, and the survivors are compacted back with ballot/popc;
 //            leaf-leaf entries go to a separate queue that is drained 32 triangle pairs at a time
-//   phase 3  if no pair collides: lanes = virtual contacts, closest point on the object, energy
-//            reduction with shuffles
+//   phase 3  poses without a collision are appended to a compact list for the energy kernel
 // Replaces GraspitCollision::allCollisions (graspitCollision.cpp:332-363) + recursion/CollisionCallback
 // (collisionAlgorithms.cpp:42-147, collisionAlgorithms_inl.h:50-81) and ContactEnergy::energy.
 // ============================================================================================
@@ -240,7 +297,7 @@ __device__ __forceinline__ int leaf_pair_test(const MeshDev &ma, const MeshDev &
   return tri_tri_filter(p2, p3, e1, e2, q1, q2, q3, f1, f2);
 }
 
-__global__ void __launch_bounds__(256) eval_kernel(EvalParams p) {
+__global__ void __launch_bounds__(256, 3) eval_kernel(EvalParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -254,7 +311,7 @@ __global__ void __launch_bounds__(256) eval_kernel(EvalParams p) {
   S.leafq = S.stack + p.stack_phys;
   S.mask = reinterpret_cast<unsigned *>(S.leafq + LEAFQ_CAP);
 
-  unsigned n_box = 0, n_tri = 0, n_pbox = 0, n_ptri = 0, n_amb = 0;
+  unsigned n_box = 0, n_tri = 0, n_amb = 0;
 
   // static bodies never change: load once per warp
   for (int i = p.nrb * 12 + lane; i < p.nb * 12; i += 32)
@@ -392,29 +449,11 @@ __global__ void __launch_bounds__(256) eval_kernel(EvalParams p) {
       p.pair_mask[(size_t)pose * p.mask_words + lane] =
           (unsigned long long)S.mask[2 * lane] | ((unsigned long long)S.mask[2 * lane + 1] << 32);
 
-    // ---- phase 3: CONTACT_PRESET energy ----
-    float energy = 0.f;
-    if (p.do_energy && !collided && p.object >= 0 && p.nvc > 0) {
-      const MeshDev &mo = p.meshes[__ldg(&p.body_mesh[p.object])];
-      const double *XO = S.bodyxf + 12 * p.object;
-      float total = 0.f;
-      for (int cbase = 0; cbase < p.nvc; cbase += 32) {
-        int c = cbase + lane;
-        float term = 0.f;
-        if (c < p.nvc) {
-          const VcDev &vc = p.vcs[c];
-          const double *XL = S.bodyxf + 12 * vc.body;
-          d3 pw = xf_apply(XL, mk<double>(vc.loc[0], vc.loc[1], vc.loc[2]));
-          d3 cnw = xf_rot(XL, mk<double>(vc.normal[0], vc.normal[1], vc.normal[2]));
-          term = contact_term(mo, XO, pw, cnw, n_pbox, n_ptri);
-        }
-        total += warp_sum(term);
-      }
-      energy = total / (float)p.nvc;
-    }
+    // ---- hand the pose over to the energy kernel ----
     if (lane == 0) {
       if (p.legal) p.legal[pose] = collided ? 0 : 1;
-      if (p.energy) p.energy[pose] = energy;
+      if (p.energy) p.energy[pose] = 0.f;
+      if (!collided && p.legal_list) p.legal_list[atomicAdd(p.legal_count, 1)] = pose;
     }
     __syncwarp();
   }
@@ -423,8 +462,6 @@ __global__ void __launch_bounds__(256) eval_kernel(EvalParams p) {
     unsigned long long v;
     v = n_box; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_BOX], v);
     v = n_tri; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_TRI], v);
-    v = n_pbox; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PBOX], v);
-    v = n_ptri; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PTRI], v);
     v = n_amb; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_AMBIG], v);
   }
 }
@@ -478,7 +515,7 @@ __global__ void point_kernel(PointParams p) {
   d3 pw = mk<double>(p.points[3 * i], p.points[3 * i + 1], p.points[3 * i + 2]);
   d3 q = xf_apply_inv(X, pw);
   f3 v; int bt; unsigned nb = 0, nt = 0;
-  float d2 = closest_point_query(p.mesh, q, v, bt, nb, nt);
+  float d2 = closest_point_query(p.mesh, nullptr, 0, q, v, bt, nb, nt);
   // refine the winning triangle in fp64 so the returned coordinates carry fp64 accuracy
   d3 cl = q;
   double dist = 0.0;
@@ -514,7 +551,7 @@ __device__ __forceinline__ unsigned long long pack_dist_entry(float lb, int a, i
 __device__ __forceinline__ float entry_lb(unsigned long long e) { return __uint_as_float(((unsigned)(e >> 48)) << 16); }
 
 
-__global__ void __launch_bounds__(256) dist_kernel(DistParams p) {
+__global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -525,6 +562,7 @@ __global__ void __launch_bounds__(256) dist_kernel(DistParams p) {
   double *XA = reinterpret_cast<double *>(leafq + DLEAF_CAP);
   double *XB = XA + 12;
   PairXf *xp = reinterpret_cast<PairXf *>(XB + 12);
+  int2 *nearq = reinterpret_cast<int2 *>(xp + 1);
   unsigned n_box = 0, n_tri = 0;
   const int total = p.npose * p.nq;
 
@@ -555,7 +593,7 @@ __global__ void __launch_bounds__(256) dist_kernel(DistParams p) {
     float best = 3.0e38f;          // squared distance, warp-uniform
     d3 bpa = mk<double>(0, 0, 0), bpb = mk<double>(0, 0, 0);   // valid on every lane after each leaf batch
     bool hit = false;
-    int sp = 0, lq = 0;
+    int sp = 0, lq = 0, nnear = 0;
     if (lane == 0) stack[0] = pack_dist_entry(0.f, 0, 0);
     sp = 1;
     __syncwarp();
@@ -568,6 +606,7 @@ __global__ void __launch_bounds__(256) dist_kernel(DistParams p) {
         int ta = 0, tb = 0;
         d3 P1 = mk<double>(0, 0, 0);
         f3 pa = mk<float>(0, 0, 0), pb = pa;
+        bool tiny = false;
         if (lane < n) {
           unsigned long long e = leafq[lq - n + lane];
           ta = (int)((e >> 24) & 0xffffffu); tb = (int)(e & 0xffffffu);
@@ -581,11 +620,26 @@ __global__ void __launch_bounds__(256) dist_kernel(DistParams p) {
             f3 e1 = tof(E1), e2 = tof(E2);
             f3 p2 = e1, p3 = tof(E1 + E2);
             f3 q1 = tof(b1 - P1), q2 = tof(b2 - P1), q3 = tof(b3 - P1);
-            res = tri_tri_filter(p2, p3, e1, e2, q1, q2, q3, tof(b2 - b1), tof(b3 - b2));
-            if (res != TT_HIT) d2 = tri_tri_dist2<float>(mk<float>(0, 0, 0), p2, p3, q1, q2, q3, pa, pb);
+            // boxes that are certainly apart cannot hold intersecting triangles: skip the SAT
+            res = entry_lb(e) > 0.f ? TT_SEP : tri_tri_filter(p2, p3, e1, e2, q1, q2, q3, tof(b2 - b1), tof(b3 - b2));
+            if (res != TT_HIT) {
+              d2 = tri_tri_dist2<float>(mk<float>(0, 0, 0), p2, p3, q1, q2, q3, pa, pb);
+              // distance small against the triangles' extent: fp32 has lost relative accuracy; remember the
+              // pair (if it is within rounding of the best so far) for the fp64 pass after the traversal
+              float sc = fmaxf(fmaxf(fmaxf(fabsf(p2.x), fabsf(p2.y)), fmaxf(fabsf(p2.z), fabsf(p3.x))), fmaxf(fabsf(p3.y), fabsf(p3.z)));
+              sc = fmaxf(sc, fmaxf(fmaxf(fabsf(q1.x), fabsf(q1.y)), fabsf(q1.z)));
+              sc = fmaxf(sc, fmaxf(fmaxf(fabsf(q2.x), fabsf(q2.y)), fabsf(q2.z)));
+              sc = fmaxf(sc, fmaxf(fmaxf(fabsf(q3.x), fabsf(q3.y)), fabsf(q3.z)));
+              tiny = d2 < 1.0e-4f * sc * sc && d2 <= best * 1.004f + 1.0e-9f;
+            }
           }
         }
         lq -= n;
+        {
+          unsigned tm = __ballot_sync(FULL, tiny);
+          if (tiny) { int at = nnear + __popc(tm & lt_mask); if (at < DNEAR_CAP) nearq[at] = make_int2(ta, tb); }
+          nnear += __popc(tm);
+        }
         if (res == TT_AMBIG) {
           int slot = atomicAdd(p.ambig_count, 1);
           if (slot < p.ambig_cap) { Ambig a; a.pose = pose; a.pair = qi; a.tri_a = ta; a.tri_b = tb; p.ambig[slot] = a; }
@@ -668,6 +722,17 @@ __global__ void __launch_bounds__(256) dist_kernel(DistParams p) {
       __syncwarp();
     }
     __syncwarp();
+    if (!hit && nnear > 0 && p.near_dir) {
+      // hand the remembered near-minimum pairs (tiny distances only) to the fp64 refinement kernel
+      int cnt = nnear < DNEAR_CAP ? nnear : DNEAR_CAP;
+      int seg = 0, ofs = 0;
+      if (lane == 0) { seg = atomicAdd(p.near_count, 1); ofs = atomicAdd(p.near_count + 1, cnt); }
+      seg = __shfl_sync(FULL, seg, 0); ofs = __shfl_sync(FULL, ofs, 0);
+      if (seg < p.near_cap_dir && ofs + cnt <= p.near_cap_ent) {
+        for (int i = lane; i < cnt; i += 32) p.near_ent[ofs + i] = nearq[i];
+        if (lane == 0) p.near_dir[seg] = make_int4(w, ofs, cnt, 0);
+      }
+    }
     if (lane == 0) {
       if (hit) {
         p.dist[w] = -1.f;
@@ -693,43 +758,289 @@ __global__ void __launch_bounds__(256) dist_kernel(DistParams p) {
 }
 
 // ============================================================================================
-// CONTACT_LIVE energy.  Per pose, per hand body: virtual contact rebuilt from the body-body closest
-// points exactly as the reference does -- including its frame quirks:
-//   bodyToBodyDistance returns p1 = T_link^-1 * mP1, p2 = T_obj^-1 * mP2 with mP1/mP2 already local
-//   (graspitCollision.cpp:473-475); World::findVirtualContact (world.cpp:1641-1651) then forms
-//   n = normalize(T_link p1 - T_obj p2) = normalize(mP1 - mP2), the contact location is T_link p1 = mP1
-//   read as a world point, and the virtual contact's world normal is -n (virtualContact.cpp:92).
-// One warp per pose, lanes = hand bodies.
+// fp64 refinement of tiny body-body distances: one warp per query that remembered near-minimum
+// triangle pairs; lanes evaluate the pairs exactly (triangleTriangleDistanceSq arithmetic in fp64),
+// the warp keeps the minimum.  Only queries whose distance is below ~1% of the triangles' extent get here.
 // ============================================================================================
-
-__global__ void __launch_bounds__(256) live_kernel(LiveParams p) {
+__global__ void __launch_bounds__(128) dist_refine_kernel(DistParams p) {
   const int lane = threadIdx.x & 31;
-  int pose = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (pose >= p.npose) return;
-  if (p.legal && !p.legal[pose]) { if (lane == 0) p.energy[pose] = 0.f; return; }
-  const MeshDev &mo = p.meshes[p.body_mesh[p.object]];
-  const double *XO = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, p.object);
-  unsigned nbx = 0, ntr = 0;
-  float total = 0.f;
-  for (int base = 0; base < p.nq; base += 32) {
-    int i = base + lane;
-    float term = 0.f;
-    if (i < p.nq) {
-      const double *o = p.pts + ((size_t)pose * p.nq + i) * 6;
-      d3 mP1 = mk<double>(o[0], o[1], o[2]), mP2 = mk<double>(o[3], o[4], o[5]);
-      d3 n = mP1 - mP2;
-      double nn = sqrt(dot(n, n));
-      if (nn > 0.0) n = n * (1.0 / nn);
-      d3 cnw = mk<double>(-n.x, -n.y, -n.z);
-      term = contact_term(mo, XO, mP1, cnw, nbx, ntr);
+  int nseg = p.near_count[0];
+  if (nseg > p.near_cap_dir) nseg = p.near_cap_dir;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < nseg; s += (gridDim.x * blockDim.x) >> 5) {
+    int4 d = p.near_dir[s];
+    int w = d.x, ofs = d.y, cnt = d.z;
+    if (cnt <= 0 || p.dist[w] < 0.f) continue;
+    int pose = w / p.nq, qi = w - pose * p.nq;
+    int2 ab = p.queries[qi];
+    const MeshDev &ma = p.meshes[p.body_mesh[ab.x]];
+    const MeshDev &mb = p.meshes[p.body_mesh[ab.y]];
+    const double *XA = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, ab.x);
+    const double *XB = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, ab.y);
+    double bd = 1.0e300;
+    d3 ba = mk<double>(0, 0, 0), bb = ba;
+    for (int i = lane; i < cnt; i += 32) {
+      int2 tt = p.near_ent[ofs + i];
+      d3 a1 = tri_vertex(ma.tris, tt.x, 0), a2 = tri_vertex(ma.tris, tt.x, 1), a3 = tri_vertex(ma.tris, tt.x, 2);
+      d3 b1 = tri_vertex(mb.tris, tt.y, 0), b2 = tri_vertex(mb.tris, tt.y, 1), b3 = tri_vertex(mb.tris, tt.y, 2);
+      d3 P1 = xf_apply_inv(XB, xf_apply(XA, a1));
+      d3 E1 = xf_rot_t(XB, xf_rot(XA, a2 - a1));
+      d3 E2 = xf_rot_t(XB, xf_rot(XA, a3 - a2));
+      d3 xa, xb;
+      double dd = tri_tri_dist2<double>(P1, P1 + E1, P1 + E1 + E2, b1, b2, b3, xa, xb);
+      if (dd < bd) { bd = dd; ba = xa; bb = xb; }
     }
-    total += warp_sum(term);
+    double m = bd;
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(FULL, m, o));
+    unsigned who = __ballot_sync(FULL, bd == m);
+    if (lane == __ffs(who) - 1 && m < 1.0e299) {
+      p.dist[w] = (float)sqrt(m);
+      if (p.pts) {
+        d3 pa_local = xf_apply_inv(XA, xf_apply(XB, ba));
+        double *o = p.pts + (size_t)w * 6;
+        o[0] = pa_local.x; o[1] = pa_local.y; o[2] = pa_local.z;
+        o[3] = bb.x; o[4] = bb.y; o[5] = bb.z;
+      }
+    }
   }
-  if (lane == 0) p.energy[pose] = total / (float)p.nq;
+}
+
+// ============================================================================================
+// K5 + K8: CONTACT_ENERGY.  One thread per (legal pose, contact): every lane of a warp is busy with its
+// own closest-point query, neighbouring lanes handle contacts of the same hand so their traversals
+// stay close together in the tree.  A block owns `ppb` poses at a time (ppb * ncontacts <= blockDim),
+// stores the per-contact terms in shared memory and sums them in a fixed order (deterministic).
+// The top levels of the object's tree (a breadth-first prefix of the node array) are staged into shared
+// memory once per block with one TMA bulk copy (cp.async.bulk + mbarrier).
+//
+// PRESET contacts come from the robot's virtual-contact table (reference robot.cpp:435-475).
+// LIVE contacts are rebuilt from the body-body closest points exactly as the reference does, including
+// its frame quirks: bodyToBodyDistance returns p1 = T_link^-1 * mP1,
+// p2 = T_obj^-1 * mP2 with mP1/mP2 already local (graspitCollision.cpp:473-475); World::findVirtualContact
+// (world.cpp:1641-1651) then forms n = normalize(T_link p1 - T_obj p2) = normalize(mP1 - mP2), the contact
+// location is T_link p1 = mP1 read as a world point, and the virtual contact's normal is -n
+// (virtualContact.cpp:92).
+// ContactEnergy::energy (contactEnergy.cpp:9-55): mean over contacts of |v| + 50 (1 - cn . v/|v|).
+// ============================================================================================
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// per-warp shared memory of the cooperative energy kernel
+constexpr int EQ_STACK_CAP = 448, EQ_STACK_PHYS = 512, EQ_LEAF_CAP = 96;
+constexpr unsigned long long EQ_NONE = 0x7f7fffffffffffffull;   // (FLT_MAX bits << 32) | no triangle
+constexpr int ENERGY_WARP_SMEM = EQ_STACK_PHYS * 8 + EQ_LEAF_CAP * 8 + 32 * 8 + 32 * 24 + 32 * 16;
+
+__device__ __forceinline__ unsigned long long eq_entry(float lb, int q, int idx) {
+  return ((unsigned long long)__float_as_uint(lb) << 32) | ((unsigned long long)(unsigned)q << 24) | (unsigned long long)(unsigned)idx;
+}
+
+// One warp = 32 closest-point queries (contacts of consecutive legal poses) traversed TOGETHER through one
+// shared work stack: every lane pops one (query, child-pair, lower bound) entry, loads the 64-byte pair of
+// sibling boxes, and pushes the children that can still beat the query's best distance (far first, near on
+// top, so each query advances depth-first, nearest first); finished queries simply stop producing entries
+// and their lanes pick up other queries' work.  Leaves are queued and tested 32 triangles at a time; the
+// per-query best (distance, triangle) is a 64-bit atomicMin in shared memory.
+__global__ void __launch_bounds__(256) energy_kernel(EnergyParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Node *top = reinterpret_cast<Node *>(smem_raw);
+  __shared__ __align__(8) unsigned long long bar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned char *wbase = smem_raw + (size_t)p.stage_nodes * sizeof(Node) + (size_t)warp * ENERGY_WARP_SMEM;
+  unsigned long long *stack = reinterpret_cast<unsigned long long *>(wbase);
+  unsigned long long *leafq = stack + EQ_STACK_PHYS;
+  unsigned long long *bestkey = leafq + EQ_LEAF_CAP;                 // [32] (d2 bits << 32) | triangle
+  double *qd = reinterpret_cast<double *>(bestkey + 32);              // [32][3] query point, object frame
+  float4 *qf = reinterpret_cast<float4 *>(qd + 96);                   // [32] fp32 copy
+  const int nc = p.live ? p.nq : p.nvc;
+  const MeshDev mo = p.meshes[p.body_mesh[p.object]];
+  const int ntop = p.stage_nodes < mo.nnodes ? p.stage_nodes : mo.nnodes;
+
+  if (ntop > 0) {
+    // TMA bulk copy of the tree's top levels (breadth-first prefix) into shared memory
+    const unsigned bytes = (unsigned)ntop * (unsigned)sizeof(Node);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(top)), "l"(mo.nodes), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(&bar)) : "memory");
+  }
+
+  const int nlegal = p.legal_count ? *p.legal_count : p.npose;
+  const int nquery = nlegal * nc;
+  const int ngroups = (nquery + 31) / 32;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  unsigned nbx = 0, ntr = 0;
+  const Node root = fetch_node(mo.nodes, top, ntop, 0);
+
+  for (int g = (blockIdx.x * blockDim.x + tid) >> 5; g < ngroups; g += warps_total) {
+    // ---- set up this lane's query
+    const int qid = g * 32 + lane;
+    bool valid = qid < nquery;
+    int pose = -1, c = 0;
+    f3 cnl = mk<float>(0.f, 0.f, 0.f);
+    if (valid) {
+      int li = qid / nc;
+      c = qid - li * nc;
+      pose = p.legal_list ? p.legal_list[li] : li;
+      if (p.legal && !p.legal[pose]) valid = false;
+    }
+    if (valid) {
+      const double *XO = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, p.object);
+      d3 pw, cnw;
+      if (p.live) {
+        const double *o = p.pts + ((size_t)pose * p.nq + c) * 6;
+        d3 mP1 = mk<double>(o[0], o[1], o[2]), mP2 = mk<double>(o[3], o[4], o[5]);
+        d3 n = mP1 - mP2;
+        double nn = sqrt(dot(n, n));
+        if (nn > 0.0) n = n * (1.0 / nn);
+        pw = mP1;
+        cnw = mk<double>(-n.x, -n.y, -n.z);
+      } else {
+        const VcDev &vc = p.vcs[c];
+        const double *XL = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, vc.body);
+        pw = xf_apply(XL, mk<double>(vc.loc[0], vc.loc[1], vc.loc[2]));
+        cnw = xf_rot(XL, mk<double>(vc.normal[0], vc.normal[1], vc.normal[2]));
+      }
+      d3 q = xf_apply_inv(XO, pw);
+      cnl = tof(xf_rot_t(XO, cnw));
+      qd[3 * lane] = q.x; qd[3 * lane + 1] = q.y; qd[3 * lane + 2] = q.z;
+      qf[lane] = make_float4((float)q.x, (float)q.y, (float)q.z, 0.f);
+    }
+    bestkey[lane] = EQ_NONE;
+    int sp = 0, lq = 0;
+    {
+      // seed: the root's child pair (or the root leaf itself for one-triangle meshes)
+      bool inner = valid && root.child >= 0, leafroot = valid && root.child < 0 && root.tri >= 0;
+      unsigned mi = __ballot_sync(FULL, inner), ml = __ballot_sync(FULL, leafroot);
+      if (inner) stack[__popc(mi & lt_mask)] = eq_entry(0.f, lane, root.child);
+      if (leafroot) leafq[__popc(ml & lt_mask)] = eq_entry(0.f, lane, root.tri);
+      sp = __popc(mi); lq = __popc(ml);
+    }
+    __syncwarp();
+
+    while (true) {
+      if (lq >= 32 || (sp == 0 && lq > 0)) {
+        // ---- 32 point-triangle tests
+        int n = lq < 32 ? lq : 32;
+        if (lane < n) {
+          unsigned long long e = leafq[lq - n + lane];
+          int qi = (int)((e >> 24) & 0xffu), tri = (int)(e & 0xffffffu);
+          float lb = __uint_as_float((unsigned)(e >> 32));
+          float best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
+          if (lb <= best) {
+            ntr++;
+            d3 q = mk<double>(qd[3 * qi], qd[3 * qi + 1], qd[3 * qi + 2]);
+            d3 a = tri_vertex(mo.tris, tri, 0) - q, b = tri_vertex(mo.tris, tri, 1) - q, cc = tri_vertex(mo.tris, tri, 2) - q;
+            f3 v = closest_pt_triangle<float>(tof(a), tof(b), tof(cc), mk<float>(0.f, 0.f, 0.f));
+            float d2 = dot(v, v);
+            atomicMin(&bestkey[qi], ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)tri);
+          }
+        }
+        lq -= n;
+        __syncwarp();
+        continue;
+      }
+      if (sp == 0) break;
+      int room = EQ_STACK_CAP - sp;
+      int k = sp < 32 ? sp : 32;
+      if (k > room) k = room > 1 ? room : 1;
+      bool have = lane < k;
+      unsigned long long e = have ? stack[sp - 1 - lane] : 0ull;
+      sp -= k;
+      __syncwarp();
+      bool pn = false, pf = false, ln = false, lf = false;
+      unsigned long long cn = 0ull, cf = 0ull;
+      if (have) {
+        int qi = (int)((e >> 24) & 0xffu), pair = (int)(e & 0xffffffu);
+        float lb = __uint_as_float((unsigned)(e >> 32));
+        float best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
+        if (lb <= best) {
+          Node c0 = fetch_node(mo.nodes, top, ntop, pair), c1 = fetch_node(mo.nodes, top, ntop, pair + 1);
+          float4 qq = qf[qi];
+          f3 qp = mk<float>(qq.x, qq.y, qq.z);
+          float cc[3], hh[3];
+          node_ch(c0, cc, hh); float d0 = point_box_dist2(cc, hh, qp);
+          node_ch(c1, cc, hh); float d1 = point_box_dist2(cc, hh, qp);
+          nbx += 2;
+          bool swap = d1 < d0;
+          float dn = swap ? d1 : d0, df = swap ? d0 : d1;
+          int chn = swap ? c1.child : c0.child, chf = swap ? c0.child : c1.child;
+          int trn = swap ? c1.tri : c0.tri, trf = swap ? c0.tri : c1.tri;
+          pn = dn <= best; pf = df <= best;
+          ln = chn < 0; lf = chf < 0;
+          cn = eq_entry(dn, qi, ln ? trn : chn);
+          cf = eq_entry(df, qi, lf ? trf : chf);
+        }
+      }
+      unsigned sF = __ballot_sync(FULL, pf && !lf), sN = __ballot_sync(FULL, pn && !ln);
+      unsigned qF = __ballot_sync(FULL, pf && lf), qN = __ballot_sync(FULL, pn && ln);
+      if (pf && !lf) stack[sp + __popc(sF & lt_mask)] = cf;
+      if (pn && !ln) stack[sp + __popc(sF) + __popc(sN & lt_mask)] = cn;
+      sp += __popc(sF) + __popc(sN);
+      if (pf && lf) leafq[lq + __popc(qF & lt_mask)] = cf;
+      if (pn && ln) leafq[lq + __popc(qF) + __popc(qN & lt_mask)] = cn;
+      lq += __popc(qF) + __popc(qN);
+      __syncwarp();
+    }
+    __syncwarp();
+
+    // ---- this lane's result: redo the winning triangle (fp64 when the distance is tiny against its extent)
+    if (valid) {
+      unsigned long long key = bestkey[lane];
+      int tri = (int)(key & 0xffffffffu);
+      float term = 0.f;
+      if (key != EQ_NONE) {
+        d3 q = mk<double>(qd[3 * lane], qd[3 * lane + 1], qd[3 * lane + 2]);
+        d3 a = tri_vertex(mo.tris, tri, 0) - q, b = tri_vertex(mo.tris, tri, 1) - q, cc = tri_vertex(mo.tris, tri, 2) - q;
+        f3 af = tof(a), bf = tof(b), cf3 = tof(cc);
+        f3 v = closest_pt_triangle<float>(af, bf, cf3, mk<float>(0.f, 0.f, 0.f));
+        float d2 = dot(v, v);
+        float sc = fmaxf(fmaxf(fmaxf(fabsf(af.x), fabsf(af.y)), fmaxf(fabsf(af.z), fabsf(bf.x))),
+                         fmaxf(fmaxf(fabsf(bf.y), fabsf(bf.z)), fmaxf(fabsf(cf3.x), fmaxf(fabsf(cf3.y), fabsf(cf3.z)))));
+        if (d2 < 1.0e-4f * sc * sc) {
+          d3 v64 = closest_pt_triangle_d(a, b, cc);
+          v = tof(v64);
+          d2 = (float)dot(v64, v64);
+        }
+        float dist = sqrtf(d2);
+        float inv = d2 > 0.f ? 1.0f / dist : 0.f;
+        term = dist + (1.0f - (cnl.x * v.x + cnl.y * v.y + cnl.z * v.z) * inv) * 50.0f;
+      }
+      p.terms[qid] = term;
+    }
+    __syncwarp();
+  }
   if (p.stats) {
     unsigned long long v;
     v = nbx; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PBOX], v);
     v = ntr; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PTRI], v);
+  }
+}
+
+// fixed-order sum of the per-contact terms of every legal pose (ContactEnergy::energy's division by the
+// contact count, contactEnergy.cpp:51)
+__global__ void energy_reduce_kernel(EnergyParams p) {
+  const int nc = p.live ? p.nq : p.nvc;
+  const int nlegal = p.legal_count ? *p.legal_count : p.npose;
+  for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < nlegal; li += gridDim.x * blockDim.x) {
+    int pose = p.legal_list ? p.legal_list[li] : li;
+    if (p.legal && !p.legal[pose]) { p.energy[pose] = 0.f; continue; }
+    float total = 0.f;
+    for (int k = 0; k < nc; k++) total += p.terms[(size_t)li * nc + k];
+    p.energy[pose] = total / (float)nc;
   }
 }
 
@@ -773,15 +1084,28 @@ cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s) {
     configured = true;
   }
   dist_kernel<<<blocks, 256, smem, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !p.near_dir) return e;
+  dist_refine_kernel<<<32, 128, 0, s>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_live(const LiveParams &p, cudaStream_t s) {
+cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s) {
   if (p.npose <= 0) return cudaSuccess;
-  int threads = 256;
-  long long total = (long long)p.npose * 32;
-  live_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(p);
+  static size_t configured = 0;
+  size_t smem = energy_block_smem_bytes(p.stage_nodes);
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  energy_kernel<<<blocks, 256, smem, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  energy_reduce_kernel<<<(p.npose + 255) / 256, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
+
+size_t energy_block_smem_bytes(int stage_nodes) { return (size_t)stage_nodes * sizeof(Node) + (size_t)8 * ENERGY_WARP_SMEM; }
 
 } // namespace b2c

@@ -235,7 +235,7 @@ class Engine:
     def last_kernel_ms(self) -> dict:
         ms = (C.c_float * 8)()
         self._ck(self.L.b2c_last_kernel_ms(self.h, ms))
-        return {"fk": ms[0], "eval": ms[1], "recheck": ms[2], "dist": ms[3], "live": ms[4]}
+        return {"fk": ms[0], "eval": ms[1], "recheck": ms[2], "dist": ms[3], "energy": ms[4]}
 
     # ---- addBody / cloneBody / removeBody / updateBodyGeometry ---------------------------------
     def create_mesh(self, tris) -> int:

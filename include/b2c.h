@@ -49,7 +49,7 @@ long long b2c_launch_count(const b2c_ctx *ctx);
 int b2c_set_stream(b2c_ctx *ctx, void *stream);
 /* per-kernel CUDA-event timing of the batched evaluation: when enabled, b2c_eval_batch brackets each kernel
  * with events on the launching stream; b2c_last_kernel_ms (which synchronises) returns the durations of the
- * last evaluation in ms: [0] fk, [1] eval (legal+energy), [2] recheck, [3] distance, [4] live energy, [5..7] 0 */
+ * last evaluation in ms: [0] fk, [1] eval (legality), [2] recheck, [3] distance (+ refine), [4] energy, [5..7] 0 */
 int b2c_set_profiling(b2c_ctx *ctx, int enabled);
 int b2c_last_kernel_ms(b2c_ctx *ctx, float ms[8]);
 
