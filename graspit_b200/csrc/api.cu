@@ -7,6 +7,7 @@
 #include "contacts_host.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -106,7 +107,7 @@ struct b2c_ctx {
   // scratch
   DevBuf<float> d_states; DevBuf<Xf> d_fk; DevBuf<double> d_fkqt; DevBuf<uint8_t> d_legal; DevBuf<float> d_energy;
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
-  DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
+  DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
   int stage_nodes = 511;           // object-tree nodes staged in shared memory by the energy kernel
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int eval_warps_per_block = 8;
@@ -392,7 +393,7 @@ void b2c_destroy(b2c_ctx *ctx) {
   }
   ctx->d_meshes.release(); ctx->d_states.release(); ctx->d_fk.release(); ctx->d_fkqt.release(); ctx->d_legal.release();
   ctx->d_energy.release(); ctx->d_mask.release(); ctx->d_ambig.release(); ctx->d_counters.release(); ctx->d_stats.release();
-  ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release(); ctx->d_legal_list.release(); ctx->d_terms.release(); ctx->d_near_dir.release(); ctx->d_near_ent.release();
+  ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release(); ctx->d_legal_list.release(); ctx->d_contacts.release(); ctx->d_flags.release(); ctx->d_terms.release(); ctx->d_near_dir.release(); ctx->d_near_ent.release();
   for (int i = 0; i < 16; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;

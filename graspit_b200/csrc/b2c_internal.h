@@ -206,6 +206,35 @@ __host__ __device__ inline size_t eval_warp_smem_bytes(int nb, int npairs, int m
   return (b + 15) & ~(size_t)15;
 }
 
+// ---- K6 / K7 ---------------------------------------------------------------------------------------
+struct ContactRec {
+  int query, tri_a, tri_b, feature;   // feature: 0-2 V(t2)-F(t1), 3-5 V(t1)-F(t2), 6-14 edge-edge
+  double c[13];                       // b1_pos, b2_pos, b1_normal, b2_normal, distSq
+};
+struct ContactParams {
+  int npose;
+  int nrb, nb;
+  int nq;
+  double threshold;
+  const int2 *queries;
+  const Xf *fk;
+  const Xf *static_xf;
+  const int *body_mesh;
+  const MeshDev *meshes;
+  ContactRec *out;
+  int out_cap;
+  int *out_count;
+  int *per_query;          // [npose * nq] contact candidates per query
+  int *work_counter;
+};
+struct RegionParams {
+  MeshDev mesh;
+  double point[3], normal[3], radius;
+  unsigned char *flags;    // [ntri]
+};
+cudaError_t launch_contacts(const ContactParams &p, int blocks, cudaStream_t s);
+cudaError_t launch_region(const RegionParams &p, cudaStream_t s);
+
 constexpr int DSTACK_CAP = 448, DSTACK_PHYS = 512, DLEAF_CAP = 96;
 constexpr int DNEAR_CAP = 64;
 constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 2 * 96 + 96 + DNEAR_CAP * 8 + 32;

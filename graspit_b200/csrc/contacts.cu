@@ -1,0 +1,257 @@
+// K6 contact-candidate extraction and K7 region extraction.
+//
+// K6 (contact_kernel): one warp per (pose, body pair).  Same cooperative work stack as the distance
+// kernel, but with the fixed contact threshold as the bound: a node pair is kept while the lower bound of
+// its box distance is <= threshold (reference ContactCallback::distanceTest, dSq <= thr^2,
+// collisionAlgorithms.h:168-172).  Surviving triangle pairs are enumerated in fp64 exactly as
+// triangleTriangleContact does (include/graspit/triangle_inl.h:284-404): nothing if the triangles
+// intersect; else every vertex-face (6) and edge-edge (9) closest pair closer than the threshold (strict),
+// skipping vertex-face pairs of triangle 1 whose foot is a vertex of triangle 2 and edge-edge pairs whose
+// foot is an endpoint.  The reference detects those duplicates with exact == on coordinates; here they are
+// detected from the feature (Voronoi region / clamped parameter), see SURVEY.md Appendix A.16.
+// Each emitted contact follows ContactCallback::leafTest (collisionAlgorithms_inl.h:96-133): p1 moved to
+// body 1's frame, n1 = normalize(p1 - p2) rotated to frame 1, n2 = -n1 in frame 2, distSq = the reference's
+// mixed-frame |p1_frame1 - p2_frame2|^2.
+//
+// K7 (region_kernel): one thread per triangle of the body: triangles whose normal does not oppose the
+// contact normal and whose closest point to the reference point lies within the radius are flagged
+// (RegionCallback::leafTest, collisionAlgorithms_inl.h:252-275); the host collects their vertices.
+#include "b2c_internal.h"
+
+namespace b2c {
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ Node c_load_node(const Node *nodes, int i) {
+  const float4 *p = reinterpret_cast<const float4 *>(nodes + i);
+  float4 a = __ldg(p), b = __ldg(p + 1);
+  Node n;
+  n.cx = a.x; n.cy = a.y; n.cz = a.z; n.hx = a.w;
+  n.hy = b.x; n.hz = b.y; n.child = __float_as_int(b.z); n.tri = __float_as_int(b.w);
+  return n;
+}
+__device__ __forceinline__ void c_node_ch(const Node &n, float *c, float *h) {
+  c[0] = n.cx; c[1] = n.cy; c[2] = n.cz; h[0] = n.hx; h[1] = n.hy; h[2] = n.hz;
+}
+__device__ __forceinline__ d3 c_tri_vertex(const Tri *tris, int t, int k) {
+  float4 v = __ldg(&tris[t].v[k]);
+  return mk<double>((double)v.x, (double)v.y, (double)v.z);
+}
+__device__ __forceinline__ const double *c_body_xf(const Xf *fk, const Xf *static_xf, int nrb, int pose, int body) {
+  return body < nrb ? reinterpret_cast<const double *>(fk + (size_t)pose * nrb + body)
+                    : reinterpret_cast<const double *>(static_xf + (body - nrb));
+}
+
+__device__ void emit_contact(const ContactParams &p, int w, int ta, int tb, int feature, d3 p1, d3 p2,
+                             const double *XA, const double *XB) {
+  int slot = atomicAdd(p.out_count, 1);
+  atomicAdd(&p.per_query[w], 1);
+  if (slot >= p.out_cap) return;
+  ContactRec r;
+  r.query = w; r.tri_a = ta; r.tri_b = tb; r.feature = feature;
+  d3 n = p1 - p2;
+  double nn = sqrt(dot(n, n));
+  d3 n1 = nn > 0.0 ? n * (1.0 / nn) : n;
+  // back to body 1's frame: mTran2To1 = T1^-1 % T2
+  d3 p1a = xf_apply_inv(XA, xf_apply(XB, p1));
+  d3 n1a = xf_rot_t(XA, xf_rot(XB, n1));
+  r.c[0] = p1a.x; r.c[1] = p1a.y; r.c[2] = p1a.z;
+  r.c[3] = p2.x; r.c[4] = p2.y; r.c[5] = p2.z;
+  r.c[6] = n1a.x; r.c[7] = n1a.y; r.c[8] = n1a.z;
+  r.c[9] = -n1.x; r.c[10] = -n1.y; r.c[11] = -n1.z;
+  d3 mixed = p1a - p2;
+  r.c[12] = dot(mixed, mixed);
+  p.out[slot] = r;
+}
+
+// all contacts of one triangle pair (a* already in B's frame)
+__device__ __noinline__ void tri_pair_contacts(const ContactParams &p, int w, int ta, int tb, d3 a1, d3 a2, d3 a3,
+                                               d3 b1, d3 b2, d3 b3, double thr2, const double *XA, const double *XB) {
+  if (tri_tri_intersect_exact(a1, a2, a3, b1, b2, b3)) return;      // "Collision found when looking for contacts"
+  d3 av[3] = {a1, a2, a3}, bv[3] = {b1, b2, b3};
+  // vertices of triangle 2 against face 1
+  for (int k = 0; k < 3; k++) {
+    d3 q = closest_pt_triangle<double>(a1, a2, a3, bv[k]);
+    d3 d = bv[k] - q;
+    if (dot(d, d) < thr2) emit_contact(p, w, ta, tb, k, q, bv[k], XA, XB);
+  }
+  // vertices of triangle 1 against face 2, unless the foot is a vertex of triangle 2 (already reported)
+  for (int k = 0; k < 3; k++) {
+    int region = 6;
+    d3 q = closest_pt_triangle<double>(b1, b2, b3, av[k], &region);
+    d3 d = q - av[k];
+    if (dot(d, d) < thr2 && region > 2) emit_contact(p, w, ta, tb, 3 + k, av[k], q, XA, XB);
+  }
+  // nine edge-edge pairs, unless a foot is an endpoint
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      d3 c1, c2;
+      double s, t;
+      double dd = seg_seg_dist2<double>(av[i], av[(i + 1) % 3], bv[j], bv[(j + 1) % 3], c1, c2, &s, &t);
+      if (dd < thr2 && s != 0.0 && s != 1.0 && t != 0.0 && t != 1.0) emit_contact(p, w, ta, tb, 6 + 3 * i + j, c1, c2, XA, XB);
+    }
+}
+
+constexpr int CSTACK_CAP = 448, CSTACK_PHYS = 512, CLEAF_CAP = 96;
+constexpr int CONTACT_WARP_SMEM = CSTACK_PHYS * 8 + CLEAF_CAP * 8 + 2 * 96 + 96 + 32;
+
+// same PairXf construction as the evaluation kernel (kept local to this translation unit)
+__device__ __forceinline__ void c_make_pair_xf(const double *XA, const double *XB, float extA, float extB, PairXf &o) {
+  double r[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) r[3 * i + j] = XA[0 + i] * XB[0 + j] + XA[3 + i] * XB[3 + j] + XA[6 + i] * XB[6 + j];
+  d3 dt = mk<double>(XB[9] - XA[9], XB[10] - XA[10], XB[11] - XA[11]);
+  d3 t = xf_rot_t(XA, dt);
+#pragma unroll
+  for (int i = 0; i < 9; i++) { o.r[i] = (float)r[i]; o.ar[i] = fabsf((float)r[i]) + 1.0e-6f; }
+  o.t[0] = (float)t.x; o.t[1] = (float)t.y; o.t[2] = (float)t.z;
+  o.eps = 1.0e-6f * (fabsf(o.t[0]) + fabsf(o.t[1]) + fabsf(o.t[2]) + extA + extB) + 1.0e-5f;
+  o.pad[0] = o.pad[1] = 0.f;
+}
+
+__global__ void __launch_bounds__(256) contact_kernel(ContactParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned char *base = smem_raw + (size_t)warp * CONTACT_WARP_SMEM;
+  unsigned long long *stack = reinterpret_cast<unsigned long long *>(base);
+  unsigned long long *leafq = stack + CSTACK_PHYS;
+  double *XA = reinterpret_cast<double *>(leafq + CLEAF_CAP);
+  double *XB = XA + 12;
+  PairXf *xp = reinterpret_cast<PairXf *>(XB + 12);
+  const int total = p.npose * p.nq;
+  const float thr = (float)p.threshold;
+  // fp32 box bound with head-room so that the fp64 leaf test, not the culling, decides
+  const float bound2 = (thr * 1.0001f + 1.0e-5f) * (thr * 1.0001f + 1.0e-5f);
+  const double thr2 = p.threshold * p.threshold;
+
+  while (true) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(p.work_counter, 1);
+    w = __shfl_sync(FULL, w, 0);
+    if (w >= total) break;
+    int pose = w / p.nq, qi = w - pose * p.nq;
+    int2 ab = __ldg(&p.queries[qi]);
+    const MeshDev &ma = p.meshes[__ldg(&p.body_mesh[ab.x])];
+    const MeshDev &mb = p.meshes[__ldg(&p.body_mesh[ab.y])];
+    {
+      const double *sa = c_body_xf(p.fk, p.static_xf, p.nrb, pose, ab.x);
+      const double *sb = c_body_xf(p.fk, p.static_xf, p.nrb, pose, ab.y);
+      if (lane < 12) XA[lane] = sa[lane];
+      else if (lane < 24) XB[lane - 12] = sb[lane - 12];
+    }
+    __syncwarp();
+    if (lane == 0) { PairXf x; c_make_pair_xf(XA, XB, ma.extent, mb.extent, x); *xp = x; }
+    __syncwarp();
+    const PairXf x = *xp;
+    int sp = 1, lq = 0;
+    if (lane == 0) stack[0] = 0ull;     // (nodeA = 0, nodeB = 0)
+    __syncwarp();
+    while (true) {
+      if (lq >= 32 || (sp == 0 && lq > 0)) {
+        int n = lq < 32 ? lq : 32;
+        if (lane < n) {
+          unsigned long long e = leafq[lq - n + lane];
+          int ta = (int)((e >> 24) & 0xffffffu), tb = (int)(e & 0xffffffu);
+          d3 a1 = xf_apply_inv(XB, xf_apply(XA, c_tri_vertex(ma.tris, ta, 0)));
+          d3 a2 = xf_apply_inv(XB, xf_apply(XA, c_tri_vertex(ma.tris, ta, 1)));
+          d3 a3 = xf_apply_inv(XB, xf_apply(XA, c_tri_vertex(ma.tris, ta, 2)));
+          d3 b1 = c_tri_vertex(mb.tris, tb, 0), b2 = c_tri_vertex(mb.tris, tb, 1), b3 = c_tri_vertex(mb.tris, tb, 2);
+          tri_pair_contacts(p, w, ta, tb, a1, a2, a3, b1, b2, b3, thr2, XA, XB);
+        }
+        lq -= n;
+        __syncwarp();
+        continue;
+      }
+      if (sp == 0) break;
+      int room = CSTACK_CAP - sp;
+      int k = sp < 32 ? sp : 32;
+      if (k > room) k = room > 1 ? room : 1;
+      bool have = lane < k;
+      unsigned long long e = have ? stack[sp - 1 - lane] : 0ull;
+      sp -= k;
+      __syncwarp();
+      bool p0 = false, p1 = false, l0 = false, l1 = false;
+      unsigned long long c0 = 0ull, c1 = 0ull;
+      if (have) {
+        int na = (int)((e >> 24) & 0xffffffu), nb = (int)(e & 0xffffffu);
+        Node a = c_load_node(ma.nodes, na), b = c_load_node(mb.nodes, nb);
+        bool la = a.child < 0, lb = b.child < 0;
+        if (la && lb) {
+          p0 = l0 = a.tri >= 0 && b.tri >= 0;
+          c0 = ((unsigned long long)(unsigned)a.tri << 24) | (unsigned)b.tri;
+        } else {
+          bool splitA = lb || (!la && (a.hx * a.hy * a.hz > b.hx * b.hy * b.hz));
+          float ca[3], ha[3], cb[3], hb[3];
+          if (splitA) {
+            Node a0 = c_load_node(ma.nodes, a.child), a1 = c_load_node(ma.nodes, a.child + 1);
+            c_node_ch(b, cb, hb);
+            c_node_ch(a0, ca, ha); p0 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
+            c_node_ch(a1, ca, ha); p1 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
+            l0 = p0 && lb && a0.child < 0; l1 = p1 && lb && a1.child < 0;
+            c0 = l0 ? (((unsigned long long)(unsigned)a0.tri << 24) | (unsigned)b.tri) : (((unsigned long long)(unsigned)a.child << 24) | (unsigned)nb);
+            c1 = l1 ? (((unsigned long long)(unsigned)a1.tri << 24) | (unsigned)b.tri) : (((unsigned long long)(unsigned)(a.child + 1) << 24) | (unsigned)nb);
+          } else {
+            Node b0 = c_load_node(mb.nodes, b.child), b1 = c_load_node(mb.nodes, b.child + 1);
+            c_node_ch(a, ca, ha);
+            c_node_ch(b0, cb, hb); p0 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
+            c_node_ch(b1, cb, hb); p1 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
+            l0 = p0 && la && b0.child < 0; l1 = p1 && la && b1.child < 0;
+            c0 = l0 ? (((unsigned long long)(unsigned)a.tri << 24) | (unsigned)b0.tri) : (((unsigned long long)(unsigned)na << 24) | (unsigned)b.child);
+            c1 = l1 ? (((unsigned long long)(unsigned)a.tri << 24) | (unsigned)b1.tri) : (((unsigned long long)(unsigned)na << 24) | (unsigned)(b.child + 1));
+          }
+        }
+      }
+      unsigned s0 = __ballot_sync(FULL, p0 && !l0), s1 = __ballot_sync(FULL, p1 && !l1);
+      unsigned q0 = __ballot_sync(FULL, p0 && l0), q1 = __ballot_sync(FULL, p1 && l1);
+      if (p0 && !l0) stack[sp + __popc(s0 & lt_mask)] = c0;
+      if (p1 && !l1) stack[sp + __popc(s0) + __popc(s1 & lt_mask)] = c1;
+      sp += __popc(s0) + __popc(s1);
+      if (p0 && l0) leafq[lq + __popc(q0 & lt_mask)] = c0;
+      if (p1 && l1) leafq[lq + __popc(q0) + __popc(q1 & lt_mask)] = c1;
+      lq += __popc(q0) + __popc(q1);
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void region_kernel(RegionParams p) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.mesh.ntri) return;
+  d3 a = c_tri_vertex(p.mesh.tris, t, 0), b = c_tri_vertex(p.mesh.tris, t, 1), c = c_tri_vertex(p.mesh.tris, t, 2);
+  d3 n = cross(b - a, c - a);
+  double nn = sqrt(dot(n, n));
+  if (nn > 0.0) n = n * (1.0 / nn);
+  d3 cn = mk<double>(p.normal[0], p.normal[1], p.normal[2]);
+  d3 ref = mk<double>(p.point[0], p.point[1], p.point[2]);
+  unsigned char flag = 0;
+  if (!(dot(n, cn) > 0.0)) {        // contact normals point inwards (collisionAlgorithms_inl.h:264-266)
+    d3 q = closest_pt_triangle<double>(a, b, c, ref);
+    d3 d = q - ref;
+    if (!(dot(d, d) > p.radius * p.radius)) flag = 1;
+  }
+  p.flags[t] = flag;
+}
+
+cudaError_t launch_contacts(const ContactParams &p, int blocks, cudaStream_t s) {
+  static bool configured = false;
+  size_t smem = (size_t)8 * CONTACT_WARP_SMEM;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  contact_kernel<<<blocks, 256, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_region(const RegionParams &p, cudaStream_t s) {
+  if (p.mesh.ntri <= 0) return cudaSuccess;
+  region_kernel<<<(p.mesh.ntri + 255) / 256, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+} // namespace b2c
