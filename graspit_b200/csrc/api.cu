@@ -38,6 +38,7 @@ struct BodyHost {
   bool alive = false;
   int mesh = -1;
   bool active = true;
+  int thread = 0;                 // CollisionModel::getThreadId (collisionModel.h): 0 = master thread
   Qt tf;
 };
 
@@ -100,6 +101,7 @@ struct b2c_ctx {
   std::vector<MeshHost> meshes;
   std::vector<BodyHost> bodies;
   std::set<std::pair<int, int>> disabled;
+  int query_thread = 0;            // CollisionInterface::getThreadId of the caller (b2c_set_thread)
   std::vector<RobotHost> robots;
   bool meshes_dirty = true;
   DevBuf<MeshDev> d_meshes;
@@ -166,9 +168,17 @@ int sync_meshes(b2c_ctx *ctx) {
   return B2C_OK;
 }
 
+// thread rule of getActivePairs (graspitCollision.cpp:64,77-78): a body takes part when it belongs to the
+// querying thread or to the master thread (0); a non-master thread never tests two master bodies
+bool thread_visible(const b2c_ctx *c, int a) { return c->bodies[a].thread == c->query_thread || c->bodies[a].thread == 0; }
+bool thread_pair_ok(const b2c_ctx *c, int a, int b) {
+  if (!thread_visible(c, a) || !thread_visible(c, b)) return false;
+  return !(c->query_thread != 0 && c->bodies[a].thread == 0 && c->bodies[b].thread == 0);
+}
+
 bool pair_active(const b2c_ctx *c, int a, int b) {
   if (a == b) return false;
-  if (!c->bodies[a].active || !c->bodies[b].active) return false;
+  if (!c->bodies[a].active || !c->bodies[b].active) return false;   // isActive() ignores threads (graspitCollision.cpp:158-198)
   return c->disabled.find({std::min(a, b), std::max(a, b)}) == c->disabled.end();
 }
 
@@ -184,6 +194,7 @@ void active_pairs(const b2c_ctx *c, const std::set<int> *interest, std::vector<s
     for (int b = a + 1; b < n; b++) {
       if (!c->bodies[b].alive || !c->bodies[b].active) continue;
       if (!ia && !interest->count(b)) continue;
+      if (!thread_pair_ok(c, a, b)) continue;
       if (c->disabled.count({a, b})) continue;
       out.push_back({a, b});
     }
@@ -487,6 +498,19 @@ int b2c_body_set_active(b2c_ctx *ctx, int body_id, int active) {
   if (!ctx || !body_ok(ctx, body_id)) return fail(ctx, B2C_EINVAL, "set_active: unknown body %d", body_id);
   ctx->bodies[body_id].active = active != 0;
   invalidate_plans(ctx);
+  return B2C_OK;
+}
+
+/* CollisionInterface::newThread / getThreadId (collisionInterface.h:181-184) and CollisionModel's thread id */
+int b2c_body_set_thread(b2c_ctx *ctx, int body_id, int thread_id) {
+  if (!ctx || !body_ok(ctx, body_id) || thread_id < 0) return fail(ctx, B2C_EINVAL, "body_set_thread: unknown body %d", body_id);
+  ctx->bodies[body_id].thread = thread_id;
+  invalidate_plans(ctx);
+  return B2C_OK;
+}
+int b2c_set_thread(b2c_ctx *ctx, int thread_id) {
+  if (!ctx || thread_id < 0) return fail(ctx, B2C_EINVAL, "set_thread: bad thread id");
+  if (ctx->query_thread != thread_id) { ctx->query_thread = thread_id; invalidate_plans(ctx); }
   return B2C_OK;
 }
 

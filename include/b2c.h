@@ -75,6 +75,13 @@ int b2c_body_set_active(b2c_ctx *ctx, int body_id, int active);
 int b2c_pair_set_active(b2c_ctx *ctx, int a, int b, int active);
 int b2c_pair_is_active(b2c_ctx *ctx, int a, int b, int *active);
 
+/* Thread rule of getActivePairs (graspitCollision.cpp:60-78; CollisionInterface::newThread / getThreadId,
+ * collisionInterface.h:181-184): every body carries the id of the thread that added it (0 = master); a query
+ * issued for thread T only pairs bodies of thread T or 0, and for T != 0 never two thread-0 bodies.
+ * b2c_set_thread selects T for the queries that follow (default 0). */
+int b2c_body_set_thread(b2c_ctx *ctx, int body_id, int thread_id);
+int b2c_set_thread(b2c_ctx *ctx, int thread_id);
+
 /* ---- single-pose queries at the bodies' current transforms -------------------------------- */
 
 /* allCollisions (collisionInterface.h:141, graspitCollision.cpp:332-363).  interest == NULL means
