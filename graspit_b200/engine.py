@@ -28,7 +28,7 @@ EXPORTS = [
     "b2c_set_stream", "b2c_set_profiling", "b2c_last_kernel_ms",
     "b2c_mesh_create", "b2c_mesh_destroy", "b2c_body_create", "b2c_body_set_mesh", "b2c_body_remove",
     "b2c_body_set_transform", "b2c_body_get_transform", "b2c_body_set_active", "b2c_pair_set_active",
-    "b2c_pair_is_active", "b2c_all_collisions", "b2c_body_distance", "b2c_point_distance", "b2c_contacts",
+    "b2c_pair_is_active", "b2c_body_set_thread", "b2c_set_thread", "b2c_all_collisions", "b2c_body_distance", "b2c_point_distance", "b2c_contacts",
     "b2c_all_contacts", "b2c_region", "b2c_bounding_volumes", "b2c_robot_define", "b2c_eval_batch",
     "b2c_robot_bodies", "b2c_robot_pairs", "b2c_last_stats", "b2c_obb_hierarchy", "b2c_contacts_postprocess",
 ]
@@ -115,6 +115,8 @@ def load_library():
     L.b2c_body_set_active.argtypes = [vp, ci, ci]
     L.b2c_pair_set_active.argtypes = [vp, ci, ci, ci]
     L.b2c_pair_is_active.argtypes = [vp, ci, ci, ip]
+    L.b2c_body_set_thread.argtypes = [vp, ci, ci]
+    L.b2c_set_thread.argtypes = [vp, ci]
     L.b2c_all_collisions.argtypes = [vp, ci, ip, ci, ip, ci, ip]
     L.b2c_body_distance.argtypes = [vp, ci, ci, dp, dp, dp, dp, dp]
     L.b2c_point_distance.argtypes = [vp, ci, dp, dp, dp, dp]
@@ -281,6 +283,14 @@ class Engine:
 
     def activate_pair(self, a: int, b: int, active: bool):
         self._ck(self.L.b2c_pair_set_active(self.h, a, b, int(bool(active))))
+
+    def set_body_thread(self, body: int, thread_id: int):
+        """thread that owns the body (CollisionModel thread id; 0 = master)"""
+        self._ck(self.L.b2c_body_set_thread(self.h, body, thread_id))
+
+    def set_thread(self, thread_id: int):
+        """thread on whose behalf the following queries run (CollisionInterface::getThreadId)"""
+        self._ck(self.L.b2c_set_thread(self.h, thread_id))
 
     def is_active(self, a: int, b: int = -1) -> bool:
         out = C.c_int(0)
