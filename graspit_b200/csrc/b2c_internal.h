@@ -237,7 +237,7 @@ cudaError_t launch_region(const RegionParams &p, cudaStream_t s);
 
 constexpr int DSTACK_CAP = 448, DSTACK_PHYS = 512, DLEAF_CAP = 96;
 constexpr int DNEAR_CAP = 64;
-constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 2 * 96 + 96 + DNEAR_CAP * 8 + 32;
+constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 3 * 96 + 96 + DNEAR_CAP * 8 + 32;
 
 // launchers (kernels.cu)
 cudaError_t launch_fk(const FkParams &p, cudaStream_t s);

@@ -403,4 +403,104 @@ __host__ __device__ __forceinline__ T tri_tri_dist2(V3<T> a1, V3<T> a2, V3<T> a3
   return dmin;
 }
 
+// ------------------------------------------------------------------------------------------
+// Compact form of the same minimum for the traversal hot path.  The minimum distance of two disjoint
+// triangles is attained either between two edges or between a vertex and the INTERIOR of the other
+// face; a vertex whose foot falls outside the face is covered by the edges that end in it.  So the
+// six vertex-face candidates reduce to a plane projection + an inside test, and all fifteen
+// candidates run as rolled loops over rotated vertex registers (small code: the unrolled form above
+// is ~60 KB of SASS once inlined in a traversal kernel and stalls on instruction fetch).
+// Same candidate order as triangleTriangleDistanceSq (triangle_inl.h:406-518), strict < on ties.
+// The reference treats an edge whose SQUARED length is <= 1e-3 as a point (triangle_inl.h:213,223), and
+// then relies on its full vertex-face tests to cover what that edge would have found; when such an edge
+// is met `degenerate` is set and the caller must use tri_tri_dist2 (the plain form) for that pair.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ float fast_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+__host__ __device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
+
+template <typename T>
+__host__ __device__ __forceinline__ T seg_seg_dist2_fast(V3<T> p1, V3<T> q1, V3<T> p2, V3<T> q2, V3<T> &c1, V3<T> &c2,
+                                                         bool &degenerate) {
+  const T EPS = T(1.0e-3);
+  V3<T> d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+  T a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), c = dot(d1, r), b = dot(d1, d2);
+  T s = T(0), t = T(0);
+  const bool da = a <= EPS, de = e <= EPS;      // degenerate segments (EPSILON on the squared length)
+  degenerate = degenerate || da || de;
+  if (!(da && de)) {
+    if (da) {
+      t = clamp01(fast_div(f, e));
+    } else if (de) {
+      s = clamp01(fast_div(-c, a));
+    } else {
+      T denom = a * e - b * b;
+      if (denom != T(0)) s = clamp01(fast_div(b * f - c * e, denom));
+      T tn = b * s + f;
+      if (tn < T(0)) { t = T(0); s = clamp01(fast_div(-c, a)); }
+      else if (tn > e) { t = T(1); s = clamp01(fast_div(b - c, a)); }
+      else t = fast_div(tn, e);
+    }
+  }
+  c1 = p1 + d1 * s;
+  c2 = p2 + d2 * t;
+  V3<T> d = c1 - c2;
+  return dot(d, d);
+}
+
+template <typename T>
+__host__ __device__ __forceinline__ T tri_tri_dist2_compact(V3<T> a0, V3<T> a1, V3<T> a2, V3<T> b0, V3<T> b1, V3<T> b2,
+                                                            V3<T> &pa, V3<T> &pb, bool &degenerate) {
+  T dmin = T(3.0e38);
+  degenerate = false;
+  pa = a0; pb = b0;
+  // vertex-face: side 0 = vertices of b against face a, side 1 = vertices of a against face b
+#pragma unroll 1
+  for (int side = 0; side < 2; side++) {
+    V3<T> ab = a1 - a0, ac = a2 - a0;
+    V3<T> n = cross(ab, ac);
+    T nn = dot(n, n);
+    if (nn > T(0)) {
+      T inv = fast_div(T(1), nn);
+#pragma unroll 1
+      for (int k = 0; k < 3; k++) {
+        V3<T> ap = b0 - a0;
+        T w2 = dot(cross(ab, ap), n);       // nn * barycentric weight of a2
+        T w1 = dot(cross(ap, ac), n);       // nn * barycentric weight of a1
+        if (w1 >= T(0) && w2 >= T(0) && w1 + w2 <= nn) {
+          T dn = dot(ap, n);
+          T d = dn * dn * inv;
+          if (d < dmin) {
+            dmin = d;
+            V3<T> foot = b0 - n * (dn * inv);
+            if (side == 0) { pa = foot; pb = b0; } else { pa = b0; pb = foot; }
+          }
+        }
+        V3<T> tmp = b0; b0 = b1; b1 = b2; b2 = tmp;
+      }
+    }
+    V3<T> t0 = a0, t1 = a1, t2 = a2;
+    a0 = b0; a1 = b1; a2 = b2; b0 = t0; b1 = t1; b2 = t2;
+  }
+  // edge-edge: (a0a1, a1a2, a2a0) x (b0b1, b1b2, b2b0)
+#pragma unroll 1
+  for (int i = 0; i < 3; i++) {
+#pragma unroll 1
+    for (int j = 0; j < 3; j++) {
+      V3<T> x, y;
+      T d = seg_seg_dist2_fast(a0, a1, b0, b1, x, y, degenerate);
+      if (d < dmin) { dmin = d; pa = x; pb = y; }
+      V3<T> tmp = b0; b0 = b1; b1 = b2; b2 = tmp;
+    }
+    V3<T> tmp = a0; a0 = a1; a1 = a2; a2 = tmp;
+  }
+  return dmin;
+}
+
+
 } // namespace b2c

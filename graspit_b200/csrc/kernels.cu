@@ -137,6 +137,17 @@ __device__ __noinline__ double tri_tri_dist2_d(d3 a1, d3 a2, d3 a3, d3 b1, d3 b2
   return d;
 }
 
+// rare paths of the distance leaf test, kept out of line so the traversal loop stays small in the i-cache
+__device__ __noinline__ int tri_tri_filter_call(f3 p2, f3 p3, f3 e1, f3 e2, f3 q1, f3 q2, f3 q3, f3 f1, f3 f2) {
+  return tri_tri_filter(p2, p3, e1, e2, q1, q2, q3, f1, f2);
+}
+__device__ __noinline__ float tri_tri_dist2_plain(f3 p2, f3 p3, f3 q1, f3 q2, f3 q3, f3 *pa, f3 *pb) {
+  f3 x, y;
+  float d = tri_tri_dist2<float>(mk<float>(0.f, 0.f, 0.f), p2, p3, q1, q2, q3, x, y);
+  *pa = x; *pb = y;
+  return d;
+}
+
 // node fetch: the first `ntop` nodes (top levels, breadth-first prefix) may live in shared memory
 __device__ __forceinline__ Node fetch_node(const Node *nodes, const Node *top, int ntop, int i) {
   if (i < ntop) {
@@ -561,7 +572,8 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
   unsigned long long *leafq = stack + DSTACK_PHYS;
   double *XA = reinterpret_cast<double *>(leafq + DLEAF_CAP);
   double *XB = XA + 12;
-  PairXf *xp = reinterpret_cast<PairXf *>(XB + 12);
+  double *XR = XB + 12;                      // B <- A, fp64: R = Rb^T Ra (row-major), t = Rb^T (ta - tb)
+  PairXf *xp = reinterpret_cast<PairXf *>(XR + 12);
   int2 *nearq = reinterpret_cast<int2 *>(xp + 1);
   unsigned n_box = 0, n_tri = 0;
   const int total = p.npose * p.nq;
@@ -587,10 +599,18 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
     }
     __syncwarp();
     if (lane == 0) { PairXf x; make_pair_xf(XA, XB, ma.extent, mb.extent, x); *xp = x; }
+    else if (lane >= 8 && lane < 17) {
+      int i = (lane - 8) / 3, j = (lane - 8) % 3;
+      XR[3 * i + j] = XB[i] * XA[j] + XB[3 + i] * XA[3 + j] + XB[6 + i] * XA[6 + j];
+    } else if (lane >= 20 && lane < 23) {
+      int i = lane - 20;
+      XR[9 + i] = XB[i] * (XA[9] - XB[9]) + XB[3 + i] * (XA[10] - XB[10]) + XB[6 + i] * (XA[11] - XB[11]);
+    }
     __syncwarp();
     const PairXf x = *xp;
 
     float best = 3.0e38f;          // squared distance, warp-uniform
+    bool seeded = false;           // false until the first leaf batch: greedy nearest-child descent for a first bound
     d3 bpa = mk<double>(0, 0, 0), bpb = mk<double>(0, 0, 0);   // valid on every lane after each leaf batch
     bool hit = false;
     int sp = 0, lq = 0, nnear = 0;
@@ -599,7 +619,8 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
     __syncwarp();
 
     while (true) {
-      if (lq >= 32 || (sp == 0 && lq > 0)) {
+      if (lq >= 32 || (lq > 0 && (sp == 0 || !seeded))) {
+        seeded = true;
         int n = lq < 32 ? lq : 32;
         float d2 = 3.0e38f;
         int res = TT_SEP;
@@ -614,16 +635,18 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
             n_tri++;
             d3 a1 = tri_vertex(ma.tris, ta, 0), a2 = tri_vertex(ma.tris, ta, 1), a3 = tri_vertex(ma.tris, ta, 2);
             d3 b1 = tri_vertex(mb.tris, tb, 0), b2 = tri_vertex(mb.tris, tb, 1), b3 = tri_vertex(mb.tris, tb, 2);
-            P1 = xf_apply_inv(XB, xf_apply(XA, a1));
-            d3 E1 = xf_rot_t(XB, xf_rot(XA, a2 - a1));
-            d3 E2 = xf_rot_t(XB, xf_rot(XA, a3 - a2));
+            P1 = xf_apply(XR, a1);
+            d3 E1 = xf_rot(XR, a2 - a1);
+            d3 E2 = xf_rot(XR, a3 - a2);
             f3 e1 = tof(E1), e2 = tof(E2);
             f3 p2 = e1, p3 = tof(E1 + E2);
             f3 q1 = tof(b1 - P1), q2 = tof(b2 - P1), q3 = tof(b3 - P1);
             // boxes that are certainly apart cannot hold intersecting triangles: skip the SAT
-            res = entry_lb(e) > 0.f ? TT_SEP : tri_tri_filter(p2, p3, e1, e2, q1, q2, q3, tof(b2 - b1), tof(b3 - b2));
+            res = entry_lb(e) > 0.f ? TT_SEP : tri_tri_filter_call(p2, p3, e1, e2, q1, q2, q3, tof(b2 - b1), tof(b3 - b2));
             if (res != TT_HIT) {
-              d2 = tri_tri_dist2<float>(mk<float>(0, 0, 0), p2, p3, q1, q2, q3, pa, pb);
+              bool degenerate;
+              d2 = tri_tri_dist2_compact<float>(mk<float>(0, 0, 0), p2, p3, q1, q2, q3, pa, pb, degenerate);
+              if (degenerate) d2 = tri_tri_dist2_plain(p2, p3, q1, q2, q3, &pa, &pb);
               // distance small against the triangles' extent: fp32 has lost relative accuracy; remember the
               // pair (if it is within rounding of the best so far) for the fp64 pass after the traversal
               float sc = fmaxf(fmaxf(fmaxf(fabsf(p2.x), fabsf(p2.y)), fmaxf(fabsf(p2.z), fabsf(p3.x))), fmaxf(fabsf(p3.y), fabsf(p3.z)));
@@ -665,6 +688,7 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
       int room = DSTACK_CAP - sp;
       int k = sp < 32 ? sp : 32;
       if (k > room) k = room > 1 ? room : 1;
+      if (!seeded) k = 1;          // greedy descent: only the nearest open entry, until a first distance is known
       bool have = lane < k;
       unsigned long long e = have ? stack[sp - 1 - lane] : 0ull;
       sp -= k;
@@ -679,27 +703,26 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
           pn = ln = true;
           cn = pack_dist_entry(entry_lb(e), a.tri, b.tri);
         } else {
-          bool splitA = lb || (!la && (a.hx * a.hy * a.hz > b.hx * b.hy * b.hz));
-          float ca[3], ha[3], cb[3], hb[3];
-          float d0, d1;
-          int i0a, i0b, i1a, i1b;
-          bool lf0, lf1;
-          if (splitA) {
-            Node a0 = load_node(ma.nodes, a.child), a1 = load_node(ma.nodes, a.child + 1);
-            node_ch(b, cb, hb);
-            node_ch(a0, ca, ha); d0 = box_dist_lb(ca, ha, cb, hb, x);
-            node_ch(a1, ca, ha); d1 = box_dist_lb(ca, ha, cb, hb, x);
-            lf0 = lb && a0.child < 0; lf1 = lb && a1.child < 0;
-            i0a = lf0 ? a0.tri : a.child; i0b = lf0 ? b.tri : nb;
-            i1a = lf1 ? a1.tri : a.child + 1; i1b = lf1 ? b.tri : nb;
-          } else {
-            Node b0 = load_node(mb.nodes, b.child), b1 = load_node(mb.nodes, b.child + 1);
-            node_ch(a, ca, ha);
-            node_ch(b0, cb, hb); d0 = box_dist_lb(ca, ha, cb, hb, x);
-            node_ch(b1, cb, hb); d1 = box_dist_lb(ca, ha, cb, hb, x);
-            lf0 = la && b0.child < 0; lf1 = la && b1.child < 0;
-            i0a = lf0 ? a.tri : na; i0b = lf0 ? b0.tri : b.child;
-            i1a = lf1 ? a.tri : na; i1b = lf1 ? b1.tri : b.child + 1;
+          const bool splitA = lb || (!la && (a.hx * a.hy * a.hz > b.hx * b.hy * b.hz));
+          // the two children of the split node against the other node: ONE copy of the box test in the loop body
+          const Node *cnodes = splitA ? ma.nodes : mb.nodes;
+          const int cbase = splitA ? a.child : b.child;
+          const Node other = splitA ? b : a;
+          const bool oleaf = splitA ? lb : la;
+          float d0 = 0.f, d1 = 0.f;
+          int i0a = 0, i0b = 0, i1a = 0, i1b = 0;
+          bool lf0 = false, lf1 = false;
+#pragma unroll 1
+          for (int c = 0; c < 2; c++) {
+            Node ch = load_node(cnodes, cbase + c);
+            float ca[3], ha[3], cb[3], hb[3];
+            if (splitA) { node_ch(ch, ca, ha); node_ch(other, cb, hb); } else { node_ch(other, ca, ha); node_ch(ch, cb, hb); }
+            float dc = box_dist_lb(ca, ha, cb, hb, x);
+            bool lfl = oleaf && ch.child < 0;
+            int mine = lfl ? ch.tri : cbase + c;
+            int theirs = lfl ? other.tri : (splitA ? nb : na);
+            int xa = splitA ? mine : theirs, xb = splitA ? theirs : mine;
+            if (c == 0) { d0 = dc; i0a = xa; i0b = xb; lf0 = lfl; } else { d1 = dc; i1a = xa; i1b = xb; lf1 = lfl; }
           }
           n_box += 2;
           bool swap = d1 < d0;
