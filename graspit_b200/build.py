@@ -28,10 +28,12 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """defines/out: tuning variants (e.g. defines=("DLEAF_TRIGGER=16",), out=".../libb2c_t16.so") for A/B runs;
+    the product build takes neither."""
+    if out is None and not force and not needs_build():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if out is None else "build_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     env = dict(os.environ)
     # the image exports CXX=/opt/gcc/bin/g++ whose static libstdc++ misbehaves in dlopen()ed libraries
@@ -39,16 +41,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     for s in SOURCES:
         o = os.path.join(objdir, os.path.splitext(s)[0] + ".o")
-        cmd = [_nvcc(), "-ccbin", ccbin, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [_nvcc(), "-ccbin", ccbin, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
             print(" ".join(cmd))
         subprocess.check_call(cmd, env=env)
         objs.append(o)
-    cmd = [_nvcc(), "-ccbin", ccbin, "-shared", "-o", LIB, *objs, "-lcudart"]
+    target = out or LIB
+    cmd = [_nvcc(), "-ccbin", ccbin, "-shared", "-o", target, *objs, "-lcudart"]
     subprocess.check_call(cmd, env=env)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

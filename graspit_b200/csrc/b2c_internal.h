@@ -236,8 +236,8 @@ cudaError_t launch_contacts(const ContactParams &p, int blocks, cudaStream_t s);
 cudaError_t launch_region(const RegionParams &p, cudaStream_t s);
 
 constexpr int DSTACK_CAP = 448, DSTACK_PHYS = 512, DLEAF_CAP = 96;
-constexpr int DNEAR_CAP = 64;
-constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 3 * 96 + 96 + DNEAR_CAP * 8 + 32;
+constexpr int DNEAR_CAP = 64, DCONF_CAP = 64;
+constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 3 * 96 + 96 + DNEAR_CAP * 8 + DCONF_CAP * 8 + 32;
 
 // launchers (kernels.cu)
 cudaError_t launch_fk(const FkParams &p, cudaStream_t s);

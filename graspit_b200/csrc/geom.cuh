@@ -455,7 +455,10 @@ __host__ __device__ __forceinline__ T seg_seg_dist2_fast(V3<T> p1, V3<T> q1, V3<
 
 template <typename T>
 __host__ __device__ __forceinline__ T tri_tri_dist2_compact(V3<T> a0, V3<T> a1, V3<T> a2, V3<T> b0, V3<T> b1, V3<T> b2,
-                                                            V3<T> &pa, V3<T> &pb, bool &degenerate) {
+                                                            V3<T> &pa, V3<T> &pb, bool &degenerate,
+                                                            T bound = T(3.0e38)) {
+  // `bound`: squared distance the caller already holds; when a triangle lies wholly on one side of the other's
+  // plane, farther than that, no candidate of this pair can matter and the routine returns early (3e38)
   T dmin = T(3.0e38);
   degenerate = false;
   pa = a0; pb = b0;
@@ -467,6 +470,11 @@ __host__ __device__ __forceinline__ T tri_tri_dist2_compact(V3<T> a0, V3<T> a1, 
     T nn = dot(n, n);
     if (nn > T(0)) {
       T inv = fast_div(T(1), nn);
+      {
+        T s0 = dot(b0 - a0, n), s1 = dot(b1 - a0, n), s2 = dot(b2 - a0, n);
+        bool pos = s0 > T(0) && s1 > T(0) && s2 > T(0), neg = s0 < T(0) && s1 < T(0) && s2 < T(0);
+        if ((pos || neg) && fmin(s0 * s0, fmin(s1 * s1, s2 * s2)) * inv > bound) return T(3.0e38);
+      }
 #pragma unroll 1
       for (int k = 0; k < 3; k++) {
         V3<T> ap = b0 - a0;

@@ -562,6 +562,9 @@ __device__ __forceinline__ unsigned long long pack_dist_entry(float lb, int a, i
 __device__ __forceinline__ float entry_lb(unsigned long long e) { return __uint_as_float(((unsigned)(e >> 48)) << 16); }
 
 
+#ifndef DLEAF_TRIGGER
+#define DLEAF_TRIGGER 32     // leaf pairs queued before a batch of triangle tests runs
+#endif
 __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -575,7 +578,11 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
   double *XR = XB + 12;                      // B <- A, fp64: R = Rb^T Ra (row-major), t = Rb^T (ta - tb)
   PairXf *xp = reinterpret_cast<PairXf *>(XR + 12);
   int2 *nearq = reinterpret_cast<int2 *>(xp + 1);
+  unsigned long long *confq = reinterpret_cast<unsigned long long *>(nearq + DNEAR_CAP);   // [DCONF_CAP] pairs that passed the pre-filter
   unsigned n_box = 0, n_tri = 0;
+#ifdef DIST_DEBUG_STATS
+  unsigned dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0;
+#endif
   const int total = p.npose * p.nq;
 
   while (true) {
@@ -608,20 +615,60 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
     }
     __syncwarp();
     const PairXf x = *xp;
+    // fp32 copy of B <- A for the pre-filter (its rounding is covered by the filter's margin)
+    float rr[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) rr[i] = (float)XR[i];
 
     float best = 3.0e38f;          // squared distance, warp-uniform
     bool seeded = false;           // false until the first leaf batch: greedy nearest-child descent for a first bound
     d3 bpa = mk<double>(0, 0, 0), bpb = mk<double>(0, 0, 0);   // valid on every lane after each leaf batch
+    f3 udir = mk<float>(0.f, 0.f, 0.f);   // unit vector from the best point on A to the best point on B (B's frame)
     bool hit = false;
-    int sp = 0, lq = 0, nnear = 0;
+    int sp = 0, lq = 0, cq = 0, nnear = 0;
     if (lane == 0) stack[0] = pack_dist_entry(0.f, 0, 0);
     sp = 1;
     __syncwarp();
 
     while (true) {
-      if (lq >= 32 || (lq > 0 && (sp == 0 || !seeded))) {
-        seeded = true;
+      if (lq >= DLEAF_TRIGGER || (lq > 0 && (sp == 0 || !seeded))) {
+        // ---- pre-filter: up to 32 queued leaf pairs against the separating direction of the best pair so far.
+        // For any unit u, dist(tA, tB) >= min_k u.b_k - max_k u.a_k; with u taken from the current closest points the
+        // bound is tight exactly where the box bound is loose (far apart, nearly facing surfaces), ~80 instructions
+        // instead of a full triangle-triangle distance.  Survivors move to confq.
         int n = lq < 32 ? lq : 32;
+        bool keep = false;
+        unsigned long long e = 0ull;
+        if (lane < n) {
+          e = leafq[lq - n + lane];
+          keep = entry_lb(e) <= best;
+          if (keep && seeded) {
+            int ta = (int)((e >> 24) & 0xffffffu), tb = (int)(e & 0xffffffu);
+            float amax = -3.0e38f, bmin = 3.0e38f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              float4 va = __ldg(&ma.tris[ta].v[k]), vb = __ldg(&mb.tris[tb].v[k]);
+              float ax = rr[0] * va.x + rr[1] * va.y + rr[2] * va.z + rr[9];
+              float ay = rr[3] * va.x + rr[4] * va.y + rr[5] * va.z + rr[10];
+              float az = rr[6] * va.x + rr[7] * va.y + rr[8] * va.z + rr[11];
+              amax = fmaxf(amax, udir.x * ax + udir.y * ay + udir.z * az);
+              bmin = fminf(bmin, udir.x * vb.x + udir.y * vb.y + udir.z * vb.z);
+            }
+            float g = bmin - amax - 4.0f * x.eps;
+            keep = !(g > 0.f && g * g > best * 1.01f);
+          }
+        }
+        lq -= n;
+        unsigned km = __ballot_sync(FULL, keep);
+        if (keep) confq[cq + __popc(km & lt_mask)] = e;
+        cq += __popc(km);
+        __syncwarp();
+        if (!(cq >= 32 || (cq > 0 && (!seeded || (sp == 0 && lq == 0))))) continue;
+      }
+      if (cq >= 32 || (cq > 0 && (!seeded || (sp == 0 && lq == 0)))) {
+        // ---- full test of up to 32 surviving pairs
+        seeded = true;
+        int n = cq < 32 ? cq : 32;
         float d2 = 3.0e38f;
         int res = TT_SEP;
         int ta = 0, tb = 0;
@@ -629,7 +676,7 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
         f3 pa = mk<float>(0, 0, 0), pb = pa;
         bool tiny = false;
         if (lane < n) {
-          unsigned long long e = leafq[lq - n + lane];
+          unsigned long long e = confq[cq - n + lane];
           ta = (int)((e >> 24) & 0xffffffu); tb = (int)(e & 0xffffffu);
           if (entry_lb(e) <= best) {
             n_tri++;
@@ -645,8 +692,14 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
             res = entry_lb(e) > 0.f ? TT_SEP : tri_tri_filter_call(p2, p3, e1, e2, q1, q2, q3, tof(b2 - b1), tof(b3 - b2));
             if (res != TT_HIT) {
               bool degenerate;
-              d2 = tri_tri_dist2_compact<float>(mk<float>(0, 0, 0), p2, p3, q1, q2, q3, pa, pb, degenerate);
+              d2 = tri_tri_dist2_compact<float>(mk<float>(0, 0, 0), p2, p3, q1, q2, q3, pa, pb, degenerate, best * 1.01f + 1.0e-9f);
               if (degenerate) d2 = tri_tri_dist2_plain(p2, p3, q1, q2, q3, &pa, &pb);
+#ifdef DIST_DEBUG_STATS
+              if (d2 > 2.9e38f) dbg0++;                 // plane-bound early outs
+              else if (d2 < best) dbg1++;               // tests that beat the batch-start best
+              else if (d2 > best * 1.21f) dbg2++;       // tests more than 10% (in distance) beyond best
+              if (sqrtf(best) > 50.f) dbg3++;           // tests done while best > 50 mm
+#endif
               // distance small against the triangles' extent: fp32 has lost relative accuracy; remember the
               // pair (if it is within rounding of the best so far) for the fp64 pass after the traversal
               float sc = fmaxf(fmaxf(fmaxf(fabsf(p2.x), fabsf(p2.y)), fmaxf(fabsf(p2.z), fabsf(p3.x))), fmaxf(fabsf(p3.y), fabsf(p3.z)));
@@ -657,7 +710,7 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
             }
           }
         }
-        lq -= n;
+        cq -= n;
         {
           unsigned tm = __ballot_sync(FULL, tiny);
           if (tiny) { int at = nnear + __popc(tm & lt_mask); if (at < DNEAR_CAP) nearq[at] = make_int2(ta, tb); }
@@ -680,6 +733,9 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
           d3 PB = mk<double>(P1.x + (double)pb.x, P1.y + (double)pb.y, P1.z + (double)pb.z);
           bpa.x = __shfl_sync(FULL, PA.x, src); bpa.y = __shfl_sync(FULL, PA.y, src); bpa.z = __shfl_sync(FULL, PA.z, src);
           bpb.x = __shfl_sync(FULL, PB.x, src); bpb.y = __shfl_sync(FULL, PB.y, src); bpb.z = __shfl_sync(FULL, PB.z, src);
+          float ux = (float)(bpb.x - bpa.x), uy = (float)(bpb.y - bpa.y), uz = (float)(bpb.z - bpa.z);
+          float inv = rsqrtf(fmaxf(ux * ux + uy * uy + uz * uz, 1.0e-30f));
+          udir = mk<float>(ux * inv, uy * inv, uz * inv);
         }
         __syncwarp();
         continue;
@@ -777,6 +833,12 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
     unsigned long long v;
     v = n_box; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_DBOX], v);
     v = n_tri; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_DTRI], v);
+#ifdef DIST_DEBUG_STATS
+    v = dbg0; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_BOX], v);
+    v = dbg1; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_TRI], v);
+    v = dbg2; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_AMBIG], v);
+    v = dbg3; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_HITFIX], v);
+#endif
   }
 }
 

@@ -17,7 +17,8 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2c.so")
+# B2C_LIB selects a tuning variant of the same engine (graspit_b200/build.py --out=...); default = the product build
+LIB_PATH = os.environ.get("B2C_LIB") or os.path.join(_HERE, "libb2c.so")
 
 B2C_INPUT_RAW, B2C_INPUT_AA_EIGEN = 0, 1
 B2C_EVAL_PRESET, B2C_EVAL_LIVE, B2C_EVAL_PAIRMASK, B2C_EVAL_LINKDIST, B2C_EVAL_DEVICE_PTRS = 0, 1, 2, 4, 8
