@@ -624,6 +624,8 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
     bool seeded = false;           // false until the first leaf batch: greedy nearest-child descent for a first bound
     d3 bpa = mk<double>(0, 0, 0), bpb = mk<double>(0, 0, 0);   // valid on every lane after each leaf batch
     f3 udir = mk<float>(0.f, 0.f, 0.f);   // unit vector from the best point on A to the best point on B (B's frame)
+    f3 udirA = udir;                      // the same direction in A's frame, and its product with the A <- B translation
+    float udt = 0.f;
     bool hit = false;
     int sp = 0, lq = 0, cq = 0, nnear = 0;
     if (lane == 0) stack[0] = pack_dist_entry(0.f, 0, 0);
@@ -736,6 +738,9 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
           float ux = (float)(bpb.x - bpa.x), uy = (float)(bpb.y - bpa.y), uz = (float)(bpb.z - bpa.z);
           float inv = rsqrtf(fmaxf(ux * ux + uy * uy + uz * uz, 1.0e-30f));
           udir = mk<float>(ux * inv, uy * inv, uz * inv);
+          udirA = mk<float>(x.r[0] * udir.x + x.r[1] * udir.y + x.r[2] * udir.z, x.r[3] * udir.x + x.r[4] * udir.y + x.r[5] * udir.z,
+                            x.r[6] * udir.x + x.r[7] * udir.y + x.r[8] * udir.z);
+          udt = udirA.x * x.t[0] + udirA.y * x.t[1] + udirA.z * x.t[2];
         }
         __syncwarp();
         continue;
@@ -774,6 +779,14 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
             float ca[3], ha[3], cb[3], hb[3];
             if (splitA) { node_ch(ch, ca, ha); node_ch(other, cb, hb); } else { node_ch(other, ca, ha); node_ch(ch, cb, hb); }
             float dc = box_dist_lb(ca, ha, cb, hb, x);
+            {
+              // gap of the two boxes along the separating direction of the best pair so far (zero vector until seeded):
+              // tight where the face-axis bound is loose (distant, nearly facing surfaces)
+              float g = (udir.x * cb[0] + udir.y * cb[1] + udir.z * cb[2] + udt) - (fabsf(udir.x) * hb[0] + fabsf(udir.y) * hb[1] + fabsf(udir.z) * hb[2])
+                      - (udirA.x * ca[0] + udirA.y * ca[1] + udirA.z * ca[2]) - (fabsf(udirA.x) * ha[0] + fabsf(udirA.y) * ha[1] + fabsf(udirA.z) * ha[2])
+                      - 4.0f * x.eps;
+              if (g > 0.f) dc = fmaxf(dc, g * g);
+            }
             bool lfl = oleaf && ch.child < 0;
             int mine = lfl ? ch.tri : cbase + c;
             int theirs = lfl ? other.tri : (splitA ? nb : na);
