@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
     f3 udirA = udir;                      // the same direction in A's frame, and its product with the A <- B translation
     float udt = 0.f;
     bool hit = false;
+    bool best_tiny = false;        // the current best came from a pair flagged for fp64 refinement
     int sp = 0, lq = 0, cq = 0, nnear = 0;
     if (lane == 0) stack[0] = pack_dist_entry(0.f, 0, 0);
     sp = 1;
@@ -730,6 +731,7 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
           unsigned who = __ballot_sync(FULL, d2 == m);
           int src = __ffs(who) - 1;
           best = m;
+          best_tiny = (__ballot_sync(FULL, tiny) >> src) & 1u;
           // closest points in B's frame, fp64: re-centred fp32 result + fp64 origin
           d3 PA = mk<double>(P1.x + (double)pa.x, P1.y + (double)pa.y, P1.z + (double)pa.z);
           d3 PB = mk<double>(P1.x + (double)pb.x, P1.y + (double)pb.y, P1.z + (double)pb.z);
@@ -822,7 +824,7 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
       seg = __shfl_sync(FULL, seg, 0); ofs = __shfl_sync(FULL, ofs, 0);
       if (seg < p.near_cap_dir && ofs + cnt <= p.near_cap_ent) {
         for (int i = lane; i < cnt; i += 32) p.near_ent[ofs + i] = nearq[i];
-        if (lane == 0) p.near_dir[seg] = make_int4(w, ofs, cnt, 0);
+        if (lane == 0) p.near_dir[seg] = make_int4(w, ofs, cnt, best_tiny ? 1 : 0);
       }
     }
     if (lane == 0) {
@@ -890,7 +892,11 @@ __global__ void __launch_bounds__(128) dist_refine_kernel(DistParams p) {
     double m = bd;
     for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(FULL, m, o));
     unsigned who = __ballot_sync(FULL, bd == m);
-    if (lane == __ffs(who) - 1 && m < 1.0e299) {
+    // the remembered pairs replace the traversal's answer when that answer itself came from such a pair; a best
+    // found on a pair that needed no refinement stands unless a refined pair beats it
+    const float cur = p.dist[w];
+    const bool replace = d.w != 0 || sqrt(m) < (double)cur;
+    if (replace && lane == __ffs(who) - 1 && m < 1.0e299) {
       p.dist[w] = (float)sqrt(m);
       if (p.pts) {
         d3 pa_local = xf_apply_inv(XA, xf_apply(XB, ba));

@@ -59,7 +59,28 @@ def save_pack(scene: Scene, path: str, extra: dict | None = None):
     np.savez_compressed(path, **arrays)
 
 
+def subdivide(tris: np.ndarray, levels: int) -> np.ndarray:
+    """midpoint subdivision in fp32, deterministic (config 5 object: mug x 4^3 = 220 800 triangles)"""
+    t = np.asarray(tris, dtype=np.float32)
+    half = np.float32(0.5)
+    for _ in range(levels):
+        a, b, c = t[:, 0], t[:, 1], t[:, 2]
+        ab = ((a + b) * half).astype(np.float32)
+        bc = ((b + c) * half).astype(np.float32)
+        ca = ((c + a) * half).astype(np.float32)
+        t = np.concatenate([np.stack([a, ab, ca], 1), np.stack([ab, b, bc], 1), np.stack([ca, bc, c], 1),
+                            np.stack([ab, bc, ca], 1)], 0)
+    return np.ascontiguousarray(t)
+
+
 def load_pack(path_or_name: str) -> Scene:
+    if path_or_name == "barrett_mug_200k":
+        # SURVEY.md 8(d) config 5: the plannerMug world with the mug midpoint-subdivided 3x; derived, not stored
+        sc = load_pack("barrett_mug")
+        sc.name = "barrett_mug_200k"
+        sc.bodies[0].tris = subdivide(sc.bodies[0].tris, 3)
+        sc.bodies[0].name = "mug_x64"
+        return sc
     path = path_or_name
     if not os.path.exists(path):
         path = os.path.join(SCENE_DIR, path_or_name if path_or_name.endswith(".npz") else path_or_name + ".npz")

@@ -271,3 +271,18 @@ def test_full_size_properties(ctx):
     assert (r4["legal"] != r1["legal"][:k]).mean() < 2e-3
     both = (r4["legal"] == 1) & (r1["legal"][:k] == 1)
     assert np.median(relerr(r4["energy"][both], r1["energy"][:k][both])) < 1e-5
+
+
+def test_small_distances_many_poses(ctx):
+    """Regression: many close poses (distances from 1e-3 mm to a few mm), where the fp64 refinement of tiny
+    distances and the fp32 traversal must agree on which triangle pair wins."""
+    sc, e, o = ctx["sc"], ctx["eng"], ctx["osc"]
+    pos, dofs = sample_aa_states(sc, 3000, seed=99, strata=("close",))
+    raw = aa_to_raw_states(sc, pos, dofs)
+    _, _, dist_o, _, _ = o.eval(0, ctx["obj"], raw, mode=0, want_dist=True)
+    res = e.eval_batch(ctx["rid"], ctx["sb"].body_ids[ctx["obj"]], raw, link_dist=True)
+    ld = res["link_dist"].astype(np.float64)
+    assert ((ld < 0) == (dist_o < 0)).all()
+    both = dist_o >= 0
+    assert (dist_o[both] < 1.0).sum() > 50
+    assert relerr(ld[both], dist_o[both]).max() < REL

@@ -105,19 +105,6 @@ def settle_scene(scene: Scene):
     return scene
 
 
-def subdivide(tris: np.ndarray, levels: int) -> np.ndarray:
-    """midpoint subdivision in fp32 (config 5 object: mug x 4^3 = 220 800 triangles)"""
-    t = tris.astype(np.float32)
-    for _ in range(levels):
-        a, b, c = t[:, 0], t[:, 1], t[:, 2]
-        ab = ((a + b) * np.float32(0.5)).astype(np.float32)
-        bc = ((b + c) * np.float32(0.5)).astype(np.float32)
-        ca = ((c + a) * np.float32(0.5)).astype(np.float32)
-        t = np.concatenate([np.stack([a, ab, ca], 1), np.stack([ab, b, bc], 1), np.stack([ca, bc, c], 1),
-                            np.stack([ab, bc, ca], 1)], 0)
-    return np.ascontiguousarray(t)
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--graspit", default="/root/reference")
@@ -125,7 +112,7 @@ def main():
     args = ap.parse_args()
     G = args.graspit
     os.makedirs(SCENE_DIR, exist_ok=True)
-    todo = args.only.split(",") if args.only else ["barrett_mug", "humanhand_flask", "dlr_flask", "staubli_barrett", "barrett_mug_200k"]
+    todo = args.only.split(",") if args.only else ["barrett_mug", "humanhand_flask", "dlr_flask", "staubli_barrett"]
 
     if "barrett_mug" in todo:
         sc = settle_scene(load_world(os.path.join(G, "worlds/plannerMug.xml"), G))
@@ -176,15 +163,7 @@ def main():
         save_pack(sc, os.path.join(SCENE_DIR, "staubli_barrett.npz"),
                   {"world": "worlds/staubli_barrett.xml + obstacles", "obstacles": [o[0] for o in obstacles]})
         print("staubli_barrett:", len(sc.bodies), "bodies", sum(len(b.tris) for b in sc.bodies), "tris; touching", sc.touching_pairs)
-
-    if "barrett_mug_200k" in todo:
-        sc = settle_scene(load_world(os.path.join(G, "worlds/plannerMug.xml"), G))
-        sc.name = "barrett_mug_200k"
-        sc.bodies[0].tris = subdivide(sc.bodies[0].tris, 3)
-        sc.bodies[0].name = "mug_x64"
-        save_pack(sc, os.path.join(SCENE_DIR, "barrett_mug_200k.npz"),
-                  {"world": "worlds/plannerMug.xml, mug midpoint-subdivided 3x (fp32)"})
-        print("barrett_mug_200k:", len(sc.bodies), "bodies", sum(len(b.tris) for b in sc.bodies), "tris")
+    # barrett_mug_200k (config 5) is derived at load time: scenepack.load_pack('barrett_mug_200k')
 
 
 if __name__ == "__main__":
