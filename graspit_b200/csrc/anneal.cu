@@ -1,0 +1,117 @@
+// Batched simulated annealing driver: K independent chains, one neighbour per chain
+// per step, evaluated by the batched pose evaluation, accepted by the Metropolis rule -- all on the device.
+//
+// Follows SimAnn (reference src/EGPlanner/simAnn.cpp):
+//   cooling              :218-227   T = T0 exp(-c k^(1/d))                     (Ingber schedule)
+//   neighborDistribution :236-250   y = T ((1 + 1/T)^|2u-1| - 1) sign(u - 1/2)
+//   variableNeighbor     :175-215   v = value + y * maxJump, redrawn until inside [min, max]; circular variables
+//                                   wrap by their range; values within TINY (1e-7) of a limit snap to it; <= 100 draws
+//   iterate              :96-158    neighbour at T(YC,YDIMS) * NBR_ADJ; accept when
+//                                   P = exp((E_old - E_new) ERR_ADJ / T(HC,HDIMS)) > U, P = 1 if E_new < E_old;
+//                                   the step counter advances only when a legal neighbour was found (FAIL otherwise)
+// The reference draws from libc rand() seeded with time(); here every draw is Philox4x32-10 keyed by the seed with
+// counter (chain, step, draw block), so a chain's trajectory does not depend on the batch layout or the GPU count.
+#include "b2c_internal.h"
+
+namespace b2c {
+
+__host__ __device__ inline void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                              unsigned out[4]) {
+  for (int r = 0; r < 10; r++) {
+    unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+    unsigned hi0 = (unsigned)(p0 >> 32), lo0 = (unsigned)p0, hi1 = (unsigned)(p1 >> 32), lo1 = (unsigned)p1;
+    unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct Draws {      // sequential uniforms in (0,1) of one (chain, step)
+  unsigned chain, step, k0, k1, block, have;
+  unsigned buf[4];
+  __device__ Draws(unsigned c, unsigned s, unsigned long long seed) : chain(c), step(s), k0((unsigned)seed), k1((unsigned)(seed >> 32)), block(0), have(0) {}
+  __device__ double next() {
+    if (have == 0) { philox4x32_10(chain, step, block, 0u, k0, k1, buf); block++; have = 4; }
+    unsigned x = buf[4 - have]; have--;
+    return ((double)x + 0.5) * (1.0 / 4294967296.0);
+  }
+};
+
+__device__ __forceinline__ double cooling(double t0, double c, int k, int d) { return t0 * exp(-c * pow((double)k, 1.0 / (double)d)); }
+
+// one neighbour per chain
+__global__ void anneal_propose_kernel(AnnealParams p) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.nchain) return;
+  const int k = p.k[c];
+  const double T = cooling(p.T0, p.YC, k, p.YDIMS) * p.NBR_ADJ;
+  Draws rng((unsigned)(p.chain_offset + c), (unsigned)p.step, p.seed);
+  const float *cur = p.cur + (size_t)c * p.nvar;
+  float *out = p.prop + (size_t)c * p.nvar;
+  const double base = 1.0 + 1.0 / T;
+  for (int i = 0; i < p.nvar; i++) {
+    const double vmin = p.vmin[i], vmax = p.vmax[i], jump = p.vjump[i], range = fabs(vmax - vmin);
+    const double val = (double)cur[i];
+    double v = vmax + 1.0;
+    int loop = 0;
+    while (v > vmax || v < vmin) {
+      loop++;
+      double u = rng.next();
+      double a = fabs(2.0 * u - 1.0);
+      double y = T * (pow(base, a) - 1.0);
+      if (u < 0.5) y = -y;
+      v = val + y * jump;
+      if (p.circular[i]) {
+        if (v > vmax) v -= range; else if (v < vmin) v += range;
+      }
+      if (v > vmax && v - vmax < 1.0e-7) v = vmax;
+      if (v < vmin && v - vmin > -1.0e-7) v = vmin;
+      if (loop == 100) break;
+    }
+    // the reference stores whatever the 100th draw gave; keep the state inside its box for the fp32 wire format
+    float vf = (float)v;
+    if (vf > (float)vmax) vf = (float)vmax;
+    if (vf < (float)vmin) vf = (float)vmin;
+    out[i] = vf;
+  }
+}
+
+// Metropolis step on the evaluated neighbours
+__global__ void anneal_accept_kernel(AnnealParams p) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.nchain) return;
+  if (!p.legal[c]) return;                       // SimAnn::FAIL: nothing changes, the step counter stays
+  const int k = p.k[c];
+  const double T = cooling(p.T0, p.HC, k, p.HDIMS);
+  const double e_old = p.ERR_ADJ * (double)p.cur_energy[c], e_new = p.ERR_ADJ * (double)p.energy[c];
+  double P = e_new < e_old ? 1.0 : exp((e_old - e_new) / T);
+  unsigned r[4];
+  philox4x32_10((unsigned)(p.chain_offset + c), (unsigned)p.step, 0xffffffffu, 1u, (unsigned)p.seed, (unsigned)(p.seed >> 32), r);
+  double U = ((double)r[0] + 0.5) * (1.0 / 4294967296.0);
+  if (P > U) {
+    const float *src = p.prop + (size_t)c * p.nvar;
+    float *dst = p.cur + (size_t)c * p.nvar;
+    for (int i = 0; i < p.nvar; i++) dst[i] = src[i];
+    p.cur_energy[c] = p.energy[c];
+    if (p.energy[c] < p.best_energy[c]) {
+      float *b = p.best + (size_t)c * p.nvar;
+      for (int i = 0; i < p.nvar; i++) b[i] = src[i];
+      p.best_energy[c] = p.energy[c];
+    }
+    atomicAdd(&p.counters[0], 1);                // jumps
+  }
+  p.k[c] = k + 1;
+  atomicAdd(&p.counters[1], 1);                  // legal neighbours
+}
+
+cudaError_t launch_anneal_propose(const AnnealParams &p, cudaStream_t s) {
+  anneal_propose_kernel<<<(p.nchain + 127) / 128, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_anneal_accept(const AnnealParams &p, cudaStream_t s) {
+  anneal_accept_kernel<<<(p.nchain + 127) / 128, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+} // namespace b2c

@@ -336,6 +336,8 @@ int run_static_distance(b2c_ctx *ctx, int a, int b, double *dist, double pa[3], 
 
 } // namespace
 
+static void anneal_release_all(b2c_ctx *ctx);      // anneal_api.inc
+
 // =================================================================================================
 extern "C" {
 
@@ -396,6 +398,7 @@ void b2c_destroy(b2c_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  anneal_release_all(ctx);
   invalidate_plans(ctx);
   for (auto &m : ctx->meshes) {
     if (m.d_nodes) cudaFree(m.d_nodes);
@@ -989,3 +992,6 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
 
 // ---- contacts / region (K6, K7) ------------------------------------------------------------------
 #include "contacts_api.inc"
+
+// ---- batched annealing (A14) ---------------------------------------------------------------------
+#include "anneal_api.inc"

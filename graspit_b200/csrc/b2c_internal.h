@@ -235,6 +235,26 @@ struct RegionParams {
 cudaError_t launch_contacts(const ContactParams &p, int blocks, cudaStream_t s);
 cudaError_t launch_region(const RegionParams &p, cudaStream_t s);
 
+// ---- batched annealing (anneal.cu) ------------------------------------------------------------------
+struct AnnealParams {
+  int nchain, nvar;
+  int step;                  // global step index (Philox counter)
+  int chain_offset;          // global id of this context's first chain (multi-GPU: chains never migrate)
+  unsigned long long seed;
+  double YC, HC, NBR_ADJ, ERR_ADJ, T0;
+  int YDIMS, HDIMS;
+  const double *vmin, *vmax, *vjump;
+  const unsigned char *circular;
+  float *cur, *prop, *best;          // [nchain][nvar]
+  float *cur_energy, *best_energy;   // [nchain]
+  const float *energy;               // [nchain] energy of the proposals
+  const unsigned char *legal;        // [nchain]
+  int *k;                            // [nchain] per-chain annealing step (SimAnn::mCurrentStep)
+  int *counters;                     // [0] jumps, [1] legal neighbours (totals)
+};
+cudaError_t launch_anneal_propose(const AnnealParams &p, cudaStream_t s);
+cudaError_t launch_anneal_accept(const AnnealParams &p, cudaStream_t s);
+
 constexpr int DSTACK_CAP = 448, DSTACK_PHYS = 512, DLEAF_CAP = 96;
 constexpr int DNEAR_CAP = 64, DCONF_CAP = 64;
 constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 3 * 96 + 96 + DNEAR_CAP * 8 + DCONF_CAP * 8 + 32;

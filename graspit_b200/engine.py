@@ -32,6 +32,8 @@ EXPORTS = [
     "b2c_pair_is_active", "b2c_body_set_thread", "b2c_set_thread", "b2c_all_collisions", "b2c_body_distance", "b2c_point_distance", "b2c_contacts",
     "b2c_all_contacts", "b2c_region", "b2c_bounding_volumes", "b2c_robot_define", "b2c_eval_batch",
     "b2c_robot_bodies", "b2c_robot_pairs", "b2c_last_stats", "b2c_obb_hierarchy", "b2c_contacts_postprocess",
+    "b2c_anneal_create", "b2c_anneal_destroy", "b2c_anneal_step", "b2c_anneal_read", "b2c_anneal_device_ptrs",
+    "b2c_anneal_propose", "b2c_anneal_write",
 ]
 
 
@@ -84,6 +86,15 @@ class EvalArgs(C.Structure):
                 ("link_dist", C.c_void_p), ("body_tf", C.c_void_p)]
 
 
+class AnnealDesc(C.Structure):
+    _fields_ = [("robot", C.c_int), ("object", C.c_int), ("nchain", C.c_int), ("nvar", C.c_int),
+                ("vmin", C.POINTER(C.c_double)), ("vmax", C.POINTER(C.c_double)), ("vjump", C.POINTER(C.c_double)),
+                ("circular", C.POINTER(C.c_ubyte)), ("ref_q", C.c_double * 4), ("ref_t", C.c_double * 3),
+                ("YC", C.c_double), ("HC", C.c_double), ("NBR_ADJ", C.c_double), ("ERR_ADJ", C.c_double), ("T0", C.c_double),
+                ("YDIMS", C.c_int), ("HDIMS", C.c_int), ("K0", C.c_int), ("seed", C.c_ulonglong),
+                ("chain_offset", C.c_int), ("flags", C.c_int)]
+
+
 _lib = None
 
 
@@ -116,6 +127,13 @@ def load_library():
     L.b2c_body_set_active.argtypes = [vp, ci, ci]
     L.b2c_pair_set_active.argtypes = [vp, ci, ci, ci]
     L.b2c_pair_is_active.argtypes = [vp, ci, ci, ip]
+    L.b2c_anneal_create.argtypes = [vp, C.POINTER(AnnealDesc), C.POINTER(C.c_float), ip]
+    L.b2c_anneal_destroy.argtypes = [vp, ci]
+    L.b2c_anneal_step.argtypes = [vp, ci, ci]
+    L.b2c_anneal_read.argtypes = [vp, ci, vp, vp, vp, vp, vp, C.POINTER(C.c_longlong)]
+    L.b2c_anneal_device_ptrs.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.b2c_anneal_propose.argtypes = [vp, ci, vp]
+    L.b2c_anneal_write.argtypes = [vp, ci, vp, vp, vp, ci]
     L.b2c_body_set_thread.argtypes = [vp, ci, ci]
     L.b2c_set_thread.argtypes = [vp, ci]
     L.b2c_all_collisions.argtypes = [vp, ci, ip, ci, ip, ci, ip]
@@ -488,6 +506,64 @@ class Engine:
         a.flags = B2C_EVAL_DEVICE_PTRS | (B2C_EVAL_LIVE if live else 0)
         a.legal, a.energy = legal_ptr, energy_ptr
         self._ck(self.L.b2c_eval_batch(self.h, C.byref(a)))
+
+
+class Annealer:
+    """K annealing chains on the device (``b2c_anneal_*``): host mirror of ``SimAnnPlanner``'s loop
+    (reference src/EGPlanner/simAnnPlanner.cpp:111-148) for a batch of independent chains."""
+
+    def __init__(self, engine: "Engine", robot: int, obj: int, variables, params, initial_states, ref_tran,
+                 seed=1234, chain_offset=0, live=False):
+        """variables: planner.SearchVariables; params: planner.SimAnnParams"""
+        self.engine = engine
+        st = np.ascontiguousarray(initial_states, dtype=np.float32)
+        self.nchain, self.nvar = st.shape
+        d = AnnealDesc()
+        d.robot, d.object, d.nchain, d.nvar = robot, obj, self.nchain, self.nvar
+        self._keep = [np.ascontiguousarray(variables.vmin, dtype=np.float64), np.ascontiguousarray(variables.vmax, dtype=np.float64),
+                      np.ascontiguousarray(variables.vjump, dtype=np.float64), np.ascontiguousarray(variables.circular, dtype=np.uint8)]
+        dp = C.POINTER(C.c_double)
+        d.vmin, d.vmax, d.vjump = (self._keep[i].ctypes.data_as(dp) for i in range(3))
+        d.circular = self._keep[3].ctypes.data_as(C.POINTER(C.c_ubyte))
+        d.ref_q[:] = list(ref_tran[0]); d.ref_t[:] = list(ref_tran[1])
+        d.YC, d.HC, d.NBR_ADJ, d.ERR_ADJ, d.T0 = params.YC, params.HC, params.NBR_ADJ, params.ERR_ADJ, params.T0
+        d.YDIMS, d.HDIMS, d.K0 = params.YDIMS, params.HDIMS, params.K0
+        d.seed, d.chain_offset, d.flags = seed, chain_offset, (B2C_EVAL_LIVE if live else 0)
+        aid = C.c_int(-1)
+        engine._ck(engine.L.b2c_anneal_create(engine.h, C.byref(d), st.ctypes.data_as(C.POINTER(C.c_float)), C.byref(aid)))
+        self.id = aid.value
+
+    def step(self, nsteps=1):
+        self.engine._ck(self.engine.L.b2c_anneal_step(self.engine.h, self.id, nsteps))
+
+    def read(self):
+        n, nv = self.nchain, self.nvar
+        out = dict(cur=np.zeros((n, nv), np.float32), cur_energy=np.zeros(n, np.float32), best=np.zeros((n, nv), np.float32),
+                   best_energy=np.zeros(n, np.float32), k=np.zeros(n, np.int32))
+        tot = (C.c_longlong * 4)()
+        self.engine._ck(self.engine.L.b2c_anneal_read(self.engine.h, self.id, out["cur"].ctypes.data, out["cur_energy"].ctypes.data,
+                                                      out["best"].ctypes.data, out["best_energy"].ctypes.data, out["k"].ctypes.data, tot))
+        out.update(jumps=int(tot[0]), legal_neighbours=int(tot[1]), steps=int(tot[2]), evaluated=int(tot[3]))
+        return out
+
+    def device_ptrs(self):
+        p = [C.c_void_p() for _ in range(4)]
+        self.engine._ck(self.engine.L.b2c_anneal_device_ptrs(self.engine.h, self.id, *[C.byref(x) for x in p]))
+        return dict(best=p[0].value, best_energy=p[1].value, cur=p[2].value, cur_energy=p[3].value)
+
+    def propose(self):
+        out = np.zeros((self.nchain, self.nvar), np.float32)
+        self.engine._ck(self.engine.L.b2c_anneal_propose(self.engine.h, self.id, out.ctypes.data))
+        return out
+
+    def write(self, cur=None, cur_energy=None, k=None, step=-1):
+        a = [None if x is None else np.ascontiguousarray(x, dtype=t) for x, t in ((cur, np.float32), (cur_energy, np.float32), (k, np.int32))]
+        self.engine._ck(self.engine.L.b2c_anneal_write(self.engine.h, self.id, *[None if x is None else x.ctypes.data for x in a], step))
+
+    def close(self):
+        if self.id >= 0 and self.engine.h:
+            self.engine.L.b2c_anneal_destroy(self.engine.h, self.id)
+        self.id = -1
 
 
 class SceneBinding:

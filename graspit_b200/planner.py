@@ -1,0 +1,176 @@
+"""Host side of the batched EGPlanner / SimAnnPlanner: search-variable tables, SimAnn parameter presets, the
+best-list merge and the multi-GPU exchange of per-rank best states.
+
+Mirrors, with the reference's names and values:
+  * ``PositionStateAA::createVariables`` / ``PostureStateEigen::createVariables``
+    (reference src/EGPlanner/searchStateImpl.cpp:50-80,147-155)
+  * ``SimAnnParams`` presets (src/EGPlanner/simAnnParams.cpp)
+  * ``SimAnnPlanner::mainLoop`` best-list rule and ``EGPlanner::addToListOfUniqueSolutions``
+    (src/EGPlanner/simAnnPlanner.cpp:111-148, egPlanner.cpp:527-557), ``HandObjectState::distance``
+    (src/EGPlanner/searchState.cpp:572-611)
+The annealing itself runs on the device (``engine.Annealer``); nothing here touches geometry.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+
+BEST_LIST_SIZE = 20          # simAnnPlanner.cpp:36
+
+
+@dataclass
+class SimAnnParams:
+    YC: float; HC: float; YDIMS: int; HDIMS: int; NBR_ADJ: float; ERR_ADJ: float; T0: float; K0: int
+
+    @staticmethod
+    def ANNEAL_DEFAULT():
+        return SimAnnParams(7.0, 7.0, 8, 8, 1.0, 1.0e-6, 1.0e6, 30000)
+
+    @staticmethod
+    def ANNEAL_LOOP():
+        return SimAnnParams(7.0, 7.0, 8, 8, 1.0, 1.0e-6, 1.0e6, 35000)
+
+    @staticmethod
+    def ANNEAL_MODIFIED():
+        return SimAnnParams(2.38, 2.38, 8, 8, 1.0e-3, 1.0e-1, 1.0e3, 0)
+
+    @staticmethod
+    def ANNEAL_STRICT():
+        return SimAnnParams(0.72, 0.22, 2, 2, 1.0, 1.0, 10.0, 0)
+
+    @staticmethod
+    def ANNEAL_ONLINE():
+        return SimAnnParams(0.24, 0.54, 2, 3, 1.0, 1.0e-2, 1.0e1, 100)
+
+
+@dataclass
+class SearchVariables:
+    names: List[str]
+    vmin: np.ndarray
+    vmax: np.ndarray
+    default: np.ndarray
+    vjump: np.ndarray
+    circular: np.ndarray
+
+    @staticmethod
+    def axis_angle_eigen(n_eg: int, eg_limits=None) -> "SearchVariables":
+        """SPACE_AXIS_ANGLE position + POSE_EIGEN posture: the planner dialog's default state layout."""
+        pi = np.pi
+        rows = [("Tx", -250, 250, 0, 150, 0), ("Ty", -250, 250, 0, 150, 0), ("Tz", -250, 350, 350, 150, 0),
+                ("theta", 0, pi, 0, pi / 5, 0), ("phi", -pi, pi, 0, pi / 2, 1), ("alpha", 0, pi, pi / 2, pi / 2, 0)]
+        for i in range(n_eg):
+            lo, hi = -4.0, 4.0
+            if eg_limits is not None and not np.isnan(eg_limits[i][0]):
+                lo, hi = float(eg_limits[i][0]), float(eg_limits[i][1])
+            rows.append((f"EG {i}", lo, hi, lo, (hi - lo) / 4.0, 0))
+        a = np.array([r[1:] for r in rows], dtype=np.float64)
+        return SearchVariables([r[0] for r in rows], a[:, 0].copy(), a[:, 1].copy(), a[:, 2].copy(), a[:, 3].copy(),
+                               a[:, 4].astype(np.uint8))
+
+
+def _quat_mul(a, b):
+    w1, x1, y1, z1 = a; w2, x2, y2, z2 = b
+    return np.array([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+                     w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2])
+
+
+def state_distance(pose_a, pose_b, max_radius: float) -> float:
+    """HandObjectState::distance (searchState.cpp:572-611) on hand poses already multiplied by the approach
+    transform: max(|dt| / maxRadius, 0.5 |angle| / pi).  pose = (q wxyz, t)."""
+    d = np.linalg.norm(np.asarray(pose_a[1]) - np.asarray(pose_b[1])) / max_radius
+    qa, qb = np.asarray(pose_a[0], dtype=np.float64), np.asarray(pose_b[0], dtype=np.float64)
+    q = _quat_mul(qa, np.array([qb[0], -qb[1], -qb[2], -qb[3]]))
+    q = q / np.linalg.norm(q)
+    if q[0] < 0:                      # Eigen::AngleAxisd(Quaternion): angle = 2 acos(w) after flipping w < 0
+        q = -q
+    angle = 2.0 * np.arctan2(np.linalg.norm(q[1:]), q[0])
+    return max(d, 0.5 * abs(angle) / np.pi)
+
+
+def aa_state_pose(state, ref_tran):
+    """total hand transform % approach, i.e. mRefTran % T(tx,ty,tz) % AxisAngle(alpha, axis(theta, phi)): the
+    approach factors cancel (searchStateImpl.cpp:156-168, searchState.cpp:592)."""
+    tx, ty, tz, th, ph, al = [float(x) for x in state[:6]]
+    axis = np.array([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)])
+    if al * al < 1.0e-6:              # transf::AXIS_ANGLE_ROTATION snaps tiny angles to identity (transform.cpp:26-29)
+        q = np.array([1.0, 0, 0, 0])
+    else:
+        q = np.concatenate([[np.cos(al / 2)], np.sin(al / 2) * axis / np.linalg.norm(axis)])
+    rq, rt = np.asarray(ref_tran[0], dtype=np.float64), np.asarray(ref_tran[1], dtype=np.float64)
+    w, v = rq[0], rq[1:]
+    t = np.array([tx, ty, tz])
+    rot_t = t + 2.0 * w * np.cross(v, t) + 2.0 * np.cross(v, np.cross(v, t))
+    return _quat_mul(rq, q), rt + rot_t
+
+
+class BestList:
+    """mBestList of SimAnnPlanner: at most BEST_LIST_SIZE states, sorted by energy, no two closer than 0.2."""
+
+    def __init__(self, ref_tran, max_radius=200.0, size=BEST_LIST_SIZE, distance=0.2):
+        self.ref_tran, self.max_radius, self.size, self.distance = ref_tran, max_radius, size, distance
+        self.states: List[np.ndarray] = []
+        self.energies: List[float] = []
+
+    def worst_energy(self) -> float:
+        return 1.0e5 if len(self.states) < self.size else self.energies[-1]      # simAnnPlanner.cpp:128-130
+
+    def offer(self, state, energy) -> bool:
+        """the JUMP branch of SimAnnPlanner::mainLoop (simAnnPlanner.cpp:131-143)"""
+        if not energy < self.worst_energy():
+            return False
+        pose = aa_state_pose(state, self.ref_tran)
+        i, add = 0, True
+        while i < len(self.states):                                              # addToListOfUniqueSolutions
+            if abs(state_distance(pose, aa_state_pose(self.states[i], self.ref_tran), self.max_radius)) < self.distance:
+                if energy < self.energies[i]:
+                    del self.states[i]; del self.energies[i]
+                else:
+                    add = False
+                    break
+            else:
+                i += 1
+        if not add:
+            return False
+        self.states.append(np.array(state, dtype=np.float32)); self.energies.append(float(energy))
+        order = np.argsort(np.array(self.energies), kind="stable")
+        self.states = [self.states[j] for j in order][: self.size]
+        self.energies = [self.energies[j] for j in order][: self.size]
+        return True
+
+    def merge(self, states: Sequence, energies: Sequence):
+        """offer candidates in ascending energy (the order a single planner would have met the better ones)"""
+        e = np.asarray(energies, dtype=np.float64)
+        for j in np.argsort(e, kind="stable"):
+            if e[j] < 1.0e7:
+                self.offer(np.asarray(states[j]), float(e[j]))
+
+
+def local_best_rows(best_states, best_energy, k=BEST_LIST_SIZE):
+    """this rank's k best (state || energy) rows as one torch tensor [k, nvar + 1]; works on CPU and CUDA tensors"""
+    import torch
+    k = min(k, best_energy.numel())
+    val, idx = torch.topk(best_energy, k, largest=False)
+    return torch.cat([best_states[idx], val[:, None]], 1).contiguous()
+
+
+def exchange_best(rows, group=None):
+    """all-gather of every rank's best rows: the ONLY collective of the path.  NCCL for CUDA tensors,
+    gloo for CPU tensors; returns [world * k, nvar + 1]."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rows
+    world = dist.get_world_size(group)
+    out = torch.empty((world * rows.shape[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(out, rows, group=group)
+    return out
+
+
+def shard(nchain_total: int, rank: int, world: int):
+    """block partition of the chains over ranks: chains [lo, hi) live on `rank` and never migrate"""
+    per = nchain_total // world
+    rem = nchain_total % world
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)

@@ -240,6 +240,45 @@ int b2c_robot_bodies(b2c_ctx *ctx, int robot, int *bodies, int cap, int *nbodies
 /* the active pairs (a,b) that a batched evaluation of `robot` tests, in pair_mask bit order */
 int b2c_robot_pairs(b2c_ctx *ctx, int robot, int *pairs, int cap, int *npairs);
 
+/* ---- batched simulated annealing: K independent chains on the device ------------------------
+ * Replaces, for K chains at once, SimAnnPlanner::mainLoop -> SimAnn::iterate (reference
+ * src/EGPlanner/simAnnPlanner.cpp:111-148, simAnn.cpp:96-261): per step every chain draws one neighbour of its
+ * current state (Ingber distribution at the neighbour temperature), the batch is evaluated by b2c_eval_batch
+ * (B2C_INPUT_AA_EIGEN states), and the Metropolis rule accepts or rejects per chain.  A chain whose neighbour is
+ * illegal keeps its state and its step counter (the reference's FAIL).  Random numbers are Philox4x32-10 keyed by
+ * `seed` with counter (chain_offset + chain, step, draw), so trajectories are independent of batch layout and of
+ * how chains are split over GPUs. */
+typedef struct b2c_anneal_desc {
+  int robot, object;
+  int nchain;
+  int nvar;                         /* 6 + number of eigengrasps */
+  const double *vmin, *vmax, *vjump;/* [nvar] SearchVariable mMinVal, mMaxVal, mMaxJump (searchStateImpl.cpp:50-80,147-155) */
+  const uint8_t *circular;          /* [nvar] SearchVariable::isCircular */
+  double ref_q[4], ref_t[3];        /* mRefTran */
+  double YC, HC, NBR_ADJ, ERR_ADJ, T0;   /* SimAnnParams (simAnnParams.cpp) */
+  int YDIMS, HDIMS, K0;
+  unsigned long long seed;
+  int chain_offset;                 /* global index of this context's first chain */
+  int flags;                        /* B2C_EVAL_PRESET or B2C_EVAL_LIVE */
+} b2c_anneal_desc;
+
+/* initial_states: [nchain][nvar] fp32 (host).  Initial energy is 1e8 and the step counter K0, as
+ * SimAnnPlanner::resetParameters sets them (simAnnPlanner.cpp:63-70). */
+int b2c_anneal_create(b2c_ctx *ctx, const b2c_anneal_desc *desc, const float *initial_states, int *anneal_id);
+int b2c_anneal_destroy(b2c_ctx *ctx, int anneal_id);
+/* nsteps annealing steps, asynchronous on the context's stream */
+int b2c_anneal_step(b2c_ctx *ctx, int anneal_id, int nsteps);
+/* host copies (any pointer may be NULL): current and best-so-far state / energy per chain, per-chain step counters;
+ * totals = {accepted jumps, legal neighbours, steps taken, neighbours evaluated}.  Synchronises. */
+int b2c_anneal_read(b2c_ctx *ctx, int anneal_id, float *cur, float *cur_energy, float *best, float *best_energy,
+                    int *k, long long totals[4]);
+/* device pointers of the per-chain best / current rows, for callers that reduce or exchange them on the device
+ * (the multi-GPU best-list all-gather) */
+int b2c_anneal_device_ptrs(b2c_ctx *ctx, int anneal_id, void **best, void **best_energy, void **cur, void **cur_energy);
+/* test hooks: the neighbours the next step would draw (no state change), and overwriting chain state */
+int b2c_anneal_propose(b2c_ctx *ctx, int anneal_id, float *proposals);
+int b2c_anneal_write(b2c_ctx *ctx, int anneal_id, const float *cur, const float *cur_energy, const int *k, int step);
+
 /* per-context counters of the last batched evaluation: box tests, triangle-pair tests,
  * point-triangle tests, fp64 rechecks (explanatory L2-level traffic) */
 int b2c_last_stats(b2c_ctx *ctx, unsigned long long stats[8]);
