@@ -109,7 +109,7 @@ struct b2c_ctx {
   // scratch
   DevBuf<float> d_states; DevBuf<Xf> d_fk; DevBuf<double> d_fkqt; DevBuf<uint8_t> d_legal; DevBuf<float> d_energy;
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
-  DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
+  DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
   int stage_nodes = 511;           // object-tree nodes staged in shared memory by the energy kernel
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int eval_warps_per_block = 8;
@@ -202,7 +202,7 @@ void active_pairs(const b2c_ctx *c, const std::set<int> *interest, std::vector<s
 }
 
 int ensure_scratch(b2c_ctx *ctx) {
-  CU(ctx->d_counters.reserve(8));
+  CU(ctx->d_counters.reserve(16));
   CU(ctx->d_stats.reserve(8));
   CU(ctx->d_ambig.reserve(1 << 20));
   CU(ctx->d_near_dir.reserve(1 << 16));
@@ -254,7 +254,7 @@ int run_static_collisions(b2c_ctx *ctx, const std::vector<std::pair<int, int>> &
   CU(cudaMemcpyAsync(ctx->d_misc.p, sx.data(), bytes_x, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d_pairs, epairs.data(), bytes_p, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d_bm, bm.data(), bytes_m, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int), ctx->stream));
   CU(cudaMemsetAsync(ctx->d_mask.p, 0, (mw + 1) * 8, ctx->stream));
   EvalParams ep;
   memset(&ep, 0, sizeof ep);
@@ -266,9 +266,9 @@ int run_static_collisions(b2c_ctx *ctx, const std::vector<std::pair<int, int>> &
   ep.legal = ctx->d_legal.p; ep.energy = nullptr; ep.pair_mask = ctx->d_mask.p;
   ep.pose_counter = ctx->d_counters.p; ep.ambig = ctx->d_ambig.p; ep.ambig_count = ctx->d_counters.p + 1;
   ep.ambig_cap = (int)ctx->d_ambig.cap; ep.stats = nullptr;
-  size_t wb = eval_warp_smem_bytes(nb, np, mw, ep.stack_phys);
-  if (wb > 200 * 1024) return fail(ctx, B2C_ECAPACITY, "too many bodies/pairs for one query (%d bodies, %d pairs)", nb, np);
-  CU(launch_eval(ep, 1, 1, wb, ctx->stream)); ctx->launches++;
+  CU(ctx->d_items.reserve((size_t)np + 32));
+  ep.items = ctx->d_items.p; ep.item_count = ctx->d_counters.p + 8; ep.item_cap = (int)ctx->d_items.cap;
+  CU(launch_collide(ep, 1, ctx->stream)); ctx->launches += 2;
   RecheckParams rp;
   memset(&rp, 0, sizeof rp);
   rp.ambig = ctx->d_ambig.p; rp.ambig_count = ctx->d_counters.p + 1; rp.ambig_cap = (int)ctx->d_ambig.cap;
@@ -299,7 +299,7 @@ int run_static_distance(b2c_ctx *ctx, int a, int b, double *dist, double pa[3], 
   CU(cudaMemcpyAsync(ctx->d_misc.p, sx, sizeof sx, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d_q, &q, sizeof q, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d_bm, bm, sizeof bm, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int), ctx->stream));
   DistParams dp;
   memset(&dp, 0, sizeof dp);
   dp.npose = 1; dp.nrb = 0; dp.nb = 2; dp.nq = 1; dp.queries = d_q; dp.fk = nullptr;
@@ -407,7 +407,7 @@ void b2c_destroy(b2c_ctx *ctx) {
   }
   ctx->d_meshes.release(); ctx->d_states.release(); ctx->d_fk.release(); ctx->d_fkqt.release(); ctx->d_legal.release();
   ctx->d_energy.release(); ctx->d_mask.release(); ctx->d_ambig.release(); ctx->d_counters.release(); ctx->d_stats.release();
-  ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release(); ctx->d_legal_list.release(); ctx->d_contacts.release(); ctx->d_flags.release(); ctx->d_terms.release(); ctx->d_near_dir.release(); ctx->d_near_ent.release();
+  ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release(); ctx->d_legal_list.release(); ctx->d_items.release(); ctx->d_contacts.release(); ctx->d_flags.release(); ctx->d_terms.release(); ctx->d_near_dir.release(); ctx->d_near_ent.release();
   for (int i = 0; i < 16; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -870,7 +870,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   std::vector<Xf> sx(nb - nrb);
   for (int i = nrb; i < nb; i++) sx[i - nrb] = qt_to_xf(ctx->bodies[P->ebodies[i]].tf);
   if (!sx.empty()) CU(cudaMemcpyAsync(P->d_static.p, sx.data(), sx.size() * sizeof(Xf), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int), ctx->stream));
   CU(cudaMemsetAsync(ctx->d_stats.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
 
   // K1
@@ -899,18 +899,23 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
     CU(ctx->d_legal_list.reserve(npose));
     ep.legal_list = ctx->d_legal_list.p; ep.legal_count = ctx->d_counters.p + 4;
   }
-  size_t wb = eval_warp_smem_bytes(nb, np, mw, ep.stack_phys);
-  if (wb > 200 * 1024) return fail(ctx, B2C_ECAPACITY, "eval_batch: %d bodies / %d pairs exceed the per-warp shared memory", nb, np);
-  int blocks, wpb; size_t smem;
-  eval_launch_shape(ctx, wb, npose, blocks, wpb, smem);
-  PROF_BEGIN(1); CU(launch_eval(ep, blocks, wpb, smem, ctx->stream)); ctx->launches++; PROF_END(1);
+  {
+    size_t want = (size_t)npose * np + 32;
+    if (want > (size_t)0x7fffffff) return fail(ctx, B2C_ECAPACITY, "eval_batch: %d poses x %d pairs exceed the work-item index range; split the batch", npose, np);
+    CU(ctx->d_items.reserve(want));
+  }
+  ep.items = ctx->d_items.p; ep.item_count = ctx->d_counters.p + 8; ep.item_cap = (int)std::min<size_t>(ctx->d_items.cap, 0x7fffffff);
+  if (want_mask) CU(cudaMemsetAsync(d_mask, 0, (size_t)npose * mw * 8, ctx->stream));
+  PROF_BEGIN(1); CU(launch_collide(ep, ctx->sm_count * 2, ctx->stream)); ctx->launches += 2; PROF_END(1);
   RecheckParams rp;
   memset(&rp, 0, sizeof rp);
   rp.ambig = ctx->d_ambig.p; rp.ambig_count = ctx->d_counters.p + 1; rp.ambig_cap = (int)ctx->d_ambig.cap;
   rp.nrb = nrb; rp.nb = nb; rp.fk = ctx->d_fk.p; rp.static_xf = P->d_static.p; rp.body_mesh = P->d_body_mesh.p;
   rp.meshes = ctx->d_meshes.p; rp.pairs = P->d_pairs.p; rp.legal = d_legal; rp.energy = d_energy; rp.pair_mask = d_mask;
   rp.mask_words = mw; rp.stats = ctx->d_stats.p;
-  PROF_BEGIN(2); CU(launch_recheck(rp, ctx->stream)); ctx->launches++; PROF_END(2);
+  PROF_BEGIN(2); CU(launch_recheck(rp, ctx->stream)); ctx->launches++;
+  if (want_energy) { CU(launch_compact(ep, ctx->stream)); ctx->launches++; }
+  PROF_END(2);
 
   // K5 + K8: CONTACT_ENERGY over the compacted legal poses
   EnergyParams gp;

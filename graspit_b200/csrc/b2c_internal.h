@@ -100,6 +100,10 @@ struct EvalParams {
   int *ambig_count;
   int ambig_cap;
   unsigned long long *stats;   // [8]: box tests, tri-pair tests, point-box, point-tri, ambiguous, ...
+  // two-phase legality (collide.cu): (pose, pair) work items that survived the root-box test
+  int2 *items;
+  int *item_count;
+  int item_cap;
 };
 
 // LIVE contacts / generic point-energy input: per pose, per contact: world location + world normal
@@ -258,6 +262,13 @@ cudaError_t launch_anneal_accept(const AnnealParams &p, cudaStream_t s);
 constexpr int DSTACK_CAP = 448, DSTACK_PHYS = 512, DLEAF_CAP = 96;
 constexpr int DNEAR_CAP = 64, DCONF_CAP = 64;
 constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 3 * 96 + 96 + DNEAR_CAP * 8 + DCONF_CAP * 8 + 32;
+
+// narrow phase of the legality test: per-warp shared memory = 32 fp64 relative transforms, 32 pair transforms,
+// 32 item descriptors, the shared work stack and the leaf queue
+constexpr int NSTACK_CAP = 448, NSTACK_PHYS = 512, NLEAF_CAP = 96;
+constexpr int NARROW_WARP_SMEM = 32 * 96 + 32 * 96 + 32 * 16 + NSTACK_PHYS * 8 + NLEAF_CAP * 8 + 32 * 4;
+cudaError_t launch_collide(const EvalParams &p, int narrow_blocks, cudaStream_t s);
+cudaError_t launch_compact(const EvalParams &p, cudaStream_t s);
 
 // launchers (kernels.cu)
 cudaError_t launch_fk(const FkParams &p, cudaStream_t s);

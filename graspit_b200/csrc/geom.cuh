@@ -145,25 +145,26 @@ __device__ __forceinline__ bool box_overlap(const float *ca, const float *ha, co
   float T1 = R[3] * cb[0] + R[4] * cb[1] + R[5] * cb[2] + x.t[1] - ca[1];
   float T2 = R[6] * cb[0] + R[7] * cb[1] + R[8] * cb[2] + x.t[2] - ca[2];
   const float e = x.eps;
-  // A's face axes
-  if (fabsf(T0) > ha[0] + hb[0] * AR[0] + hb[1] * AR[1] + hb[2] * AR[2] + e) return false;
-  if (fabsf(T1) > ha[1] + hb[0] * AR[3] + hb[1] * AR[4] + hb[2] * AR[5] + e) return false;
-  if (fabsf(T2) > ha[2] + hb[0] * AR[6] + hb[1] * AR[7] + hb[2] * AR[8] + e) return false;
-  // B's face axes
-  if (fabsf(T0 * R[0] + T1 * R[3] + T2 * R[6]) > hb[0] + ha[0] * AR[0] + ha[1] * AR[3] + ha[2] * AR[6] + e) return false;
-  if (fabsf(T0 * R[1] + T1 * R[4] + T2 * R[7]) > hb[1] + ha[0] * AR[1] + ha[1] * AR[4] + ha[2] * AR[7] + e) return false;
-  if (fabsf(T0 * R[2] + T1 * R[5] + T2 * R[8]) > hb[2] + ha[0] * AR[2] + ha[1] * AR[5] + ha[2] * AR[8] + e) return false;
+  // the six face axes without branches (most separated pairs are separated on one of them), then ONE branch, then
+  // the nine edge-edge axes: lanes of a warp diverge at most once inside a test
+  bool sep = fabsf(T0) > ha[0] + hb[0] * AR[0] + hb[1] * AR[1] + hb[2] * AR[2] + e;
+  sep |= fabsf(T1) > ha[1] + hb[0] * AR[3] + hb[1] * AR[4] + hb[2] * AR[5] + e;
+  sep |= fabsf(T2) > ha[2] + hb[0] * AR[6] + hb[1] * AR[7] + hb[2] * AR[8] + e;
+  sep |= fabsf(T0 * R[0] + T1 * R[3] + T2 * R[6]) > hb[0] + ha[0] * AR[0] + ha[1] * AR[3] + ha[2] * AR[6] + e;
+  sep |= fabsf(T0 * R[1] + T1 * R[4] + T2 * R[7]) > hb[1] + ha[0] * AR[1] + ha[1] * AR[4] + ha[2] * AR[7] + e;
+  sep |= fabsf(T0 * R[2] + T1 * R[5] + T2 * R[8]) > hb[2] + ha[0] * AR[2] + ha[1] * AR[5] + ha[2] * AR[8] + e;
+  if (sep) return false;
   // 9 edge-edge axes A_i x B_j
-  if (fabsf(T2 * R[3] - T1 * R[6]) > ha[1] * AR[6] + ha[2] * AR[3] + hb[1] * AR[2] + hb[2] * AR[1] + e) return false;
-  if (fabsf(T2 * R[4] - T1 * R[7]) > ha[1] * AR[7] + ha[2] * AR[4] + hb[0] * AR[2] + hb[2] * AR[0] + e) return false;
-  if (fabsf(T2 * R[5] - T1 * R[8]) > ha[1] * AR[8] + ha[2] * AR[5] + hb[0] * AR[1] + hb[1] * AR[0] + e) return false;
-  if (fabsf(T0 * R[6] - T2 * R[0]) > ha[0] * AR[6] + ha[2] * AR[0] + hb[1] * AR[5] + hb[2] * AR[4] + e) return false;
-  if (fabsf(T0 * R[7] - T2 * R[1]) > ha[0] * AR[7] + ha[2] * AR[1] + hb[0] * AR[5] + hb[2] * AR[3] + e) return false;
-  if (fabsf(T0 * R[8] - T2 * R[2]) > ha[0] * AR[8] + ha[2] * AR[2] + hb[0] * AR[4] + hb[1] * AR[3] + e) return false;
-  if (fabsf(T1 * R[0] - T0 * R[3]) > ha[0] * AR[3] + ha[1] * AR[0] + hb[1] * AR[8] + hb[2] * AR[7] + e) return false;
-  if (fabsf(T1 * R[1] - T0 * R[4]) > ha[0] * AR[4] + ha[1] * AR[1] + hb[0] * AR[8] + hb[2] * AR[6] + e) return false;
-  if (fabsf(T1 * R[2] - T0 * R[5]) > ha[0] * AR[5] + ha[1] * AR[2] + hb[0] * AR[7] + hb[1] * AR[6] + e) return false;
-  return true;
+  sep |= fabsf(T2 * R[3] - T1 * R[6]) > ha[1] * AR[6] + ha[2] * AR[3] + hb[1] * AR[2] + hb[2] * AR[1] + e;
+  sep |= fabsf(T2 * R[4] - T1 * R[7]) > ha[1] * AR[7] + ha[2] * AR[4] + hb[0] * AR[2] + hb[2] * AR[0] + e;
+  sep |= fabsf(T2 * R[5] - T1 * R[8]) > ha[1] * AR[8] + ha[2] * AR[5] + hb[0] * AR[1] + hb[1] * AR[0] + e;
+  sep |= fabsf(T0 * R[6] - T2 * R[0]) > ha[0] * AR[6] + ha[2] * AR[0] + hb[1] * AR[5] + hb[2] * AR[4] + e;
+  sep |= fabsf(T0 * R[7] - T2 * R[1]) > ha[0] * AR[7] + ha[2] * AR[1] + hb[0] * AR[5] + hb[2] * AR[3] + e;
+  sep |= fabsf(T0 * R[8] - T2 * R[2]) > ha[0] * AR[8] + ha[2] * AR[2] + hb[0] * AR[4] + hb[1] * AR[3] + e;
+  sep |= fabsf(T1 * R[0] - T0 * R[3]) > ha[0] * AR[3] + ha[1] * AR[0] + hb[1] * AR[8] + hb[2] * AR[7] + e;
+  sep |= fabsf(T1 * R[1] - T0 * R[4]) > ha[0] * AR[4] + ha[1] * AR[1] + hb[0] * AR[8] + hb[2] * AR[6] + e;
+  sep |= fabsf(T1 * R[2] - T0 * R[5]) > ha[0] * AR[5] + ha[1] * AR[2] + hb[0] * AR[7] + hb[1] * AR[6] + e;
+  return !sep;
 }
 
 // Lower bound on the squared distance between the two boxes: squared positive gaps along the three

@@ -9,30 +9,9 @@
 //
 // See DESIGN.md for the data layout and the roofline that bounds each kernel.
 #include "b2c_internal.h"
+#include "traverse.cuh"
 
 namespace b2c {
-
-#define FULL 0xffffffffu
-
-__device__ __forceinline__ Node load_node(const Node *nodes, int i) {
-  const float4 *p = reinterpret_cast<const float4 *>(nodes + i);
-  float4 a = __ldg(p), b = __ldg(p + 1);
-  Node n;
-  n.cx = a.x; n.cy = a.y; n.cz = a.z; n.hx = a.w;
-  n.hy = b.x; n.hz = b.y; n.child = __float_as_int(b.z); n.tri = __float_as_int(b.w);
-  return n;
-}
-__device__ __forceinline__ void node_ch(const Node &n, float *c, float *h) {
-  c[0] = n.cx; c[1] = n.cy; c[2] = n.cz; h[0] = n.hx; h[1] = n.hy; h[2] = n.hz;
-}
-__device__ __forceinline__ d3 tri_vertex(const Tri *tris, int t, int k) {
-  float4 v = __ldg(&tris[t].v[k]);
-  return mk<double>((double)v.x, (double)v.y, (double)v.z);
-}
-
-__device__ __forceinline__ unsigned long long pack_entry(int pair, int a, int b) {
-  return ((unsigned long long)(unsigned)pair << 48) | ((unsigned long long)(unsigned)a << 24) | (unsigned long long)(unsigned)b;
-}
 
 // ============================================================================================
 // K1: forward kinematics.  One thread per pose, fp64 quaternion algebra in the reference's
@@ -275,22 +254,6 @@ struct WarpSmem {
 };
 
 
-__device__ __forceinline__ void make_pair_xf(const double *XA, const double *XB, float extA, float extB, PairXf &o) {
-  // A <- B : R = Ra^T Rb, t = Ra^T (tb - ta), fp64 then rounded
-  double r[9];
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++) r[3 * i + j] = XA[0 + i] * XB[0 + j] + XA[3 + i] * XB[3 + j] + XA[6 + i] * XB[6 + j];
-  d3 dt = mk<double>(XB[9] - XA[9], XB[10] - XA[10], XB[11] - XA[11]);
-  d3 t = xf_rot_t(XA, dt);
-#pragma unroll
-  for (int i = 0; i < 9; i++) { o.r[i] = (float)r[i]; o.ar[i] = fabsf((float)r[i]) + 1.0e-6f; }
-  o.t[0] = (float)t.x; o.t[1] = (float)t.y; o.t[2] = (float)t.z;
-  o.eps = 1.0e-6f * (fabsf(o.t[0]) + fabsf(o.t[1]) + fabsf(o.t[2]) + extA + extB) + 1.0e-5f;
-  o.pad[0] = o.pad[1] = 0.f;
-}
-
 // triangle pair (tri_a of body A, tri_b of body B) -> TT_SEP / TT_HIT / TT_AMBIG.
 // Triangle A is moved into B's frame in fp64 (reference: t1.applyTransform(mTran1To2),
 // collisionAlgorithms_inl.h:58-60) and everything is re-centred on its first vertex before rounding.
@@ -482,11 +445,6 @@ __global__ void __launch_bounds__(256, 3) eval_kernel(EvalParams p) {
 // A confirmed intersection clears legal/energy, sets the pair bit, and (distance queries) forces -1.
 // ============================================================================================
 
-__device__ __forceinline__ const double *body_xf_ptr(const Xf *fk, const Xf *static_xf, int nrb, int pose, int body) {
-  return body < nrb ? reinterpret_cast<const double *>(fk + (size_t)pose * nrb + body)
-                    : reinterpret_cast<const double *>(static_xf + (body - nrb));
-}
-
 __global__ void recheck_kernel(RecheckParams p) {
   int n = *p.ambig_count;
   if (n > p.ambig_cap) n = p.ambig_cap;
@@ -632,6 +590,22 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
     if (lane == 0) stack[0] = pack_dist_entry(0.f, 0, 0);
     sp = 1;
     __syncwarp();
+#ifdef DIST_ORACLE_SEED
+    // experiment: start from the answer of a previous run (how much of the work is unavoidable with these bounds?)
+    if (p.dist[w] > 0.f && p.pts) {
+      float dprev = p.dist[w] * 1.0001f;
+      best = dprev * dprev; seeded = true;
+      const double *o = p.pts + (size_t)w * 6;
+      d3 pa0 = xf_apply(XR, mk<double>(o[0], o[1], o[2]));
+      bpa = pa0; bpb = mk<double>(o[3], o[4], o[5]);
+      float ux = (float)(bpb.x - bpa.x), uy = (float)(bpb.y - bpa.y), uz = (float)(bpb.z - bpa.z);
+      float inv = rsqrtf(fmaxf(ux * ux + uy * uy + uz * uz, 1.0e-30f));
+      udir = mk<float>(ux * inv, uy * inv, uz * inv);
+      udirA = mk<float>(x.r[0] * udir.x + x.r[1] * udir.y + x.r[2] * udir.z, x.r[3] * udir.x + x.r[4] * udir.y + x.r[5] * udir.z,
+                        x.r[6] * udir.x + x.r[7] * udir.y + x.r[8] * udir.z);
+      udt = udirA.x * x.t[0] + udirA.y * x.t[1] + udirA.z * x.t[2];
+    }
+#endif
 
     while (true) {
       if (lq >= DLEAF_TRIGGER || (lq > 0 && (sp == 0 || !seeded))) {

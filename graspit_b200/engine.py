@@ -551,6 +551,17 @@ class Annealer:
         self.engine._ck(self.engine.L.b2c_anneal_device_ptrs(self.engine.h, self.id, *[C.byref(x) for x in p]))
         return dict(best=p[0].value, best_energy=p[1].value, cur=p[2].value, cur_energy=p[3].value)
 
+    def torch_views(self, device):
+        """torch tensors aliasing the annealer's device rows (no copy): best, best_energy, cur, cur_energy"""
+        import torch
+
+        class _Dev:
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
+        p = self.device_ptrs()
+        shp = {"best": (self.nchain, self.nvar), "best_energy": (self.nchain,), "cur": (self.nchain, self.nvar), "cur_energy": (self.nchain,)}
+        return {k: torch.as_tensor(_Dev(p[k], shp[k]), device=device) for k in shp}
+
     def propose(self):
         out = np.zeros((self.nchain, self.nvar), np.float32)
         self.engine._ck(self.engine.L.b2c_anneal_propose(self.engine.h, self.id, out.ctypes.data))
