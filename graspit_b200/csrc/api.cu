@@ -26,8 +26,9 @@ struct MeshHost {
   bool alive = false;
   int ntri = 0;
   std::vector<float> tri9;        // kept for the host-side OBB hierarchy / region / contact post-processing
-  std::vector<Node> nodes;
-  Node *d_nodes = nullptr;
+  std::vector<NodeQ> nodes;
+  BvhQuant quant;
+  NodeQ *d_nodes = nullptr;
   Tri *d_tris = nullptr;
   int depth = 0;
   float extent = 0.f;
@@ -110,7 +111,7 @@ struct b2c_ctx {
   DevBuf<float> d_states; DevBuf<Xf> d_fk; DevBuf<double> d_fkqt; DevBuf<uint8_t> d_legal; DevBuf<float> d_energy;
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
   DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
-  int stage_nodes = 511;           // object-tree nodes staged in shared memory by the energy kernel
+  int stage_nodes = 1024;          // object-tree nodes staged in shared memory by the energy kernel
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int eval_warps_per_block = 8;
   int eval_blocks_per_sm = 0;      // 0 = derive from shared memory
@@ -160,6 +161,7 @@ int sync_meshes(b2c_ctx *ctx) {
     md[i].nodes = m.d_nodes; md[i].tris = m.d_tris;
     md[i].nnodes = (int)m.nodes.size(); md[i].ntri = m.ntri;
     md[i].extent = m.extent; md[i].depth = m.depth;
+    for (int k = 0; k < 3; k++) { md[i].q0[k] = m.quant.q0[k]; md[i].qs[k] = m.quant.qs[k]; }
   }
   CU(ctx->d_meshes.reserve(md.size() + 1));
   if (!md.empty()) CU(cudaMemcpyAsync(ctx->d_meshes.p, md.data(), md.size() * sizeof(MeshDev), cudaMemcpyHostToDevice, ctx->stream));
@@ -210,19 +212,6 @@ int ensure_scratch(b2c_ctx *ctx) {
   return B2C_OK;
 }
 
-// launch geometry of the evaluation kernel for a given per-warp shared-memory need
-void eval_launch_shape(const b2c_ctx *c, size_t warp_bytes, int work, int &blocks, int &wpb, size_t &smem) {
-  wpb = c->eval_warps_per_block;
-  const size_t limit = 200 * 1024;
-  while (wpb > 1 && warp_bytes * wpb > limit) wpb >>= 1;
-  smem = warp_bytes * wpb;
-  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(limit / smem, 64 / wpb));
-  if (c->eval_blocks_per_sm > 0) per_sm = std::min(per_sm, c->eval_blocks_per_sm);
-  blocks = c->sm_count * per_sm;
-  int need = (work + wpb - 1) / wpb;
-  if (blocks > need) blocks = std::max(1, need);
-}
-
 // Run the collision traversal over explicit static bodies (single-pose CollisionInterface queries).
 int run_static_collisions(b2c_ctx *ctx, const std::vector<std::pair<int, int>> &pairs, bool all_mode,
                           std::vector<unsigned long long> &mask, int &legal) {
@@ -259,8 +248,7 @@ int run_static_collisions(b2c_ctx *ctx, const std::vector<std::pair<int, int>> &
   EvalParams ep;
   memset(&ep, 0, sizeof ep);
   ep.npose = 1; ep.nrb = 0; ep.nb = nb; ep.npairs = np; ep.nvc = 0; ep.object = -1;
-  ep.mode_all = all_mode ? 1 : 0; ep.do_energy = 0; ep.mask_words = mw;
-  ep.stack_phys = std::max(256, np + 96); ep.stack_cap = ep.stack_phys - 64;
+  ep.mode_all = all_mode ? 1 : 0; ep.mask_words = mw;
   ep.fk = nullptr; ep.static_xf = reinterpret_cast<const Xf *>(ctx->d_misc.p);
   ep.body_mesh = d_bm; ep.meshes = ctx->d_meshes.p; ep.pairs = d_pairs; ep.vcs = nullptr;
   ep.legal = ctx->d_legal.p; ep.energy = nullptr; ep.pair_mask = ctx->d_mask.p;
@@ -427,16 +415,19 @@ int b2c_mesh_create(b2c_ctx *ctx, const float *tri9, int ntri, int *mesh_id) {
   m.alive = true;
   m.ntri = ntri;
   m.tri9.assign(tri9, tri9 + 9 * (size_t)ntri);
-  build_bvh(m.tri9.data(), ntri, m.nodes, &m.depth);
-  const Node &r = m.nodes[0];
+  Node r;
+  build_bvh(m.tri9.data(), ntri, m.nodes, &m.quant, &m.depth, &r);
   m.extent = ntri > 0 ? std::fabs(r.cx) + std::fabs(r.cy) + std::fabs(r.cz) + r.hx + r.hy + r.hz : 0.f;
   std::vector<Tri> tris(std::max(ntri, 1));
+  // an empty mesh is one far-away degenerate triangle (its leaf box sits at the same place): every query answers
+  // "no collision, nothing near" without special cases in the kernels
+  if (ntri == 0) for (int v = 0; v < 3; v++) tris[0].v[v] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
   for (int i = 0; i < ntri; i++)
     for (int v = 0; v < 3; v++)
       tris[i].v[v] = make_float4(tri9[9 * (size_t)i + 3 * v], tri9[9 * (size_t)i + 3 * v + 1], tri9[9 * (size_t)i + 3 * v + 2], 0.f);
-  CU(cudaMalloc(&m.d_nodes, m.nodes.size() * sizeof(Node)));
+  CU(cudaMalloc(&m.d_nodes, m.nodes.size() * sizeof(NodeQ)));
   CU(cudaMalloc(&m.d_tris, tris.size() * sizeof(Tri)));
-  CU(cudaMemcpy(m.d_nodes, m.nodes.data(), m.nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(m.d_nodes, m.nodes.data(), m.nodes.size() * sizeof(NodeQ), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(m.d_tris, tris.data(), tris.size() * sizeof(Tri), cudaMemcpyHostToDevice));
   ctx->meshes.push_back(std::move(m));
   ctx->meshes_dirty = true;
@@ -590,6 +581,7 @@ int b2c_point_distance(b2c_ctx *ctx, int body, const double point[3], double *di
   pp.n = 1; pp.points = d_p; pp.body_xf = reinterpret_cast<const Xf *>(d_x);
   const MeshHost &m = ctx->meshes[ctx->bodies[body].mesh];
   pp.mesh.nodes = m.d_nodes; pp.mesh.tris = m.d_tris; pp.mesh.nnodes = (int)m.nodes.size(); pp.mesh.ntri = m.ntri;
+  for (int k = 0; k < 3; k++) { pp.mesh.q0[k] = m.quant.q0[k]; pp.mesh.qs[k] = m.quant.qs[k]; }
   pp.mesh.extent = m.extent; pp.mesh.depth = m.depth;
   pp.out = d_o;
   CU(launch_point(pp, ctx->stream)); ctx->launches++;
@@ -887,9 +879,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   memset(&ep, 0, sizeof ep);
   ep.npose = npose; ep.nrb = nrb; ep.nb = nb; ep.npairs = np; ep.nvc = P->nvc; ep.object = P->object_e;
   ep.mode_all = want_mask ? 1 : 0;
-  ep.do_energy = 0;   // energy runs in its own kernel on the compacted list of legal poses
   ep.mask_words = mw;
-  ep.stack_phys = std::max(256, np + 96); ep.stack_cap = ep.stack_phys - 64;
   ep.fk = ctx->d_fk.p; ep.static_xf = P->d_static.p; ep.body_mesh = P->d_body_mesh.p; ep.meshes = ctx->d_meshes.p;
   ep.pairs = P->d_pairs.p; ep.vcs = P->d_vcs.p; ep.legal = d_legal; ep.energy = d_energy; ep.pair_mask = d_mask;
   ep.pose_counter = ctx->d_counters.p; ep.ambig = ctx->d_ambig.p; ep.ambig_count = ctx->d_counters.p + 1;

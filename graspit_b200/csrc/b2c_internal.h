@@ -13,12 +13,13 @@ struct Tri {
 };
 
 struct MeshDev {
-  const Node *nodes;
+  const NodeQ *nodes;
   const Tri *tris;
   int nnodes;
   int ntri;
   float extent;      // |root centre|_1 + |root half|_1 : coordinate scale of the mesh
   int depth;
+  float q0[3], qs[3]; // quantisation grid of the stored boxes (bvh.h)
 };
 
 // ---- forward-kinematics program ----------------------------------------
@@ -79,11 +80,7 @@ struct EvalParams {
   int nvc;
   int object;          // eval-body index of the target object, -1 if none
   int mode_all;        // 1: evaluate every pair (ALL_COLLISIONS mask); 0: stop at the first hit
-  int do_energy;       // 1: CONTACT_PRESET energy fused behind the legality test
   int mask_words;      // 64-bit words per pose in pair_mask
-  int stage_nodes;     // top-of-tree nodes of the object mesh staged in shared memory (0 = off)
-  int stack_cap;       // logical / physical entries of the per-warp work stack
-  int stack_phys;
   const Xf *fk;
   const Xf *static_xf;     // [nb - nrb]
   const int *body_mesh;    // [nb]
@@ -138,10 +135,6 @@ struct DistParams {
 
 enum { STAT_BOX = 0, STAT_TRI = 1, STAT_PBOX = 2, STAT_PTRI = 3, STAT_AMBIG = 4, STAT_DBOX = 5, STAT_DTRI = 6, STAT_HITFIX = 7 };
 
-// per-warp shared-memory budget of the evaluation kernel
-constexpr int STACK_CAP = 192;     // logical capacity (entries popped per step are limited to the room left)
-constexpr int STACK_PHYS = 256;    // physical entries: + combined tree depth of slack
-constexpr int LEAFQ_CAP = 96;
 
 struct FkParams {
   FkProgram prog;
@@ -203,12 +196,6 @@ struct EnergyParams {
   float *terms;             // [legal poses x contacts] per-contact energy terms (scratch)
   unsigned long long *stats;
 };
-
-__host__ __device__ inline size_t eval_warp_smem_bytes(int nb, int npairs, int mask_words, int stack_phys) {
-  size_t b = (size_t)nb * 96 + (size_t)npairs * sizeof(PairXf) + (size_t)stack_phys * 8 + (size_t)LEAFQ_CAP * 8 +
-             (size_t)mask_words * 8;
-  return (b + 15) & ~(size_t)15;
-}
 
 // ---- K6 / K7 ---------------------------------------------------------------------------------------
 struct ContactRec {
@@ -272,7 +259,6 @@ cudaError_t launch_compact(const EvalParams &p, cudaStream_t s);
 
 // launchers (kernels.cu)
 cudaError_t launch_fk(const FkParams &p, cudaStream_t s);
-cudaError_t launch_eval(const EvalParams &p, int blocks, int warps_per_block, size_t smem, cudaStream_t s);
 cudaError_t launch_recheck(const RecheckParams &p, cudaStream_t s);
 cudaError_t launch_point(const PointParams &p, cudaStream_t s);
 cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s);

@@ -73,17 +73,19 @@ struct Builder {
 };
 } // namespace
 
-void build_bvh(const float *tri9, int ntri, std::vector<Node> &nodes, int *depth_out) {
+void build_bvh(const float *tri9, int ntri, std::vector<NodeQ> &nodes, BvhQuant *quant, int *depth_out, Node *root_out) {
   nodes.clear();
+  BvhQuant g;
   if (ntri <= 0) {
-    // empty mesh: a single far-away degenerate leaf that nothing can reach
-    Node n;
-    n.cx = n.cy = n.cz = 1.0e18f;
-    n.hx = n.hy = n.hz = 0.f;
-    n.child = -1;
-    n.tri = -1;
-    nodes.push_back(n);
+    // empty mesh: one far-away leaf holding triangle 0 (the caller stores a degenerate triangle there)
+    for (int k = 0; k < 3; k++) { g.q0[k] = 1.0e18f; g.qs[k] = 0.f; }
+    NodeQ n;
+    for (int k = 0; k < 3; k++) { n.lo[k] = 0; n.hi[k] = 0; }
+    n.link = ~0;
+    nodes.push_back(n); nodes.push_back(n);
+    if (quant) *quant = g;
     if (depth_out) *depth_out = 0;
+    if (root_out) *root_out = decode_node(n, g);
     return;
   }
   Builder B;
@@ -97,11 +99,43 @@ void build_bvh(const float *tri9, int ntri, std::vector<Node> &nodes, int *depth
   B.tmp.reserve(2 * (size_t)ntri);
   B.build(0, ntri);
 
-  // breadth-first renumbering, siblings adjacent
-  nodes.resize(B.tmp.size());
+  // padding: keeps fp32 culling conservative (the reference pads by Leaf::TOLERANCE = 0.01 mm,
+  // collisionModel.cpp:43,122-128)
+  auto pad_of = [](const Build &b) {
+    float maxabs = 0.f;
+    for (int k = 0; k < 3; k++) maxabs = std::max(maxabs, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])));
+    return 1.0e-3f + 2.0e-6f * maxabs;
+  };
+  // quantisation grid: the padded root box split into 65535 steps per axis (a little slack so that every padded
+  // child box, which the root contains up to its own padding, lands inside the grid)
+  {
+    const Build &r = B.tmp[0];
+    float pad = 4.0f * pad_of(r);
+    for (int k = 0; k < 3; k++) {
+      g.q0[k] = r.lo[k] - pad;
+      float span = (r.hi[k] + pad) - g.q0[k];
+      g.qs[k] = std::max(span / 65535.0f, 1.0e-12f);
+    }
+  }
+  auto quant_lo = [&](float v, int k) {
+    double q = std::floor(((double)v - (double)g.q0[k]) / (double)g.qs[k]);
+    // the device decodes q0 + q * qs in fp32: step down until the decoded value is not above v
+    long long qi = (long long)std::max(0.0, std::min(65535.0, q));
+    while (qi > 0 && std::fmaf((float)qi, g.qs[k], g.q0[k]) > v) qi--;
+    return (unsigned short)qi;
+  };
+  auto quant_hi = [&](float v, int k) {
+    double q = std::ceil(((double)v - (double)g.q0[k]) / (double)g.qs[k]);
+    long long qi = (long long)std::max(0.0, std::min(65535.0, q));
+    while (qi < 65535 && std::fmaf((float)qi, g.qs[k], g.q0[k]) < v) qi++;
+    return (unsigned short)qi;
+  };
+
+  // breadth-first renumbering: [0] root, [1] unused, sibling pairs from index 2 on
+  nodes.resize(B.tmp.size() + 1);
   std::vector<int> newidx(B.tmp.size(), -1);
   std::queue<std::pair<int, int>> q;   // (tmp index, depth)
-  int next = 1, depth = 0;
+  int next = 2, depth = 0;
   newidx[0] = 0;
   q.push({0, 0});
   while (!q.empty()) {
@@ -109,33 +143,25 @@ void build_bvh(const float *tri9, int ntri, std::vector<Node> &nodes, int *depth
     q.pop();
     depth = std::max(depth, d);
     const Build &b = B.tmp[ti];
-    Node n;
-    float maxabs = 0.f;
-    for (int k = 0; k < 3; k++) maxabs = std::max(maxabs, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])));
-    // padding: keeps fp32 culling conservative (the reference pads by Leaf::TOLERANCE = 0.01 mm,
-    // collisionModel.cpp:43,122-128)
-    const float pad = 1.0e-3f + 2.0e-6f * maxabs;
-    n.cx = 0.5f * (b.lo[0] + b.hi[0]);
-    n.cy = 0.5f * (b.lo[1] + b.hi[1]);
-    n.cz = 0.5f * (b.lo[2] + b.hi[2]);
-    n.hx = 0.5f * (b.hi[0] - b.lo[0]) + pad;
-    n.hy = 0.5f * (b.hi[1] - b.lo[1]) + pad;
-    n.hz = 0.5f * (b.hi[2] - b.lo[2]) + pad;
+    const float pad = pad_of(b);
+    NodeQ n;
+    for (int k = 0; k < 3; k++) { n.lo[k] = quant_lo(b.lo[k] - pad, k); n.hi[k] = quant_hi(b.hi[k] + pad, k); }
     if (b.left < 0) {
-      n.child = -1;
-      n.tri = b.tri;
+      n.link = ~b.tri;
     } else {
       newidx[b.left] = next;
       newidx[b.right] = next + 1;
-      n.child = next;
-      n.tri = b.count;
+      n.link = next;
       next += 2;
       q.push({b.left, d + 1});
       q.push({b.right, d + 1});
     }
     nodes[newidx[ti]] = n;
   }
+  nodes[1] = nodes[0];
+  if (quant) *quant = g;
   if (depth_out) *depth_out = depth;
+  if (root_out) *root_out = decode_node(nodes[0], g);
 }
 
 } // namespace b2c

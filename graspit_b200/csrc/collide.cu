@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) broad_kernel(EvalParams p) {
     const double *XB = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, ab.y);
     PairXf x;
     make_pair_xf(XA, XB, ma.extent, mb.extent, x);
-    Node ra = load_node(ma.nodes, 0), rb = load_node(mb.nodes, 0);
+    Node ra = load_node(ma, 0), rb = load_node(mb, 0);
     float ca[3], ha[3], cb[3], hb[3];
     node_ch(ra, ca, ha); node_ch(rb, cb, hb);
     ov = box_overlap(ca, ha, cb, hb, x);
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256, 2) narrow_kernel(EvalParams p) {
         int4 mt = S.meta[slot];
         const MeshDev &ma = p.meshes[mt.z];
         const MeshDev &mb = p.meshes[mt.w];
-        Node a = load_node(ma.nodes, na), b = load_node(mb.nodes, nb);
+        Node a = load_node(ma, na), b = load_node(mb, nb);
         bool la = a.child < 0, lb = b.child < 0;
         if (la && lb) {
           push0 = leaf0 = true;
@@ -233,12 +233,13 @@ __global__ void __launch_bounds__(256, 2) narrow_kernel(EvalParams p) {
           const bool splitA = lb || (!la && (a.hx * a.hy * a.hz > b.hx * b.hy * b.hz));
           // both children of the split node against the other node, on ONE code path for every lane (operands are
           // selected, not branched on: lanes that split A and lanes that split B run the same box test together)
-          const Node *cnodes = splitA ? ma.nodes : mb.nodes;
+          const MeshDev &cm = splitA ? ma : mb;
           const int cbase = splitA ? a.child : b.child;
           const Node other = splitA ? b : a;
           const bool oleaf = splitA ? lb : la;
           const int oidx = splitA ? nb : na;
-          Node ch0 = load_node(cnodes, cbase), ch1 = load_node(cnodes, cbase + 1);
+          Node ch0, ch1;
+          load_pair(cm, cbase, ch0, ch1);
           float co[3], ho[3], cc[3], hc[3];
           node_ch(other, co, ho);
           node_ch(ch0, cc, hc);

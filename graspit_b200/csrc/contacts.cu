@@ -17,19 +17,10 @@
 // contact normal and whose closest point to the reference point lies within the radius are flagged
 // (RegionCallback::leafTest, collisionAlgorithms_inl.h:252-275); the host collects their vertices.
 #include "b2c_internal.h"
+#include "traverse.cuh"
 
 namespace b2c {
 
-#define FULL 0xffffffffu
-
-__device__ __forceinline__ Node c_load_node(const Node *nodes, int i) {
-  const float4 *p = reinterpret_cast<const float4 *>(nodes + i);
-  float4 a = __ldg(p), b = __ldg(p + 1);
-  Node n;
-  n.cx = a.x; n.cy = a.y; n.cz = a.z; n.hx = a.w;
-  n.hy = b.x; n.hz = b.y; n.child = __float_as_int(b.z); n.tri = __float_as_int(b.w);
-  return n;
-}
 __device__ __forceinline__ void c_node_ch(const Node &n, float *c, float *h) {
   c[0] = n.cx; c[1] = n.cy; c[2] = n.cz; h[0] = n.hx; h[1] = n.hy; h[2] = n.hz;
 }
@@ -177,7 +168,7 @@ __global__ void __launch_bounds__(256) contact_kernel(ContactParams p) {
       unsigned long long c0 = 0ull, c1 = 0ull;
       if (have) {
         int na = (int)((e >> 24) & 0xffffffu), nb = (int)(e & 0xffffffu);
-        Node a = c_load_node(ma.nodes, na), b = c_load_node(mb.nodes, nb);
+        Node a = load_node(ma, na), b = load_node(mb, nb);
         bool la = a.child < 0, lb = b.child < 0;
         if (la && lb) {
           p0 = l0 = a.tri >= 0 && b.tri >= 0;
@@ -186,7 +177,8 @@ __global__ void __launch_bounds__(256) contact_kernel(ContactParams p) {
           bool splitA = lb || (!la && (a.hx * a.hy * a.hz > b.hx * b.hy * b.hz));
           float ca[3], ha[3], cb[3], hb[3];
           if (splitA) {
-            Node a0 = c_load_node(ma.nodes, a.child), a1 = c_load_node(ma.nodes, a.child + 1);
+            Node a0, a1;
+            load_pair(ma, a.child, a0, a1);
             c_node_ch(b, cb, hb);
             c_node_ch(a0, ca, ha); p0 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
             c_node_ch(a1, ca, ha); p1 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
@@ -194,7 +186,8 @@ __global__ void __launch_bounds__(256) contact_kernel(ContactParams p) {
             c0 = l0 ? (((unsigned long long)(unsigned)a0.tri << 24) | (unsigned)b.tri) : (((unsigned long long)(unsigned)a.child << 24) | (unsigned)nb);
             c1 = l1 ? (((unsigned long long)(unsigned)a1.tri << 24) | (unsigned)b.tri) : (((unsigned long long)(unsigned)(a.child + 1) << 24) | (unsigned)nb);
           } else {
-            Node b0 = c_load_node(mb.nodes, b.child), b1 = c_load_node(mb.nodes, b.child + 1);
+            Node b0, b1;
+            load_pair(mb, b.child, b0, b1);
             c_node_ch(a, ca, ha);
             c_node_ch(b0, cb, hb); p0 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
             c_node_ch(b1, cb, hb); p1 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;

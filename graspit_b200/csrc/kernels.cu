@@ -1,7 +1,7 @@
 // CUDA kernels of the B200 collision engine (sm_100a).
 //
 //   fk_kernel        K1  search state -> hand pose -> per-link transforms          (thread / pose)
-//   eval_kernel      K3  legality over all active pairs, cooperative work stack      (warp / pose)
+//   (legality, K3: collide.cu -- broad_kernel thread / (pose, pair), narrow_kernel warp / 32 work items)
 //   recheck_kernel   fp64 re-decision of triangle pairs the fp32 SAT could not call
 //   point_kernel     K5 stand-alone closest point queries                            (thread / query)
 //   dist_kernel      K4 body-body minimum distance                                   (warp / query)
@@ -127,19 +127,6 @@ __device__ __noinline__ float tri_tri_dist2_plain(f3 p2, f3 p3, f3 q1, f3 q2, f3
   return d;
 }
 
-// node fetch: the first `ntop` nodes (top levels, breadth-first prefix) may live in shared memory
-__device__ __forceinline__ Node fetch_node(const Node *nodes, const Node *top, int ntop, int i) {
-  if (i < ntop) {
-    const float4 *p = reinterpret_cast<const float4 *>(top + i);
-    float4 a = p[0], b = p[1];
-    Node n;
-    n.cx = a.x; n.cy = a.y; n.cz = a.z; n.hx = a.w;
-    n.hy = b.x; n.hz = b.y; n.child = __float_as_int(b.z); n.tri = __float_as_int(b.w);
-    return n;
-  }
-  return load_node(nodes, i);
-}
-
 // ============================================================================================
 // closest point on a mesh to a query point (object frame).  Per-lane depth-first, nearer child
 // first, "while-while" form: a lane descends inner nodes until it holds a leaf, then all lanes of the
@@ -150,9 +137,8 @@ __device__ __forceinline__ Node fetch_node(const Node *nodes, const Node *top, i
 // Must agree with ClosestPtCallback (collisionAlgorithms_inl.h:210-238, collisionAlgorithms.h:220-242).
 // ============================================================================================
 #define CPQ_STACK 40
-__device__ __forceinline__ float closest_point_query(const MeshDev &m, const Node *top, int ntop, d3 q, f3 &bestv,
+__device__ __forceinline__ float closest_point_query(const MeshDev &m, const NodeQ *top, int ntop, d3 q, f3 &bestv,
                                                      int &best_tri, unsigned &n_box, unsigned &n_tri) {
-  const Node *nodes = m.nodes;
   const f3 qf = tof(q);
   float best = 1.0e30f, best_sc = 0.f;
   bestv = mk<float>(0.f, 0.f, 0.f);
@@ -167,12 +153,13 @@ __device__ __forceinline__ float closest_point_query(const MeshDev &m, const Nod
     // ---- descend until this lane holds a leaf or runs out of work
     while (cur >= 0) {
       if (curd <= best) {
-        Node n = fetch_node(nodes, top, ntop, cur);
+        Node n = fetch_node(m, top, ntop, cur);
         if (n.child < 0) {
           leaf = n.tri;
           cur = -1;
         } else {
-          Node c0 = fetch_node(nodes, top, ntop, n.child), c1 = fetch_node(nodes, top, ntop, n.child + 1);
+          Node c0, c1;
+          fetch_pair(m, top, ntop, n.child, c0, c1);
           float cc[3], hh[3];
           node_ch(c0, cc, hh); float d0 = point_box_dist2(cc, hh, qf);
           node_ch(c1, cc, hh); float d1 = point_box_dist2(cc, hh, qf);
@@ -221,7 +208,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ContactEnergy::energy (src/EGPlanner/energy/contactEnergy.cpp:9-55) for one contact: world contact
 // location p and world normal cn -> |v| + 50 (1 - cn . v/|v|), v = closest object point - p.
-__device__ __forceinline__ float contact_term(const MeshDev &mo, const Node *top, int ntop, const double *XO, d3 pw, d3 cnw,
+__device__ __forceinline__ float contact_term(const MeshDev &mo, const NodeQ *top, int ntop, const double *XO, d3 pw, d3 cnw,
                                               unsigned &n_box, unsigned &n_tri) {
   d3 q = xf_apply_inv(XO, pw);
   f3 cnl = tof(xf_rot_t(XO, cnw));
@@ -231,213 +218,6 @@ __device__ __forceinline__ float contact_term(const MeshDev &mo, const Node *top
   float inv = d2 > 0.f ? 1.0f / dist : 0.f;
   float c = (cnl.x * v.x + cnl.y * v.y + cnl.z * v.z) * inv;
   return dist + (1.0f - c) * 50.0f;
-}
-
-// ============================================================================================
-// K3 + K5 + K8: one warp evaluates one pose.
-//   phase 1  load the pose's body transforms, build the fp32 relative transform of every active
-//            pair (lanes = pairs) and test the root boxes
-//   phase 2  warp-cooperative traversal of ALL surviving pairs through one shared work stack:
-//            each lane pops one (pair, nodeA, nodeB) entry, tests the two children of the larger
-//            node against the other node, and the survivors are compacted back with ballot/popc;
-//            leaf-leaf entries go to a separate queue that is drained 32 triangle pairs at a time
-//   phase 3  poses without a collision are appended to a compact list for the energy kernel
-// Replaces GraspitCollision::allCollisions (graspitCollision.cpp:332-363) + recursion/CollisionCallback
-// (collisionAlgorithms.cpp:42-147, collisionAlgorithms_inl.h:50-81) and ContactEnergy::energy.
-// ============================================================================================
-struct WarpSmem {
-  double *bodyxf;                // [nb][12]
-  PairXf *pxf;                   // [npairs]
-  unsigned long long *stack;     // [STACK_PHYS]
-  unsigned long long *leafq;     // [LEAFQ_CAP]
-  unsigned *mask;                // [mask_words * 2]
-};
-
-
-// triangle pair (tri_a of body A, tri_b of body B) -> TT_SEP / TT_HIT / TT_AMBIG.
-// Triangle A is moved into B's frame in fp64 (reference: t1.applyTransform(mTran1To2),
-// collisionAlgorithms_inl.h:58-60) and everything is re-centred on its first vertex before rounding.
-__device__ __forceinline__ int leaf_pair_test(const MeshDev &ma, const MeshDev &mb, const double *XA, const double *XB,
-                                              int ta, int tb) {
-  d3 a1 = tri_vertex(ma.tris, ta, 0), a2 = tri_vertex(ma.tris, ta, 1), a3 = tri_vertex(ma.tris, ta, 2);
-  d3 b1 = tri_vertex(mb.tris, tb, 0), b2 = tri_vertex(mb.tris, tb, 1), b3 = tri_vertex(mb.tris, tb, 2);
-  d3 P1 = xf_apply_inv(XB, xf_apply(XA, a1));
-  d3 E1 = xf_rot_t(XB, xf_rot(XA, a2 - a1));
-  d3 E2 = xf_rot_t(XB, xf_rot(XA, a3 - a2));
-  f3 e1 = tof(E1), e2 = tof(E2);
-  f3 p2 = e1, p3 = tof(E1 + E2);
-  f3 q1 = tof(b1 - P1), q2 = tof(b2 - P1), q3 = tof(b3 - P1);
-  f3 f1 = tof(b2 - b1), f2 = tof(b3 - b2);
-  return tri_tri_filter(p2, p3, e1, e2, q1, q2, q3, f1, f2);
-}
-
-__global__ void __launch_bounds__(256, 3) eval_kernel(EvalParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const size_t wbytes = eval_warp_smem_bytes(p.nb, p.npairs, p.mask_words, p.stack_phys);
-  unsigned char *base = smem_raw + (size_t)warp * wbytes;
-  WarpSmem S;
-  S.bodyxf = reinterpret_cast<double *>(base);
-  S.pxf = reinterpret_cast<PairXf *>(base + (size_t)p.nb * 96);
-  S.stack = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(S.pxf) + (size_t)p.npairs * sizeof(PairXf));
-  S.leafq = S.stack + p.stack_phys;
-  S.mask = reinterpret_cast<unsigned *>(S.leafq + LEAFQ_CAP);
-
-  unsigned n_box = 0, n_tri = 0, n_amb = 0;
-
-  // static bodies never change: load once per warp
-  for (int i = p.nrb * 12 + lane; i < p.nb * 12; i += 32)
-    S.bodyxf[i] = reinterpret_cast<const double *>(p.static_xf)[i - p.nrb * 12];
-
-  while (true) {
-    int pose = 0;
-    if (lane == 0) pose = atomicAdd(p.pose_counter, 1);
-    pose = __shfl_sync(FULL, pose, 0);
-    if (pose >= p.npose) break;
-
-    // ---- phase 1 ----
-    {
-      const double *src = reinterpret_cast<const double *>(p.fk + (size_t)pose * p.nrb);
-      for (int i = lane; i < p.nrb * 12; i += 32) S.bodyxf[i] = src[i];
-      for (int i = lane; i < p.mask_words * 2; i += 32) S.mask[i] = 0u;
-    }
-    __syncwarp();
-    int sp = 0, lq = 0;
-    bool collided = false;
-    for (int pbase = 0; pbase < p.npairs; pbase += 32) {
-      int pi = pbase + lane;
-      bool ov = false;
-      if (pi < p.npairs) {
-        int2 ab = __ldg(&p.pairs[pi]);
-        const MeshDev &ma = p.meshes[__ldg(&p.body_mesh[ab.x])];
-        const MeshDev &mb = p.meshes[__ldg(&p.body_mesh[ab.y])];
-        PairXf x;
-        make_pair_xf(S.bodyxf + 12 * ab.x, S.bodyxf + 12 * ab.y, ma.extent, mb.extent, x);
-        S.pxf[pi] = x;
-        Node ra = load_node(ma.nodes, 0), rb = load_node(mb.nodes, 0);
-        float ca[3], ha[3], cb[3], hb[3];
-        node_ch(ra, ca, ha); node_ch(rb, cb, hb);
-        ov = box_overlap(ca, ha, cb, hb, x);
-        n_box++;
-      }
-      unsigned m = __ballot_sync(FULL, ov);
-      if (ov) S.stack[sp + __popc(m & lt_mask)] = pack_entry(pi, 0, 0);
-      sp += __popc(m);
-    }
-    __syncwarp();
-
-    // ---- phase 2 ----
-    while (true) {
-      if (lq >= 32 || (sp == 0 && lq > 0)) {
-        int n = lq < 32 ? lq : 32;
-        int res = TT_SEP;
-        int pair = 0, ta = 0, tb = 0;
-        if (lane < n) {
-          unsigned long long e = S.leafq[lq - n + lane];
-          pair = (int)(e >> 48); ta = (int)((e >> 24) & 0xffffffu); tb = (int)(e & 0xffffffu);
-          bool skip = p.mode_all && ((S.mask[pair >> 5] >> (pair & 31)) & 1u);
-          if (!skip) {
-            int2 ab = __ldg(&p.pairs[pair]);
-            res = leaf_pair_test(p.meshes[__ldg(&p.body_mesh[ab.x])], p.meshes[__ldg(&p.body_mesh[ab.y])],
-                                 S.bodyxf + 12 * ab.x, S.bodyxf + 12 * ab.y, ta, tb);
-            n_tri++;
-          }
-        }
-        lq -= n;
-        if (res == TT_HIT) atomicOr(&S.mask[pair >> 5], 1u << (pair & 31));
-        if (res == TT_AMBIG) {
-          n_amb++;
-          int slot = atomicAdd(p.ambig_count, 1);
-          if (slot < p.ambig_cap) { Ambig a; a.pose = pose; a.pair = pair; a.tri_a = ta; a.tri_b = tb; p.ambig[slot] = a; }
-        }
-        bool any = __any_sync(FULL, res == TT_HIT);
-        __syncwarp();
-        if (any) { collided = true; if (!p.mode_all) break; }
-        continue;
-      }
-      if (sp == 0) break;
-      int room = p.stack_cap - sp;
-      int k = sp < 32 ? sp : 32;
-      if (k > room) k = room > 1 ? room : 1;
-      bool have = lane < k;
-      unsigned long long e = have ? S.stack[sp - 1 - lane] : 0ull;
-      sp -= k;
-      __syncwarp();
-      bool push0 = false, push1 = false, leaf0 = false, leaf1 = false;
-      unsigned long long c0 = 0ull, c1 = 0ull;
-      if (have) {
-        int pair = (int)(e >> 48), na = (int)((e >> 24) & 0xffffffu), nb = (int)(e & 0xffffffu);
-        bool skip = p.mode_all && ((S.mask[pair >> 5] >> (pair & 31)) & 1u);
-        if (!skip) {
-          int2 ab = __ldg(&p.pairs[pair]);
-          const MeshDev &ma = p.meshes[__ldg(&p.body_mesh[ab.x])];
-          const MeshDev &mb = p.meshes[__ldg(&p.body_mesh[ab.y])];
-          Node a = load_node(ma.nodes, na), b = load_node(mb.nodes, nb);
-          bool la = a.child < 0, lb = b.child < 0;
-          if (la && lb) {
-            push0 = leaf0 = true;
-            c0 = pack_entry(pair, a.tri, b.tri);
-          } else {
-            const PairXf &x = S.pxf[pair];
-            bool splitA = lb || (!la && (a.hx * a.hy * a.hz > b.hx * b.hy * b.hz));
-            float ca[3], ha[3], cb[3], hb[3];
-            if (splitA) {
-              Node a0 = load_node(ma.nodes, a.child), a1 = load_node(ma.nodes, a.child + 1);
-              node_ch(b, cb, hb);
-              node_ch(a0, ca, ha); push0 = box_overlap(ca, ha, cb, hb, x);
-              node_ch(a1, ca, ha); push1 = box_overlap(ca, ha, cb, hb, x);
-              leaf0 = push0 && lb && a0.child < 0;
-              leaf1 = push1 && lb && a1.child < 0;
-              c0 = leaf0 ? pack_entry(pair, a0.tri, b.tri) : pack_entry(pair, a.child, nb);
-              c1 = leaf1 ? pack_entry(pair, a1.tri, b.tri) : pack_entry(pair, a.child + 1, nb);
-            } else {
-              Node b0 = load_node(mb.nodes, b.child), b1 = load_node(mb.nodes, b.child + 1);
-              node_ch(a, ca, ha);
-              node_ch(b0, cb, hb); push0 = box_overlap(ca, ha, cb, hb, x);
-              node_ch(b1, cb, hb); push1 = box_overlap(ca, ha, cb, hb, x);
-              leaf0 = push0 && la && b0.child < 0;
-              leaf1 = push1 && la && b1.child < 0;
-              c0 = leaf0 ? pack_entry(pair, a.tri, b0.tri) : pack_entry(pair, na, b.child);
-              c1 = leaf1 ? pack_entry(pair, a.tri, b1.tri) : pack_entry(pair, na, b.child + 1);
-            }
-            n_box += 2;
-          }
-        }
-      }
-      unsigned s0 = __ballot_sync(FULL, push0 && !leaf0), s1 = __ballot_sync(FULL, push1 && !leaf1);
-      unsigned l0 = __ballot_sync(FULL, push0 && leaf0), l1 = __ballot_sync(FULL, push1 && leaf1);
-      if (push0 && !leaf0) S.stack[sp + __popc(s0 & lt_mask)] = c0;
-      if (push1 && !leaf1) S.stack[sp + __popc(s0) + __popc(s1 & lt_mask)] = c1;
-      sp += __popc(s0) + __popc(s1);
-      if (push0 && leaf0) S.leafq[lq + __popc(l0 & lt_mask)] = c0;
-      if (push1 && leaf1) S.leafq[lq + __popc(l0) + __popc(l1 & lt_mask)] = c1;
-      lq += __popc(l0) + __popc(l1);
-      __syncwarp();
-    }
-    __syncwarp();
-
-    // ---- results of the legality test ----
-    if (p.pair_mask && lane < p.mask_words)
-      p.pair_mask[(size_t)pose * p.mask_words + lane] =
-          (unsigned long long)S.mask[2 * lane] | ((unsigned long long)S.mask[2 * lane + 1] << 32);
-
-    // ---- hand the pose over to the energy kernel ----
-    if (lane == 0) {
-      if (p.legal) p.legal[pose] = collided ? 0 : 1;
-      if (p.energy) p.energy[pose] = 0.f;
-      if (!collided && p.legal_list) p.legal_list[atomicAdd(p.legal_count, 1)] = pose;
-    }
-    __syncwarp();
-  }
-
-  if (p.stats) {
-    unsigned long long v;
-    v = n_box; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_BOX], v);
-    v = n_tri; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_TRI], v);
-    v = n_amb; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_AMBIG], v);
-  }
 }
 
 // ============================================================================================
@@ -734,7 +514,7 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
       unsigned long long cn = 0ull, cf = 0ull;
       if (have && entry_lb(e) <= best) {
         int na = (int)((e >> 24) & 0xffffffu), nb = (int)(e & 0xffffffu);
-        Node a = load_node(ma.nodes, na), b = load_node(mb.nodes, nb);
+        Node a = load_node(ma, na), b = load_node(mb, nb);
         bool la = a.child < 0, lb = b.child < 0;
         if (la && lb) {
           pn = ln = true;
@@ -742,8 +522,10 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
         } else {
           const bool splitA = lb || (!la && (a.hx * a.hy * a.hz > b.hx * b.hy * b.hz));
           // the two children of the split node against the other node: ONE copy of the box test in the loop body
-          const Node *cnodes = splitA ? ma.nodes : mb.nodes;
+          const MeshDev &cm = splitA ? ma : mb;
           const int cbase = splitA ? a.child : b.child;
+          Node chp[2];
+          load_pair(cm, cbase, chp[0], chp[1]);
           const Node other = splitA ? b : a;
           const bool oleaf = splitA ? lb : la;
           float d0 = 0.f, d1 = 0.f;
@@ -751,7 +533,7 @@ __global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
           bool lf0 = false, lf1 = false;
 #pragma unroll 1
           for (int c = 0; c < 2; c++) {
-            Node ch = load_node(cnodes, cbase + c);
+            const Node ch = c == 0 ? chp[0] : chp[1];
             float ca[3], ha[3], cb[3], hb[3];
             if (splitA) { node_ch(ch, ca, ha); node_ch(other, cb, hb); } else { node_ch(other, ca, ha); node_ch(ch, cb, hb); }
             float dc = box_dist_lb(ca, ha, cb, hb, x);
@@ -918,11 +700,11 @@ __device__ __forceinline__ unsigned long long eq_entry(float lb, int q, int idx)
 // per-query best (distance, triangle) is a 64-bit atomicMin in shared memory.
 __global__ void __launch_bounds__(256) energy_kernel(EnergyParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Node *top = reinterpret_cast<Node *>(smem_raw);
+  NodeQ *top = reinterpret_cast<NodeQ *>(smem_raw);
   __shared__ __align__(8) unsigned long long bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  unsigned char *wbase = smem_raw + (size_t)p.stage_nodes * sizeof(Node) + (size_t)warp * ENERGY_WARP_SMEM;
+  unsigned char *wbase = smem_raw + (size_t)p.stage_nodes * sizeof(NodeQ) + (size_t)warp * ENERGY_WARP_SMEM;
   unsigned long long *stack = reinterpret_cast<unsigned long long *>(wbase);
   unsigned long long *leafq = stack + EQ_STACK_PHYS;
   unsigned long long *bestkey = leafq + EQ_LEAF_CAP;                 // [32] (d2 bits << 32) | triangle
@@ -934,7 +716,7 @@ __global__ void __launch_bounds__(256) energy_kernel(EnergyParams p) {
 
   if (ntop > 0) {
     // TMA bulk copy of the tree's top levels (breadth-first prefix) into shared memory
-    const unsigned bytes = (unsigned)ntop * (unsigned)sizeof(Node);
+    const unsigned bytes = (unsigned)ntop * (unsigned)sizeof(NodeQ);
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -961,7 +743,7 @@ __global__ void __launch_bounds__(256) energy_kernel(EnergyParams p) {
   const int ngroups = (nquery + 31) / 32;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   unsigned nbx = 0, ntr = 0;
-  const Node root = fetch_node(mo.nodes, top, ntop, 0);
+  const Node root = fetch_node(mo, top, ntop, 0);
 
   for (int g = (blockIdx.x * blockDim.x + tid) >> 5; g < ngroups; g += warps_total) {
     // ---- set up this lane's query
@@ -1046,7 +828,8 @@ __global__ void __launch_bounds__(256) energy_kernel(EnergyParams p) {
         float lb = __uint_as_float((unsigned)(e >> 32));
         float best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
         if (lb <= best) {
-          Node c0 = fetch_node(mo.nodes, top, ntop, pair), c1 = fetch_node(mo.nodes, top, ntop, pair + 1);
+          Node c0, c1;
+          fetch_pair(mo, top, ntop, pair, c0, c1);
           float4 qq = qf[qi];
           f3 qp = mk<float>(qq.x, qq.y, qq.z);
           float cc[3], hh[3];
@@ -1131,17 +914,6 @@ cudaError_t launch_fk(const FkParams &p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_eval(const EvalParams &p, int blocks, int warps_per_block, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  eval_kernel<<<blocks, warps_per_block * 32, smem, s>>>(p);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_recheck(const RecheckParams &p, cudaStream_t s) {
   recheck_kernel<<<64, 128, 0, s>>>(p);
   return cudaGetLastError();
@@ -1184,6 +956,6 @@ cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-size_t energy_block_smem_bytes(int stage_nodes) { return (size_t)stage_nodes * sizeof(Node) + (size_t)8 * ENERGY_WARP_SMEM; }
+size_t energy_block_smem_bytes(int stage_nodes) { return (size_t)stage_nodes * sizeof(NodeQ) + (size_t)8 * ENERGY_WARP_SMEM; }
 
 } // namespace b2c

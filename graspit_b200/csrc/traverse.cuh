@@ -6,13 +6,49 @@ namespace b2c {
 
 #define FULL 0xffffffffu
 
-__device__ __forceinline__ Node load_node(const Node *nodes, int i) {
-  const float4 *p = reinterpret_cast<const float4 *>(nodes + i);
-  float4 a = __ldg(p), b = __ldg(p + 1);
+// stored node (16 B, bvh.h) -> decoded box.  q0 + q * qs with one fused rounding, like the host's decode_node.
+__device__ __forceinline__ Node decode_nodeq(unsigned wx, unsigned wy, unsigned wz, unsigned ww, const float *q0, const float *qs) {
+  float l0 = __fmaf_rn((float)(wx & 0xffffu), qs[0], q0[0]), l1 = __fmaf_rn((float)(wx >> 16), qs[1], q0[1]);
+  float l2 = __fmaf_rn((float)(wy & 0xffffu), qs[2], q0[2]), h0 = __fmaf_rn((float)(wy >> 16), qs[0], q0[0]);
+  float h1 = __fmaf_rn((float)(wz & 0xffffu), qs[1], q0[1]), h2 = __fmaf_rn((float)(wz >> 16), qs[2], q0[2]);
   Node n;
-  n.cx = a.x; n.cy = a.y; n.cz = a.z; n.hx = a.w;
-  n.hy = b.x; n.hz = b.y; n.child = __float_as_int(b.z); n.tri = __float_as_int(b.w);
+  n.cx = 0.5f * (l0 + h0); n.cy = 0.5f * (l1 + h1); n.cz = 0.5f * (l2 + h2);
+  n.hx = 0.5f * (h0 - l0); n.hy = 0.5f * (h1 - l1); n.hz = 0.5f * (h2 - l2);
+  const int link = (int)ww;
+  n.child = link >= 0 ? link : -1;
+  n.tri = link >= 0 ? -1 : ~link;
   return n;
+}
+__device__ __forceinline__ Node load_node(const MeshDev &m, int i) {
+  uint4 w = __ldg(reinterpret_cast<const uint4 *>(m.nodes + i));
+  return decode_nodeq(w.x, w.y, w.z, w.w, m.q0, m.qs);
+}
+// both children of a node (i = the parent's link, always even): one 256-bit load
+__device__ __forceinline__ void load_pair(const MeshDev &m, int i, Node &c0, Node &c1) {
+  unsigned r0, r1, r2, r3, r4, r5, r6, r7;
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+               : "l"(m.nodes + i));
+  c0 = decode_nodeq(r0, r1, r2, r3, m.q0, m.qs);
+  c1 = decode_nodeq(r4, r5, r6, r7, m.q0, m.qs);
+}
+// the same from a copy of the top of the tree in shared memory (i < ntop), else from global memory
+__device__ __forceinline__ void fetch_pair(const MeshDev &m, const NodeQ *top, int ntop, int i, Node &c0, Node &c1) {
+  if (i + 1 < ntop) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(top + i);
+    uint4 a = p[0], b = p[1];
+    c0 = decode_nodeq(a.x, a.y, a.z, a.w, m.q0, m.qs);
+    c1 = decode_nodeq(b.x, b.y, b.z, b.w, m.q0, m.qs);
+  } else {
+    load_pair(m, i, c0, c1);
+  }
+}
+__device__ __forceinline__ Node fetch_node(const MeshDev &m, const NodeQ *top, int ntop, int i) {
+  if (i < ntop) {
+    uint4 a = *reinterpret_cast<const uint4 *>(top + i);
+    return decode_nodeq(a.x, a.y, a.z, a.w, m.q0, m.qs);
+  }
+  return load_node(m, i);
 }
 __device__ __forceinline__ void node_ch(const Node &n, float *c, float *h) {
   c[0] = n.cx; c[1] = n.cy; c[2] = n.cz; h[0] = n.hx; h[1] = n.hy; h[2] = n.hz;
