@@ -264,11 +264,18 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     eng.set_profiling(True)
 
+    # N > 1: every step ends with the all-gather of each rank's BEST_LIST_SIZE best (state || energy) rows.  The rows
+    # come from the engine's incremental best list (one-warp kernel over the chains that improved this step), so the
+    # exchange costs one tiny kernel + one 720-byte-per-rank NCCL all-gather
+    rows = torch.empty((BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) if anneal else None
+    gathered = torch.empty((world * BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) if world > 1 else None
+
     def step_device(i):
         if anneal:
             an.step(1)
             if world > 1:
-                exchange_best(local_best_rows(views["best"], views["best_energy"], BEST_LIST_SIZE))
+                an.best_rows(BEST_LIST_SIZE, rows.data_ptr())
+                dist.all_gather_into_tensor(gathered, rows)
         else:
             st = dev_batches[i]
             eng.eval_batch_device(rid, oid, st.data_ptr(), npose, nvar, legal_d.data_ptr(), energy_d.data_ptr(),

@@ -98,11 +98,59 @@ __global__ void anneal_accept_kernel(AnnealParams p) {
       float *b = p.best + (size_t)c * p.nvar;
       for (int i = 0; i < p.nvar; i++) b[i] = src[i];
       p.best_energy[c] = p.energy[c];
+      // candidate for this context's best list (merged by anneal_toplist_kernel)
+      if (p.cand && p.energy[c] < *p.top_thresh) {
+        int at = atomicAdd(p.cand_count, 1);
+        if (at < p.nchain) p.cand[at] = c;
+      }
     }
     atomicAdd(&p.counters[0], 1);                // jumps
   }
   p.k[c] = k + 1;
   atomicAdd(&p.counters[1], 1);                  // legal neighbours
+}
+
+// This context's BEST_LIST_SIZE best chains (by best-so-far energy), kept incrementally: one warp, lane = list slot.
+// Candidates are the chains whose best improved below the list's current worst entry since the last call.  A chain
+// already listed is updated in place; otherwise it replaces the worst entry if it beats it.  Then the rows
+// (state || energy) of the listed chains are written out for the all-gather.  Empty slots carry energy 3e38.
+__global__ void anneal_toplist_kernel(AnnealParams p, int k, float *rows) {
+  const int lane = threadIdx.x;
+  int chain = lane < k ? p.top_chain[lane] : -2;
+  float e = lane < k ? (chain >= 0 ? p.best_energy[chain] : 3.0e38f) : -3.0e38f;   // lanes >= k never count as worst
+  int n = *p.cand_count;
+  const bool overflow = n > p.nchain;      // the queue was not drained for many steps: rescan every chain
+  if (overflow) n = p.nchain;
+  for (int i = 0; i < n; i++) {
+    const int c = overflow ? i : p.cand[i];
+    const float ce = p.best_energy[c];
+    const unsigned hit = __ballot_sync(0xffffffffu, chain == c);
+    if (hit) {
+      if (chain == c) e = ce;
+      continue;
+    }
+    // worst slot (largest energy; empty slots are 3e38), lowest lane on ties
+    float w = e;
+    for (int o = 16; o > 0; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if (ce < w) {
+      const unsigned who = __ballot_sync(0xffffffffu, e == w);
+      if (lane == __ffs(who) - 1) { chain = c; e = ce; }
+    }
+  }
+  float w = e;
+  for (int o = 16; o > 0; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
+  if (lane < k) {
+    p.top_chain[lane] = chain;
+    float *r = rows + (size_t)lane * (p.nvar + 1);
+    for (int i = 0; i < p.nvar; i++) r[i] = chain >= 0 ? p.best[(size_t)chain * p.nvar + i] : 0.f;
+    r[p.nvar] = e;
+  }
+  if (lane == 0) { *p.top_thresh = w; *p.cand_count = 0; }
+}
+
+cudaError_t launch_anneal_toplist(const AnnealParams &p, int k, float *rows, cudaStream_t s) {
+  anneal_toplist_kernel<<<1, 32, 0, s>>>(p, k, rows);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_anneal_propose(const AnnealParams &p, cudaStream_t s) {

@@ -242,7 +242,13 @@ struct AnnealParams {
   const unsigned char *legal;        // [nchain]
   int *k;                            // [nchain] per-chain annealing step (SimAnn::mCurrentStep)
   int *counters;                     // [0] jumps, [1] legal neighbours (totals)
+  // incremental best list of this context (anneal_toplist_kernel)
+  int *cand;                         // [nchain] chains whose best improved below the list threshold
+  int *cand_count;
+  float *top_thresh;                 // worst energy in the list (3e38 while it has free slots)
+  int *top_chain;                    // [32] listed chains, -1 = empty
 };
+cudaError_t launch_anneal_toplist(const AnnealParams &p, int k, float *rows, cudaStream_t s);
 cudaError_t launch_anneal_propose(const AnnealParams &p, cudaStream_t s);
 cudaError_t launch_anneal_accept(const AnnealParams &p, cudaStream_t s);
 

@@ -33,7 +33,7 @@ EXPORTS = [
     "b2c_all_contacts", "b2c_region", "b2c_bounding_volumes", "b2c_robot_define", "b2c_eval_batch",
     "b2c_robot_bodies", "b2c_robot_pairs", "b2c_last_stats", "b2c_obb_hierarchy", "b2c_contacts_postprocess",
     "b2c_anneal_create", "b2c_anneal_destroy", "b2c_anneal_step", "b2c_anneal_read", "b2c_anneal_device_ptrs",
-    "b2c_anneal_propose", "b2c_anneal_write",
+    "b2c_anneal_propose", "b2c_anneal_write", "b2c_anneal_best_rows",
 ]
 
 
@@ -132,6 +132,7 @@ def load_library():
     L.b2c_anneal_step.argtypes = [vp, ci, ci]
     L.b2c_anneal_read.argtypes = [vp, ci, vp, vp, vp, vp, vp, C.POINTER(C.c_longlong)]
     L.b2c_anneal_device_ptrs.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.b2c_anneal_best_rows.argtypes = [vp, ci, ci, vp]
     L.b2c_anneal_propose.argtypes = [vp, ci, vp]
     L.b2c_anneal_write.argtypes = [vp, ci, vp, vp, vp, ci]
     L.b2c_body_set_thread.argtypes = [vp, ci, ci]
@@ -550,6 +551,10 @@ class Annealer:
         p = [C.c_void_p() for _ in range(4)]
         self.engine._ck(self.engine.L.b2c_anneal_device_ptrs(self.engine.h, self.id, *[C.byref(x) for x in p]))
         return dict(best=p[0].value, best_energy=p[1].value, cur=p[2].value, cur_energy=p[3].value)
+
+    def best_rows(self, k: int, rows_device_ptr: int):
+        """this context's k best (state || energy) rows into device memory [k][nvar + 1]; asynchronous"""
+        self.engine._ck(self.engine.L.b2c_anneal_best_rows(self.engine.h, self.id, k, rows_device_ptr))
 
     def torch_views(self, device):
         """torch tensors aliasing the annealer's device rows (no copy): best, best_energy, cur, cur_energy"""

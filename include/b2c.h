@@ -275,6 +275,11 @@ int b2c_anneal_read(b2c_ctx *ctx, int anneal_id, float *cur, float *cur_energy, 
 /* device pointers of the per-chain best / current rows, for callers that reduce or exchange them on the device
  * (the multi-GPU best-list all-gather) */
 int b2c_anneal_device_ptrs(b2c_ctx *ctx, int anneal_id, void **best, void **best_energy, void **cur, void **cur_energy);
+/* this context's k (<= 32) best chains by best-so-far energy as rows [k][nvar + 1] = (state || energy) in DEVICE
+ * memory (empty slots: energy 3e38), maintained incrementally from the chains that improved since the last call;
+ * asynchronous on the context's stream.  It is the payload of the per-step multi-GPU all-gather that feeds the
+ * planner's best list (SimAnnPlanner::mainLoop, simAnnPlanner.cpp:126-143).  Always call it with the same k. */
+int b2c_anneal_best_rows(b2c_ctx *ctx, int anneal_id, int k, void *rows_device);
 /* test hooks: the neighbours the next step would draw (no state change), and overwriting chain state */
 int b2c_anneal_propose(b2c_ctx *ctx, int anneal_id, float *proposals);
 int b2c_anneal_write(b2c_ctx *ctx, int anneal_id, const float *cur, const float *cur_energy, const int *k, int step);

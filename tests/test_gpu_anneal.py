@@ -102,6 +102,21 @@ def test_annealing_lowers_energy_and_is_layout_independent(ctx):
     idx = np.argsort(w2["best_energy"])[:512]
     r = eng.eval_batch(ctx["rid"], ctx["oid"], w2["best"][idx], input_mode=B2C_INPUT_AA_EIGEN, ref_tran=ctx["ref"])
     assert r["legal"].all() and np.allclose(r["energy"], w2["best_energy"][idx], rtol=1e-5)
+    # the engine's incremental per-context best list = the 20 lowest per-chain best energies
+    import torch
+    rows = torch.zeros((20, 9), dtype=torch.float32, device="cuda")
+    whole.best_rows(20, rows.data_ptr())
+    torch.cuda.synchronize()
+    r = rows.cpu().numpy()
+    assert np.allclose(np.sort(r[:, -1]), np.sort(w2["best_energy"])[:20])
+    for row in r:
+        j = int(np.argmin(np.abs(w2["best_energy"] - row[-1])))
+        assert (w2["best"][j] == row[:-1]).all()
+    # and it keeps tracking as the chains move on
+    whole.step(25)
+    whole.best_rows(20, rows.data_ptr())
+    torch.cuda.synchronize()
+    assert np.allclose(np.sort(rows.cpu().numpy()[:, -1]), np.sort(whole.read()["best_energy"])[:20])
     # host best list (mBestList): unique, sorted, at most 20
     bl = BestList(ctx["ref"])
     bl.merge(w2["best"][idx], w2["best_energy"][idx])
