@@ -147,6 +147,56 @@ class BestList:
                 self.offer(np.asarray(states[j]), float(e[j]))
 
 
+def complete_dof_to_raw(states, ref_tran):
+    """SPACE_COMPLETE + POSE_DOF rows (Tx Ty Tz Qw Qx Qy Qz, DOFs) -> RAW engine rows (q wxyz, t, DOFs) with
+    base = mRefTran % transf(Q, T) (HandObjectState::execute, searchState.cpp:515-527; getCoreTran, searchStateImpl.cpp:125-135)"""
+    st = np.asarray(states, dtype=np.float64)
+    rq, rt = np.asarray(ref_tran[0], dtype=np.float64), np.asarray(ref_tran[1], dtype=np.float64)
+    out = np.zeros((st.shape[0], st.shape[1]), dtype=np.float64)
+    for i, r in enumerate(st):
+        q = r[3:7] / np.linalg.norm(r[3:7])
+        w, v = rq[0], rq[1:]
+        t = r[0:3]
+        rot_t = t + 2.0 * w * np.cross(v, t) + 2.0 * np.cross(v, np.cross(v, t))
+        qq = _quat_mul(rq, q)
+        out[i, 0:4] = qq / np.linalg.norm(qq); out[i, 4:7] = rt + rot_t; out[i, 7:] = r[7:]
+    return out.astype(np.float32)
+
+
+class ListPlanner:
+    """Batched ListPlanner (reference src/EGPlanner/listPlanner.cpp:126-170): every input state is evaluated (one
+    b2c_eval_batch call instead of one analyzeState per planner step) and the legal ones enter the best list in input
+    order: kept if the list has room or they beat its worst entry; sorted by energy; at most BEST_LIST_SIZE.  Unlike
+    SimAnnPlanner no similarity pruning is applied (the reference's ListPlanner does none)."""
+
+    def __init__(self, engine, robot_id: int, object_id: int, ref_tran, live=False, size=BEST_LIST_SIZE):
+        self.engine, self.robot, self.object, self.ref_tran, self.live, self.size = engine, robot_id, object_id, ref_tran, live, size
+        self.best = []           # (energy, input index)
+        self.legal = self.energy = None
+
+    def run(self, states):
+        from .engine import B2C_INPUT_AA_EIGEN, B2C_INPUT_RAW
+        from .formats.statefile import to_engine_batch
+        kind, arr = to_engine_batch(states)
+        if len(arr) == 0:
+            self.legal, self.energy, self.best = np.zeros(0, np.uint8), np.zeros(0, np.float32), []
+            return self.best
+        if kind == "aa_eigen":
+            r = self.engine.eval_batch(self.robot, self.object, arr, input_mode=B2C_INPUT_AA_EIGEN, ref_tran=self.ref_tran, live=self.live)
+        else:
+            r = self.engine.eval_batch(self.robot, self.object, complete_dof_to_raw(arr, self.ref_tran), input_mode=B2C_INPUT_RAW, live=self.live)
+        self.legal, self.energy = r["legal"], r["energy"]
+        best = []
+        for i in np.nonzero(self.legal)[0]:
+            worst = 1.0e5 if len(best) < self.size else best[-1][0]
+            if self.energy[i] < worst:
+                best.append((float(self.energy[i]), int(i)))
+                best.sort(key=lambda x: x[0])          # std::list::sort is stable
+                best = best[: self.size]
+        self.best = best
+        return best
+
+
 def local_best_rows(best_states, best_energy, k=BEST_LIST_SIZE):
     """this rank's k best (state || energy) rows as one torch tensor [k, nvar + 1]; works on CPU and CUDA tensors"""
     import torch
