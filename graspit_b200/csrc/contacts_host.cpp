@@ -455,4 +455,121 @@ void compact_contact_set(std::vector<b2c_contact> &contacts) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Contact frames and point-contact friction cones (World::findAllContacts -> addContacts,
+// reference src/contactSetting.cpp:54-81,193-221; Contact::Contact, src/contact/contact.cpp:67-99;
+// PointContact::setUpFrictionEdges, src/contact/pointContact.cpp:44-56; Contact::setUpFrictionEllipsoid,
+// contact.cpp:180-216; Contact::wrenchFromFrictionEdge / computeWrenches, contact.cpp:124-165).
+// Closed-form and tiny per contact: host work.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct V3d { double x, y, z; };
+inline V3d vsub(V3d a, V3d b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3d vadd(V3d a, V3d b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3d vmul(V3d a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+inline double vdot(V3d a, V3d b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3d vcross(V3d a, V3d b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline V3d vnormalized(V3d a) {           // Eigen's normalized(): unchanged when the squared norm is 0
+  double n2 = vdot(a, a);
+  return n2 > 0.0 ? vmul(a, 1.0 / std::sqrt(n2)) : a;
+}
+inline V3d qrot(const double q[4], V3d v) {   // Eigen quaternion * vector: v + w*2(u x v) + u x 2(u x v)
+  V3d u = {q[1], q[2], q[3]};
+  V3d uv = vcross(u, v); uv = vadd(uv, uv);
+  return vadd(vadd(v, vmul(uv, q[0])), vcross(u, uv));
+}
+} // namespace
+
+int contact_frames(const b2c_contact *c, int n, int side, double *frame7, double *tangents6) {
+  for (int i = 0; i < n; i++) {
+    const double *pos = side == 1 ? c[i].b1_pos : c[i].b2_pos;
+    const double *nrm = side == 1 ? c[i].b1_normal : c[i].b2_normal;
+    V3d normal = vnormalized({nrm[0], nrm[1], nrm[2]});
+    V3d tx, ty;
+    // MACHINE_ZERO = 1e-9 (matvec3D.h:53)
+    if (std::fabs(vdot(normal, {1, 0, 0})) > 1.0 - 1.0e-9) tx = vnormalized(vcross(normal, {0, 0, 1}));
+    else tx = vnormalized(vcross(normal, {1, 0, 0}));
+    ty = vnormalized(vcross(normal, tx));
+    // transf::COORDINATE(loc, tangentX, tangentY) (transform.cpp:40-50)
+    V3d nx = vnormalized(tx);
+    V3d nz = vnormalized(vcross(nx, ty));
+    V3d ny = vnormalized(vcross(nz, nx));
+    M3 R;
+    R.m[0][0] = nx.x; R.m[1][0] = nx.y; R.m[2][0] = nx.z;
+    R.m[0][1] = ny.x; R.m[1][1] = ny.y; R.m[2][1] = ny.z;
+    R.m[0][2] = nz.x; R.m[1][2] = nz.y; R.m[2][2] = nz.z;
+    double q[4];
+    matrix_to_quat(R, q);
+    double *f = frame7 + 7 * (size_t)i;
+    f[0] = q[0]; f[1] = q[1]; f[2] = q[2]; f[3] = q[3]; f[4] = pos[0]; f[5] = pos[1]; f[6] = pos[2];
+    if (tangents6) {
+      // what wrenchFromFrictionEdge reads back: frame.affine().col(0), col(1) -- transf::set(mat3) keeps R = the matrix
+      double *t = tangents6 + 6 * (size_t)i;
+      t[0] = nx.x; t[1] = nx.y; t[2] = nx.z; t[3] = ny.x; t[4] = ny.y; t[5] = ny.z;
+    }
+  }
+  return n;
+}
+
+void friction_ellipsoid_edges(int nlat, const int *ndirs, const double *phi, const double *eccen, std::vector<double> &edges) {
+  edges.clear();
+  for (int i = 0; i < nlat; i++) {
+    double cosphi = std::cos(phi[i]), sinphi = std::sin(phi[i]);
+    for (int j = 0; j < ndirs[i]; j++) {
+      double theta = j * 2 * M_PI / ndirs[i];
+      double num = std::cos(theta) * cosphi;
+      double denom = num * num / (eccen[0] * eccen[0]);
+      num = std::sin(theta) * cosphi;
+      denom += num * num / (eccen[1] * eccen[1]);
+      num = sinphi;
+      denom += num * num / (eccen[2] * eccen[2]);
+      denom = std::sqrt(denom);
+      double e[6] = {std::cos(theta) * cosphi / denom, std::sin(theta) * cosphi / denom, 0, 0, 0, sinphi / denom};
+      edges.insert(edges.end(), e, e + 6);
+    }
+  }
+}
+
+int point_contact_wrenches(const b2c_contact *c, int n, int side, double cof, const double cog[3], double max_radius, double *wrench48) {
+  // PCWF: one latitude (phi = 0), 8 directions, unit eccentricities (pointContact.cpp:44-56)
+  const int ndirs[1] = {8};
+  const double phi[1] = {0.0}, eccen[3] = {1, 1, 1};
+  std::vector<double> edges;
+  friction_ellipsoid_edges(1, ndirs, phi, eccen, edges);
+  std::vector<double> frames(7 * (size_t)n), tang(6 * (size_t)n);
+  contact_frames(c, n, side, frames.data(), tang.data());
+  for (int i = 0; i < n; i++) {
+    const double *pos = side == 1 ? c[i].b1_pos : c[i].b2_pos;
+    const double *nrm = side == 1 ? c[i].b1_normal : c[i].b2_normal;
+    V3d normal = vnormalized({nrm[0], nrm[1], nrm[2]});
+    V3d tx = {tang[6 * i], tang[6 * i + 1], tang[6 * i + 2]}, ty = {tang[6 * i + 3], tang[6 * i + 4], tang[6 * i + 5]};
+    V3d radius = vsub({pos[0], pos[1], pos[2]}, {cog[0], cog[1], cog[2]});
+    for (int k = 0; k < 8; k++) {
+      const double *e = &edges[6 * k];
+      V3d force = vadd(vadd(normal, vmul(tx, cof * e[0])), vmul(ty, cof * e[1]));
+      V3d torque = vmul(vadd(vcross(radius, force), vmul(normal, cof * e[5])), 1.0 / max_radius);
+      double *w = wrench48 + 48 * (size_t)i + 6 * k;
+      w[0] = force.x; w[1] = force.y; w[2] = force.z; w[3] = torque.x; w[4] = torque.y; w[5] = torque.z;
+    }
+  }
+  return n;
+}
+
+int check_contact_normals(b2c_contact *c, int n, const double q1[4], const double t1[3], const double q2[4], const double t2[3]) {
+  int flipped = 0;
+  for (int i = 0; i < n; i++) {
+    V3d n1 = qrot(q1, {c[i].b1_normal[0], c[i].b1_normal[1], c[i].b1_normal[2]});
+    V3d n2 = qrot(q2, {c[i].b2_normal[0], c[i].b2_normal[1], c[i].b2_normal[2]});
+    V3d p1 = vadd(qrot(q1, {c[i].b1_pos[0], c[i].b1_pos[1], c[i].b1_pos[2]}), {t1[0], t1[1], t1[2]});
+    V3d p2 = vadd(qrot(q2, {c[i].b2_pos[0], c[i].b2_pos[1], c[i].b2_pos[2]}), {t2[0], t2[1], t2[2]});
+    V3d d = vsub(p2, p1);
+    bool ok = true;
+    if (vdot(d, n1) > 0) { ok = false; for (int k = 0; k < 3; k++) c[i].b1_normal[k] = -c[i].b1_normal[k]; }
+    if (vdot(d, n2) < 0) { ok = false; for (int k = 0; k < 3; k++) c[i].b2_normal[k] = -c[i].b2_normal[k]; }
+    if (!ok) flipped++;
+  }
+  return flipped;
+}
+
+
 } // namespace b2c

@@ -33,4 +33,13 @@ void remove_contact_duplicates(std::vector<b2c_contact> &contacts, double duplic
 // CollisionInterface::compactContactSet / replaceContactSetWithPerimeter (collisionInterface.cpp:74-252)
 void compact_contact_set(std::vector<b2c_contact> &contacts);
 
+// Contact::Contact frame (contact.cpp:67-99): frame7 = [n][q wxyz, t]; tangents6 (optional) = [n][tangentX, tangentY]
+int contact_frames(const b2c_contact *c, int n, int side, double *frame7, double *tangents6);
+// Contact::setUpFrictionEllipsoid (contact.cpp:180-216): edges = 6 doubles per sample
+void friction_ellipsoid_edges(int nlat, const int *ndirs, const double *phi, const double *eccen, std::vector<double> &edges);
+// PointContact friction cone -> boundary wrenches (contact.cpp:124-165): wrench48 = [n][8][force(3), torque(3)]
+int point_contact_wrenches(const b2c_contact *c, int n, int side, double cof, const double cog[3], double max_radius, double *wrench48);
+// checkContactNormals (contactSetting.cpp:54-81): flips ill-oriented normals in place, returns how many contacts changed
+int check_contact_normals(b2c_contact *c, int n, const double q1[4], const double t1[3], const double q2[4], const double t2[3]);
+
 } // namespace b2c

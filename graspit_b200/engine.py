@@ -34,6 +34,7 @@ EXPORTS = [
     "b2c_robot_bodies", "b2c_robot_pairs", "b2c_last_stats", "b2c_obb_hierarchy", "b2c_contacts_postprocess",
     "b2c_anneal_create", "b2c_anneal_destroy", "b2c_anneal_step", "b2c_anneal_read", "b2c_anneal_device_ptrs",
     "b2c_anneal_propose", "b2c_anneal_write", "b2c_anneal_best_rows",
+    "b2c_check_contact_normals", "b2c_contact_frames", "b2c_point_contact_wrenches",
 ]
 
 
@@ -127,6 +128,9 @@ def load_library():
     L.b2c_body_set_active.argtypes = [vp, ci, ci]
     L.b2c_pair_set_active.argtypes = [vp, ci, ci, ci]
     L.b2c_pair_is_active.argtypes = [vp, ci, ci, ip]
+    L.b2c_check_contact_normals.argtypes = [C.POINTER(Contact), ci, dp, dp, dp, dp, ip]
+    L.b2c_contact_frames.argtypes = [C.POINTER(Contact), ci, ci, dp]
+    L.b2c_point_contact_wrenches.argtypes = [C.POINTER(Contact), ci, ci, C.c_double, dp, C.c_double, dp]
     L.b2c_anneal_create.argtypes = [vp, C.POINTER(AnnealDesc), C.POINTER(C.c_float), ip]
     L.b2c_anneal_destroy.argtypes = [vp, ci]
     L.b2c_anneal_step.argtypes = [vp, ci, ci]
@@ -507,6 +511,53 @@ class Engine:
         a.flags = B2C_EVAL_DEVICE_PTRS | (B2C_EVAL_LIVE if live else 0)
         a.legal, a.energy = legal_ptr, energy_ptr
         self._ck(self.L.b2c_eval_batch(self.h, C.byref(a)))
+
+
+def _contact_array(rows):
+    rows = np.asarray(rows, dtype=np.float64).reshape(-1, 13)
+    arr = (Contact * max(1, len(rows)))()
+    for i, r in enumerate(rows):
+        arr[i].b1_pos[:] = list(r[0:3]); arr[i].b2_pos[:] = list(r[3:6])
+        arr[i].b1_normal[:] = list(r[6:9]); arr[i].b2_normal[:] = list(r[9:12]); arr[i].distSq = float(r[12])
+    return arr, len(rows)
+
+
+def check_contact_normals(rows, tran1, tran2):
+    """checkContactNormals over contact rows [n][13]; returns (rows with flipped normals, number changed).  Host only."""
+    L = load_library()
+    arr, n = _contact_array(rows)
+    q1, t1, q2, t2 = [np.ascontiguousarray(x, dtype=np.float64) for x in (tran1[0], tran1[1], tran2[0], tran2[1])]
+    dp = C.POINTER(C.c_double)
+    nf = C.c_int(0)
+    rc = L.b2c_check_contact_normals(arr, n, q1.ctypes.data_as(dp), t1.ctypes.data_as(dp), q2.ctypes.data_as(dp), t2.ctypes.data_as(dp), C.byref(nf))
+    if rc:
+        raise B2CError(f"b2c_check_contact_normals failed ({rc})")
+    out = np.array([list(a.b1_pos) + list(a.b2_pos) + list(a.b1_normal) + list(a.b2_normal) + [a.distSq] for a in arr[:n]]).reshape(-1, 13)
+    return out, nf.value
+
+
+def contact_frames(rows, side=1):
+    """Contact::Contact frames of contact rows [n][13]: (n, 7) = q wxyz, t.  Host only."""
+    L = load_library()
+    arr, n = _contact_array(rows)
+    out = np.zeros((n, 7))
+    rc = L.b2c_contact_frames(arr, n, side, out.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc:
+        raise B2CError(f"b2c_contact_frames failed ({rc})")
+    return out
+
+
+def point_contact_wrenches(rows, side, cof, cog, max_radius):
+    """PCWF friction-cone boundary wrenches of contact rows [n][13]: (n, 8, 6) = force, torque.  Host only."""
+    L = load_library()
+    arr, n = _contact_array(rows)
+    out = np.zeros((n, 8, 6))
+    g = np.ascontiguousarray(cog, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    rc = L.b2c_point_contact_wrenches(arr, n, side, float(cof), g.ctypes.data_as(dp), float(max_radius), out.ctypes.data_as(dp))
+    if rc:
+        raise B2CError(f"b2c_point_contact_wrenches failed ({rc})")
+    return out
 
 
 class Annealer:

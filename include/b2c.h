@@ -144,6 +144,22 @@ int b2c_bounding_volumes(b2c_ctx *ctx, int body, int depth, b2c_obb *out, int ca
 int b2c_obb_hierarchy(const float *tri9, int ntri, int depth, b2c_obb *out, int cap, int *nboxes);
 int b2c_contacts_postprocess(b2c_contact *contacts, int *n, double duplicate_threshold, int compact);
 
+/* Contact frames and point-contact friction cones, the last step of World::findAllContacts -> addContacts
+ * (reference src/contactSetting.cpp:193-221).  Context-free host utilities (closed form, a few hundred flops per contact).
+ * side = 1: the contact as seen from body 1 (b1_pos, b1_normal), side = 2: its mate on body 2.
+ *   b2c_check_contact_normals  checkContactNormals (contactSetting.cpp:54-81): flips normals that point the wrong way
+ *                              given the bodies' world transforms; *nflipped = contacts changed
+ *   b2c_contact_frames         Contact::Contact (src/contact/contact.cpp:67-99): frame7 = [n][q wxyz, t], x/y = tangents
+ *   b2c_point_contact_wrenches PointContact (PCWF) friction cone: 8 edges of the unit circle
+ *                              (pointContact.cpp:44-56, contact.cpp:180-216) turned into boundary wrenches
+ *                              f = n + cof (e0 tx + e1 ty), tau = (r x f + n cof e5) / max_radius, r = pos - cog
+ *                              (contact.cpp:124-165); wrench48 = [n][8][force 3, torque 3] */
+int b2c_check_contact_normals(b2c_contact *contacts, int n, const double q1_wxyz[4], const double t1[3],
+                              const double q2_wxyz[4], const double t2[3], int *nflipped);
+int b2c_contact_frames(const b2c_contact *contacts, int n, int side, double *frame7);
+int b2c_point_contact_wrenches(const b2c_contact *contacts, int n, int side, double cof, const double cog[3],
+                               double max_radius, double *wrench48);
+
 /* ---- batched pose evaluation: FK -> legal -> proximity -> CONTACT_ENERGY --------------------
  * Replaces, for whole batches of candidate states, the loop
  *   HandObjectState::execute -> Robot::setTran / forceDOFVals -> KinematicChain::fwdKinematics

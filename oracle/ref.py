@@ -69,6 +69,7 @@ def lib():
         L.ref_transf_apply.argtypes = [C.POINTER(C.c_double)] * 4
         L.ref_transf_rotate.argtypes = [C.POINTER(C.c_double)] * 4
         L.ref_transf_axis_angle.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_transf_coordinate.argtypes = [C.POINTER(C.c_double)] * 5
         L.ref_transf_jacobian.argtypes = [C.POINTER(C.c_double)] * 3
         L.ref_quat_roundtrip.argtypes = [C.POINTER(C.c_double)] * 3
         L.ref_eval_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,
@@ -233,6 +234,13 @@ def transf_axis_angle(angle, axis):
     ax = _d(axis, 3); out = np.zeros(7)
     lib().ref_transf_axis_angle(float(angle), _dp(ax), _dp(out))
     return out[:4].copy(), out[4:].copy()
+
+
+def transf_coordinate(o, x, y):
+    """the reference's transf::COORDINATE: returns (q wxyz, t, affine 3x3)"""
+    o, x, y = _d(o, 3), _d(x, 3), _d(y, 3); out = np.zeros(7); aff = np.zeros(9)
+    lib().ref_transf_coordinate(_dp(o), _dp(x), _dp(y), _dp(out), _dp(aff))
+    return out[:4].copy(), out[4:].copy(), aff.reshape(3, 3).copy()
 
 
 def transf_jacobian(a):

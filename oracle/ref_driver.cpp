@@ -314,6 +314,13 @@ void ref_transf_axis_angle(double angle, const double *axis, double *out7) {
   out7[0] = r.rotation().w(); out7[1] = r.rotation().x(); out7[2] = r.rotation().y(); out7[3] = r.rotation().z();
   for (int k = 0; k < 3; k++) out7[4 + k] = r.translation()[k];
 }
+// transf::COORDINATE (src/transform.cpp:40-50): the frame constructor used by Contact::Contact; out7 = (q wxyz, t), out9 = affine()
+void ref_transf_coordinate(const double *o, const double *x, const double *y, double *out7, double *out9) {
+  transf r = transf::COORDINATE(position(o[0], o[1], o[2]), vec3(x[0], x[1], x[2]), vec3(y[0], y[1], y[2]));
+  out7[0] = r.rotation().w(); out7[1] = r.rotation().x(); out7[2] = r.rotation().y(); out7[3] = r.rotation().z();
+  for (int k = 0; k < 3; k++) out7[4 + k] = r.translation()[k];
+  if (out9) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out9[3 * i + j] = r.affine()(i, j);
+}
 void ref_transf_jacobian(const double *q, const double *t, double *out36) {
   makeTransf(q, t).jacobian(out36);
 }

@@ -89,7 +89,7 @@ def test_config3_allcontacts_with_region(human):
     inv_o = {v: k for k, v in osc.ids.items()}
     inv_e = {v: k for k, v in sb.body_ids.items()}
     w = osc.w
-    done = npairs = ncontacts = exact = 0
+    done = npairs = ncontacts = exact = ncones = 0
     for p in np.nonzero(legal_o)[0]:
         if done >= 25:
             break
@@ -131,6 +131,20 @@ def test_config3_allcontacts_with_region(human):
                 assert min(np.linalg.norm(ec[:, :3] - r[:3], axis=1)) < 6.0
             if len(ec) == len(cl) and {tuple(np.round(r[:6], 5)) for r in ec} == {tuple(np.round(r[:6], 5)) for r in cl}:
                 exact += 1
+                # friction-cone setup per contact (addContacts: checkContactNormals -> PointContact frames + cone wrenches)
+                from graspit_b200 import engine as E
+                from oracle.port import contact_np as cn
+                ta = (tf7[p, order.index(key[0]), :4], tf7[p, order.index(key[0]), 4:] + shift) if key[0] in order else sc.body_tran[key[0]]
+                tb = (tf7[p, order.index(key[1]), :4], tf7[p, order.index(key[1]), 4:] + shift) if key[1] in order else sc.body_tran[key[1]]
+                fixed, _ = E.check_contact_normals(ec, ta, tb)
+                wr = E.point_contact_wrenches(fixed, 1, 0.5, [0.0, 0.0, 0.0], 100.0)
+                fr = E.contact_frames(fixed, 1)
+                for i, row in enumerate(fixed):
+                    rr, _ok = cn.check_contact_normals(ec[i], ta, tb)
+                    assert np.allclose(rr, row)
+                    assert np.allclose(wr[i], cn.point_contact_wrenches(row[0:3], row[6:9], 0.5, [0.0, 0.0, 0.0], 100.0), atol=1e-10)
+                    assert np.allclose(fr[i, 4:], row[0:3])
+                ncones += len(fixed)
             # region around the first contact on the object side (elastic fingertip neighbourhoods)
             a_is_obj = key[0] == obj
             cpos = cl[0][0:3] if a_is_obj else cl[0][3:6]
@@ -140,6 +154,7 @@ def test_config3_allcontacts_with_region(human):
             assert {tuple(r) for r in ro} == {tuple(r) for r in re}
     assert done >= 10 and npairs >= done and ncontacts >= done
     assert exact >= 0.7 * npairs
+    assert ncones >= 5
 
 
 # ------------------------------------------------------------------------------------------------ config 4
