@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
         subprocess.check_call(cmd, env=env)
         objs.append(o)
     target = out or LIB
-    cmd = [_nvcc(), "-ccbin", ccbin, "-shared", "-o", target, *objs, "-lcudart"]
+    cmd = [_nvcc(), "-ccbin", ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target, *objs, "-lcudart"]
     subprocess.check_call(cmd, env=env)
     return target
 
