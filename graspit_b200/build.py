@@ -53,6 +53,26 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
     return target
 
 
+def build_host_planner_check() -> str:
+    """tests/host/b200planner_check: the C++ planner host (graspit_b200/host/b200Planner.cpp) + its test harness, linked
+    with libb2c.so.  Needs nothing from the reference."""
+    root = os.path.dirname(HERE)
+    out = os.path.join(HERE, "build", "b200planner_check")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cudart = None
+    for d in ("/usr/local/cuda/lib64", "/usr/local/cuda/targets/x86_64-linux/lib"):
+        if os.path.exists(os.path.join(d, "libcudart.so")):
+            cudart = d
+    cmd = [ccbin, "-std=c++14", "-O2", "-Wall", "-I", os.path.join(root, "include"), "-I", os.path.join(HERE, "host"),
+           os.path.join(HERE, "host", "b200Planner.cpp"), os.path.join(root, "tests", "host", "b200planner_check.cpp"),
+           "-o", out, "-L", HERE, "-lb2c", "-Wl,-rpath,$ORIGIN/.."]
+    if cudart:
+        cmd += ["-L", cudart, "-lcudart", f"-Wl,-rpath,{cudart}"]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
