@@ -111,7 +111,7 @@ struct b2c_ctx {
   DevBuf<float> d_states; DevBuf<Xf> d_fk; DevBuf<double> d_fkqt; DevBuf<uint8_t> d_legal; DevBuf<float> d_energy;
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
   DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
-  int stage_nodes = 1024;          // object-tree nodes staged in shared memory by the energy kernel
+  int stage_nodes = 256;           // object-tree nodes staged in shared memory by the energy kernel
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int eval_warps_per_block = 8;
   int eval_blocks_per_sm = 0;      // 0 = derive from shared memory
@@ -914,7 +914,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   gp.stage_nodes = ctx->stage_nodes;
   gp.fk = ctx->d_fk.p; gp.static_xf = P->d_static.p; gp.body_mesh = P->d_body_mesh.p; gp.meshes = ctx->d_meshes.p;
   gp.vcs = P->d_vcs.p; gp.legal = d_legal; gp.legal_list = ctx->d_legal_list.p; gp.legal_count = ctx->d_counters.p + 4;
-  gp.energy = d_energy; gp.stats = ctx->d_stats.p;
+  gp.energy = d_energy; gp.stats = ctx->d_stats.p; gp.work_counter = ctx->d_counters.p + 9;
   auto energy_blocks = [&](int contacts) {
     size_t smem = energy_block_smem_bytes(gp.stage_nodes);
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / smem));

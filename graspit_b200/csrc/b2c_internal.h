@@ -194,6 +194,7 @@ struct EnergyParams {
   const int *legal_count;
   float *energy;
   float *terms;             // [legal poses x contacts] per-contact energy terms (scratch)
+  int *work_counter;        // dynamic hand-out of 32-query groups (zeroed by the caller)
   unsigned long long *stats;
 };
 

@@ -684,7 +684,10 @@ __global__ void __launch_bounds__(128) dist_refine_kernel(DistParams p) {
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // per-warp shared memory of the cooperative energy kernel
-constexpr int EQ_STACK_CAP = 448, EQ_STACK_PHYS = 512, EQ_LEAF_CAP = 96;
+#ifndef EQ_STACK_PHYS_N
+#define EQ_STACK_PHYS_N 512
+#endif
+constexpr int EQ_STACK_PHYS = EQ_STACK_PHYS_N, EQ_STACK_CAP = EQ_STACK_PHYS_N - 64, EQ_LEAF_CAP = 96;
 constexpr unsigned long long EQ_NONE = 0x7f7fffffffffffffull;   // (FLT_MAX bits << 32) | no triangle
 constexpr int ENERGY_WARP_SMEM = EQ_STACK_PHYS * 8 + EQ_LEAF_CAP * 8 + 32 * 8 + 32 * 24 + 32 * 16;
 
@@ -698,7 +701,10 @@ __device__ __forceinline__ unsigned long long eq_entry(float lb, int q, int idx)
 // top, so each query advances depth-first, nearest first); finished queries simply stop producing entries
 // and their lanes pick up other queries' work.  Leaves are queued and tested 32 triangles at a time; the
 // per-query best (distance, triangle) is a 64-bit atomicMin in shared memory.
-__global__ void __launch_bounds__(256) energy_kernel(EnergyParams p) {
+#ifndef ENERGY_MIN_BLOCKS
+#define ENERGY_MIN_BLOCKS 4      // 64 registers: 4 blocks (32 warps) per SM; measured best against 3 x 80 registers
+#endif
+__global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   NodeQ *top = reinterpret_cast<NodeQ *>(smem_raw);
   __shared__ __align__(8) unsigned long long bar;
@@ -741,11 +747,15 @@ __global__ void __launch_bounds__(256) energy_kernel(EnergyParams p) {
   const int nlegal = p.legal_count ? *p.legal_count : p.npose;
   const int nquery = nlegal * nc;
   const int ngroups = (nquery + 31) / 32;
-  const int warps_total = (gridDim.x * blockDim.x) >> 5;
   unsigned nbx = 0, ntr = 0;
   const Node root = fetch_node(mo, top, ntop, 0);
 
-  for (int g = (blockIdx.x * blockDim.x + tid) >> 5; g < ngroups; g += warps_total) {
+  while (true) {
+    // groups of 32 queries are handed out dynamically, so the grid need not match the resident block count
+    int g = 0;
+    if (lane == 0) g = atomicAdd(p.work_counter, 1);
+    g = __shfl_sync(FULL, g, 0);
+    if (g >= ngroups) break;
     // ---- set up this lane's query
     const int qid = g * 32 + lane;
     bool valid = qid < nquery;
