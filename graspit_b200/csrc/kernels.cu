@@ -303,7 +303,10 @@ __device__ __forceinline__ float entry_lb(unsigned long long e) { return __uint_
 #ifndef DLEAF_TRIGGER
 #define DLEAF_TRIGGER 32     // leaf pairs queued before a batch of triangle tests runs
 #endif
-__global__ void __launch_bounds__(256, 2) dist_kernel(DistParams p) {
+#ifndef DIST_MIN_BLOCKS
+#define DIST_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
