@@ -10,6 +10,7 @@
 #include "bvh.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <numeric>
 #include <queue>
@@ -29,6 +30,7 @@ struct Builder {
   std::vector<float> cen;         // 3 per triangle
   std::vector<int> order;
   std::vector<Build> tmp;
+  bool use_sah = true;
 
   int build(int lo, int hi) {
     Build b;
@@ -55,15 +57,69 @@ struct Builder {
       tmp[me].tri = order[lo];
       return me;
     }
+    // split: binned surface-area heuristic over the three axes (16 bins on the centroid bounds); object median along
+    // the longest centroid axis when no SAH split separates the set.  (B2C_BVH_MEDIAN=1 forces the median split.)
     int axis = 0;
     float ext = chi[0] - clo[0];
     for (int k = 1; k < 3; k++)
       if (chi[k] - clo[k] > ext) { ext = chi[k] - clo[k]; axis = k; }
     int mid = lo + (hi - lo) / 2;
-    std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi, [&](int a, int c) {
-      float ca = cen[3 * (size_t)a + axis], cc = cen[3 * (size_t)c + axis];
-      return ca < cc || (ca == cc && a < c);
-    });
+    bool done = false;
+    if (use_sah && hi - lo > 2) {
+      const int NB = 16;
+      float best_cost = 3.0e38f; int best_axis = -1, best_bin = -1;
+      for (int ax = 0; ax < 3; ax++) {
+        float w = chi[ax] - clo[ax];
+        if (!(w > 1.0e-9f)) continue;
+        float blo[NB][3], bhi[NB][3]; int cnt[NB];
+        for (int b = 0; b < NB; b++) { cnt[b] = 0; for (int k = 0; k < 3; k++) { blo[b][k] = 1e30f; bhi[b][k] = -1e30f; } }
+        for (int i = lo; i < hi; i++) {
+          int t = order[i];
+          int b = (int)((cen[3 * (size_t)t + ax] - clo[ax]) / w * NB);
+          b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+          cnt[b]++;
+          const float *tv = tri9 + 9 * (size_t)t;
+          for (int v = 0; v < 3; v++)
+            for (int k = 0; k < 3; k++) { blo[b][k] = std::min(blo[b][k], tv[3 * v + k]); bhi[b][k] = std::max(bhi[b][k], tv[3 * v + k]); }
+        }
+        // sweep: area of the left / right unions
+        float la[NB], ra[NB]; int lc[NB], rc[NB];
+        float l0[3] = {1e30f, 1e30f, 1e30f}, l1[3] = {-1e30f, -1e30f, -1e30f}; int c = 0;
+        auto area = [](const float *a, const float *b) { float x = b[0] - a[0], y = b[1] - a[1], z = b[2] - a[2]; return x * y + y * z + z * x; };
+        for (int b = 0; b < NB; b++) {
+          if (cnt[b]) for (int k = 0; k < 3; k++) { l0[k] = std::min(l0[k], blo[b][k]); l1[k] = std::max(l1[k], bhi[b][k]); }
+          c += cnt[b]; lc[b] = c; la[b] = c ? area(l0, l1) : 0.f;
+        }
+        float r0[3] = {1e30f, 1e30f, 1e30f}, r1[3] = {-1e30f, -1e30f, -1e30f}; c = 0;
+        for (int b = NB - 1; b >= 0; b--) {
+          if (cnt[b]) for (int k = 0; k < 3; k++) { r0[k] = std::min(r0[k], blo[b][k]); r1[k] = std::max(r1[k], bhi[b][k]); }
+          c += cnt[b]; rc[b] = c; ra[b] = c ? area(r0, r1) : 0.f;
+        }
+        for (int b = 0; b + 1 < NB; b++) {
+          if (lc[b] == 0 || rc[b + 1] == 0) continue;
+          float cost = la[b] * lc[b] + ra[b + 1] * rc[b + 1];
+          if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = b; }
+        }
+      }
+      if (best_axis >= 0) {
+        float w = chi[best_axis] - clo[best_axis];
+        auto part = std::stable_partition(order.begin() + lo, order.begin() + hi, [&](int t) {
+          int b = (int)((cen[3 * (size_t)t + best_axis] - clo[best_axis]) / w * 16);
+          b = b < 0 ? 0 : (b >= 16 ? 15 : b);
+          return b <= best_bin;
+        });
+        int m = (int)(part - order.begin());
+        // keep the tree from degenerating: a split more lopsided than 1:7 falls back to the median
+        if (m > lo && m < hi && std::min(m - lo, hi - m) * 8 >= (hi - lo)) { mid = m; done = true; }
+      }
+    }
+    if (!done) {
+      mid = lo + (hi - lo) / 2;
+      std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi, [&](int a, int c) {
+        float ca = cen[3 * (size_t)a + axis], cc = cen[3 * (size_t)c + axis];
+        return ca < cc || (ca == cc && a < c);
+      });
+    }
     int l = build(lo, mid);
     int r = build(mid, hi);
     tmp[me].left = l;
@@ -97,7 +153,22 @@ void build_bvh(const float *tri9, int ntri, std::vector<NodeQ> &nodes, BvhQuant 
     for (int k = 0; k < 3; k++)
       B.cen[3 * (size_t)i + k] = (tri9[9 * (size_t)i + k] + tri9[9 * (size_t)i + 3 + k] + tri9[9 * (size_t)i + 6 + k]) / 3.0f;
   B.tmp.reserve(2 * (size_t)ntri);
+  if (const char *e = getenv("B2C_BVH_MEDIAN")) B.use_sah = atoi(e) == 0;
   B.build(0, ntri);
+  if (B.use_sah) {
+    // per-lane traversal stacks (point_kernel) hold one pending sibling per level: keep the depth well inside them
+    std::vector<int> dep(B.tmp.size(), 0);
+    int maxd = 0;
+    for (size_t i = 0; i < B.tmp.size(); i++) {      // parents precede children in tmp
+      if (B.tmp[i].left >= 0) { dep[B.tmp[i].left] = dep[i] + 1; dep[B.tmp[i].right] = dep[i] + 1; maxd = std::max(maxd, dep[i] + 1); }
+    }
+    if (maxd > 48) {
+      B.use_sah = false;
+      B.tmp.clear();
+      std::iota(B.order.begin(), B.order.end(), 0);
+      B.build(0, ntri);
+    }
+  }
 
   // padding: keeps fp32 culling conservative (the reference pads by Leaf::TOLERANCE = 0.01 mm,
   // collisionModel.cpp:43,122-128)

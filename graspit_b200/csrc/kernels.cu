@@ -136,7 +136,7 @@ __device__ __noinline__ float tri_tri_dist2_plain(f3 p2, f3 p3, f3 q1, f3 q2, f3
 // triangle's extent the winner is redone in fp64.
 // Must agree with ClosestPtCallback (collisionAlgorithms_inl.h:210-238, collisionAlgorithms.h:220-242).
 // ============================================================================================
-#define CPQ_STACK 40
+#define CPQ_STACK 64
 __device__ __forceinline__ float closest_point_query(const MeshDev &m, const NodeQ *top, int ntop, d3 q, f3 &bestv,
                                                      int &best_tri, unsigned &n_box, unsigned &n_tri) {
   const f3 qf = tof(q);
