@@ -31,6 +31,7 @@ struct Builder {
   std::vector<int> order;
   std::vector<Build> tmp;
   bool use_sah = true;
+  int nbins = 16, balance = 8;
 
   int build(int lo, int hi) {
     Build b;
@@ -66,17 +67,17 @@ struct Builder {
     int mid = lo + (hi - lo) / 2;
     bool done = false;
     if (use_sah && hi - lo > 2) {
-      const int NB = 16;
+      const int NB = 64; const int nb = nbins;
       float best_cost = 3.0e38f; int best_axis = -1, best_bin = -1;
       for (int ax = 0; ax < 3; ax++) {
         float w = chi[ax] - clo[ax];
         if (!(w > 1.0e-9f)) continue;
         float blo[NB][3], bhi[NB][3]; int cnt[NB];
-        for (int b = 0; b < NB; b++) { cnt[b] = 0; for (int k = 0; k < 3; k++) { blo[b][k] = 1e30f; bhi[b][k] = -1e30f; } }
+        for (int b = 0; b < nb; b++) { cnt[b] = 0; for (int k = 0; k < 3; k++) { blo[b][k] = 1e30f; bhi[b][k] = -1e30f; } }
         for (int i = lo; i < hi; i++) {
           int t = order[i];
-          int b = (int)((cen[3 * (size_t)t + ax] - clo[ax]) / w * NB);
-          b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+          int b = (int)((cen[3 * (size_t)t + ax] - clo[ax]) / w * nb);
+          b = b < 0 ? 0 : (b >= nb ? nb - 1 : b);
           cnt[b]++;
           const float *tv = tri9 + 9 * (size_t)t;
           for (int v = 0; v < 3; v++)
@@ -86,16 +87,16 @@ struct Builder {
         float la[NB], ra[NB]; int lc[NB], rc[NB];
         float l0[3] = {1e30f, 1e30f, 1e30f}, l1[3] = {-1e30f, -1e30f, -1e30f}; int c = 0;
         auto area = [](const float *a, const float *b) { float x = b[0] - a[0], y = b[1] - a[1], z = b[2] - a[2]; return x * y + y * z + z * x; };
-        for (int b = 0; b < NB; b++) {
+        for (int b = 0; b < nb; b++) {
           if (cnt[b]) for (int k = 0; k < 3; k++) { l0[k] = std::min(l0[k], blo[b][k]); l1[k] = std::max(l1[k], bhi[b][k]); }
           c += cnt[b]; lc[b] = c; la[b] = c ? area(l0, l1) : 0.f;
         }
         float r0[3] = {1e30f, 1e30f, 1e30f}, r1[3] = {-1e30f, -1e30f, -1e30f}; c = 0;
-        for (int b = NB - 1; b >= 0; b--) {
+        for (int b = nb - 1; b >= 0; b--) {
           if (cnt[b]) for (int k = 0; k < 3; k++) { r0[k] = std::min(r0[k], blo[b][k]); r1[k] = std::max(r1[k], bhi[b][k]); }
           c += cnt[b]; rc[b] = c; ra[b] = c ? area(r0, r1) : 0.f;
         }
-        for (int b = 0; b + 1 < NB; b++) {
+        for (int b = 0; b + 1 < nb; b++) {
           if (lc[b] == 0 || rc[b + 1] == 0) continue;
           float cost = la[b] * lc[b] + ra[b + 1] * rc[b + 1];
           if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = b; }
@@ -104,13 +105,13 @@ struct Builder {
       if (best_axis >= 0) {
         float w = chi[best_axis] - clo[best_axis];
         auto part = std::stable_partition(order.begin() + lo, order.begin() + hi, [&](int t) {
-          int b = (int)((cen[3 * (size_t)t + best_axis] - clo[best_axis]) / w * 16);
-          b = b < 0 ? 0 : (b >= 16 ? 15 : b);
+          int b = (int)((cen[3 * (size_t)t + best_axis] - clo[best_axis]) / w * nbins);
+          b = b < 0 ? 0 : (b >= nbins ? nbins - 1 : b);
           return b <= best_bin;
         });
         int m = (int)(part - order.begin());
         // keep the tree from degenerating: a split more lopsided than 1:7 falls back to the median
-        if (m > lo && m < hi && std::min(m - lo, hi - m) * 8 >= (hi - lo)) { mid = m; done = true; }
+        if (m > lo && m < hi && std::min(m - lo, hi - m) * balance >= (hi - lo)) { mid = m; done = true; }
       }
     }
     if (!done) {
@@ -154,6 +155,8 @@ void build_bvh(const float *tri9, int ntri, std::vector<NodeQ> &nodes, BvhQuant 
       B.cen[3 * (size_t)i + k] = (tri9[9 * (size_t)i + k] + tri9[9 * (size_t)i + 3 + k] + tri9[9 * (size_t)i + 6 + k]) / 3.0f;
   B.tmp.reserve(2 * (size_t)ntri);
   if (const char *e = getenv("B2C_BVH_MEDIAN")) B.use_sah = atoi(e) == 0;
+  if (const char *e = getenv("B2C_BVH_BINS")) B.nbins = std::max(2, std::min(64, atoi(e)));
+  if (const char *e = getenv("B2C_BVH_BALANCE")) B.balance = std::max(2, atoi(e));
   B.build(0, ntri);
   if (B.use_sah) {
     // per-lane traversal stacks (point_kernel) hold one pending sibling per level: keep the depth well inside them
