@@ -841,18 +841,18 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
         float lb = __uint_as_float((unsigned)(e >> 32));
         float best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
         if (lb <= best) {
-          Node c0, c1;
-          fetch_pair(mo, top, ntop, pair, c0, c1);
+          uint4 w0, w1;
+          fetch_pair_raw(mo, top, ntop, pair, w0, w1);
           float4 qq = qf[qi];
-          f3 qp = mk<float>(qq.x, qq.y, qq.z);
-          float cc[3], hh[3];
-          node_ch(c0, cc, hh); float d0 = point_box_dist2(cc, hh, qp);
-          node_ch(c1, cc, hh); float d1 = point_box_dist2(cc, hh, qp);
+          float d0 = point_nodeq_dist2(w0, mo.q0, mo.qs, qq.x, qq.y, qq.z);
+          float d1 = point_nodeq_dist2(w1, mo.q0, mo.qs, qq.x, qq.y, qq.z);
           nbx += 2;
           bool swap = d1 < d0;
           float dn = swap ? d1 : d0, df = swap ? d0 : d1;
-          int chn = swap ? c1.child : c0.child, chf = swap ? c0.child : c1.child;
-          int trn = swap ? c1.tri : c0.tri, trf = swap ? c0.tri : c1.tri;
+          // link >= 0: child pair index; link < 0: leaf holding triangle ~link
+          int lkn = (int)(swap ? w1.w : w0.w), lkf = (int)(swap ? w0.w : w1.w);
+          int chn = lkn >= 0 ? lkn : -1, chf = lkf >= 0 ? lkf : -1;
+          int trn = ~lkn, trf = ~lkf;
           pn = dn <= best; pf = df <= best;
           ln = chn < 0; lf = chf < 0;
           cn = eq_entry(dn, qi, ln ? trn : chn);

@@ -43,6 +43,25 @@ __device__ __forceinline__ void fetch_pair(const MeshDev &m, const NodeQ *top, i
     load_pair(m, i, c0, c1);
   }
 }
+// sibling pair as raw words (for kernels that test boxes in their stored lo/hi form)
+__device__ __forceinline__ void fetch_pair_raw(const MeshDev &m, const NodeQ *top, int ntop, int i, uint4 &a, uint4 &b) {
+  if (i + 1 < ntop) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(top + i);
+    a = p[0]; b = p[1];
+  } else {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(m.nodes + i));
+  }
+}
+// squared distance from p to a stored box, straight from its quantised corners (no centre / half-extent decode)
+__device__ __forceinline__ float point_nodeq_dist2(uint4 w, const float *q0, const float *qs, float px, float py, float pz) {
+  float l0 = __fmaf_rn((float)(w.x & 0xffffu), qs[0], q0[0]), l1 = __fmaf_rn((float)(w.x >> 16), qs[1], q0[1]);
+  float l2 = __fmaf_rn((float)(w.y & 0xffffu), qs[2], q0[2]), h0 = __fmaf_rn((float)(w.y >> 16), qs[0], q0[0]);
+  float h1 = __fmaf_rn((float)(w.z & 0xffffu), qs[1], q0[1]), h2 = __fmaf_rn((float)(w.z >> 16), qs[2], q0[2]);
+  float dx = fmaxf(fmaxf(l0 - px, px - h0), 0.f), dy = fmaxf(fmaxf(l1 - py, py - h1), 0.f), dz = fmaxf(fmaxf(l2 - pz, pz - h2), 0.f);
+  return dx * dx + dy * dy + dz * dz;
+}
 __device__ __forceinline__ Node fetch_node(const MeshDev &m, const NodeQ *top, int ntop, int i) {
   if (i < ntop) {
     uint4 a = *reinterpret_cast<const uint4 *>(top + i);
