@@ -259,7 +259,10 @@ constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 3 * 96 + 96 + D
 
 // narrow phase of the legality test: per-warp shared memory = 32 fp64 relative transforms, 32 pair transforms,
 // 32 item descriptors, the shared work stack and the leaf queue
-constexpr int NSTACK_CAP = 448, NSTACK_PHYS = 512, NLEAF_CAP = 96;
+#ifndef NSTACK_PHYS_N
+#define NSTACK_PHYS_N 512
+#endif
+constexpr int NSTACK_PHYS = NSTACK_PHYS_N, NSTACK_CAP = NSTACK_PHYS_N - 64, NLEAF_CAP = 96;
 constexpr int NARROW_WARP_SMEM = 32 * 96 + 32 * 96 + 32 * 16 + NSTACK_PHYS * 8 + NLEAF_CAP * 8 + 32 * 4;
 cudaError_t launch_collide(const EvalParams &p, int narrow_blocks, cudaStream_t s);
 cudaError_t launch_compact(const EvalParams &p, cudaStream_t s);

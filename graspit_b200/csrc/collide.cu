@@ -78,7 +78,10 @@ __device__ __forceinline__ unsigned long long pack_item_entry(int slot, int a, i
   return ((unsigned long long)(unsigned)slot << 48) | ((unsigned long long)(unsigned)a << 24) | (unsigned long long)(unsigned)b;
 }
 
-__global__ void __launch_bounds__(256, 2) narrow_kernel(EvalParams p) {
+#ifndef NARROW_MIN_BLOCKS
+#define NARROW_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, NARROW_MIN_BLOCKS) narrow_kernel(EvalParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
