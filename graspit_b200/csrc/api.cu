@@ -207,8 +207,8 @@ int ensure_scratch(b2c_ctx *ctx) {
   CU(ctx->d_counters.reserve(16));
   CU(ctx->d_stats.reserve(8));
   CU(ctx->d_ambig.reserve(1 << 20));
-  CU(ctx->d_near_dir.reserve(1 << 16));
-  CU(ctx->d_near_ent.reserve(1 << 20));
+  CU(ctx->d_near_dir.reserve(1 << 18));
+  CU(ctx->d_near_ent.reserve(1 << 21));
   return B2C_OK;
 }
 
@@ -295,7 +295,7 @@ int run_static_distance(b2c_ctx *ctx, int a, int b, double *dist, double pa[3], 
   dp.legal = nullptr; dp.dist = ctx->d_dist.p; dp.pts = ctx->d_pts.p; dp.work_counter = ctx->d_counters.p;
   dp.ambig = ctx->d_ambig.p; dp.ambig_count = ctx->d_counters.p + 1; dp.ambig_cap = (int)ctx->d_ambig.cap; dp.stats = nullptr;
   dp.near_dir = ctx->d_near_dir.p; dp.near_ent = ctx->d_near_ent.p; dp.near_count = ctx->d_counters.p + 5;
-  dp.near_cap_dir = 1 << 16; dp.near_cap_ent = 1 << 20;
+  dp.near_cap_dir = (int)ctx->d_near_dir.cap; dp.near_cap_ent = (int)ctx->d_near_ent.cap;
   CU(launch_dist(dp, 1, ctx->stream)); ctx->launches += 2;
   RecheckParams rp;
   memset(&rp, 0, sizeof rp);
@@ -945,11 +945,10 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
     dp.legal = want_dist ? nullptr : d_legal;       // LIVE alone only needs legal poses
     dp.dist = d_dist; dp.pts = ctx->d_pts.p; dp.work_counter = ctx->d_counters.p + 2;
     dp.ambig = ctx->d_ambig.p; dp.ambig_count = ctx->d_counters.p + 3; dp.ambig_cap = (int)ctx->d_ambig.cap; dp.stats = ctx->d_stats.p;
-    if (want_dist) {   // distances handed to the caller get the fp64 pass for tiny values
-      dp.near_dir = ctx->d_near_dir.p; dp.near_ent = ctx->d_near_ent.p; dp.near_count = ctx->d_counters.p + 5;
-      dp.near_cap_dir = 1 << 16; dp.near_cap_ent = 1 << 20;
-      ctx->launches++;
-    }
+    // near-ties and tiny distances are settled in fp64 (dist_refine_kernel): the closest POINTS feed CONTACT_LIVE
+    dp.near_dir = ctx->d_near_dir.p; dp.near_ent = ctx->d_near_ent.p; dp.near_count = ctx->d_counters.p + 5;
+    dp.near_cap_dir = (int)ctx->d_near_dir.cap; dp.near_cap_ent = (int)ctx->d_near_ent.cap;
+    ctx->launches++;
     int dblocks = std::min(ctx->sm_count * 4, (npose * nq + 7) / 8);
     PROF_BEGIN(3); CU(launch_dist(dp, std::max(1, dblocks), ctx->stream)); ctx->launches++; PROF_END(3);
     RecheckParams rd;

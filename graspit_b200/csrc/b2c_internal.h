@@ -255,7 +255,7 @@ cudaError_t launch_anneal_accept(const AnnealParams &p, cudaStream_t s);
 
 constexpr int DSTACK_CAP = 448, DSTACK_PHYS = 512, DLEAF_CAP = 96;
 constexpr int DNEAR_CAP = 64, DCONF_CAP = 64;
-constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 3 * 96 + 96 + DNEAR_CAP * 8 + DCONF_CAP * 8 + 32;
+constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 3 * 96 + 96 + DNEAR_CAP * 8 + DCONF_CAP * 8 + DNEAR_CAP * 8 + 32;
 
 // narrow phase of the legality test: per-warp shared memory = 32 fp64 relative transforms, 32 pair transforms,
 // 32 item descriptors, the shared work stack and the leaf queue

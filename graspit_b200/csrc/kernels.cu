@@ -300,6 +300,64 @@ __device__ __forceinline__ unsigned long long pack_dist_entry(float lb, int a, i
 __device__ __forceinline__ float entry_lb(unsigned long long e) { return __uint_as_float(((unsigned)(e >> 48)) << 16); }
 
 
+constexpr int NEAR_TINY_BIT = 1 << 30;   // marks near-list entries kept because their fp32 distance is unreliable
+// ---- near-minimum list of the distance kernel (rare paths, kept out of line: the traversal loop is register-bound) ----
+// drop entries the improving best has left behind; returns the new length
+__device__ __noinline__ int near_compact(int2 *nearq, float *neard, float *nearf, int nnear, float best) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int kept = 0;
+  for (int b0 = 0; b0 < nnear; b0 += 32) {
+    const int i = b0 + lane;
+    bool k = false; int2 en = make_int2(0, 0); float dn = 0.f, fn = 0.f;
+    if (i < nnear) { en = nearq[i]; dn = neard[i]; fn = nearf[i]; k = dn <= best * ((en.y & NEAR_TINY_BIT) ? 1.004f : 1.0002f) + 1.0e-9f; }
+    const unsigned km = __ballot_sync(FULL, k);
+    __syncwarp();
+    if (k) { const int at = kept + __popc(km & lt_mask); nearq[at] = en; neard[at] = dn; nearf[at] = fn; }
+    kept += __popc(km);
+    __syncwarp();
+  }
+  return kept;
+}
+// pairs still within tolerance of the FINAL best go to the fp64 refinement kernel -- only when there is a decision to
+// make: two or more candidates with different closest points, or a distance fp32 could not resolve.  Candidates that tie
+// because they share the closest vertex or edge describe one solution: nothing to arbitrate.
+__device__ __noinline__ void near_emit(const DistParams &p, const int2 *nearq, const float *neard, const float *nearf, int nnear,
+                                       float best, float best_fp, bool overflow, int w) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  __syncwarp();
+  int cnt = 0; bool anytiny = false, anydiff = false;
+  unsigned km[(DNEAR_CAP + 31) / 32];
+#pragma unroll
+  for (int r = 0; r < (DNEAR_CAP + 31) / 32; r++) {
+    const int i = r * 32 + lane;
+    bool k = false, t = false, differs = false;
+    if (i < nnear) {
+      t = (nearq[i].y & NEAR_TINY_BIT) != 0;
+      k = neard[i] <= best * (t ? 1.004f : 1.0002f) + 1.0e-9f;
+      differs = k && fabsf(nearf[i] - best_fp) > 0.05f + 1.0e-5f * fabsf(best_fp);
+    }
+    km[r] = __ballot_sync(FULL, k);
+    anytiny = anytiny || __any_sync(FULL, k && t);
+    anydiff = anydiff || __any_sync(FULL, differs);
+    cnt += __popc(km[r]);
+  }
+  if (!((cnt >= 2 && anydiff) || anytiny)) return;
+  int seg = 0, ofs = 0;
+  if (lane == 0) { seg = atomicAdd(p.near_count, 1); ofs = atomicAdd(p.near_count + 1, cnt); }
+  seg = __shfl_sync(FULL, seg, 0); ofs = __shfl_sync(FULL, ofs, 0);
+  if (seg >= p.near_cap_dir || ofs + cnt > p.near_cap_ent) return;
+  int at0 = 0;
+#pragma unroll
+  for (int r = 0; r < (DNEAR_CAP + 31) / 32; r++) {
+    const int i = r * 32 + lane;
+    if ((km[r] >> lane) & 1u) { int2 en = nearq[i]; en.y &= ~NEAR_TINY_BIT; p.near_ent[ofs + at0 + __popc(km[r] & lt_mask)] = en; }
+    at0 += __popc(km[r]);
+  }
+  if (lane == 0) p.near_dir[seg] = make_int4(w, ofs, cnt, overflow ? 0 : 1);
+}
+
 #ifndef DLEAF_TRIGGER
 #define DLEAF_TRIGGER 32     // leaf pairs queued before a batch of triangle tests runs
 #endif
@@ -320,6 +378,8 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
   PairXf *xp = reinterpret_cast<PairXf *>(XR + 12);
   int2 *nearq = reinterpret_cast<int2 *>(xp + 1);
   unsigned long long *confq = reinterpret_cast<unsigned long long *>(nearq + DNEAR_CAP);   // [DCONF_CAP] pairs that passed the pre-filter
+  float *neard = reinterpret_cast<float *>(confq + DCONF_CAP);                             // [DNEAR_CAP] fp32 squared distance of nearq entries
+  float *nearf = neard + DNEAR_CAP;                                                          // [DNEAR_CAP] fingerprint of their closest points
   unsigned n_box = 0, n_tri = 0;
 #ifdef DIST_DEBUG_STATS
   unsigned dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0;
@@ -368,7 +428,8 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
     f3 udirA = udir;                      // the same direction in A's frame, and its product with the A <- B translation
     float udt = 0.f;
     bool hit = false;
-    bool best_tiny = false;        // the current best came from a pair flagged for fp64 refinement
+    bool near_overflow = false;    // the near-minimum list lost entries: its fp64 minimum is no longer authoritative
+    float best_fp = 0.f;           // fingerprint (a fixed linear form) of the best pair's closest points
     int sp = 0, lq = 0, cq = 0, nnear = 0;
     if (lane == 0) stack[0] = pack_dist_entry(0.f, 0, 0);
     sp = 1;
@@ -471,10 +532,25 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
           }
         }
         cq -= n;
+        float fpr_lane = 0.f;
         {
-          unsigned tm = __ballot_sync(FULL, tiny);
-          if (tiny) { int at = nnear + __popc(tm & lt_mask); if (at < DNEAR_CAP) nearq[at] = make_int2(ta, tb); }
-          nnear += __popc(tm);
+          // near-minimum list: every pair within 1e-4 (relative, in distance) of the best so far, plus the pairs whose
+          // fp32 distance is unreliable (tiny against their extent).  fp32 cannot order candidates that close, and the
+          // reference's outputs depend on WHICH pair wins (closest points feed CONTACT_LIVE), so the final choice among
+          // them is made in fp64 by dist_refine_kernel.  `best` here is the value before this batch: a superset.
+          // fingerprint of this pair's closest points (B's frame): pairs that share the closest vertex / edge tie exactly
+          // but describe the SAME solution and need no arbitration
+          const float fpr = fpr_lane = ((float)P1.x + 2.f * (float)P1.y + 3.f * (float)P1.z) * 6.0f + (pa.x + 2.f * pa.y + 3.f * pa.z) + 5.f * (pb.x + 2.f * pb.y + 3.f * pb.z);
+          const bool cand = res != TT_HIT && d2 < 2.9e38f && (tiny || d2 <= best * 1.0002f + 1.0e-12f);
+          const unsigned cm = __ballot_sync(FULL, cand);
+          const int add = __popc(cm);
+          if (add) {
+            if (nnear + add > DNEAR_CAP) nnear = near_compact(nearq, neard, nearf, nnear, best);
+            const int at = nnear + __popc(cm & lt_mask);
+            if (cand && at < DNEAR_CAP) { nearq[at] = make_int2(ta, tb | (tiny ? NEAR_TINY_BIT : 0)); neard[at] = d2; nearf[at] = fpr; }
+            if (nnear + add > DNEAR_CAP) near_overflow = true;
+            nnear = nnear + add < DNEAR_CAP ? nnear + add : DNEAR_CAP;
+          }
         }
         if (res == TT_AMBIG) {
           int slot = atomicAdd(p.ambig_count, 1);
@@ -488,12 +564,12 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
           unsigned who = __ballot_sync(FULL, d2 == m);
           int src = __ffs(who) - 1;
           best = m;
-          best_tiny = (__ballot_sync(FULL, tiny) >> src) & 1u;
           // closest points in B's frame, fp64: re-centred fp32 result + fp64 origin
           d3 PA = mk<double>(P1.x + (double)pa.x, P1.y + (double)pa.y, P1.z + (double)pa.z);
           d3 PB = mk<double>(P1.x + (double)pb.x, P1.y + (double)pb.y, P1.z + (double)pb.z);
           bpa.x = __shfl_sync(FULL, PA.x, src); bpa.y = __shfl_sync(FULL, PA.y, src); bpa.z = __shfl_sync(FULL, PA.z, src);
           bpb.x = __shfl_sync(FULL, PB.x, src); bpb.y = __shfl_sync(FULL, PB.y, src); bpb.z = __shfl_sync(FULL, PB.z, src);
+          best_fp = __shfl_sync(FULL, fpr_lane, src);
           float ux = (float)(bpb.x - bpa.x), uy = (float)(bpb.y - bpa.y), uz = (float)(bpb.z - bpa.z);
           float inv = rsqrtf(fmaxf(ux * ux + uy * uy + uz * uz, 1.0e-30f));
           udir = mk<float>(ux * inv, uy * inv, uz * inv);
@@ -575,17 +651,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
       __syncwarp();
     }
     __syncwarp();
-    if (!hit && nnear > 0 && p.near_dir) {
-      // hand the remembered near-minimum pairs (tiny distances only) to the fp64 refinement kernel
-      int cnt = nnear < DNEAR_CAP ? nnear : DNEAR_CAP;
-      int seg = 0, ofs = 0;
-      if (lane == 0) { seg = atomicAdd(p.near_count, 1); ofs = atomicAdd(p.near_count + 1, cnt); }
-      seg = __shfl_sync(FULL, seg, 0); ofs = __shfl_sync(FULL, ofs, 0);
-      if (seg < p.near_cap_dir && ofs + cnt <= p.near_cap_ent) {
-        for (int i = lane; i < cnt; i += 32) p.near_ent[ofs + i] = nearq[i];
-        if (lane == 0) p.near_dir[seg] = make_int4(w, ofs, cnt, best_tiny ? 1 : 0);
-      }
-    }
+    if (!hit && nnear > 0 && p.near_dir) near_emit(p, nearq, neard, nearf, nnear, best, best_fp, near_overflow, w);
     if (lane == 0) {
       if (hit) {
         p.dist[w] = -1.f;
@@ -651,8 +717,8 @@ __global__ void __launch_bounds__(128) dist_refine_kernel(DistParams p) {
     double m = bd;
     for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(FULL, m, o));
     unsigned who = __ballot_sync(FULL, bd == m);
-    // the remembered pairs replace the traversal's answer when that answer itself came from such a pair; a best
-    // found on a pair that needed no refinement stands unless a refined pair beats it
+    // the list holds every pair within tolerance of the fp32 best (flag 1): its fp64 minimum IS the answer; if the list
+    // overflowed (flag 0) the fp32 answer stands unless a refined pair beats it
     const float cur = p.dist[w];
     const bool replace = d.w != 0 || sqrt(m) < (double)cur;
     if (replace && lane == __ffs(who) - 1 && m < 1.0e299) {
@@ -949,7 +1015,7 @@ cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s) {
   dist_kernel<<<blocks, 256, smem, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || !p.near_dir) return e;
-  dist_refine_kernel<<<32, 128, 0, s>>>(p);
+  dist_refine_kernel<<<blocks > 1 ? 148 * 8 : 8, 128, 0, s>>>(p);     // one warp per near-tie query, grid-stride
   return cudaGetLastError();
 }
 

@@ -286,3 +286,30 @@ def test_small_distances_many_poses(ctx):
     both = dist_o >= 0
     assert (dist_o[both] < 1.0).sum() > 50
     assert relerr(ld[both], dist_o[both]).max() < REL
+
+
+def test_large_random_batches(ctx):
+    """20 000 poses (PRESET) and 4 000 poses (LIVE) in the planner's state layout against the reference: legality exact,
+    energies within the stated tolerance -- a wider net than config 1 for rare traversal / precision paths."""
+    from oracle.port import fk as ofk
+    sc, e, o = ctx["sc"], ctx["eng"], ctx["osc"]
+    r = sc.robots[0]
+    rng = np.random.default_rng(77)
+    n = 20000
+    pos, _ = sample_aa_states(sc, n, seed=4242, strata=("far", "near", "close"))
+    states = np.concatenate([pos, rng.uniform(-4, 4, size=(n, r.eg.shape[0]))], 1).astype(np.float32)
+    s64 = states.astype(np.float64)
+    base = ofk.aa_state_to_base(r, sc.body_tran[ctx["obj"]], s64[:, :6])
+    raw64 = np.concatenate([base[0], base[1], ofk.eigen_to_dof(r, s64[:, 6:])], 1)
+    legal_o, energy_o, _, _, _ = o.eval(0, ctx["obj"], raw64, mode=0)
+    res = e.eval_batch(ctx["rid"], ctx["sb"].body_ids[ctx["obj"]], states, input_mode=B2C_INPUT_AA_EIGEN, ref_tran=sc.body_tran[ctx["obj"]])
+    assert (res["legal"] == legal_o).all()
+    m = legal_o == 1
+    assert 3000 < m.sum() < 19000
+    assert relerr(res["energy"][m], energy_o[m]).max() < REL
+    k = 4000
+    legal_l, energy_l, _, _, _ = o.eval(0, ctx["obj"], raw64[:k], mode=1)
+    live = e.eval_batch(ctx["rid"], ctx["sb"].body_ids[ctx["obj"]], states[:k], input_mode=B2C_INPUT_AA_EIGEN, ref_tran=sc.body_tran[ctx["obj"]], live=True)
+    assert (live["legal"] == legal_l).all()
+    ml = legal_l == 1
+    assert relerr(live["energy"][ml], energy_l[ml]).max() < REL
