@@ -111,7 +111,7 @@ struct b2c_ctx {
   DevBuf<float> d_states; DevBuf<Xf> d_fk; DevBuf<double> d_fkqt; DevBuf<uint8_t> d_legal; DevBuf<float> d_energy;
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
   DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
-  int stage_nodes = 256;           // object-tree nodes staged in shared memory by the energy kernel
+  int stage_nodes = 128;           // object-tree nodes staged in shared memory by the energy kernel
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int eval_warps_per_block = 8;
   int eval_blocks_per_sm = 0;      // 0 = derive from shared memory

@@ -300,6 +300,9 @@ __device__ __forceinline__ unsigned long long pack_dist_entry(float lb, int a, i
 __device__ __forceinline__ float entry_lb(unsigned long long e) { return __uint_as_float(((unsigned)(e >> 48)) << 16); }
 
 
+// Candidates whose squared distance is within this factor of the best are ordered in fp64, not fp32.  Pruning uses the
+// same band, so every such candidate is visited whatever order the traversal takes (deterministic results).
+constexpr float NEAR_BAND = 1.0002f;
 constexpr int NEAR_TINY_BIT = 1 << 30;   // marks near-list entries kept because their fp32 distance is unreliable
 // ---- near-minimum list of the distance kernel (rare paths, kept out of line: the traversal loop is register-bound) ----
 // drop entries the improving best has left behind; returns the new length
@@ -310,7 +313,7 @@ __device__ __noinline__ int near_compact(int2 *nearq, float *neard, float *nearf
   for (int b0 = 0; b0 < nnear; b0 += 32) {
     const int i = b0 + lane;
     bool k = false; int2 en = make_int2(0, 0); float dn = 0.f, fn = 0.f;
-    if (i < nnear) { en = nearq[i]; dn = neard[i]; fn = nearf[i]; k = dn <= best * ((en.y & NEAR_TINY_BIT) ? 1.004f : 1.0002f) + 1.0e-9f; }
+    if (i < nnear) { en = nearq[i]; dn = neard[i]; fn = nearf[i]; k = dn <= best * ((en.y & NEAR_TINY_BIT) ? 1.004f : NEAR_BAND) + 1.0e-9f; }
     const unsigned km = __ballot_sync(FULL, k);
     __syncwarp();
     if (k) { const int at = kept + __popc(km & lt_mask); nearq[at] = en; neard[at] = dn; nearf[at] = fn; }
@@ -335,7 +338,7 @@ __device__ __noinline__ void near_emit(const DistParams &p, const int2 *nearq, c
     bool k = false, t = false, differs = false;
     if (i < nnear) {
       t = (nearq[i].y & NEAR_TINY_BIT) != 0;
-      k = neard[i] <= best * (t ? 1.004f : 1.0002f) + 1.0e-9f;
+      k = neard[i] <= best * (t ? 1.004f : NEAR_BAND) + 1.0e-9f;
       differs = k && fabsf(nearf[i] - best_fp) > 0.05f + 1.0e-5f * fabsf(best_fp);
     }
     km[r] = __ballot_sync(FULL, k);
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
         unsigned long long e = 0ull;
         if (lane < n) {
           e = leafq[lq - n + lane];
-          keep = entry_lb(e) <= best;
+          keep = entry_lb(e) <= best * NEAR_BAND + 1.0e-12f;
           if (keep && seeded) {
             int ta = (int)((e >> 24) & 0xffffffu), tb = (int)(e & 0xffffffu);
             float amax = -3.0e38f, bmin = 3.0e38f;
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
         if (lane < n) {
           unsigned long long e = confq[cq - n + lane];
           ta = (int)((e >> 24) & 0xffffffu); tb = (int)(e & 0xffffffu);
-          if (entry_lb(e) <= best) {
+          if (entry_lb(e) <= best * NEAR_BAND + 1.0e-12f) {
             n_tri++;
             d3 a1 = tri_vertex(ma.tris, ta, 0), a2 = tri_vertex(ma.tris, ta, 1), a3 = tri_vertex(ma.tris, ta, 2);
             d3 b1 = tri_vertex(mb.tris, tb, 0), b2 = tri_vertex(mb.tris, tb, 1), b3 = tri_vertex(mb.tris, tb, 2);
@@ -541,7 +544,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
           // fingerprint of this pair's closest points (B's frame): pairs that share the closest vertex / edge tie exactly
           // but describe the SAME solution and need no arbitration
           const float fpr = fpr_lane = ((float)P1.x + 2.f * (float)P1.y + 3.f * (float)P1.z) * 6.0f + (pa.x + 2.f * pa.y + 3.f * pa.z) + 5.f * (pb.x + 2.f * pb.y + 3.f * pb.z);
-          const bool cand = res != TT_HIT && d2 < 2.9e38f && (tiny || d2 <= best * 1.0002f + 1.0e-12f);
+          const bool cand = res != TT_HIT && d2 < 2.9e38f && (tiny || d2 <= best * NEAR_BAND + 1.0e-12f);
           const unsigned cm = __ballot_sync(FULL, cand);
           const int add = __popc(cm);
           if (add) {
@@ -591,7 +594,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
       __syncwarp();
       bool pn = false, pf = false, ln = false, lf = false;      // near / far child: push?, leaf pair?
       unsigned long long cn = 0ull, cf = 0ull;
-      if (have && entry_lb(e) <= best) {
+      if (have && entry_lb(e) <= best * NEAR_BAND + 1.0e-12f) {
         int na = (int)((e >> 24) & 0xffffffu), nb = (int)(e & 0xffffffu);
         Node a = load_node(ma, na), b = load_node(mb, nb);
         bool la = a.child < 0, lb = b.child < 0;
@@ -633,7 +636,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
           n_box += 2;
           bool swap = d1 < d0;
           float dn = swap ? d1 : d0, df = swap ? d0 : d1;
-          pn = dn <= best; pf = df <= best;
+          pn = dn <= best * NEAR_BAND + 1.0e-12f; pf = df <= best * NEAR_BAND + 1.0e-12f;
           ln = swap ? lf1 : lf0; lf = swap ? lf0 : lf1;
           cn = pack_dist_entry(dn, swap ? i1a : i0a, swap ? i1b : i0b);
           cf = pack_dist_entry(df, swap ? i0a : i1a, swap ? i0b : i1b);
@@ -758,7 +761,7 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 #endif
 constexpr int EQ_STACK_PHYS = EQ_STACK_PHYS_N, EQ_STACK_CAP = EQ_STACK_PHYS_N - 64, EQ_LEAF_CAP = 96;
 constexpr unsigned long long EQ_NONE = 0x7f7fffffffffffffull;   // (FLT_MAX bits << 32) | no triangle
-constexpr int ENERGY_WARP_SMEM = EQ_STACK_PHYS * 8 + EQ_LEAF_CAP * 8 + 32 * 8 + 32 * 24 + 32 * 16;
+constexpr int ENERGY_WARP_SMEM = EQ_STACK_PHYS * 8 + EQ_LEAF_CAP * 8 + 32 * 8 + 32 * 24 + 32 * 16 + 32 * 8;
 
 __device__ __forceinline__ unsigned long long eq_entry(float lb, int q, int idx) {
   return ((unsigned long long)__float_as_uint(lb) << 32) | ((unsigned long long)(unsigned)q << 24) | (unsigned long long)(unsigned)idx;
@@ -785,6 +788,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
   unsigned long long *bestkey = leafq + EQ_LEAF_CAP;                 // [32] (d2 bits << 32) | triangle
   double *qd = reinterpret_cast<double *>(bestkey + 32);              // [32][3] query point, object frame
   float4 *qf = reinterpret_cast<float4 *>(qd + 96);                   // [32] fp32 copy
+  unsigned long long *secondkey = reinterpret_cast<unsigned long long *>(qf + 32);   // [32] best loser within 1e-4 of the winner
   const int nc = p.live ? p.nq : p.nvc;
   const MeshDev mo = p.meshes[p.body_mesh[p.object]];
   const int ntop = p.stage_nodes < mo.nnodes ? p.stage_nodes : mo.nnodes;
@@ -859,6 +863,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
       qf[lane] = make_float4((float)q.x, (float)q.y, (float)q.z, 0.f);
     }
     bestkey[lane] = EQ_NONE;
+    secondkey[lane] = EQ_NONE;
     int sp = 0, lq = 0;
     {
       // seed: the root's child pair (or the root leaf itself for one-triangle meshes)
@@ -879,13 +884,19 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
           int qi = (int)((e >> 24) & 0xffu), tri = (int)(e & 0xffffffu);
           float lb = __uint_as_float((unsigned)(e >> 32));
           float best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
-          if (lb <= best) {
+          if (lb <= best * NEAR_BAND + 1.0e-12f) {
             ntr++;
             d3 q = mk<double>(qd[3 * qi], qd[3 * qi + 1], qd[3 * qi + 2]);
             d3 a = tri_vertex(mo.tris, tri, 0) - q, b = tri_vertex(mo.tris, tri, 1) - q, cc = tri_vertex(mo.tris, tri, 2) - q;
             f3 v = closest_pt_triangle<float>(tof(a), tof(b), tof(cc), mk<float>(0.f, 0.f, 0.f));
             float d2 = dot(v, v);
-            atomicMin(&bestkey[qi], ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)tri);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)tri;
+            const unsigned long long old = atomicMin(&bestkey[qi], key);
+            // runner-up: fp32 cannot order two triangles whose distances agree to 1e-4, and the energy depends on
+            // WHICH closest point wins (its direction enters the normal term); the final stage arbitrates in fp64
+            const unsigned long long win = old < key ? old : key, lose = old < key ? key : old;
+            if (lose != EQ_NONE && __uint_as_float((unsigned)(lose >> 32)) <= __uint_as_float((unsigned)(win >> 32)) * NEAR_BAND + 1.0e-12f)
+              atomicMin(&secondkey[qi], lose);
           }
         }
         lq -= n;
@@ -906,7 +917,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
         int qi = (int)((e >> 24) & 0xffu), pair = (int)(e & 0xffffffu);
         float lb = __uint_as_float((unsigned)(e >> 32));
         float best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
-        if (lb <= best) {
+        if (lb <= best * NEAR_BAND + 1.0e-12f) {
           uint4 w0, w1;
           fetch_pair_raw(mo, top, ntop, pair, w0, w1);
           float4 qq = qf[qi];
@@ -919,7 +930,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
           int lkn = (int)(swap ? w1.w : w0.w), lkf = (int)(swap ? w0.w : w1.w);
           int chn = lkn >= 0 ? lkn : -1, chf = lkf >= 0 ? lkf : -1;
           int trn = ~lkn, trf = ~lkf;
-          pn = dn <= best; pf = df <= best;
+          pn = dn <= best * NEAR_BAND + 1.0e-12f; pf = df <= best * NEAR_BAND + 1.0e-12f;
           ln = chn < 0; lf = chf < 0;
           cn = eq_entry(dn, qi, ln ? trn : chn);
           cf = eq_entry(df, qi, lf ? trf : chf);
@@ -950,8 +961,17 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
         float d2 = dot(v, v);
         float sc = fmaxf(fmaxf(fmaxf(fabsf(af.x), fabsf(af.y)), fmaxf(fabsf(af.z), fabsf(bf.x))),
                          fmaxf(fmaxf(fabsf(bf.y), fabsf(bf.z)), fmaxf(fabsf(cf3.x), fmaxf(fabsf(cf3.y), fabsf(cf3.z)))));
-        if (d2 < 1.0e-4f * sc * sc) {
+        const unsigned long long key2 = secondkey[lane];
+        const bool contested = key2 != EQ_NONE && (int)(key2 & 0xffffffffu) != tri &&
+                               __uint_as_float((unsigned)(key2 >> 32)) <= d2 * NEAR_BAND + 1.0e-12f;
+        if (d2 < 1.0e-4f * sc * sc || contested) {
           d3 v64 = closest_pt_triangle_d(a, b, cc);
+          if (contested) {
+            const int tri2 = (int)(key2 & 0xffffffffu);
+            d3 a2 = tri_vertex(mo.tris, tri2, 0) - q, b2 = tri_vertex(mo.tris, tri2, 1) - q, c2 = tri_vertex(mo.tris, tri2, 2) - q;
+            d3 w64 = closest_pt_triangle_d(a2, b2, c2);
+            if (dot(w64, w64) < dot(v64, v64)) v64 = w64;
+          }
           v = tof(v64);
           d2 = (float)dot(v64, v64);
         }
