@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
   unsigned char *wbase = smem_raw + (size_t)p.stage_nodes * sizeof(NodeQ) + (size_t)warp * ENERGY_WARP_SMEM;
   unsigned long long *stack = reinterpret_cast<unsigned long long *>(wbase);
   unsigned long long *leafq = stack + EQ_STACK_PHYS;
-  unsigned long long *bestkey = leafq + EQ_LEAF_CAP;                 // [32] (d2 bits << 32) | triangle
+  unsigned long long *bestkey = leafq + EQ_LEAF_CAP;                 // [32] (d2 bits << 32) | point hash << 24 | triangle
   double *qd = reinterpret_cast<double *>(bestkey + 32);              // [32][3] query point, object frame
   float4 *qf = reinterpret_cast<float4 *>(qd + 96);                   // [32] fp32 copy
   unsigned long long *secondkey = reinterpret_cast<unsigned long long *>(qf + 32);   // [32] best loser within 1e-4 of the winner
@@ -890,12 +890,18 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
             d3 a = tri_vertex(mo.tris, tri, 0) - q, b = tri_vertex(mo.tris, tri, 1) - q, cc = tri_vertex(mo.tris, tri, 2) - q;
             f3 v = closest_pt_triangle<float>(tof(a), tof(b), tof(cc), mk<float>(0.f, 0.f, 0.f));
             float d2 = dot(v, v);
-            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)tri;
+            // key = squared distance | 8-bit hash of the closest point (1/64 mm grid) | triangle.  Triangles that share the
+            // closest vertex return bit-identical points: same hash, one solution, nothing to arbitrate.
+            const unsigned h = ((unsigned)__float2int_rd(v.x * 64.f) * 73856093u ^ (unsigned)__float2int_rd(v.y * 64.f) * 19349663u ^
+                                (unsigned)__float2int_rd(v.z * 64.f) * 83492791u) & 0xffu;
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)h << 24) | (unsigned)tri;
             const unsigned long long old = atomicMin(&bestkey[qi], key);
-            // runner-up: fp32 cannot order two triangles whose distances agree to 1e-4, and the energy depends on
-            // WHICH closest point wins (its direction enters the normal term); the final stage arbitrates in fp64
+            // runner-up with a DIFFERENT closest point: fp32 cannot order two candidates whose distances agree to 1e-4,
+            // and the energy depends on which closest point wins (its direction enters the normal term); the final stage
+            // arbitrates in fp64
             const unsigned long long win = old < key ? old : key, lose = old < key ? key : old;
-            if (lose != EQ_NONE && __uint_as_float((unsigned)(lose >> 32)) <= __uint_as_float((unsigned)(win >> 32)) * NEAR_BAND + 1.0e-12f)
+            if (lose != EQ_NONE && ((win ^ lose) & 0xff000000ull) != 0ull &&
+                __uint_as_float((unsigned)(lose >> 32)) <= __uint_as_float((unsigned)(win >> 32)) * NEAR_BAND + 1.0e-12f)
               atomicMin(&secondkey[qi], lose);
           }
         }
@@ -951,7 +957,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
     // ---- this lane's result: redo the winning triangle (fp64 when the distance is tiny against its extent)
     if (valid) {
       unsigned long long key = bestkey[lane];
-      int tri = (int)(key & 0xffffffffu);
+      int tri = (int)(key & 0xffffffu);
       float term = 0.f;
       if (key != EQ_NONE) {
         d3 q = mk<double>(qd[3 * lane], qd[3 * lane + 1], qd[3 * lane + 2]);
@@ -962,12 +968,12 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
         float sc = fmaxf(fmaxf(fmaxf(fabsf(af.x), fabsf(af.y)), fmaxf(fabsf(af.z), fabsf(bf.x))),
                          fmaxf(fmaxf(fabsf(bf.y), fabsf(bf.z)), fmaxf(fabsf(cf3.x), fmaxf(fabsf(cf3.y), fabsf(cf3.z)))));
         const unsigned long long key2 = secondkey[lane];
-        const bool contested = key2 != EQ_NONE && (int)(key2 & 0xffffffffu) != tri &&
+        const bool contested = key2 != EQ_NONE && ((key2 ^ key) & 0xff000000ull) != 0ull &&
                                __uint_as_float((unsigned)(key2 >> 32)) <= d2 * NEAR_BAND + 1.0e-12f;
         if (d2 < 1.0e-4f * sc * sc || contested) {
           d3 v64 = closest_pt_triangle_d(a, b, cc);
           if (contested) {
-            const int tri2 = (int)(key2 & 0xffffffffu);
+            const int tri2 = (int)(key2 & 0xffffffu);
             d3 a2 = tri_vertex(mo.tris, tri2, 0) - q, b2 = tri_vertex(mo.tris, tri2, 1) - q, c2 = tri_vertex(mo.tris, tri2, 2) - q;
             d3 w64 = closest_pt_triangle_d(a2, b2, c2);
             if (dot(w64, w64) < dot(v64, v64)) v64 = w64;
