@@ -136,11 +136,16 @@ __device__ __noinline__ float tri_tri_dist2_plain(f3 p2, f3 p3, f3 q1, f3 q2, f3
 // triangle's extent the winner is redone in fp64.
 // Must agree with ClosestPtCallback (collisionAlgorithms_inl.h:210-238, collisionAlgorithms.h:220-242).
 // ============================================================================================
+// Candidates whose squared distance is within this factor of the best are ordered in fp64, not fp32.  Pruning uses the
+// same band, so every such candidate is visited whatever order the traversal takes (deterministic results).
+constexpr float NEAR_BAND = 1.0002f;
 #define CPQ_STACK 64
 __device__ __forceinline__ float closest_point_query(const MeshDev &m, const NodeQ *top, int ntop, d3 q, f3 &bestv,
-                                                     int &best_tri, unsigned &n_box, unsigned &n_tri) {
+                                                     int &best_tri, unsigned &n_box, unsigned &n_tri, int *second_tri = nullptr) {
   const f3 qf = tof(q);
   float best = 1.0e30f, best_sc = 0.f;
+  // runner-up with a different closest point inside the near-tie band (arbitrated in fp64 by the caller)
+  float second = 3.0e38f; int tri2 = -1; f3 v2 = mk<float>(0.f, 0.f, 0.f);
   bestv = mk<float>(0.f, 0.f, 0.f);
   best_tri = -1;
   int stk_n[CPQ_STACK];
@@ -152,7 +157,7 @@ __device__ __forceinline__ float closest_point_query(const MeshDev &m, const Nod
     int leaf = -1;
     // ---- descend until this lane holds a leaf or runs out of work
     while (cur >= 0) {
-      if (curd <= best) {
+      if (curd <= best * NEAR_BAND + 1.0e-12f) {
         Node n = fetch_node(m, top, ntop, cur);
         if (n.child < 0) {
           leaf = n.tri;
@@ -166,8 +171,8 @@ __device__ __forceinline__ float closest_point_query(const MeshDev &m, const Nod
           n_box += 2;
           int near = n.child, far = n.child + 1;
           if (d1 < d0) { near = n.child + 1; far = n.child; float t = d0; d0 = d1; d1 = t; }
-          if (d1 <= best && sp < CPQ_STACK) { stk_n[sp] = far; stk_d[sp] = d1; sp++; }
-          if (d0 <= best) { cur = near; curd = d0; continue; }
+          if (d1 <= best * NEAR_BAND + 1.0e-12f && sp < CPQ_STACK) { stk_n[sp] = far; stk_d[sp] = d1; sp++; }
+          if (d0 <= best * NEAR_BAND + 1.0e-12f) { cur = near; curd = d0; continue; }
           cur = -1;
         }
       } else {
@@ -182,15 +187,22 @@ __device__ __forceinline__ float closest_point_query(const MeshDev &m, const Nod
       f3 af = tof(a), bf = tof(b), cf = tof(c);
       f3 v = closest_pt_triangle<float>(af, bf, cf, mk<float>(0.f, 0.f, 0.f));
       float d2 = dot(v, v);
+      auto differs = [](f3 x, f3 y) { return fabsf(x.x - y.x) + fabsf(x.y - y.y) + fabsf(x.z - y.z) > 2.0e-4f; };
       if (d2 < best) {
+        // the displaced best becomes the runner-up if it describes another point and is still inside the band
+        if (best_tri >= 0 && best <= d2 * NEAR_BAND + 1.0e-12f && differs(bestv, v)) { second = best; tri2 = best_tri; v2 = bestv; }
+        else if (tri2 >= 0 && (second > d2 * NEAR_BAND + 1.0e-12f || !differs(v2, v))) { tri2 = -1; second = 3.0e38f; }
         best = d2; bestv = v; best_tri = leaf;
         best_sc = fmaxf(fmaxf(fmaxf(fabsf(af.x), fabsf(af.y)), fmaxf(fabsf(af.z), fabsf(bf.x))),
                         fmaxf(fmaxf(fabsf(bf.y), fabsf(bf.z)), fmaxf(fabsf(cf.x), fmaxf(fabsf(cf.y), fabsf(cf.z)))));
+      } else if (d2 <= best * NEAR_BAND + 1.0e-12f && d2 < second && differs(v, bestv)) {
+        second = d2; tri2 = leaf; v2 = v;
       }
       if (sp > 0) { sp--; cur = stk_n[sp]; curd = stk_d[sp]; }
     }
     if (cur < 0) break;
   }
+  if (second_tri) *second_tri = tri2;
   // fp32 loses relative accuracy once the distance is small against the triangle's own extent
   if (best_tri >= 0 && best < 1.0e-4f * best_sc * best_sc) {
     d3 a = tri_vertex(m.tris, best_tri, 0) - q, b = tri_vertex(m.tris, best_tri, 1) - q, c = tri_vertex(m.tris, best_tri, 2) - q;
@@ -199,6 +211,38 @@ __device__ __forceinline__ float closest_point_query(const MeshDev &m, const Nod
     best = (float)dot(v64, v64);
   }
   return best;
+}
+
+// fp64 re-run of a closest-point query whose fp32 traversal met near-ties: same tree, every candidate inside
+// `bound2` (squared) evaluated in double, the true minimum kept.  Rare path of the single-pose API (point_kernel).
+__device__ __noinline__ double closest_point_query_d(const MeshDev &m, d3 q, double bound2, d3 *closest) {
+  int stk[CPQ_STACK];
+  int sp = 0;
+  stk[sp++] = 0;
+  double best = bound2;
+  d3 bestc = q;
+  bool found = false;
+  while (sp > 0) {
+    const int i = stk[--sp];
+    Node n = load_node(m, i);
+    // stored boxes are padded: the fp32 box distance (minus a rounding margin) is a valid lower bound
+    float c[3], h[3];
+    node_ch(n, c, h);
+    double dx = fmax(fabs(q.x - (double)c[0]) - (double)h[0], 0.0), dy = fmax(fabs(q.y - (double)c[1]) - (double)h[1], 0.0),
+           dz = fmax(fabs(q.z - (double)c[2]) - (double)h[2], 0.0);
+    if (dx * dx + dy * dy + dz * dz > best) continue;
+    if (n.child < 0) {
+      d3 a = tri_vertex(m.tris, n.tri, 0), b = tri_vertex(m.tris, n.tri, 1), cc = tri_vertex(m.tris, n.tri, 2);
+      d3 cl = closest_pt_triangle<double>(a, b, cc, q);
+      d3 dv = cl - q;
+      double d2 = dot(dv, dv);
+      if (d2 < best || (!found && d2 <= best)) { best = d2; bestc = cl; found = true; }
+    } else if (sp + 2 <= CPQ_STACK) {
+      stk[sp++] = n.child; stk[sp++] = n.child + 1;
+    }
+  }
+  *closest = bestc;
+  return found ? best : -1.0;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -263,16 +307,23 @@ __global__ void point_kernel(PointParams p) {
   const double *X = reinterpret_cast<const double *>(p.body_xf);
   d3 pw = mk<double>(p.points[3 * i], p.points[3 * i + 1], p.points[3 * i + 2]);
   d3 q = xf_apply_inv(X, pw);
-  f3 v; int bt; unsigned nb = 0, nt = 0;
-  float d2 = closest_point_query(p.mesh, nullptr, 0, q, v, bt, nb, nt);
-  // refine the winning triangle in fp64 so the returned coordinates carry fp64 accuracy
+  f3 v; int bt, bt2 = -1; unsigned nb = 0, nt = 0;
+  float d2 = closest_point_query(p.mesh, nullptr, 0, q, v, bt, nb, nt, &bt2);
+  // refine the winning triangle in fp64 so the returned coordinates carry fp64 accuracy; a runner-up with another
+  // closest point inside the near-tie band is compared in fp64 (the reference's fp64 traversal would have ordered them)
   d3 cl = q;
   double dist = 0.0;
   if (bt >= 0) {
     d3 a = tri_vertex(p.mesh.tris, bt, 0), b = tri_vertex(p.mesh.tris, bt, 1), c = tri_vertex(p.mesh.tris, bt, 2);
     cl = closest_pt_triangle<double>(a, b, c, q);
     d3 dv = cl - q;
-    dist = sqrt(dot(dv, dv));
+    double dd = dot(dv, dv);
+    if (bt2 >= 0) {
+      d3 cl2;
+      double d2r = closest_point_query_d(p.mesh, q, dd * (1.0 + 1.0e-9), &cl2);
+      if (d2r >= 0.0 && d2r < dd) { cl = cl2; dd = d2r; }
+    }
+    dist = sqrt(dd);
   }
   (void)d2;
   d3 cw = xf_apply(X, cl);
@@ -300,9 +351,6 @@ __device__ __forceinline__ unsigned long long pack_dist_entry(float lb, int a, i
 __device__ __forceinline__ float entry_lb(unsigned long long e) { return __uint_as_float(((unsigned)(e >> 48)) << 16); }
 
 
-// Candidates whose squared distance is within this factor of the best are ordered in fp64, not fp32.  Pruning uses the
-// same band, so every such candidate is visited whatever order the traversal takes (deterministic results).
-constexpr float NEAR_BAND = 1.0002f;
 constexpr int NEAR_TINY_BIT = 1 << 30;   // marks near-list entries kept because their fp32 distance is unreliable
 // ---- near-minimum list of the distance kernel (rare paths, kept out of line: the traversal loop is register-bound) ----
 // drop entries the improving best has left behind; returns the new length

@@ -36,3 +36,20 @@ ld = live["link_dist"].astype(np.float64); both = (dl >= 0) & (ld >= 0)
 d = rel(ld[both], dl[both])
 print("LIVE n=%d legal mismatches=%d  energy rel err: max %.3g  >1e-4: %d | link dist sign mismatches=%d rel err max %.3g >1e-4: %d" % (
     nlive, int((ll != live["legal"]).sum()), e.max(), int((e > 1e-4).sum()), int(((dl < 0) != (ld < 0)).sum()), d.max(), int((d > 1e-4).sum())))
+# single-pose pointToBodyDistance: closest points (not only distances) against the reference
+w = osc.w
+w.set_transform(osc.ids[obj], *sc.body_tran[obj]); eng.set_body_transform(sb.body_ids[obj], *sc.body_tran[obj])
+cen = sc.bodies[obj].tris.reshape(-1, 3).mean(0) + sc.body_tran[obj][1]
+npt = 20000
+v = rng.normal(size=(npt, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+pts = cen[None, :] + v * rng.uniform(5, 300, size=(npt, 1))
+bad = worse = 0; maxrel = 0.0
+for pnt in pts:
+    do, cpo, _ = w.point_distance(osc.ids[obj], pnt)
+    de, cpe, _ = eng.point_to_body_distance(sb.body_ids[obj], pnt)
+    maxrel = max(maxrel, abs(de - do) / max(do, 1e-9))
+    if np.linalg.norm(cpe - cpo) > 1e-3:
+        bad += 1
+        if de > do * (1 + 1e-12):
+            worse += 1
+print("POINT n=%d dist rel err max %.3g | closest point differs > 1e-3 mm: %d (of which engine distance larger than the reference's: %d)" % (npt, maxrel, bad, worse))
