@@ -42,4 +42,14 @@ int point_contact_wrenches(const b2c_contact *c, int n, int side, double cof, co
 // checkContactNormals (contactSetting.cpp:54-81): flips ill-oriented normals in place, returns how many contacts changed
 int check_contact_normals(b2c_contact *c, int n, const double q1[4], const double t1[3], const double q2[4], const double t2[3]);
 
+// soft-finger contacts (soft_contact_host.cpp; contactSetting.cpp:83-191, softContact.cpp, FitParabola.h)
+double soft_neighborhood_radius(double youngs1, double youngs2);
+int soft_contact_merge(std::vector<b2c_contact> &contacts, std::vector<std::vector<double>> &n1,
+                       std::vector<std::vector<double>> &n2, const double q1[4], const double t1[3], const double q2[4],
+                       const double t2[3]);
+int soft_contact_fit(const b2c_contact *c, int n, int side, const double *nghbd_xyz, const int *offsets, b2c_soft_fit *fit);
+int soft_contact_wrenches(const b2c_contact *c, int n, int side, const b2c_soft_fit *fit_this, const b2c_soft_fit *fit_mate,
+                          const double q_this[4], const double q_mate[4], double youngs, double cof, const double cog[3],
+                          double max_radius, double *wrench120, double *ellipse6);
+
 } // namespace b2c

@@ -35,6 +35,7 @@ EXPORTS = [
     "b2c_anneal_create", "b2c_anneal_destroy", "b2c_anneal_step", "b2c_anneal_read", "b2c_anneal_device_ptrs",
     "b2c_anneal_propose", "b2c_anneal_write", "b2c_anneal_best_rows",
     "b2c_check_contact_normals", "b2c_contact_frames", "b2c_point_contact_wrenches",
+    "b2c_soft_neighborhood_radius", "b2c_soft_contact_merge", "b2c_soft_contact_fit", "b2c_soft_contact_wrenches",
 ]
 
 
@@ -45,6 +46,11 @@ class B2CError(RuntimeError):
 class Contact(C.Structure):
     _fields_ = [("b1_pos", C.c_double * 3), ("b2_pos", C.c_double * 3), ("b1_normal", C.c_double * 3),
                 ("b2_normal", C.c_double * 3), ("distSq", C.c_double)]
+
+
+class SoftFit(C.Structure):
+    _fields_ = [("a", C.c_double), ("b", C.c_double), ("c", C.c_double), ("r1", C.c_double), ("r2", C.c_double),
+                ("rot_angle", C.c_double)]
 
 
 class Obb(C.Structure):
@@ -131,6 +137,12 @@ def load_library():
     L.b2c_check_contact_normals.argtypes = [C.POINTER(Contact), ci, dp, dp, dp, dp, ip]
     L.b2c_contact_frames.argtypes = [C.POINTER(Contact), ci, ci, dp]
     L.b2c_point_contact_wrenches.argtypes = [C.POINTER(Contact), ci, ci, C.c_double, dp, C.c_double, dp]
+    L.b2c_soft_neighborhood_radius.argtypes = [C.c_double, C.c_double]
+    L.b2c_soft_neighborhood_radius.restype = C.c_double
+    L.b2c_soft_contact_merge.argtypes = [C.POINTER(Contact), ip, dp, dp, dp, dp, dp, ip, dp, ip, ip]
+    L.b2c_soft_contact_fit.argtypes = [C.POINTER(Contact), ci, ci, dp, ip, C.POINTER(SoftFit)]
+    L.b2c_soft_contact_wrenches.argtypes = [C.POINTER(Contact), ci, ci, C.POINTER(SoftFit), C.POINTER(SoftFit), dp, dp,
+                                            C.c_double, C.c_double, dp, C.c_double, dp, dp]
     L.b2c_anneal_create.argtypes = [vp, C.POINTER(AnnealDesc), C.POINTER(C.c_float), ip]
     L.b2c_anneal_destroy.argtypes = [vp, ci]
     L.b2c_anneal_step.argtypes = [vp, ci, ci]
@@ -558,6 +570,80 @@ def point_contact_wrenches(rows, side, cof, cog, max_radius):
     if rc:
         raise B2CError(f"b2c_point_contact_wrenches failed ({rc})")
     return out
+
+
+def _rows_of(arr, n):
+    return np.array([list(a.b1_pos) + list(a.b2_pos) + list(a.b1_normal) + list(a.b2_normal) + [a.distSq] for a in arr[:n]]).reshape(-1, 13)
+
+
+def _ragged(lists):
+    """list of (k_i, 3) point arrays -> (flat xyz float64, offsets int32[n + 1])"""
+    off = np.zeros(len(lists) + 1, dtype=np.int32)
+    for i, l in enumerate(lists):
+        off[i + 1] = off[i] + len(np.asarray(l).reshape(-1, 3))
+    flat = np.zeros((max(int(off[-1]), 1), 3))
+    for i, l in enumerate(lists):
+        flat[off[i]:off[i + 1]] = np.asarray(l, dtype=np.float64).reshape(-1, 3)
+    return np.ascontiguousarray(flat), off
+
+
+def soft_neighborhood_radius(youngs1, youngs2):
+    """findSoftNeighborhoods' bodyRegion radius in mm (contactSetting.cpp:129-133).  Host only."""
+    return float(load_library().b2c_soft_neighborhood_radius(float(youngs1), float(youngs2)))
+
+
+def soft_contact_merge(rows, tran1, tran2, nghbd1, nghbd2):
+    """mergeSoftNeighborhoods: returns (rows', nghbd1', nghbd2', merges); nghbd* are lists of (k, 3) arrays.  Host only."""
+    L = load_library()
+    arr, n = _contact_array(rows)
+    q1, t1, q2, t2 = [np.ascontiguousarray(x, dtype=np.float64) for x in (tran1[0], tran1[1], tran2[0], tran2[1])]
+    x1, o1 = _ragged(nghbd1); x2, o2 = _ragged(nghbd2)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    nn, nm = C.c_int(n), C.c_int(0)
+    rc = L.b2c_soft_contact_merge(arr, C.byref(nn), q1.ctypes.data_as(dp), t1.ctypes.data_as(dp), q2.ctypes.data_as(dp),
+                                  t2.ctypes.data_as(dp), x1.ctypes.data_as(dp), o1.ctypes.data_as(ip), x2.ctypes.data_as(dp),
+                                  o2.ctypes.data_as(ip), C.byref(nm))
+    if rc:
+        raise B2CError(f"b2c_soft_contact_merge failed ({rc})")
+    k = nn.value
+    return (_rows_of(arr, k), [x1[o1[i]:o1[i + 1]].copy() for i in range(k)], [x2[o2[i]:o2[i + 1]].copy() for i in range(k)],
+            nm.value)
+
+
+def soft_contact_fit(rows, side, nghbd):
+    """SoftContact surface fit per contact: (n, 6) = a, b, c, r1, r2, rotAngle.  Host only."""
+    L = load_library()
+    arr, n = _contact_array(rows)
+    x, o = _ragged(nghbd)
+    assert len(nghbd) == n
+    fit = (SoftFit * max(n, 1))()
+    rc = L.b2c_soft_contact_fit(arr, n, side, x.ctypes.data_as(C.POINTER(C.c_double)), o.ctypes.data_as(C.POINTER(C.c_int)), fit)
+    if rc:
+        raise B2CError(f"b2c_soft_contact_fit failed ({rc})")
+    return np.array([[f.a, f.b, f.c, f.r1, f.r2, f.rot_angle] for f in fit[:n]]).reshape(-1, 6)
+
+
+def soft_contact_wrenches(rows, side, fit_this, fit_mate, q_this, q_mate, youngs, cof, cog, max_radius):
+    """SFCL friction ellipsoid -> boundary wrenches: ((n, 20, 6) force/torque, (n, 6) major, minor, relPhi, r1', r2',
+    torque/N).  Host only."""
+    L = load_library()
+    arr, n = _contact_array(rows)
+
+    def fits(a):
+        a = np.asarray(a, dtype=np.float64).reshape(-1, 6)
+        f = (SoftFit * max(n, 1))()
+        for i in range(n):
+            f[i].a, f[i].b, f[i].c, f[i].r1, f[i].r2, f[i].rot_angle = [float(v) for v in a[i]]
+        return f
+    out = np.zeros((n, 20, 6)); ell = np.zeros((n, 6))
+    qa, qb, g = [np.ascontiguousarray(v, dtype=np.float64) for v in (q_this, q_mate, cog)]
+    dp = C.POINTER(C.c_double)
+    rc = L.b2c_soft_contact_wrenches(arr, n, side, fits(fit_this), fits(fit_mate), qa.ctypes.data_as(dp), qb.ctypes.data_as(dp),
+                                     float(youngs), float(cof), g.ctypes.data_as(dp), float(max_radius),
+                                     out.ctypes.data_as(dp), ell.ctypes.data_as(dp))
+    if rc:
+        raise B2CError(f"b2c_soft_contact_wrenches failed ({rc})")
+    return out, ell
 
 
 class Annealer:

@@ -160,6 +160,44 @@ int b2c_contact_frames(const b2c_contact *contacts, int n, int side, double *fra
 int b2c_point_contact_wrenches(const b2c_contact *contacts, int n, int side, double cof, const double cog[3],
                                double max_radius, double *wrench48);
 
+/* Soft-finger contacts (SFCL), the elastic branch of addContacts (reference src/contactSetting.cpp:114-221,
+ * src/contact/softContact.cpp:22-125,186-358, include/graspit/FitParabola.h).  Context-free host utilities; the
+ * neighbourhoods they consume are the output of b2c_region (bodyRegion) around each contact.
+ * Neighbourhood lists are ragged: xyz = points back to back (3 doubles each, body frame), offsets[n + 1] = first point
+ * of each contact's list (offsets[0] = 0).
+ *   b2c_soft_neighborhood_radius  findSoftNeighborhoods' radius (contactSetting.cpp:129-133), mm
+ *   b2c_soft_contact_merge        mergeSoftNeighborhoods (contactSetting.cpp:141-184): contacts whose body-1
+ *                                 neighbourhoods share a vertex are one contact; the closer one (world distance between
+ *                                 its two points, contactSetting.cpp:39-47) survives and takes the union of both lists.
+ *                                 In place: contacts, *n, both xyz arrays and both offset arrays are rewritten.
+ *   b2c_soft_contact_fit          SoftContact::SoftContact + FitPoints (softContact.cpp:22-58,186-199): paraboloid
+ *                                 z = a x^2 + b y^2 + c xy through the neighbourhood in the contact frame, then
+ *                                 RotateParaboloid -> radii of curvature r1, r2 (mm, -1 = flat) and the rotation angle.
+ *                                 As in the reference, the neighbourhood is ROTATED into the contact frame but not
+ *                                 re-centred on the contact (softContact.cpp:41-43).
+ *   b2c_soft_contact_wrenches     setUpFrictionEdges of one side (softContact.cpp:69-117): CalcRelPhi, CalcRprimes,
+ *                                 CalcContact_Mattress(5 N, 3 mm mattress, youngs = max of the two bodies, Pa) -> contact
+ *                                 ellipse -> friction ellipsoid with latitudes {1,5,8,5,1} (20 edges,
+ *                                 contact.cpp:180-216) -> boundary wrenches (contact.cpp:124-165).
+ *                                 wrench120 = [n][20][force 3, torque 3]; ellipse6 (optional) = [n][major axis m,
+ *                                 minor axis m, relPhi, r1', r2' (mm), max torque / (mu N) m].  q_this / q_mate: world
+ *                                 rotations of the body on `side` and of the other body. */
+typedef struct b2c_soft_fit {
+  double a, b, c;
+  double r1, r2;
+  double rot_angle;
+} b2c_soft_fit;
+double b2c_soft_neighborhood_radius(double youngs1, double youngs2);
+int b2c_soft_contact_merge(b2c_contact *contacts, int *n, const double q1_wxyz[4], const double t1[3],
+                           const double q2_wxyz[4], const double t2[3], double *nghbd1_xyz, int *offsets1,
+                           double *nghbd2_xyz, int *offsets2, int *nmerged);
+int b2c_soft_contact_fit(const b2c_contact *contacts, int n, int side, const double *nghbd_xyz, const int *offsets,
+                         b2c_soft_fit *fit);
+int b2c_soft_contact_wrenches(const b2c_contact *contacts, int n, int side, const b2c_soft_fit *fit_this,
+                              const b2c_soft_fit *fit_mate, const double q_this_wxyz[4], const double q_mate_wxyz[4],
+                              double youngs, double cof, const double cog[3], double max_radius, double *wrench120,
+                              double *ellipse6);
+
 /* ---- batched pose evaluation: FK -> legal -> proximity -> CONTACT_ENERGY --------------------
  * Replaces, for whole batches of candidate states, the loop
  *   HandObjectState::execute -> Robot::setTran / forceDOFVals -> KinematicChain::fwdKinematics

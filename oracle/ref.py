@@ -71,6 +71,8 @@ def lib():
         L.ref_transf_axis_angle.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_transf_coordinate.argtypes = [C.POINTER(C.c_double)] * 5
         L.ref_transf_jacobian.argtypes = [C.POINTER(C.c_double)] * 3
+        L.ref_soft_fit.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
+                                   C.POINTER(C.c_double)]
         L.ref_quat_roundtrip.argtypes = [C.POINTER(C.c_double)] * 3
         L.ref_eval_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,
                                      C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double),
@@ -241,6 +243,16 @@ def transf_coordinate(o, x, y):
     o, x, y = _d(o, 3), _d(x, 3), _d(y, 3); out = np.zeros(7); aff = np.zeros(9)
     lib().ref_transf_coordinate(_dp(o), _dp(x), _dp(y), _dp(out), _dp(aff))
     return out[:4].copy(), out[4:].copy(), aff.reshape(3, 3).copy()
+
+
+def soft_fit(pos, normal, nghbd):
+    """SoftContact::SoftContact + FitPoints with the reference's own FitParaboloid / RotateParaboloid (FitParabola.h):
+    returns (a, b, c, r1, r2, rotAngle, fitRot 3x3)"""
+    p, n = _d(pos, 3), _d(normal, 3)
+    pts = np.ascontiguousarray(np.asarray(nghbd, dtype=np.float64).reshape(-1, 3))
+    out = np.zeros(15)
+    lib().ref_soft_fit(_dp(p), _dp(n), _dp(pts if len(pts) else np.zeros(3)), len(pts), _dp(out))
+    return out[:6].copy(), out[6:].reshape(3, 3).copy()
 
 
 def transf_jacobian(a):

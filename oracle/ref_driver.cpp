@@ -30,6 +30,7 @@
 #include "graspit/Collision/Graspit/collisionModel.h"
 #include "graspit/Collision/Graspit/collisionAlgorithms.h"
 #include "graspit/bBox.h"
+#include "graspit/FitParabola.h"      // the reference's own paraboloid fit (header-only)
 
 // symbols the reference expects from translation units we do not compile
 QMutex qhull_mutex;                                                   // src/gws.cpp
@@ -331,6 +332,35 @@ void ref_quat_roundtrip(const double *q_wxyz, double *mat9_rowmajor, double *q_o
   for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) mat9_rowmajor[3 * r + c] = m(r, c);
   Quaternion q2(m);
   q_out_wxyz[0] = q2.w(); q_out_wxyz[1] = q2.x(); q_out_wxyz[2] = q2.y(); q_out_wxyz[3] = q2.z();
+}
+
+// Soft-finger contact surface fit.  FitParaboloid / RotateParaboloid are the reference's own (include/graspit/FitParabola.h,
+// header-only, compiled verbatim above).  Restated around them (softContact.cpp and contact.cpp are Qt/Coin-bound):
+// the contact frame of Contact::Contact (contact.cpp:77-90) built with the reference's transf::COORDINATE, and the
+// neighbourhood mapping of SoftContact::SoftContact (softContact.cpp:33-45), which applies frame.inverse().affine(),
+// i.e. the ROTATION only -- the contact location is not subtracted (the corrected line is commented out upstream).
+// out15 = a, b, c, r1, r2, rotAngle, fitRot (row-major 3x3)
+void ref_soft_fit(const double *pos, const double *nrm, const double *nghbd_xyz, int npts, double *out15) {
+  vec3 normal = vec3(nrm[0], nrm[1], nrm[2]).normalized();
+  vec3 tangentX, tangentY;
+  if (fabs(normal.dot(vec3(1, 0, 0))) > 1.0 - MACHINE_ZERO) tangentX = normal.cross(vec3(0, 0, 1)).normalized();
+  else tangentX = normal.cross(vec3(1, 0, 0)).normalized();
+  tangentY = (normal.cross(tangentX)).normalized();
+  transf frame = transf::COORDINATE(position(pos[0], pos[1], pos[2]), tangentX, tangentY);
+  std::vector<vec3> pts(npts > 0 ? npts : 1);
+  for (int i = 0; i < npts; i++) {
+    vec3 temp(nghbd_xyz[3 * i], nghbd_xyz[3 * i + 1], nghbd_xyz[3 * i + 2]);
+    position posit;
+    posit = frame.inverse().affine() * (temp);
+    pts[i] = posit;
+  }
+  double coeffs[3], r1 = 0, r2 = 0, ang = 0;
+  mat3 rot = mat3::Identity();
+  FitParaboloid(pts.data(), npts, coeffs);
+  out15[0] = coeffs[0]; out15[1] = coeffs[1]; out15[2] = coeffs[2];
+  RotateParaboloid(coeffs, &r1, &r2, &rot, &ang);
+  out15[3] = r1; out15[4] = r2; out15[5] = ang;
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) out15[6 + 3 * r + c] = rot(r, c);
 }
 
 // ---------------------------------------------------------------------------------------

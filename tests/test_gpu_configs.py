@@ -79,6 +79,16 @@ def _canon(a, b, contacts, inv):
     return (ia, ib), c
 
 
+def _fit_cond(pos, normal, pts):
+    from oracle.port import contact_np as cn
+    if len(pts) < 3:
+        return 1.0
+    _, _, aff, _ = cn.contact_frame(pos, normal)
+    p = np.asarray(pts) @ aff
+    B = np.stack([p[:, 0] ** 2, p[:, 1] ** 2, p[:, 0] * p[:, 1]], axis=1)
+    return float(np.linalg.cond(B.T @ B))
+
+
 def test_config3_allcontacts_with_region(human):
     """allContacts(0.2) over the whole hand for poses pushed into contact, + bodyRegion around each contact
     (the soft-finger neighbourhood radius of contactSetting.cpp:129 for E = 1.5e6: 3.5 mm)."""
@@ -89,7 +99,7 @@ def test_config3_allcontacts_with_region(human):
     inv_o = {v: k for k, v in osc.ids.items()}
     inv_e = {v: k for k, v in sb.body_ids.items()}
     w = osc.w
-    done = npairs = ncontacts = exact = ncones = 0
+    done = npairs = ncontacts = exact = ncones = nsoft = 0
     for p in np.nonzero(legal_o)[0]:
         if done >= 25:
             break
@@ -145,6 +155,37 @@ def test_config3_allcontacts_with_region(human):
                     assert np.allclose(wr[i], cn.point_contact_wrenches(row[0:3], row[6:9], 0.5, [0.0, 0.0, 0.0], 100.0), atol=1e-10)
                     assert np.allclose(fr[i, 4:], row[0:3])
                 ncones += len(fixed)
+                # elastic fingertips: the soft branch of addContacts -- neighbourhoods of both bodies around every
+                # contact (device region kernel), merge, paraboloid fit, contact ellipse, 20-edge ellipsoid wrenches
+                ya, yb = sc.bodies[key[0]].youngs, sc.bodies[key[1]].youngs
+                if max(ya, yb) > 0:
+                    rad = E.soft_neighborhood_radius(ya, yb)
+                    assert abs(rad - cn.soft_neighborhood_radius(ya, yb)) < 1e-12
+                    n1e = [eng.body_region(sb.body_ids[key[0]], r[0:3], r[6:9], rad) for r in fixed]
+                    n2e = [eng.body_region(sb.body_ids[key[1]], r[3:6], r[9:12], rad) for r in fixed]
+                    for r, a1, a2 in zip(fixed, n1e, n2e):
+                        assert {tuple(x) for x in w.region(osc.ids[key[0]], r[0:3], r[6:9], rad)} == {tuple(x) for x in a1}
+                        assert {tuple(x) for x in w.region(osc.ids[key[1]], r[3:6], r[9:12], rad)} == {tuple(x) for x in a2}
+                    mr, m1, m2, nm = E.soft_contact_merge(fixed, ta, tb, n1e, n2e)
+                    mr_o, m1_o, m2_o, nm_o = cn.merge_soft_neighborhoods(fixed, ta, tb, n1e, n2e)
+                    assert nm == nm_o and np.array_equal(mr, mr_o)
+                    assert all(np.array_equal(x, y) for x, y in zip(m1 + m2, m1_o + m2_o))
+                    f1 = E.soft_contact_fit(mr, 1, m1); f2 = E.soft_contact_fit(mr, 2, m2)
+                    wr1, el1 = E.soft_contact_wrenches(mr, 1, f1, f2, ta[0], tb[0], max(ya, yb), 1.0, [0.0, 0.0, 0.0], 100.0)
+                    for i, row in enumerate(mr):
+                        fo1, _ = ref.soft_fit(row[0:3], row[6:9], m1[i]); fo2, _ = ref.soft_fit(row[3:6], row[9:12], m2[i])
+                        # un-recentred neighbourhoods => ill-conditioned normal equations (tests/test_soft_contacts.py)
+                        tol = max(1e-9, 1e-13 * max(_fit_cond(row[0:3], row[6:9], m1[i]), _fit_cond(row[3:6], row[9:12], m2[i])))
+                        if tol > 1e-3:
+                            continue
+                        assert np.allclose(f1[i], fo1, rtol=tol, atol=1e-12, equal_nan=True)
+                        assert np.allclose(f2[i], fo2, rtol=tol, atol=1e-12, equal_nan=True)
+                        sa = cn.soft_contact_side(row[0:3], row[6:9], m1[i], ta[0]); sb_ = cn.soft_contact_side(row[3:6], row[9:12], m2[i], tb[0])
+                        wo, eo = cn.soft_contact_wrenches(sa, sb_, max(ya, yb), 1.0, [0.0, 0.0, 0.0], 100.0)
+                        if np.isfinite(eo).all() and np.isfinite(el1[i]).all():
+                            assert np.allclose(el1[i], eo, rtol=max(1e-6, 100 * tol), atol=1e-9)
+                            assert np.allclose(wr1[i], wo, rtol=max(1e-6, 100 * tol), atol=1e-7)
+                            nsoft += 1
             # region around the first contact on the object side (elastic fingertip neighbourhoods)
             a_is_obj = key[0] == obj
             cpos = cl[0][0:3] if a_is_obj else cl[0][3:6]
@@ -155,6 +196,7 @@ def test_config3_allcontacts_with_region(human):
     assert done >= 10 and npairs >= done and ncontacts >= done
     assert exact >= 0.7 * npairs
     assert ncones >= 5
+    print('soft contacts checked:', nsoft)
 
 
 # ------------------------------------------------------------------------------------------------ config 4
