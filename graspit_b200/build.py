@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2c.so")
-SOURCES = ["api.cu", "kernels.cu", "collide.cu", "contacts.cu", "anneal.cu", "bvh.cpp", "contacts_host.cpp", "soft_contact_host.cpp"]
+SOURCES = ["api.cu", "kernels.cu", "collide.cu", "contacts.cu", "anneal.cu", "autograsp.cu", "bvh.cpp", "contacts_host.cpp", "soft_contact_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xcompiler", "-O3"]
 

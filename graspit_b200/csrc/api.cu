@@ -325,6 +325,7 @@ int run_static_distance(b2c_ctx *ctx, int a, int b, double *dist, double pa[3], 
 } // namespace
 
 static void anneal_release_all(b2c_ctx *ctx);      // anneal_api.inc
+static void autograsp_release_all(b2c_ctx *ctx);   // autograsp_api.inc
 
 // =================================================================================================
 extern "C" {
@@ -387,6 +388,7 @@ void b2c_destroy(b2c_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   anneal_release_all(ctx);
+  autograsp_release_all(ctx);
   invalidate_plans(ctx);
   for (auto &m : ctx->meshes) {
     if (m.d_nodes) cudaFree(m.d_nodes);
@@ -989,3 +991,6 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
 
 // ---- batched annealing (A14) ---------------------------------------------------------------------
 #include "anneal_api.inc"
+
+// ---- batched autograsp (section 8(f).4) -------------------------------------------------------------
+#include "autograsp_api.inc"

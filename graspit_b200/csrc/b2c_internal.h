@@ -119,6 +119,9 @@ struct DistParams {
   const int *body_mesh;
   const MeshDev *meshes;
   const uint8_t *legal;    // optional: skip poses with legal == 0
+  const int *wlist;        // optional compact work list: entries pose * nq + query (autograsp bisection); length
+  const int *wcount;       //   *wcount (device), capped at wcap; entries not listed keep their old dist value
+  int wcap;
   float *dist;             // [npose][nq]  (-1 = interpenetration)
   double *pts;             // optional [npose][nq][6]: closest points, each in its own body frame
   int *work_counter;
@@ -142,6 +145,7 @@ struct FkParams {
   int input_mode;          // B2C_INPUT_RAW = 0, B2C_INPUT_AA_EIGEN = 1
   int stride;
   const float *states;
+  const double *jstates;   // input_mode 2: per pose base (q wxyz, t) + one value per joint (program joint order), fp64
   Qt ref;                  // mRefTran for AA_EIGEN
   Xf *out;                 // [npose][nslots]
   double *out_qt;          // optional [npose][nslots][7]
@@ -275,4 +279,49 @@ cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s);
 cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s);
 size_t energy_block_smem_bytes(int stage_nodes);
 
+} // namespace b2c
+
+// ---- batched autograsp (autograsp.cu): Robot::moveDOFToContacts for a batch of poses ----------------------------
+namespace b2c {
+constexpr int AG_MAXD = 32, AG_MAXJ = 32, AG_MAXL = 32, AG_MAXP = 256, AG_MW = AG_MAXP / 64;
+enum { AG_CHECK = 1, AG_INTERP = 2, AG_DONE = 3 };
+enum { AG_ST_MOVED = 1, AG_ST_INTERP_ERROR = 2, AG_ST_FAILSAFE = 4, AG_ST_STOPPED_AT_CONTACT = 8 };
+struct AgDesc {
+  int ndof, nj, nlinks, npairs;
+  int one_step;                    // desiredSteps == NULL: WorldElement::ONE_STEP for every DOF
+  int stop_at_contact;
+  int max_iters;                   // moveDOFToContacts failsafe (500)
+  double threshold;                // Contact::THRESHOLD
+  int dof_breakaway[AG_MAXD];      // 1: BreakAwayDOF, 0: RigidDOF
+  double desired[AG_MAXD], step[AG_MAXD];
+  int joint_dof[AG_MAXJ];
+  double joint_ratio[AG_MAXJ];
+  int link_last_joint[AG_MAXL];    // global joint index after which the link pose is read
+  int link_first_joint[AG_MAXL];   // first joint of the link's chain
+  short pair_link_a[AG_MAXP], pair_link_b[AG_MAXP];   // link index of each side of an active pair, -1 = not a link
+};
+struct AgState {
+  double q[AG_MAXD], desired[AG_MAXD], step[AG_MAXD], new_dof[AG_MAXD], initial_dof[AG_MAXD];
+  double jv[AG_MAXJ], initial_jv[AG_MAXJ], final_jv[AG_MAXJ], break_val[AG_MAXJ];
+  double t, deltat;
+  unsigned long long late[AG_MW], col[AG_MW], interest[AG_MW];
+  unsigned char stopped[AG_MAXJ], in_break[AG_MAXJ];
+  int phase, iters, status, ncols;
+};
+struct AgParams {
+  int npose;
+  int init;                        // 1: build the state from `states` and start the first step
+  const AgDesc *desc;
+  AgState *st;
+  const float *states;             // init: raw states, base (q wxyz, t) + DOF values
+  int stride;
+  double *jstates;                 // [npose][7 + nj]: input of the joint-level FK
+  const unsigned long long *pair_mask;   // [npose][mask_words] colliding pairs at the joint values of the last FK
+  int mask_words;
+  const float *dist;               // [npose][npairs] distances of the pairs listed in the previous round
+  int *wlist;                      // distance work list for the next round
+  int *counters;                   // [0] poses not finished, [1] work-list length
+  int wcap;
+};
+cudaError_t launch_autograsp_step(const AgParams &p, cudaStream_t s);
 } // namespace b2c

@@ -30,7 +30,14 @@ __global__ void __launch_bounds__(128) fk_kernel(FkParams p) {
   const FkProgram &g = p.prog;
   double dof[FK_MAX_DOF];
   Qt base;
-  if (p.input_mode == 0) {
+  const double *jv = nullptr;      // joint-level input (autograsp): joint values replace dof * ratio
+  if (p.input_mode == 2) {
+    const double *sj = p.jstates + (size_t)pose * p.stride;
+    base.w = sj[0]; base.x = sj[1]; base.y = sj[2]; base.z = sj[3];
+    base.tx = sj[4]; base.ty = sj[5]; base.tz = sj[6];
+    q_normalize(base);
+    jv = sj + 7;
+  } else if (p.input_mode == 0) {
     base.w = s[0]; base.x = s[1]; base.y = s[2]; base.z = s[3];
     base.tx = s[4]; base.ty = s[5]; base.tz = s[6];
     q_normalize(base);
@@ -80,7 +87,7 @@ __global__ void __launch_bounds__(128) fk_kernel(FkParams p) {
       int l = 0;
       for (int j = 0; j < c.njoints; j++) {
         const FkJoint &jd = g.joints[c.first_joint + j];
-        double val = dof[jd.dof] * jd.ratio;
+        double val = jv ? jv[c.first_joint + j] : dof[jd.dof] * jd.ratio;
         double theta = jd.revolute ? val + jd.theta : jd.theta;
         double dd = jd.revolute ? jd.d : val + jd.d;
         Qt tz = q_identity(); tz.tz = dd;
@@ -435,13 +442,17 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
 #ifdef DIST_DEBUG_STATS
   unsigned dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0;
 #endif
-  const int total = p.npose * p.nq;
+  const int total = p.wlist ? min(*p.wcount, p.wcap) : p.npose * p.nq;
 
   while (true) {
     int w = 0;
-    if (lane == 0) w = atomicAdd(p.work_counter, 1);
+    if (lane == 0) {
+      w = atomicAdd(p.work_counter, 1);
+      // optional compact work list (autograsp bisection): entry = pose * nq + query; other entries keep their value
+      if (p.wlist) w = w < total ? __ldg(&p.wlist[w]) : 0x7fffffff;
+    }
     w = __shfl_sync(FULL, w, 0);
-    if (w >= total) break;
+    if (w >= (p.wlist ? 0x7fffffff : total)) break;
     int pose = w / p.nq, qi = w - pose * p.nq;
     if (p.legal && !p.legal[pose]) {
       if (lane == 0) { p.dist[w] = -1.f; if (p.pts) for (int k = 0; k < 6; k++) p.pts[(size_t)w * 6 + k] = 0.0; }

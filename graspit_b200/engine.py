@@ -35,6 +35,7 @@ EXPORTS = [
     "b2c_anneal_create", "b2c_anneal_destroy", "b2c_anneal_step", "b2c_anneal_read", "b2c_anneal_device_ptrs",
     "b2c_anneal_propose", "b2c_anneal_write", "b2c_anneal_best_rows",
     "b2c_check_contact_normals", "b2c_contact_frames", "b2c_point_contact_wrenches",
+    "b2c_autograsp_batch",
     "b2c_soft_neighborhood_radius", "b2c_soft_contact_merge", "b2c_soft_contact_fit", "b2c_soft_contact_wrenches",
 ]
 
@@ -91,6 +92,18 @@ class EvalArgs(C.Structure):
                 ("ref_q", C.c_double * 4), ("ref_t", C.c_double * 3), ("flags", C.c_int),
                 ("legal", C.c_void_p), ("energy", C.c_void_p), ("pair_mask", C.c_void_p),
                 ("link_dist", C.c_void_p), ("body_tf", C.c_void_p)]
+
+
+class AutoGraspArgs(C.Structure):
+    _fields_ = [("robot", C.c_int), ("npose", C.c_int), ("states", C.c_void_p), ("stride", C.c_int),
+                ("desired", C.c_void_p), ("steps", C.c_void_p), ("dof_breakaway", C.c_void_p),
+                ("stop_at_contact", C.c_int), ("contact_threshold", C.c_double), ("max_rounds", C.c_int),
+                ("dof_out", C.c_void_p), ("joint_out", C.c_void_p), ("status", C.c_void_p), ("stopped_out", C.c_void_p),
+                ("rounds", C.c_void_p)]
+
+
+AG_MOVED, AG_INTERP_ERROR, AG_FAILSAFE, AG_STOPPED_AT_CONTACT = 1, 2, 4, 8
+AUTO_GRASP_TIME_STEP = 0.01       # Robot::AUTO_GRASP_TIME_STEP (reference src/robot.cpp:68)
 
 
 class AnnealDesc(C.Structure):
@@ -162,6 +175,7 @@ def load_library():
     L.b2c_bounding_volumes.argtypes = [vp, ci, ci, C.POINTER(Obb), ci, ip]
     L.b2c_robot_define.argtypes = [vp, C.POINTER(RobotDescC), ip]
     L.b2c_eval_batch.argtypes = [vp, C.POINTER(EvalArgs)]
+    L.b2c_autograsp_batch.argtypes = [vp, C.POINTER(AutoGraspArgs)]
     L.b2c_robot_bodies.argtypes = [vp, ci, ip, ci, ip]
     L.b2c_robot_pairs.argtypes = [vp, ci, ip, ci, ip]
     L.b2c_last_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
@@ -508,6 +522,43 @@ class Engine:
             res["body_tf"] = bt
         self._ck(self.L.b2c_eval_batch(self.h, C.byref(a)))
         return res
+
+    def move_dof_to_contacts(self, robot: int, states, desired, steps, dof_breakaway, stop_at_contact=False,
+                             contact_threshold=0.2, njoints=None):
+        """Robot::moveDOFToContacts for a batch: states (npose, 7 + ndof) float32 RAW rows (collision-free start).
+        Returns dict(dof (npose, ndof), joints, status (B2C_AG_* flags), iters, stopped, rounds)."""
+        st = np.ascontiguousarray(states, dtype=np.float32)
+        npose, stride = st.shape
+        des = np.ascontiguousarray(desired, dtype=np.float64)
+        ndof = des.size
+        stp = None if steps is None else np.ascontiguousarray(steps, dtype=np.float64)
+        brk = np.ascontiguousarray(dof_breakaway, dtype=np.uint8)
+        assert brk.size == ndof and (stp is None or stp.size == ndof)
+        nj = int(njoints) if njoints is not None else 32
+        dof = np.zeros((npose, ndof)); joints = np.zeros((npose, nj)); status = np.zeros((npose, 2), dtype=np.int32)
+        stopped = np.zeros((npose, nj), dtype=np.uint8)
+        rounds = C.c_int(0)
+        a = AutoGraspArgs()
+        a.robot, a.npose, a.states, a.stride = robot, npose, st.ctypes.data, stride
+        a.desired, a.steps, a.dof_breakaway = des.ctypes.data, (None if stp is None else stp.ctypes.data), brk.ctypes.data
+        a.stop_at_contact, a.contact_threshold, a.max_rounds = int(bool(stop_at_contact)), float(contact_threshold), 0
+        a.dof_out = dof.ctypes.data
+        if njoints is not None:
+            a.joint_out, a.stopped_out = joints.ctypes.data, stopped.ctypes.data
+        a.status = status.ctypes.data
+        a.rounds = C.addressof(rounds)
+        self._ck(self.L.b2c_autograsp_batch(self.h, C.byref(a)))
+        return {"dof": dof, "joints": joints if njoints is not None else None, "status": status[:, 0].copy(),
+                "iters": status[:, 1].copy(), "stopped": stopped if njoints is not None else None, "rounds": rounds.value}
+
+    def auto_grasp(self, robot: int, robot_desc, states, speed_factor=1.0, stop_at_contact=False):
+        """Hand::autoGrasp (static branch, reference src/robot.cpp:2427-2462) for a batch of RAW states; robot_desc is the
+        scene's RobotDesc (DOF limits, types and <defaultVelocity>)."""
+        vel = np.asarray(robot_desc.dof_velocity, dtype=np.float64)
+        desired = np.where(speed_factor * vel >= 0, robot_desc.dof_max, robot_desc.dof_min).astype(np.float64)
+        steps = vel * speed_factor * AUTO_GRASP_TIME_STEP
+        brk = [1 if t == "b" else 0 for t in robot_desc.dof_type]
+        return self.move_dof_to_contacts(robot, states, desired, steps, brk, stop_at_contact, njoints=robot_desc.n_joints)
 
     def _root_bodies(self, robot: int) -> int:
         return getattr(self, "_nroot", {}).get(robot, len(self.robot_bodies(robot)))

@@ -43,6 +43,7 @@ def save_pack(scene: Scene, path: str, extra: dict | None = None):
             "name": r.name, "base_body": r.base_body, "mount_body": r.mount_body, "n_dof": r.n_dof,
             "dof_type": r.dof_type, "dof_min": list(map(float, r.dof_min)), "dof_max": list(map(float, r.dof_max)),
             "dof_default": list(map(float, r.dof_default)), "dof_values": list(map(float, r.dof_values)),
+            "dof_velocity": None if r.dof_velocity is None else list(map(float, r.dof_velocity)),
             "tran": _tf(r.tran), "approach": _tf(r.approach), "parent": r.parent, "parent_chain": r.parent_chain,
             "eg": None if r.eg is None else [list(map(float, e)) for e in r.eg],
             "eg_origin": None if r.eg_origin is None else list(map(float, r.eg_origin)),
@@ -109,7 +110,8 @@ def load_pack(path_or_name: str) -> Scene:
                        eg_norm=None if r["eg_norm"] is None else np.array(r["eg_norm"]),
                        eg_limits=None if r["eg_limits"] is None else np.array(
                            [[np.nan if v is None else v for v in e] for e in r["eg_limits"]]),
-                       mount_body=r["mount_body"], parent=r["parent"], parent_chain=r["parent_chain"])
+                       mount_body=r["mount_body"], parent=r["parent"], parent_chain=r["parent_chain"],
+                       dof_velocity=None if r.get("dof_velocity") is None else np.array(r["dof_velocity"]))
         for v in r["vcontacts"]:
             rd.vcontacts.append(VirtualContactDesc(v[0], v[1], v[2], np.array(v[3]), np.array(v[4]), _untf(v[5])))
         sc.robots.append(rd)

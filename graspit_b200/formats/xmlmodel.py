@@ -96,6 +96,7 @@ class RobotDesc:
     mount_body: int = -1
     parent: int = -1
     parent_chain: int = -1
+    dof_velocity: Optional[np.ndarray] = None   # <defaultVelocity> per DOF (Hand::autoGrasp step = velocity x 0.01)
 
     @property
     def n_joints(self):
@@ -278,6 +279,7 @@ def load_robot(scene: Scene, xml_path: str, tran: Transf, dof_values=None) -> in
     n_dof = len(dofs)
     dof_type = [(d.get("type") or "r").strip() for d in dofs]
     dof_default = np.array([(_get_double(d, "defaultValue", 0.0) or 0.0) * math.pi / 180.0 for d in dofs])
+    dof_velocity = np.array([(_get_double(d, "defaultVelocity", 0.0) or 0.0) for d in dofs])
 
     chains: List[ChainDesc] = []
     for ci, ce in enumerate(root.findall("chain")):
@@ -364,7 +366,7 @@ def load_robot(scene: Scene, xml_path: str, tran: Transf, dof_values=None) -> in
 
     robot = RobotDesc(name=rname, base_body=base_idx, chains=chains, n_dof=n_dof, dof_type=dof_type,
                       dof_min=dof_min, dof_max=dof_max, dof_default=dof_default,
-                      dof_values=dof_default.copy(), tran=tran, approach=approach)
+                      dof_values=dof_default.copy(), tran=tran, approach=approach, dof_velocity=dof_velocity)
 
     eg = root.find("eigenGrasps")
     if eg is not None and _text(eg):

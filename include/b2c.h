@@ -294,6 +294,46 @@ int b2c_robot_bodies(b2c_ctx *ctx, int robot, int *bodies, int cap, int *nbodies
 /* the active pairs (a,b) that a batched evaluation of `robot` tests, in pair_mask bit order */
 int b2c_robot_pairs(b2c_ctx *ctx, int robot, int *pairs, int cap, int *npairs);
 
+/* ---- batched autograsp: Robot::moveDOFToContacts for whole batches of hand poses -------------------------------
+ * Replaces, per pose, Hand::autoGrasp -> Robot::moveDOFToContacts -> jumpDOFToContact -> getJointValuesFromDOF /
+ * interpolateJoints / stopJointsFromLink and the distance filter of World::findContacts (reference src/robot.cpp:
+ * 2427-2462, 1708-1815, 1593-1706, 1507-1560, 1418-1472, 1474-1489; src/world.cpp:1682-1707; RigidDOF / BreakAwayDOF in
+ * src/dof.cpp:497-514, 540-648).  Every pose starts from its own base pose and DOF values (a RAW row, as in
+ * b2c_eval_batch; the DOFs are taken as freshly forced: no break-away memory) and is closed towards `desired` in
+ * increments of `steps` until every DOF reached its target, is stopped by contacts, or the reference's 500-step
+ * failsafe hits.  Collisions are found among the active pairs that touch a still-moving link (allCollisions with the
+ * reference's interest list); a colliding step is bisected on bodyToBodyDistance of the colliding pairs exactly as
+ * interpolateJoints does (accept when 0 < distance < contact_threshold / 2).
+ * The start posture must be free of contacts on the links (the state HandObjectState::execute leaves:
+ * Body::setTran breaks a moved link's contacts, body.cpp:928-931); then Link::contactsPreventMotion inside
+ * getJointValuesFromDOF cannot fire and is not evaluated.  Robots with other robots attached are refused.
+ * Hand::autoGrasp(speedFactor): desired[d] = speedFactor * defaultVelocity[d] >= 0 ? max : min,
+ * steps[d] = defaultVelocity[d] * speedFactor * 0.01 (Robot::AUTO_GRASP_TIME_STEP). */
+enum {
+  B2C_AG_MOVED = 1,                /* moveDOFToContacts' return value */
+  B2C_AG_INTERP_ERROR = 2,         /* "Robot joint interpolation error": the start was already colliding; DOFs not updated */
+  B2C_AG_FAILSAFE = 4,             /* more than 500 steps */
+  B2C_AG_STOPPED_AT_CONTACT = 8
+};
+typedef struct b2c_autograsp_args {
+  int robot;
+  int npose;
+  const float *states;             /* npose x stride floats: base (qw qx qy qz tx ty tz) + ndof DOF values */
+  int stride;
+  const double *desired;           /* [ndof] desiredVals */
+  const double *steps;             /* [ndof] desiredSteps (0: the DOF does not move); NULL = WorldElement::ONE_STEP */
+  const unsigned char *dof_breakaway;  /* [ndof] 1 = BreakAwayDOF (<dof type="b">), 0 = RigidDOF */
+  int stop_at_contact;
+  double contact_threshold;        /* Contact::THRESHOLD; <= 0 selects the reference's 0.2 mm */
+  int max_rounds;                  /* safety bound on host-loop rounds; <= 0 selects the default */
+  double *dof_out;                 /* [npose x ndof] final DOF values */
+  double *joint_out;               /* optional [npose x njoints] final joint values (chain-major joint order) */
+  int *status;                     /* optional [npose x 2]: B2C_AG_* flags, moveDOFToContacts iterations */
+  unsigned char *stopped_out;      /* optional [npose x njoints] stoppedJoints bits (1 positive, 2 negative direction) */
+  int *rounds;                     /* optional: host-loop rounds used (each = state step + FK + collide + distances) */
+} b2c_autograsp_args;
+int b2c_autograsp_batch(b2c_ctx *ctx, const b2c_autograsp_args *args);
+
 /* ---- batched simulated annealing: K independent chains on the device ------------------------
  * Replaces, for K chains at once, SimAnnPlanner::mainLoop -> SimAnn::iterate (reference
  * src/EGPlanner/simAnnPlanner.cpp:111-148, simAnn.cpp:96-261): per step every chain draws one neighbour of its

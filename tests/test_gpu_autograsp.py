@@ -1,0 +1,116 @@
+"""GPU: batched autograsp (b2c_autograsp_batch = Robot::moveDOFToContacts for a batch of poses) against the per-pose
+restatement of the reference's control flow driven by the reference's own collision backend (oracle/port/autograsp.py)."""
+import numpy as np
+import pytest
+
+from graspit_b200.engine import AG_INTERP_ERROR, AG_MOVED, Engine, SceneBinding
+from graspit_b200.formats.scenepack import load_pack
+from oracle.port.autograsp import AutoGraspOracle, auto_grasp_targets
+from tests.common import OracleScene, aa_to_raw_states, object_body, sample_aa_states
+
+pytestmark = pytest.mark.gpu
+
+
+def _open_hand_states(sc, n, seed):
+    """near-object Barrett poses with the fingers open (DOF 1-3 = 0) and a random spread"""
+    pos, dofs = sample_aa_states(sc, n, seed=seed, strata=("near",))
+    dofs = dofs.copy()
+    dofs[:, 1:] = 0.0
+    return aa_to_raw_states(sc, pos, dofs)
+
+
+@pytest.fixture(scope="module")
+def barrett():
+    sc = load_pack("barrett_mug")
+    eng = Engine(0)
+    sb = SceneBinding(eng, sc)
+    osc = OracleScene(sc, nthreads=1)
+    return dict(sc=sc, eng=eng, sb=sb, osc=osc, obj=object_body(sc), rid=sb.robot_ids[0])
+
+
+def test_autograsp_matches_reference_control_flow(barrett):
+    sc, eng, osc, rid = barrett["sc"], barrett["eng"], barrett["osc"], barrett["rid"]
+    raw = _open_hand_states(sc, 400, 21)
+    res = eng.eval_batch(rid, barrett["sb"].body_ids[barrett["obj"]], raw)
+    start = np.nonzero(res["legal"])[0][:48]
+    illegal = np.nonzero(res["legal"] == 0)[0][:6]
+    sel = np.concatenate([start, illegal])
+    out = eng.auto_grasp(rid, sc.robots[0], raw[sel])
+    ag = AutoGraspOracle(sc, 0, osc.w, osc.ids)
+    exact = close = 0
+    grasped = 0
+    for k, p in enumerate(sel):
+        r = ag.auto_grasp((raw[p, 0:4].astype(np.float64), raw[p, 4:7].astype(np.float64)), raw[p, 7:].astype(np.float64))
+        st = int(out["status"][k])
+        assert bool(st & AG_INTERP_ERROR) == r["error"], (p, st, r)
+        assert bool(st & AG_MOVED) == r["moved"], (p, st, r)
+        if r["error"]:
+            continue
+        # every collide / distance decision agrees => the bisection parameter, hence the DOF values, are identical up
+        # to the rounding of t*a + (1-t)*b; a decision within fp32 rounding of a threshold may move one bisection level
+        err = np.abs(out["dof"][k] - r["dof"]).max()
+        exact += err < 1e-9
+        close += err < 2e-3
+        assert err < 2e-2, (p, out["dof"][k], r["dof"])
+        if err < 1e-9:
+            assert int(out["iters"][k]) == r["iters"]
+            assert (out["stopped"][k] == r["stopped"]).all()
+            assert np.abs(out["joints"][k] - r["joints"]).max() < 1e-9
+        grasped += (r["stopped"] != 0).any()
+    n_ok = len(sel) - int(sum(bool(s & AG_INTERP_ERROR) for s in out["status"]))
+    assert n_ok >= 40 and grasped >= 20
+    assert exact >= 0.9 * n_ok and close >= 0.97 * n_ok
+    # poses that start in collision fail the first interpolation, as in the reference ("Robot joint interpolation error")
+    assert all(int(s) & AG_INTERP_ERROR for s in out["status"][len(start):])
+
+
+def test_autograsp_result_is_a_legal_contact_posture(barrett):
+    """size-independent properties on a larger batch: the closed posture is collision-free, every stopped finger is
+    within Contact::THRESHOLD of something, DOFs stay inside their limits, and a second autograsp does not move."""
+    sc, eng, sb, rid = barrett["sc"], barrett["eng"], barrett["sb"], barrett["rid"]
+    obj = sb.body_ids[barrett["obj"]]
+    raw = _open_hand_states(sc, 6000, 22)
+    legal = eng.eval_batch(rid, obj, raw)["legal"] == 1
+    raw = raw[legal][:2048]
+    out = eng.auto_grasp(rid, sc.robots[0], raw)
+    assert (out["status"] & AG_INTERP_ERROR == 0).all() and (out["status"] & AG_MOVED != 0).all()
+    r = sc.robots[0]
+    assert (out["dof"] >= r.dof_min - 1e-9).all() and (out["dof"] <= r.dof_max + 1e-9).all()
+    assert (out["dof"][:, 0] == raw[:, 7].astype(np.float64)).all()          # the spread DOF has velocity 0
+    closed = raw.copy()
+    # break-away: distal joints may have run ahead of ratio x DOF, so evaluate the closed posture from the joint values
+    # through a second autograsp call instead of eval_batch when a finger is in break-away
+    same = np.abs(out["joints"] - out["dof"][:, [jd.dof for c in r.chains for jd in c.joints]] *
+                  np.array([jd.ratio for c in r.chains for jd in c.joints])).max(axis=1) < 1e-12
+    assert same.sum() > 100
+    closed[:, 7:] = out["dof"].astype(np.float32)
+    res = eng.eval_batch(rid, obj, closed[same], link_dist=True)
+    # fp32 rounding of the DOF values moves the links by < 1e-4 mm: the bisection leaves 0 < d < 0.1 mm, so still legal
+    assert res["legal"].mean() > 0.995
+    touching = (res["link_dist"] >= 0) & (res["link_dist"] < 0.2)
+    stopped_any = (out["stopped"][same] != 0).any(axis=1)
+    assert stopped_any.mean() > 0.9
+    print("rounds", out["rounds"], "fingers touching the object per pose", touching.sum(axis=1).mean())
+
+
+def test_move_dof_one_step_and_stop_at_contact(barrett):
+    sc, eng, sb, rid, osc = barrett["sc"], barrett["eng"], barrett["sb"], barrett["rid"], barrett["osc"]
+    raw = _open_hand_states(sc, 300, 23)
+    legal = eng.eval_batch(rid, sb.body_ids[barrett["obj"]], raw)["legal"] == 1
+    raw = raw[legal][:12]
+    r = sc.robots[0]
+    desired, steps = auto_grasp_targets(r, 1.0)
+    brk = [1 if t == "b" else 0 for t in r.dof_type]
+    ag = AutoGraspOracle(sc, 0, osc.w, osc.ids)
+    for kwargs in (dict(steps=None, stop=False), dict(steps=steps * 5, stop=True)):
+        out = eng.move_dof_to_contacts(rid, raw, desired if kwargs["steps"] is not None else np.concatenate([raw[0, 7:8], desired[1:]]),
+                                       kwargs["steps"], brk, stop_at_contact=kwargs["stop"], njoints=r.n_joints)
+        for k in range(len(raw)):
+            des = desired.copy()
+            if kwargs["steps"] is None:
+                des[0] = raw[0, 7]
+            o = ag.move_dof_to_contacts((raw[k, 0:4].astype(np.float64), raw[k, 4:7].astype(np.float64)),
+                                        raw[k, 7:].astype(np.float64), des, kwargs["steps"], kwargs["stop"])
+            assert bool(int(out["status"][k]) & AG_INTERP_ERROR) == o["error"]
+            if not o["error"]:
+                assert np.abs(out["dof"][k] - o["dof"]).max() < 2e-2
