@@ -115,3 +115,33 @@ def test_move_dof_one_step_and_stop_at_contact(barrett):
             assert bool(int(out["status"][k]) & AG_INTERP_ERROR) == o["error"]
             if not o["error"]:
                 assert np.abs(out["dof"][k] - o["dof"]).max() < 2e-2
+
+
+def test_autograsp_humanhand_20dof():
+    """20 rigid DOFs, 15 links, ~16k triangles, 116 active pairs (finger-finger included): closing from the rest posture"""
+    sc = load_pack("humanhand_flask")
+    eng = Engine(0)
+    sb = SceneBinding(eng, sc)
+    osc = OracleScene(sc, nthreads=1)
+    rid, obj = sb.robot_ids[0], sb.body_ids[object_body(sc)]
+    r = sc.robots[0]
+    pos, dofs = sample_aa_states(sc, 300, seed=31, strata=("near",))
+    rest = np.clip(r.dof_default, r.dof_min, r.dof_max)
+    raw = aa_to_raw_states(sc, pos, np.tile(rest[None, :], (len(pos), 1)).astype(np.float32))
+    legal = eng.eval_batch(rid, obj, raw)["legal"] == 1
+    assert legal.sum() >= 10
+    raw = raw[legal][:10]
+    out = eng.auto_grasp(rid, r, raw)
+    ag = AutoGraspOracle(sc, 0, osc.w, osc.ids)
+    exact = 0
+    for k in range(len(raw)):
+        o = ag.auto_grasp((raw[k, 0:4].astype(np.float64), raw[k, 4:7].astype(np.float64)), raw[k, 7:].astype(np.float64))
+        assert bool(int(out["status"][k]) & AG_INTERP_ERROR) == o["error"]
+        if o["error"]:
+            continue
+        err = np.abs(out["dof"][k] - o["dof"]).max()
+        assert err < 2e-2, (k, out["dof"][k], o["dof"])
+        if err < 1e-9:
+            exact += 1
+            assert (out["stopped"][k] == o["stopped"]).all() and int(out["iters"][k]) == o["iters"]
+    assert exact >= 8
