@@ -271,6 +271,18 @@ constexpr int NARROW_WARP_SMEM = 32 * 96 + 32 * 96 + 32 * 16 + NSTACK_PHYS * 8 +
 cudaError_t launch_collide(const EvalParams &p, int narrow_blocks, cudaStream_t s);
 cudaError_t launch_compact(const EvalParams &p, cudaStream_t s);
 
+// cudaFuncSetAttribute applies to the CURRENT device only: remember per device the largest dynamic shared memory size
+// already granted to a kernel (one process may hold contexts on several GPUs).
+inline cudaError_t ensure_dyn_smem(const void *fn, size_t smem, size_t (&granted)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (smem <= granted[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) granted[dev] = smem;
+  return e;
+}
+
 // launchers (kernels.cu)
 cudaError_t launch_fk(const FkParams &p, cudaStream_t s);
 cudaError_t launch_recheck(const RecheckParams &p, cudaStream_t s);

@@ -302,13 +302,9 @@ cudaError_t launch_collide(const EvalParams &p, int narrow_blocks, cudaStream_t 
     if (p.npose > 0 && p.energy) { cudaError_t e = cudaMemsetAsync(p.energy, 0, sizeof(float) * (size_t)p.npose, s); if (e != cudaSuccess) return e; }
     return cudaSuccess;
   }
-  static bool configured = false;
   const size_t smem = (size_t)8 * NARROW_WARP_SMEM;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static size_t granted[64] = {};
+  { cudaError_t e = ensure_dyn_smem((const void *)narrow_kernel, smem, granted); if (e != cudaSuccess) return e; }
   const long long total = (long long)p.npose * p.npairs;
   broad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
   cudaError_t e = cudaGetLastError();

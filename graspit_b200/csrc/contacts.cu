@@ -230,13 +230,9 @@ __global__ void region_kernel(RegionParams p) {
 }
 
 cudaError_t launch_contacts(const ContactParams &p, int blocks, cudaStream_t s) {
-  static bool configured = false;
   size_t smem = (size_t)8 * CONTACT_WARP_SMEM;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static size_t granted[64] = {};
+  { cudaError_t e = ensure_dyn_smem((const void *)contact_kernel, smem, granted); if (e != cudaSuccess) return e; }
   contact_kernel<<<blocks, 256, smem, s>>>(p);
   return cudaGetLastError();
 }

@@ -1090,13 +1090,9 @@ cudaError_t launch_point(const PointParams &p, cudaStream_t s) {
 }
 
 cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s) {
-  static bool configured = false;
   size_t smem = (size_t)8 * DIST_WARP_SMEM;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static size_t granted[64] = {};
+  { cudaError_t e = ensure_dyn_smem((const void *)dist_kernel, smem, granted); if (e != cudaSuccess) return e; }
   dist_kernel<<<blocks, 256, smem, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || !p.near_dir) return e;
@@ -1106,13 +1102,9 @@ cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s) {
 
 cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s) {
   if (p.npose <= 0) return cudaSuccess;
-  static size_t configured = 0;
   size_t smem = energy_block_smem_bytes(p.stage_nodes);
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static size_t granted[64] = {};
+  { cudaError_t e = ensure_dyn_smem((const void *)energy_kernel, smem, granted); if (e != cudaSuccess) return e; }
   energy_kernel<<<blocks, 256, smem, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
