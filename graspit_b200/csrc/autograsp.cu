@@ -197,6 +197,8 @@ __global__ void __launch_bounds__(128) autograsp_step_kernel(AgParams p) {
       }
     }
   }
+  for (int w = 0; w < p.mask_words; w++)
+    p.pair_enable[(size_t)pose * p.mask_words + w] = (S.phase != AG_DONE && w < AG_MW) ? S.interest[w] : 0ull;
   if (S.phase != AG_DONE) {
     for (int j = 0; j < D.nj; j++) js[7 + j] = S.jv[j];
     atomicAdd(&p.counters[0], 1);

@@ -90,6 +90,7 @@ struct EvalParams {
   uint8_t *legal;
   float *energy;
   unsigned long long *pair_mask;
+  const unsigned long long *pair_enable;   // optional [npose][mask_words]: pairs to test per pose (others are skipped)
   int *pose_counter;
   int *legal_list;         // poses without a collision, in completion order (for the energy kernel)
   int *legal_count;
@@ -331,6 +332,7 @@ struct AgParams {
   const unsigned long long *pair_mask;   // [npose][mask_words] colliding pairs at the joint values of the last FK
   int mask_words;
   const float *dist;               // [npose][npairs] distances of the pairs listed in the previous round
+  unsigned long long *pair_enable; // [npose][mask_words] pairs the next collision round has to test (0 once finished)
   int *wlist;                      // distance work list for the next round
   int *counters;                   // [0] poses not finished, [1] work-list length
   int wcap;

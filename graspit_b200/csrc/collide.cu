@@ -36,17 +36,21 @@ __global__ void __launch_bounds__(256) broad_kernel(EvalParams p) {
       if (p.legal) p.legal[pose] = 1;
       if (p.energy) p.energy[pose] = 0.f;
     }
-    int2 ab = __ldg(&p.pairs[pi]);
-    const MeshDev &ma = p.meshes[__ldg(&p.body_mesh[ab.x])];
-    const MeshDev &mb = p.meshes[__ldg(&p.body_mesh[ab.y])];
-    const double *XA = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, ab.x);
-    const double *XB = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, ab.y);
-    PairXf x;
-    make_pair_xf(XA, XB, ma.extent, mb.extent, x);
-    Node ra = load_node(ma, 0), rb = load_node(mb, 0);
-    float ca[3], ha[3], cb[3], hb[3];
-    node_ch(ra, ca, ha); node_ch(rb, cb, hb);
-    ov = box_overlap(ca, ha, cb, hb, x);
+    // optional per-pose pair selection (autograsp: only the pairs on the interest list of a pose that still moves)
+    const bool on = !p.pair_enable || ((__ldg(&p.pair_enable[(size_t)pose * p.mask_words + (pi >> 6)]) >> (pi & 63)) & 1ull);
+    if (on) {
+      int2 ab = __ldg(&p.pairs[pi]);
+      const MeshDev &ma = p.meshes[__ldg(&p.body_mesh[ab.x])];
+      const MeshDev &mb = p.meshes[__ldg(&p.body_mesh[ab.y])];
+      const double *XA = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, ab.x);
+      const double *XB = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, ab.y);
+      PairXf x;
+      make_pair_xf(XA, XB, ma.extent, mb.extent, x);
+      Node ra = load_node(ma, 0), rb = load_node(mb, 0);
+      float ca[3], ha[3], cb[3], hb[3];
+      node_ch(ra, ca, ha); node_ch(rb, cb, hb);
+      ov = box_overlap(ca, ha, cb, hb, x);
+    }
   }
   // warp-aggregated append
   unsigned m = __ballot_sync(FULL, ov);
