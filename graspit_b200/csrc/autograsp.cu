@@ -21,7 +21,7 @@ namespace b2c {
 
 namespace {
 
-__device__ inline bool bit(const unsigned long long *m, int i) { return (m[i >> 6] >> (i & 63)) & 1ull; }
+__device__ inline bool bit(const AgCol<unsigned long long> &m, int i) { return (m[i >> 6] >> (i & 63)) & 1ull; }
 
 // RigidDOF::accumulateMove (dof.cpp:500-514) / BreakAwayDOF::accumulateMove (dof.cpp:577-620)
 __device__ bool accumulate_move(const AgDesc &D, const AgState &S, int d, double q1, double *jv) {
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(128) autograsp_step_kernel(AgParams p) {
   const int pose = blockIdx.x * blockDim.x + threadIdx.x;
   if (pose >= p.npose) return;
   const AgDesc &D = *p.desc;
-  AgState &S = p.st[pose];
+  AgState S(p.st, pose);
   double *js = p.jstates + (size_t)pose * (7 + D.nj);
   if (p.init) {
     const float *s = p.states + (size_t)pose * p.stride;

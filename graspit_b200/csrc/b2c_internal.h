@@ -313,19 +313,49 @@ struct AgDesc {
   int link_first_joint[AG_MAXL];   // first joint of the link's chain
   short pair_link_a[AG_MAXP], pair_link_b[AG_MAXP];   // link index of each side of an active pair, -1 = not a link
 };
-struct AgState {
-  double q[AG_MAXD], desired[AG_MAXD], step[AG_MAXD], new_dof[AG_MAXD], initial_dof[AG_MAXD];
-  double jv[AG_MAXJ], initial_jv[AG_MAXJ], final_jv[AG_MAXJ], break_val[AG_MAXJ];
-  double t, deltat;
-  unsigned long long late[AG_MW], col[AG_MW], interest[AG_MW];
-  unsigned char stopped[AG_MAXJ], in_break[AG_MAXJ];
-  int phase, iters, status, ncols;
+// Per-pose state, stored field-major ([field][element][pose]) so that the threads of a warp touch consecutive
+// addresses; AgState is the per-thread view of one pose.
+template <typename T> struct AgCol {
+  T *p;
+  size_t stride;
+  __host__ __device__ T &operator[](int i) const { return p[(size_t)i * stride]; }
 };
+struct AgStore {
+  double *d;                   // (5 * AG_MAXD + 4 * AG_MAXJ + 2) x npose
+  unsigned long long *u;       // 3 * AG_MW x npose
+  unsigned char *b;            // 2 * AG_MAXJ x npose
+  int *i;                      // 4 x npose
+  int npose;
+};
+struct AgState {
+  AgCol<double> q, desired, step, new_dof, initial_dof, jv, initial_jv, final_jv, break_val;
+  double &t, &deltat;
+  AgCol<unsigned long long> late, col, interest;
+  AgCol<unsigned char> stopped, in_break;
+  int &phase, &iters, &status, &ncols;
+  __host__ __device__ AgState(const AgStore &s, int pose)
+      : q{s.d + pose, (size_t)s.npose}, desired{s.d + (size_t)AG_MAXD * s.npose + pose, (size_t)s.npose},
+        step{s.d + (size_t)2 * AG_MAXD * s.npose + pose, (size_t)s.npose},
+        new_dof{s.d + (size_t)3 * AG_MAXD * s.npose + pose, (size_t)s.npose},
+        initial_dof{s.d + (size_t)4 * AG_MAXD * s.npose + pose, (size_t)s.npose},
+        jv{s.d + (size_t)(5 * AG_MAXD) * s.npose + pose, (size_t)s.npose},
+        initial_jv{s.d + (size_t)(5 * AG_MAXD + AG_MAXJ) * s.npose + pose, (size_t)s.npose},
+        final_jv{s.d + (size_t)(5 * AG_MAXD + 2 * AG_MAXJ) * s.npose + pose, (size_t)s.npose},
+        break_val{s.d + (size_t)(5 * AG_MAXD + 3 * AG_MAXJ) * s.npose + pose, (size_t)s.npose},
+        t(s.d[(size_t)(5 * AG_MAXD + 4 * AG_MAXJ) * s.npose + pose]),
+        deltat(s.d[(size_t)(5 * AG_MAXD + 4 * AG_MAXJ + 1) * s.npose + pose]),
+        late{s.u + pose, (size_t)s.npose}, col{s.u + (size_t)AG_MW * s.npose + pose, (size_t)s.npose},
+        interest{s.u + (size_t)2 * AG_MW * s.npose + pose, (size_t)s.npose},
+        stopped{s.b + pose, (size_t)s.npose}, in_break{s.b + (size_t)AG_MAXJ * s.npose + pose, (size_t)s.npose},
+        phase(s.i[pose]), iters(s.i[(size_t)s.npose + pose]), status(s.i[(size_t)2 * s.npose + pose]),
+        ncols(s.i[(size_t)3 * s.npose + pose]) {}
+};
+constexpr int AG_STORE_D = 5 * AG_MAXD + 4 * AG_MAXJ + 2, AG_STORE_U = 3 * AG_MW, AG_STORE_B = 2 * AG_MAXJ, AG_STORE_I = 4;
 struct AgParams {
   int npose;
   int init;                        // 1: build the state from `states` and start the first step
   const AgDesc *desc;
-  AgState *st;
+  AgStore st;
   const float *states;             // init: raw states, base (q wxyz, t) + DOF values
   int stride;
   double *jstates;                 // [npose][7 + nj]: input of the joint-level FK
