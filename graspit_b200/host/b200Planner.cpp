@@ -283,4 +283,44 @@ bool listPlannerRun(b2c_ctx *ctx, int robot, int object, const transf7 &refTran,
   return true;
 }
 
+
+bool autoGraspBatch(b2c_ctx *ctx, int robot, const std::vector<transf7> &handPoses, const std::vector<double> &dofVals,
+                    const std::vector<DofDesc> &dofs, double speedFactor, bool stopAtContact,
+                    std::vector<double> *closedDofs, std::vector<int> *status, std::vector<double> *closedJoints, int nJoints)
+{
+  const int n = (int)handPoses.size(), nd = (int)dofs.size();
+  if (!ctx || !closedDofs || nd <= 0 || dofVals.size() != (size_t)n * nd) {return false;}
+  closedDofs->assign((size_t)n * nd, 0.0);
+  std::vector<int> st((size_t)n * 2, 0);
+  if (status) {status->assign(n, 0);}
+  if (closedJoints) {closedJoints->assign((size_t)n * nJoints, 0.0);}
+  if (n == 0) {return true;}
+  const int stride = 7 + nd;
+  std::vector<float> rows((size_t)n * stride);
+  for (int i = 0; i < n; i++) {
+    float *r = &rows[(size_t)i * stride];
+    for (int k = 0; k < 4; k++) {r[k] = (float)handPoses[i].q[k];}
+    for (int k = 0; k < 3; k++) {r[4 + k] = (float)handPoses[i].t[k];}
+    for (int d = 0; d < nd; d++) {r[7 + d] = (float)dofVals[(size_t)i * nd + d];}
+  }
+  // Hand::autoGrasp: target = max or min by the sign of speedFactor * defaultVelocity, step = velocity * speedFactor * 0.01
+  std::vector<double> desired(nd), steps(nd);
+  std::vector<unsigned char> brk(nd);
+  for (int d = 0; d < nd; d++) {
+    desired[d] = speedFactor * dofs[d].defaultVelocity >= 0 ? dofs[d].max : dofs[d].min;
+    steps[d] = dofs[d].defaultVelocity * speedFactor * 0.01;
+    brk[d] = dofs[d].breakAway ? 1 : 0;
+  }
+  b2c_autograsp_args a;
+  memset(&a, 0, sizeof a);
+  a.robot = robot; a.npose = n; a.states = rows.data(); a.stride = stride;
+  a.desired = desired.data(); a.steps = steps.data(); a.dof_breakaway = brk.data();
+  a.stop_at_contact = stopAtContact ? 1 : 0;
+  a.dof_out = closedDofs->data(); a.status = st.data();
+  if (closedJoints && nJoints > 0) {a.joint_out = closedJoints->data();}
+  if (b2c_autograsp_batch(ctx, &a) != B2C_OK) {return false;}
+  if (status) {for (int i = 0; i < n; i++) {(*status)[i] = st[2 * (size_t)i];}}
+  return true;
+}
+
 }  // namespace b200

@@ -113,6 +113,21 @@ bool listPlannerRun(b2c_ctx *ctx, int robot, int object, const transf7 &refTran,
                     bool contactLive, std::vector<unsigned char> *legal, std::vector<float> *energy,
                     std::vector<PlannerState> *bestList, int nEigenGrasps);
 
+//! one DOF as Hand::autoGrasp sees it (reference dof.h: getMin / getMax / getDefaultVelocity, DOF::getType)
+struct DofDesc {
+  double min, max, defaultVelocity;
+  bool breakAway;              // <dof type="b"> (BreakAwayDOF); false: RigidDOF
+};
+
+//! Hand::autoGrasp(renderIt = false, speedFactor, stopAtContact), static branch (reference robot.cpp:2427-2462), for a
+//! batch of hand states in one b2c_autograsp_batch call.  handPoses[i] = hand->getTran(), dofVals = [n][nDOF] row-major
+//! (the contact-free posture HandObjectState::execute left).  closedDofs gets what hand->getDOFVals() would return after
+//! the call, status the B2C_AG_* flags (B2C_AG_MOVED = autoGrasp's return value).
+bool autoGraspBatch(b2c_ctx *ctx, int robot, const std::vector<transf7> &handPoses, const std::vector<double> &dofVals,
+                    const std::vector<DofDesc> &dofs, double speedFactor, bool stopAtContact,
+                    std::vector<double> *closedDofs, std::vector<int> *status, std::vector<double> *closedJoints = NULL,
+                    int nJoints = 0);
+
 }  // namespace b200
 
 #endif

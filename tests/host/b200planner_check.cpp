@@ -77,8 +77,11 @@ static void cpuChecks()
 // ---- scene dump reader ----
 struct Scene {
   b2c_ctx *ctx;
-  int robot, object, neg;
+  int robot, object, neg, njoints;
   transf7 ref;
+  std::vector<DofDesc> dofs;
+  std::vector<int> jointDof;
+  std::vector<double> jointRatio;
 };
 
 static bool loadScene(const char *path, Scene *S)
@@ -138,6 +141,11 @@ static bool loadScene(const char *path, Scene *S)
   d.vcontacts = vcs.data();
   int obj; in >> obj;
   in >> S->ref.q[0] >> S->ref.q[1] >> S->ref.q[2] >> S->ref.q[3] >> S->ref.t[0] >> S->ref.t[1] >> S->ref.t[2];
+  S->dofs.resize(d.ndof);
+  for (int i = 0; i < d.ndof; i++) { S->dofs[i].min = dmin[i]; S->dofs[i].max = dmax[i]; in >> S->dofs[i].defaultVelocity; }
+  for (int i = 0; i < d.ndof; i++) { int b; in >> b; S->dofs[i].breakAway = b != 0; }
+  S->njoints = d.njoints;
+  for (auto &j : joints) { S->jointDof.push_back(j.dof); S->jointRatio.push_back(j.ratio); }
   if (!in) return false;
   S->object = ids[obj]; S->neg = d.neg;
   return b2c_robot_define(S->ctx, &d, &S->robot) == B2C_OK;
@@ -176,6 +184,45 @@ static void gpuChecks(const char *scenePath)
   std::sort(le.begin(), le.end());
   CHECK(lbest.size() == std::min<size_t>(BEST_LIST_SIZE, le.size()) && !le.empty(), "%zu listed of %zu legal", lbest.size(), le.size());
   for (size_t i = 0; i < lbest.size(); i++) CHECK(lbest[i].energy == le[i], "rank %zu", i);
+  // Hand::autoGrasp over a batch: open hands at the hand poses of the legal random states
+  {
+    std::vector<transf7> poses; std::vector<double> dofv;
+    const int nd = (int)S.dofs.size();
+    for (size_t i = 0; i < rnd.size() && poses.size() < 512; i++) {
+      if (!legal[i]) continue;
+      poses.push_back(statePose(rnd[i], S.ref));
+      for (int d = 0; d < nd; d++) dofv.push_back(d == 0 ? 0.5 : 0.0);
+    }
+    std::vector<double> closed, cj; std::vector<int> st;
+    CHECK(autoGraspBatch(S.ctx, S.robot, poses, dofv, S.dofs, 1.0, false, &closed, &st, &cj, S.njoints), "%s", b2c_last_error(S.ctx));
+    int moved = 0, errors = 0, coupled = 0;
+    std::vector<float> rows; std::vector<int> rowOf;
+    for (size_t i = 0; i < poses.size(); i++) {
+      if (st[i] & B2C_AG_INTERP_ERROR) { errors++; continue; }
+      if (st[i] & B2C_AG_MOVED) moved++;
+      bool in = true, same = true;
+      for (int d = 0; d < nd; d++) in = in && closed[i * nd + d] >= S.dofs[d].min - 1e-9 && closed[i * nd + d] <= S.dofs[d].max + 1e-9;
+      CHECK(in, "pose %zu: DOF outside its limits", i);
+      CHECK(closed[i * nd] == (double)(float)0.5, "pose %zu: the spread DOF (velocity 0) moved", i);
+      for (int j = 0; j < S.njoints; j++) same = same && std::fabs(cj[i * S.njoints + j] - closed[i * nd + S.jointDof[j]] * S.jointRatio[j]) < 1e-12;
+      if (!same) continue;            // a finger in break-away: joints no longer equal ratio x DOF
+      coupled++;
+      rowOf.push_back((int)i);
+      for (int k = 0; k < 4; k++) rows.push_back((float)poses[i].q[k]);
+      for (int k = 0; k < 3; k++) rows.push_back((float)poses[i].t[k]);
+      for (int d = 0; d < nd; d++) rows.push_back((float)closed[i * nd + d]);
+    }
+    CHECK(poses.size() >= 100 && moved + errors == (int)poses.size() && moved > 50, "%zu poses, %d moved, %d errors", poses.size(), moved, errors);
+    // the closed posture is collision-free (the bisection stops 0 < d < THRESHOLD / 2 short of touching)
+    std::vector<unsigned char> lg(rowOf.size()); std::vector<float> en(rowOf.size());
+    b2c_eval_args a; memset(&a, 0, sizeof a);
+    a.robot = S.robot; a.object = S.object; a.npose = (int)rowOf.size(); a.input_mode = B2C_INPUT_RAW; a.states = rows.data(); a.stride = 7 + nd;
+    a.ref_q[0] = 1; a.flags = B2C_EVAL_PRESET; a.legal = lg.data(); a.energy = en.data();
+    CHECK(coupled > 20 && b2c_eval_batch(S.ctx, &a) == B2C_OK, "%d coupled postures; %s", coupled, b2c_last_error(S.ctx));
+    int nlegal = 0; for (unsigned char v : lg) nlegal += v;
+    CHECK(nlegal >= (int)(0.99 * lg.size()), "%d of %zu closed postures are collision-free", nlegal, lg.size());
+    printf("autoGraspBatch: %zu poses, %d moved, %d start in collision, %d coupled, %d legal\n", poses.size(), moved, errors, coupled, nlegal);
+  }
   b2c_destroy(S.ctx);
 }
 

@@ -47,6 +47,8 @@ def _dump_scene(tmp_path):
     for v in r.vcontacts:
         lines.append(f"{v.body} {f(v.loc)} {f(v.normal)}")
     lines.append(str(obj)); lines.append(f"{f(sc.body_tran[obj][0])} {f(sc.body_tran[obj][1])}")
+    # DOF data of Hand::autoGrasp: default velocities, break-away flags
+    lines.append(f(r.dof_velocity)); lines.append(" ".join("1" if t == "b" else "0" for t in r.dof_type))
     p = str(tmp_path / "scene.txt")
     open(p, "w").write("\n".join(lines) + "\n")
     return p
