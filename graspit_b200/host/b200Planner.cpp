@@ -284,6 +284,43 @@ bool listPlannerRun(b2c_ctx *ctx, int robot, int object, const transf7 &refTran,
 }
 
 
+BatchedTimeTester::BatchedTimeTester(b2c_ctx *ctx, int robot, int object, const transf7 &refTran,
+                                     const std::vector<SearchVariable> &variables, const PlannerState &current, int nEG,
+                                     int batch, bool contactLive, unsigned long long seed)
+  : mCtx(ctx), mRobot(robot), mObject(object), mNumEG(nEG), mBatch(batch), mLive(contactLive), mRefTran(refTran),
+    mVars(variables), mCurrentState(current), mSeed(seed), mCount(0), mIllegalCount(0), mLoops(0) {}
+
+bool BatchedTimeTester::mainLoop()
+{
+  const int nv = 6 + mNumEG;
+  if (mBatch <= 0 || (int)mCurrentState.vars.size() < nv || (int)mVars.size() < nv) {return false;}
+  std::vector<float> x((size_t)mBatch * nv);
+  for (int i = 0; i < mBatch; i++) {
+    // splitmix64 keyed by (seed, loop, i): r = rand() / RAND_MAX - 0.5 of the reference, one r per perturbed state
+    unsigned long long z = mSeed + 0x9e3779b97f4a7c15ULL * (unsigned long long)(mLoops * (long long)mBatch + i + 1);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL; z ^= z >> 31;
+    const double r = (double)(z >> 11) / 9007199254740992.0 - 0.5;
+    for (int k = 0; k < nv; k++) {
+      double v = mCurrentState.vars[k];
+      v += r * mVars[k].mMaxJump * 0.1;            // no variable of this layout is fixed (SearchVariable::isFixed)
+      x[(size_t)i * nv + k] = (float)v;
+    }
+  }
+  std::vector<unsigned char> legal(mBatch);
+  std::vector<float> energy(mBatch);
+  b2c_eval_args a;
+  memset(&a, 0, sizeof a);
+  a.robot = mRobot; a.object = mObject; a.npose = mBatch; a.input_mode = B2C_INPUT_AA_EIGEN; a.states = x.data(); a.stride = nv;
+  for (int k = 0; k < 4; k++) {a.ref_q[k] = mRefTran.q[k];}
+  for (int k = 0; k < 3; k++) {a.ref_t[k] = mRefTran.t[k];}
+  a.flags = mLive ? B2C_EVAL_LIVE : B2C_EVAL_PRESET;
+  a.legal = legal.data(); a.energy = energy.data();
+  if (b2c_eval_batch(mCtx, &a) != B2C_OK) {return false;}
+  for (int i = 0; i < mBatch; i++) {if (legal[i]) {mCount++;} else {mIllegalCount++;}}
+  mLoops++;
+  return true;
+}
+
 bool autoGraspBatch(b2c_ctx *ctx, int robot, const std::vector<transf7> &handPoses, const std::vector<double> &dofVals,
                     const std::vector<DofDesc> &dofs, double speedFactor, bool stopAtContact,
                     std::vector<double> *closedDofs, std::vector<int> *status, std::vector<double> *closedJoints, int nJoints)

@@ -113,6 +113,30 @@ bool listPlannerRun(b2c_ctx *ctx, int robot, int object, const transf7 &refTran,
                     bool contactLive, std::vector<unsigned char> *legal, std::vector<float> *energy,
                     std::vector<PlannerState> *bestList, int nEigenGrasps);
 
+//! TimeTester (reference src/EGPlanner/timeTest.cpp:35-64): the reference's in-tree throughput probe.  Each mainLoop
+//! there perturbs the current state once (every free variable by r * mMaxJump * 0.1, one r in [-0.5, 0.5) per call) and
+//! counts legal / illegal analyzeState results; here a loop perturbs it `batch` times and evaluates the batch in one call.
+class BatchedTimeTester
+{
+    b2c_ctx *mCtx;
+    int mRobot, mObject, mNumEG, mBatch;
+    bool mLive;
+    transf7 mRefTran;
+    std::vector<SearchVariable> mVars;
+    PlannerState mCurrentState;
+    unsigned long long mSeed;
+    long long mCount, mIllegalCount, mLoops;
+  public:
+    BatchedTimeTester(b2c_ctx *ctx, int robot, int object, const transf7 &refTran, const std::vector<SearchVariable> &variables,
+                      const PlannerState &current, int nEigenGrasps, int batch, bool contactLive = false,
+                      unsigned long long seed = 1234);
+    //! one batched mainLoop; false on an engine error
+    bool mainLoop();
+    long long getCount() const {return mCount;}                // legal states so far (TimeTester::mCount)
+    long long getIllegalCount() const {return mIllegalCount;}
+    long long getLoops() const {return mLoops;}
+};
+
 //! one DOF as Hand::autoGrasp sees it (reference dof.h: getMin / getMax / getDefaultVelocity, DOF::getType)
 struct DofDesc {
   double min, max, defaultVelocity;

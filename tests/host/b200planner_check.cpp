@@ -184,6 +184,17 @@ static void gpuChecks(const char *scenePath)
   std::sort(le.begin(), le.end());
   CHECK(lbest.size() == std::min<size_t>(BEST_LIST_SIZE, le.size()) && !le.empty(), "%zu listed of %zu legal", lbest.size(), le.size());
   for (size_t i = 0; i < lbest.size(); i++) CHECK(lbest[i].energy == le[i], "rank %zu", i);
+  // TimeTester, batched: perturbations of one legal state, legal + illegal = evaluated, deterministic for a seed
+  {
+    size_t pick = 0;
+    while (pick < rnd.size() && !legal[pick]) pick++;
+    CHECK(pick < rnd.size(), "a legal random state exists");
+    BatchedTimeTester tt(S.ctx, S.robot, S.object, S.ref, vars, rnd[pick], S.neg, 4096), tt2(S.ctx, S.robot, S.object, S.ref, vars, rnd[pick], S.neg, 4096);
+    for (int it = 0; it < 3; it++) CHECK(tt.mainLoop() && tt2.mainLoop(), "%s", b2c_last_error(S.ctx));
+    CHECK(tt.getCount() + tt.getIllegalCount() == 3 * 4096 && tt.getLoops() == 3, "%lld + %lld", tt.getCount(), tt.getIllegalCount());
+    CHECK(tt.getCount() == tt2.getCount() && tt.getCount() > 0, "deterministic: %lld vs %lld legal", tt.getCount(), tt2.getCount());
+    printf("BatchedTimeTester: %lld legal, %lld illegal\n", tt.getCount(), tt.getIllegalCount());
+  }
   // Hand::autoGrasp over a batch: open hands at the hand poses of the legal random states
   {
     std::vector<transf7> poses; std::vector<double> dofv;

@@ -145,3 +145,28 @@ def test_autograsp_humanhand_20dof():
             exact += 1
             assert (out["stopped"][k] == o["stopped"]).all() and int(out["iters"][k]) == o["iters"]
     assert exact >= 8
+
+
+def test_autograsp_opening_direction(barrett):
+    """speedFactor < 0 (Hand::autoGrasp opens): targets are the DOF minima, steps are negative; BreakAwayDOF refuses to
+    move a finger in the negative direction once one of its joints is stopped (dof.cpp:588-596)"""
+    sc, eng, sb, rid, osc = barrett["sc"], barrett["eng"], barrett["sb"], barrett["rid"], barrett["osc"]
+    pos, dofs = sample_aa_states(sc, 600, seed=24, strata=("near",))
+    raw = aa_to_raw_states(sc, pos, dofs)            # random finger postures
+    legal = eng.eval_batch(rid, sb.body_ids[barrett["obj"]], raw)["legal"] == 1
+    raw = raw[legal][:16]
+    r = sc.robots[0]
+    out = eng.auto_grasp(rid, r, raw, speed_factor=-1.0)
+    ag = AutoGraspOracle(sc, 0, osc.w, osc.ids)
+    exact = 0
+    for k in range(len(raw)):
+        o = ag.auto_grasp((raw[k, 0:4].astype(np.float64), raw[k, 4:7].astype(np.float64)), raw[k, 7:].astype(np.float64), speed_factor=-1.0)
+        assert bool(int(out["status"][k]) & AG_INTERP_ERROR) == o["error"]
+        if o["error"]:
+            continue
+        err = np.abs(out["dof"][k] - o["dof"]).max()
+        assert err < 2e-2
+        exact += err < 1e-9
+    assert exact >= 12
+    # an unobstructed finger opens all the way to its lower limit
+    assert (np.abs(out["dof"][:, 1:] - r.dof_min[None, 1:]) < 1e-9).any()
