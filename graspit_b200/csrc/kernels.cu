@@ -818,6 +818,9 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 #ifndef EQ_STACK_PHYS_N
 #define EQ_STACK_PHYS_N 512
 #endif
+#ifndef EQ_LEAF_TRIGGER
+#define EQ_LEAF_TRIGGER 32      // queued leaves that start a batch of point-triangle tests
+#endif
 constexpr int EQ_STACK_PHYS = EQ_STACK_PHYS_N, EQ_STACK_CAP = EQ_STACK_PHYS_N - 64, EQ_LEAF_CAP = 96;
 constexpr unsigned long long EQ_NONE = 0x7f7fffffffffffffull;   // (FLT_MAX bits << 32) | no triangle
 constexpr int ENERGY_WARP_SMEM = EQ_STACK_PHYS * 8 + EQ_LEAF_CAP * 8 + 32 * 8 + 32 * 24 + 32 * 16 + 32 * 8;
@@ -935,8 +938,8 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
     __syncwarp();
 
     while (true) {
-      if (lq >= 32 || (sp == 0 && lq > 0)) {
-        // ---- 32 point-triangle tests
+      if (lq >= EQ_LEAF_TRIGGER || (sp == 0 && lq > 0)) {
+        // ---- up to 32 point-triangle tests
         int n = lq < 32 ? lq : 32;
         if (lane < n) {
           unsigned long long e = leafq[lq - n + lane];
