@@ -7,6 +7,8 @@
 #include "contacts_host.h"
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <array>
 #include <cmath>
 #include <cstdarg>
@@ -111,6 +113,12 @@ struct b2c_ctx {
   DevBuf<float> d_states; DevBuf<Xf> d_fk; DevBuf<double> d_fkqt; DevBuf<uint8_t> d_legal; DevBuf<float> d_energy;
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
   DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
+  ContactRec *h_contacts = nullptr; // pinned staging of contact candidates (b2c_contacts_batch)
+  DevBuf<ContactRec> d_contacts2;   // the same records grouped by query
+  DevBuf<int> d_coffsets;           // per query: first record, fill cursor
+  DevBuf<unsigned char> d_cubtemp;
+  std::vector<int> h_coffsets;
+  size_t h_contacts_cap = 0;
   int stage_nodes = 128;           // object-tree nodes staged in shared memory by the energy kernel
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int eval_warps_per_block = 8;
@@ -389,6 +397,7 @@ void b2c_destroy(b2c_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   anneal_release_all(ctx);
   autograsp_release_all(ctx);
+  if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
   invalidate_plans(ctx);
   for (auto &m : ctx->meshes) {
     if (m.d_nodes) cudaFree(m.d_nodes);
@@ -837,7 +846,11 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   const bool live = (a->flags & B2C_EVAL_LIVE) != 0;
   const bool want_mask = (a->flags & B2C_EVAL_PAIRMASK) != 0 && a->pair_mask;
   const bool want_dist = (a->flags & B2C_EVAL_LINKDIST) != 0 && a->link_dist;
-  int min_stride = a->input_mode == B2C_INPUT_RAW ? 7 + P->ndof_total : 6 + root.d.neg;
+  const bool joints_in = a->input_mode == B2C_INPUT_JOINTS;
+  int njoints_total = 0;
+  for (int r : P->robots) njoints_total += ctx->robots[r].d.njoints;
+  int min_stride = joints_in ? 7 + njoints_total : (a->input_mode == B2C_INPUT_RAW ? 7 + P->ndof_total : 6 + root.d.neg);
+  if (a->input_mode < 0 || a->input_mode > B2C_INPUT_JOINTS) return fail(ctx, B2C_EINVAL, "eval_batch: unknown input mode %d", a->input_mode);
   if (a->stride < min_stride) return fail(ctx, B2C_EINVAL, "eval_batch: stride %d < %d", a->stride, min_stride);
   if (a->input_mode == B2C_INPUT_AA_EIGEN && root.d.neg <= 0) return fail(ctx, B2C_EINVAL, "eval_batch: robot has no eigengrasps");
   if ((live || want_dist) && a->object < 0) return fail(ctx, B2C_EINVAL, "eval_batch: LIVE / LINKDIST need an object");
@@ -847,8 +860,9 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   // inputs
   const float *d_states = a->states;
   if (!dev) {
-    CU(ctx->d_states.reserve((size_t)npose * a->stride));
-    CU(cudaMemcpyAsync(ctx->d_states.p, a->states, (size_t)npose * a->stride * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t elem = joints_in ? sizeof(double) : sizeof(float);
+    CU(ctx->d_states.reserve((size_t)npose * a->stride * (elem / sizeof(float))));
+    CU(cudaMemcpyAsync(ctx->d_states.p, a->states, (size_t)npose * a->stride * elem, cudaMemcpyHostToDevice, ctx->stream));
     d_states = ctx->d_states.p;
   }
   CU(ctx->d_fk.reserve((size_t)npose * nrb));
@@ -871,6 +885,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   FkParams fp;
   memset(&fp, 0, sizeof fp);
   fp.prog = P->prog; fp.npose = npose; fp.input_mode = a->input_mode; fp.stride = a->stride; fp.states = d_states;
+  fp.jstates = joints_in ? reinterpret_cast<const double *>(d_states) : nullptr;
   fp.ref = make_qt(a->ref_q, a->ref_t);
   fp.out = ctx->d_fk.p;
   fp.out_qt = want_tf ? (dev ? a->body_tf : ctx->d_fkqt.p) : nullptr;

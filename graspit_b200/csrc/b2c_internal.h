@@ -231,6 +231,9 @@ struct RegionParams {
 };
 cudaError_t launch_contacts(const ContactParams &p, int blocks, cudaStream_t s);
 cudaError_t launch_region(const RegionParams &p, cudaStream_t s);
+size_t contact_group_temp_bytes(int nqueries);
+cudaError_t launch_contact_group(const ContactRec *in, int n, const int *per_query, int nqueries, int *offsets, int *cursor,
+                                 ContactRec *out, void *temp, size_t temp_bytes, cudaStream_t s);
 
 // ---- batched annealing (anneal.cu) ------------------------------------------------------------------
 struct AnnealParams {

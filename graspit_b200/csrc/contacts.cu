@@ -16,6 +16,8 @@
 // K7 (region_kernel): one thread per triangle of the body: triangles whose normal does not oppose the
 // contact normal and whose closest point to the reference point lies within the radius are flagged
 // (RegionCallback::leafTest, collisionAlgorithms_inl.h:252-275); the host collects their vertices.
+#include <cub/cub.cuh>
+#include <algorithm>
 #include "b2c_internal.h"
 #include "traverse.cuh"
 
@@ -234,6 +236,33 @@ cudaError_t launch_contacts(const ContactParams &p, int blocks, cudaStream_t s) 
   static size_t granted[64] = {};
   { cudaError_t e = ensure_dyn_smem((const void *)contact_kernel, smem, granted); if (e != cudaSuccess) return e; }
   contact_kernel<<<blocks, 256, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+// ---- grouping of the candidate records by query (batched contacts) ------------------------------------------------
+// contact_kernel emits records in arbitrary order and counts them per query; an exclusive scan of the counts gives each
+// query its range, and one pass moves every record there.  The host then finds each (pose, pair) group contiguous.
+__global__ void contact_scatter_kernel(const ContactRec *in, int n, const int *offsets, int *cursor, ContactRec *out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int q = in[i].query;
+    const int slot = offsets[q] + atomicAdd(&cursor[q], 1);
+    out[slot] = in[i];
+  }
+}
+
+size_t contact_group_temp_bytes(int nqueries) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int *)nullptr, (int *)nullptr, nqueries);
+  return bytes;
+}
+
+cudaError_t launch_contact_group(const ContactRec *in, int n, const int *per_query, int nqueries, int *offsets, int *cursor,
+                                 ContactRec *out, void *temp, size_t temp_bytes, cudaStream_t s) {
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, per_query, offsets, nqueries, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)nqueries, s);
+  if (e != cudaSuccess || n <= 0) return e;
+  contact_scatter_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, s>>>(in, n, offsets, cursor, out);
   return cudaGetLastError();
 }
 

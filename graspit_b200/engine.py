@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B2C_LIB selects a tuning variant of the same engine (graspit_b200/build.py --out=...); default = the product build
 LIB_PATH = os.environ.get("B2C_LIB") or os.path.join(_HERE, "libb2c.so")
 
-B2C_INPUT_RAW, B2C_INPUT_AA_EIGEN = 0, 1
+B2C_INPUT_RAW, B2C_INPUT_AA_EIGEN, B2C_INPUT_JOINTS = 0, 1, 2
 B2C_EVAL_PRESET, B2C_EVAL_LIVE, B2C_EVAL_PAIRMASK, B2C_EVAL_LINKDIST, B2C_EVAL_DEVICE_PTRS = 0, 1, 2, 4, 8
 FAST_COLLISION, ALL_COLLISIONS = 0, 1
 
@@ -35,7 +35,7 @@ EXPORTS = [
     "b2c_anneal_create", "b2c_anneal_destroy", "b2c_anneal_step", "b2c_anneal_read", "b2c_anneal_device_ptrs",
     "b2c_anneal_propose", "b2c_anneal_write", "b2c_anneal_best_rows",
     "b2c_check_contact_normals", "b2c_contact_frames", "b2c_point_contact_wrenches",
-    "b2c_autograsp_batch",
+    "b2c_autograsp_batch", "b2c_contacts_batch",
     "b2c_soft_neighborhood_radius", "b2c_soft_contact_merge", "b2c_soft_contact_fit", "b2c_soft_contact_wrenches",
 ]
 
@@ -92,6 +92,13 @@ class EvalArgs(C.Structure):
                 ("ref_q", C.c_double * 4), ("ref_t", C.c_double * 3), ("flags", C.c_int),
                 ("legal", C.c_void_p), ("energy", C.c_void_p), ("pair_mask", C.c_void_p),
                 ("link_dist", C.c_void_p), ("body_tf", C.c_void_p)]
+
+
+class ContactsBatchArgs(C.Structure):
+    _fields_ = [("robot", C.c_int), ("npose", C.c_int), ("input_mode", C.c_int), ("states", C.c_void_p), ("stride", C.c_int),
+                ("ref_q", C.c_double * 4), ("ref_t", C.c_double * 3), ("threshold", C.c_double), ("raw", C.c_int),
+                ("contacts", C.c_void_p), ("contact_pose", C.c_void_p), ("contact_pair", C.c_void_p), ("cap_contacts", C.c_int),
+                ("ncontacts", C.c_void_p), ("pose_offsets", C.c_void_p)]
 
 
 class AutoGraspArgs(C.Structure):
@@ -176,6 +183,7 @@ def load_library():
     L.b2c_robot_define.argtypes = [vp, C.POINTER(RobotDescC), ip]
     L.b2c_eval_batch.argtypes = [vp, C.POINTER(EvalArgs)]
     L.b2c_autograsp_batch.argtypes = [vp, C.POINTER(AutoGraspArgs)]
+    L.b2c_contacts_batch.argtypes = [vp, C.POINTER(ContactsBatchArgs)]
     L.b2c_robot_bodies.argtypes = [vp, ci, ip, ci, ip]
     L.b2c_robot_pairs.argtypes = [vp, ci, ip, ci, ip]
     L.b2c_last_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
@@ -201,12 +209,10 @@ def _ip(a):
 
 
 def _contacts_to_array(buf, n):
-    out = np.zeros((n, 13))
-    for i in range(n):
-        c = buf[i]
-        out[i, 0:3] = c.b1_pos[:]; out[i, 3:6] = c.b2_pos[:]
-        out[i, 6:9] = c.b1_normal[:]; out[i, 9:12] = c.b2_normal[:]; out[i, 12] = c.distSq
-    return out
+    """ctypes Contact array -> (n, 13) float64 (b2c_contact is 13 consecutive doubles)"""
+    if n <= 0:
+        return np.zeros((0, 13))
+    return np.frombuffer(buf, dtype=np.float64, count=13 * n).reshape(n, 13).copy()
 
 
 def obb_hierarchy(tris, depth: int, cap=1 << 16):
@@ -493,7 +499,7 @@ class Engine:
                    pair_mask=False, link_dist=False, body_tf=False):
         """Host-buffer batched evaluation.  states: (npose, stride) float32.
         Returns dict(legal, energy[, pair_mask, link_dist, body_tf])."""
-        st = np.ascontiguousarray(states, dtype=np.float32)
+        st = np.ascontiguousarray(states, dtype=np.float64 if input_mode == B2C_INPUT_JOINTS else np.float32)
         npose, stride = st.shape
         a = EvalArgs()
         a.robot, a.object, a.npose, a.input_mode = robot, obj, npose, input_mode
@@ -522,6 +528,29 @@ class Engine:
             res["body_tf"] = bt
         self._ck(self.L.b2c_eval_batch(self.h, C.byref(a)))
         return res
+
+    def contacts_batch(self, robot: int, states, threshold=0.2, input_mode=B2C_INPUT_RAW, ref_tran=None, raw=False,
+                       cap_contacts=None):
+        """allContacts(threshold, interest = the robot's bodies) for every pose: returns dict(contacts (n, 13), pose (n,),
+        pair (n,) indexing robot_pairs(robot), offsets (npose + 1,))."""
+        st = np.ascontiguousarray(states, dtype=np.float64 if input_mode == B2C_INPUT_JOINTS else np.float32)
+        npose, stride = st.shape
+        cap = int(cap_contacts) if cap_contacts is not None else max(1024, 16 * npose)
+        buf = np.empty((cap, 13), dtype=np.float64)              # b2c_contact = 13 doubles
+        cpose = np.empty(cap, dtype=np.int32); cpair = np.empty(cap, dtype=np.int32); off = np.zeros(npose + 1, dtype=np.int32)
+        n = C.c_int(0)
+        a = ContactsBatchArgs()
+        a.robot, a.npose, a.input_mode, a.states, a.stride = robot, npose, input_mode, st.ctypes.data, stride
+        rq, rt = ref_tran if ref_tran is not None else (np.array([1.0, 0, 0, 0]), np.zeros(3))
+        a.ref_q[:] = list(rq); a.ref_t[:] = list(rt)
+        a.threshold, a.raw = float(threshold), int(bool(raw))
+        a.contacts, a.contact_pose, a.contact_pair, a.cap_contacts = buf.ctypes.data, cpose.ctypes.data, cpair.ctypes.data, cap
+        a.ncontacts, a.pose_offsets = C.addressof(n), off.ctypes.data
+        self._ck(self.L.b2c_contacts_batch(self.h, C.byref(a)))
+        if n.value > cap:
+            return self.contacts_batch(robot, states, threshold, input_mode, ref_tran, raw, cap_contacts=n.value)
+        k = n.value
+        return {"contacts": buf[:k].copy(), "pose": cpose[:k].copy(), "pair": cpair[:k].copy(), "offsets": off}
 
     def move_dof_to_contacts(self, robot: int, states, desired, steps, dof_breakaway, stop_at_contact=False,
                              contact_threshold=0.2, njoints=None):
@@ -577,12 +606,13 @@ class Engine:
 
 
 def _contact_array(rows):
-    rows = np.asarray(rows, dtype=np.float64).reshape(-1, 13)
-    arr = (Contact * max(1, len(rows)))()
-    for i, r in enumerate(rows):
-        arr[i].b1_pos[:] = list(r[0:3]); arr[i].b2_pos[:] = list(r[3:6])
-        arr[i].b1_normal[:] = list(r[6:9]); arr[i].b2_normal[:] = list(r[9:12]); arr[i].distSq = float(r[12])
-    return arr, len(rows)
+    """(n, 13) rows -> (ctypes Contact array, n); one memcpy, b2c_contact is 13 consecutive doubles"""
+    rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 13)
+    n = len(rows)
+    arr = (Contact * max(1, n))()
+    if n:
+        C.memmove(arr, rows.ctypes.data, 13 * 8 * n)
+    return arr, n
 
 
 def check_contact_normals(rows, tran1, tran2):
@@ -595,8 +625,7 @@ def check_contact_normals(rows, tran1, tran2):
     rc = L.b2c_check_contact_normals(arr, n, q1.ctypes.data_as(dp), t1.ctypes.data_as(dp), q2.ctypes.data_as(dp), t2.ctypes.data_as(dp), C.byref(nf))
     if rc:
         raise B2CError(f"b2c_check_contact_normals failed ({rc})")
-    out = np.array([list(a.b1_pos) + list(a.b2_pos) + list(a.b1_normal) + list(a.b2_normal) + [a.distSq] for a in arr[:n]]).reshape(-1, 13)
-    return out, nf.value
+    return _contacts_to_array(arr, n), nf.value
 
 
 def contact_frames(rows, side=1):
@@ -624,7 +653,7 @@ def point_contact_wrenches(rows, side, cof, cog, max_radius):
 
 
 def _rows_of(arr, n):
-    return np.array([list(a.b1_pos) + list(a.b2_pos) + list(a.b1_normal) + list(a.b2_normal) + [a.distSq] for a in arr[:n]]).reshape(-1, 13)
+    return _contacts_to_array(arr, n)
 
 
 def _ragged(lists):

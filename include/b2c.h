@@ -257,8 +257,12 @@ int b2c_robot_define(b2c_ctx *ctx, const b2c_robot_desc *desc, int *robot_id);
 enum {
   B2C_INPUT_RAW = 0,       /* per pose: base (qw qx qy qz tx ty tz) + ndof DOF values (root robot first,
                               then attached robots' DOFs in robot id order); stride = 7 + total dofs */
-  B2C_INPUT_AA_EIGEN = 1   /* per pose: Tx Ty Tz theta phi alpha + neg eigengrasp amplitudes
+  B2C_INPUT_AA_EIGEN = 1,  /* per pose: Tx Ty Tz theta phi alpha + neg eigengrasp amplitudes
                               (SPACE_AXIS_ANGLE + POSE_EIGEN, searchStateImpl.cpp:83-95,156-168) */
+  B2C_INPUT_JOINTS = 2     /* per pose: base (qw qx qy qz tx ty tz) + one value per JOINT (chain-major, the order of
+                              b2c_robot_desc.joints), as DOUBLES: `states` points to doubles, stride counts doubles.
+                              For postures whose joints no longer equal ratio x DOF (break-away fingers after
+                              b2c_autograsp_batch: feed joint_out) */
 };
 
 enum {
@@ -274,7 +278,7 @@ typedef struct b2c_eval_args {
   int object;                /* body id of the target object (energy / distances); -1 = legality only */
   int npose;
   int input_mode;
-  const float *states;       /* npose x stride floats */
+  const float *states;       /* npose x stride floats (B2C_INPUT_JOINTS: doubles behind the same pointer) */
   int stride;
   double ref_q[4], ref_t[3]; /* B2C_INPUT_AA_EIGEN: mRefTran (normally the object pose) */
   int flags;
@@ -293,6 +297,30 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *args);
 int b2c_robot_bodies(b2c_ctx *ctx, int robot, int *bodies, int cap, int *nbodies);
 /* the active pairs (a,b) that a batched evaluation of `robot` tests, in pair_mask bit order */
 int b2c_robot_pairs(b2c_ctx *ctx, int robot, int *pairs, int cap, int *npairs);
+
+/* ---- batched contacts: allContacts(threshold, interest = the robot's bodies) for every pose of a batch -----------
+ * Per pose what World::findContacts / findAllContacts ask of the backend for the hand (reference world.cpp:1682-1760,
+ * graspitCollision.cpp:365-405): every active pair that touches a robot body, contact() with the reference's duplicate
+ * removal (3 mm) and perimeter compaction per pair (raw != 0: the unprocessed candidates).  Contacts come back grouped
+ * by pose, then by pair; contact_pair indexes b2c_robot_pairs(robot).  *ncontacts is the total found; when it exceeds
+ * cap_contacts the arrays hold the first cap_contacts. */
+typedef struct b2c_contacts_batch_args {
+  int robot;
+  int npose;
+  int input_mode;            /* B2C_INPUT_* */
+  const void *states;        /* floats (RAW, AA_EIGEN) or doubles (JOINTS) */
+  int stride;
+  double ref_q[4], ref_t[3]; /* B2C_INPUT_AA_EIGEN */
+  double threshold;          /* Contact::THRESHOLD = 0.2 mm in the reference */
+  int raw;
+  b2c_contact *contacts;     /* [cap_contacts] */
+  int *contact_pose;         /* [cap_contacts] */
+  int *contact_pair;         /* [cap_contacts] */
+  int cap_contacts;
+  int *ncontacts;
+  int *pose_offsets;         /* optional [npose + 1]: first contact of each pose in the (untruncated) listing */
+} b2c_contacts_batch_args;
+int b2c_contacts_batch(b2c_ctx *ctx, const b2c_contacts_batch_args *args);
 
 /* ---- batched autograsp: Robot::moveDOFToContacts for whole batches of hand poses -------------------------------
  * Replaces, per pose, Hand::autoGrasp -> Robot::moveDOFToContacts -> jumpDOFToContact -> getJointValuesFromDOF /

@@ -1,0 +1,111 @@
+"""GPU: batched contacts (b2c_contacts_batch = allContacts(threshold, interest = hand) per pose) and the joint-level
+input mode, on hands closed by the batched autograsp: against the reference backend, and against the single-pose path."""
+import os
+
+import numpy as np
+import pytest
+
+from graspit_b200.engine import AG_INTERP_ERROR, B2C_INPUT_JOINTS, Engine, SceneBinding
+from graspit_b200.formats.scenepack import load_pack
+from oracle.port.autograsp import AutoGraspOracle
+from tests.common import OracleScene, object_body
+
+pytestmark = pytest.mark.gpu
+AG_FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "barrett_mug_autograsp.npz")
+THR = 0.2
+
+
+@pytest.fixture(scope="module")
+def closed():
+    sc = load_pack("barrett_mug")
+    eng = Engine(0)
+    sb = SceneBinding(eng, sc)
+    rid = sb.robot_ids[0]
+    raw = np.load(AG_FIX)["raw"]
+    out = eng.auto_grasp(rid, sc.robots[0], raw)
+    ok = (out["status"] & AG_INTERP_ERROR) == 0
+    js = np.concatenate([raw[ok, :7].astype(np.float64), out["joints"][ok]], axis=1)
+    return dict(sc=sc, eng=eng, sb=sb, rid=rid, js=js, raw=raw[ok], dof=out["dof"][ok])
+
+
+def _by_pose_pair(res, pairs, inv):
+    out = {}
+    for c, p, q in zip(res["contacts"], res["pose"], res["pair"]):
+        a, b = pairs[q]
+        out.setdefault((int(p), tuple(sorted((inv[a], inv[b])))), []).append((inv[a] > inv[b], c))
+    return out
+
+
+def test_joint_input_fk_and_legality(closed):
+    sc, eng, sb, rid, js = closed["sc"], closed["eng"], closed["sb"], closed["rid"], closed["js"]
+    obj = sb.body_ids[object_body(sc)]
+    res = eng.eval_batch(rid, obj, js, input_mode=B2C_INPUT_JOINTS, body_tf=True, link_dist=True)
+    # the bisection leaves every finger 0 < d < THRESHOLD / 2 short of touching: collision-free, including break-away postures
+    assert res["legal"].all()
+    # (fingers that miss the mug stop against each other instead: only part of the poses touch the object)
+    assert (res["link_dist"] > 0).all() and ((res["link_dist"] < 0.1).sum(axis=1) >= 1).mean() > 0.3
+    # joint-level FK equals DOF-level FK wherever the joints still equal ratio x DOF
+    r = sc.robots[0]
+    jd = [j for c in r.chains for j in c.joints]
+    coupled = np.abs(js[:, 7:] - closed["dof"][:, [j.dof for j in jd]] * np.array([j.ratio for j in jd])).max(axis=1) < 1e-12
+    raw2 = closed["raw"].copy(); raw2[:, 7:] = closed["dof"].astype(np.float32)
+    res2 = eng.eval_batch(rid, obj, raw2[coupled], body_tf=True)
+    assert coupled.sum() > 20 and (~coupled).sum() > 5
+    assert np.abs(res2["body_tf"] - res["body_tf"][coupled]).max() < 2e-4      # fp32 rounding of the DOF values only
+
+
+def test_contacts_batch_matches_single_pose_path_and_reference(closed):
+    sc, eng, sb, rid, js = closed["sc"], closed["eng"], closed["sb"], closed["rid"], closed["js"]
+    osc = OracleScene(sc, nthreads=1)
+    ag = AutoGraspOracle(sc, 0, osc.w, osc.ids)
+    res = eng.contacts_batch(rid, js, THR, input_mode=B2C_INPUT_JOINTS)
+    assert res["offsets"][-1] == len(res["contacts"]) and (np.diff(res["offsets"]) >= 0).all()
+    assert (np.diff(res["pose"]) >= 0).all()
+    pairs = eng.robot_pairs(rid)
+    inv_e = {v: k for k, v in sb.body_ids.items()}
+    inv_o = {v: k for k, v in osc.ids.items()}
+    got = _by_pose_pair(res, pairs, inv_e)
+    bodies = eng.robot_bodies(rid)
+    tf = eng.eval_batch(rid, -1, js, input_mode=B2C_INPUT_JOINTS, body_tf=True)["body_tf"]
+    interest_o = [osc.ids[inv_e[b]] for b in bodies]
+    npairs = exact = nsingle = same_single = 0
+    for p in range(0, len(js), 3):
+        # (1) the single-pose interface on the same link poses (which it re-derives from q, t: 1e-14 apart) returns the same contacts
+        for k, b in enumerate(bodies):
+            eng.set_body_transform(b, tf[p, k, :4], tf[p, k, 4:])
+        single = eng.all_contacts(THR, interest=bodies)
+        want = {}
+        for (a, b), cs in single:
+            want[tuple(sorted((inv_e[a], inv_e[b])))] = np.array(cs).reshape(-1, 13)
+        mine = {k[1]: np.array([c for _, c in v]) for k, v in got.items() if k[0] == p}
+        assert set(mine) == set(want)
+        for key in want:
+            nsingle += 1
+            if mine[key].shape == want[key].shape and np.allclose(mine[key], want[key], rtol=1e-9, atol=1e-9):
+                same_single += 1
+            else:
+                # flat-on-flat contacts tie exactly; which of the tied candidates survives the 3 mm duplicate rule then
+                # hangs on the last bit of the transforms: the clusters must still agree
+                for r in want[key]:
+                    assert min(np.linalg.norm(mine[key][:, :3] - r[:3], axis=1)) < 6.0, (p, key)
+        # (2) the reference backend at the same joint values: same contacting pairs, same clusters
+        ag.set_joints((js[p, 0:4], js[p, 4:7]), js[p, 7:])
+        ref_pairs = {}
+        for (a, b), cs in osc.w.all_contacts(THR, interest=interest_o):
+            ref_pairs[tuple(sorted((inv_o[a], inv_o[b])))] = (inv_o[a] > inv_o[b], np.array(cs).reshape(-1, 13))
+        assert set(ref_pairs) == set(mine), (p, set(ref_pairs), set(mine))
+        for key, (swapped_o, co) in ref_pairs.items():
+            swapped_e = got[(p, key)][0][0]
+            ce = mine[key]
+            if swapped_o != swapped_e:
+                co = co[:, [3, 4, 5, 0, 1, 2, 9, 10, 11, 6, 7, 8, 12]]
+            npairs += 1
+            for r in co:
+                assert min(np.linalg.norm(ce[:, :3] - r[:3], axis=1)) < 6.0      # same cluster (3 mm duplicate rule)
+            if len(ce) == len(co) and {tuple(np.round(r[:6], 5)) for r in ce} == {tuple(np.round(r[:6], 5)) for r in co}:
+                exact += 1
+    assert npairs >= 30 and exact >= 0.7 * npairs
+    assert same_single >= 0.9 * nsingle
+    # raw candidates are a superset of the processed contacts
+    raw = eng.contacts_batch(rid, js[:8], THR, input_mode=B2C_INPUT_JOINTS, raw=True)
+    assert len(raw["contacts"]) >= res["offsets"][8]
