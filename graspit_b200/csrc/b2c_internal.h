@@ -231,6 +231,18 @@ struct RegionParams {
 };
 cudaError_t launch_contacts(const ContactParams &p, int blocks, cudaStream_t s);
 cudaError_t launch_region(const RegionParams &p, cudaStream_t s);
+struct RegionBatchParams {
+  int nquery;
+  const int *mesh_of;        // [nquery] mesh index of the query's body
+  const MeshDev *meshes;
+  const double *point;       // [nquery][3] body frame
+  const double *normal;      // [nquery][3]
+  const double *radius;      // [nquery]
+  int2 *out;                 // (query, triangle) of every flagged triangle, arbitrary order
+  int out_cap;
+  int *out_count;
+};
+cudaError_t launch_region_batch(const RegionBatchParams &p, cudaStream_t s);
 size_t contact_group_temp_bytes(int nqueries);
 cudaError_t launch_contact_group(const ContactRec *in, int n, const int *per_query, int nqueries, int *offsets, int *cursor,
                                  ContactRec *out, void *temp, size_t temp_bytes, cudaStream_t s);

@@ -231,6 +231,52 @@ __global__ void region_kernel(RegionParams p) {
   p.flags[t] = flag;
 }
 
+// K7 batched: one warp per (body, point, normal, radius) query, lanes stride over the body's triangles with the same test
+// as region_kernel; flagged triangles are appended to one list with warp-aggregated atomics.  Brute force over the
+// triangles is deliberate: the bodies that get neighbourhoods are elastic fingertips and small objects (a few thousand
+// triangles), and the test is ~100 fp64 flops.
+__global__ void __launch_bounds__(256) region_batch_kernel(RegionBatchParams p) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < p.nquery; q += nwarps) {
+    const MeshDev &m = p.meshes[p.mesh_of[q]];
+    const d3 cn = mk<double>(p.normal[3 * q], p.normal[3 * q + 1], p.normal[3 * q + 2]);
+    const d3 ref = mk<double>(p.point[3 * q], p.point[3 * q + 1], p.point[3 * q + 2]);
+    const double r2 = p.radius[q] * p.radius[q];
+    for (int t0 = 0; t0 < m.ntri; t0 += 32) {
+      const int t = t0 + lane;
+      bool flag = false;
+      if (t < m.ntri) {
+        d3 a = c_tri_vertex(m.tris, t, 0), b = c_tri_vertex(m.tris, t, 1), c = c_tri_vertex(m.tris, t, 2);
+        d3 n = cross(b - a, c - a);
+        double nn = sqrt(dot(n, n));
+        if (nn > 0.0) n = n * (1.0 / nn);
+        if (!(dot(n, cn) > 0.0)) {
+          d3 d = closest_pt_triangle<double>(a, b, c, ref) - ref;
+          flag = !(dot(d, d) > r2);
+        }
+      }
+      const unsigned mk_ = __ballot_sync(0xffffffffu, flag);
+      if (mk_) {
+        int base = 0;
+        if (lane == __ffs(mk_) - 1) base = atomicAdd(p.out_count, __popc(mk_));
+        base = __shfl_sync(0xffffffffu, base, __ffs(mk_) - 1);
+        if (flag) {
+          const int at = base + __popc(mk_ & ((1u << lane) - 1u));
+          if (at < p.out_cap) p.out[at] = make_int2(q, t);
+        }
+      }
+    }
+  }
+}
+
+cudaError_t launch_region_batch(const RegionBatchParams &p, cudaStream_t s) {
+  if (p.nquery <= 0) return cudaSuccess;
+  const int blocks = std::max(1, std::min((p.nquery + 7) / 8, 148 * 8));
+  region_batch_kernel<<<blocks, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_contacts(const ContactParams &p, int blocks, cudaStream_t s) {
   size_t smem = (size_t)8 * CONTACT_WARP_SMEM;
   static size_t granted[64] = {};

@@ -35,7 +35,7 @@ EXPORTS = [
     "b2c_anneal_create", "b2c_anneal_destroy", "b2c_anneal_step", "b2c_anneal_read", "b2c_anneal_device_ptrs",
     "b2c_anneal_propose", "b2c_anneal_write", "b2c_anneal_best_rows",
     "b2c_check_contact_normals", "b2c_contact_frames", "b2c_point_contact_wrenches",
-    "b2c_autograsp_batch", "b2c_contacts_batch",
+    "b2c_autograsp_batch", "b2c_contacts_batch", "b2c_region_batch",
     "b2c_soft_neighborhood_radius", "b2c_soft_contact_merge", "b2c_soft_contact_fit", "b2c_soft_contact_wrenches",
 ]
 
@@ -184,6 +184,7 @@ def load_library():
     L.b2c_eval_batch.argtypes = [vp, C.POINTER(EvalArgs)]
     L.b2c_autograsp_batch.argtypes = [vp, C.POINTER(AutoGraspArgs)]
     L.b2c_contacts_batch.argtypes = [vp, C.POINTER(ContactsBatchArgs)]
+    L.b2c_region_batch.argtypes = [vp, ci, ip, dp, dp, dp, dp, ci, ip, ip]
     L.b2c_robot_bodies.argtypes = [vp, ci, ip, ci, ip]
     L.b2c_robot_pairs.argtypes = [vp, ci, ip, ci, ip]
     L.b2c_last_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
@@ -415,6 +416,21 @@ class Engine:
         n = C.c_int(0)
         self._ck(self.L.b2c_region(self.h, body, _dp(p), _dp(nn), float(radius), _dp(out), cap, C.byref(n)))
         return out[: 3 * min(n.value, cap)].reshape(-1, 3).copy()
+
+    def body_region_batch(self, bodies, points, normals, radii, cap=None):
+        """bodyRegion for n (body, point, normal, radius) queries in one call: list of (k_i, 3) arrays"""
+        b = np.ascontiguousarray(bodies, dtype=np.int32)
+        n = b.size
+        p = np.ascontiguousarray(points, dtype=np.float64).reshape(n, 3)
+        nn = np.ascontiguousarray(normals, dtype=np.float64).reshape(n, 3)
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, dtype=np.float64), (n,)))
+        cap = int(cap) if cap is not None else max(4096, 96 * n)
+        out = np.empty((cap, 3)); off = np.zeros(n + 1, dtype=np.int32)
+        tot = C.c_int(0)
+        self._ck(self.L.b2c_region_batch(self.h, n, _ip(b), _dp(p), _dp(nn), _dp(r), _dp(out), cap, _ip(off), C.byref(tot)))
+        if tot.value > cap:
+            return self.body_region_batch(bodies, points, normals, radii, cap=tot.value)
+        return [out[off[i]:off[i + 1]].copy() for i in range(n)]
 
     def get_bounding_volumes(self, body: int, depth: int, cap=1 << 16):
         buf = (Obb * cap)()

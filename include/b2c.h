@@ -127,6 +127,13 @@ int b2c_all_contacts(b2c_ctx *ctx, double threshold, const int *interest, int ni
 int b2c_region(b2c_ctx *ctx, int body, const double point[3], const double normal[3], double radius,
                double *out_xyz, int cap, int *npoints);
 
+/* bodyRegion for many (body, point, normal, radius) queries in one call -- the neighbourhoods of every contact of a
+ * batch (findSoftNeighborhoods, reference contactSetting.cpp:114-139).  out_xyz receives the lists back to back, each as
+ * b2c_region returns it (vertices of the flagged triangles in triangle order, repeats removed, the query point last);
+ * offsets[n + 1] gives the first point of each list.  *npoints is the total; lists beyond cap points are truncated. */
+int b2c_region_batch(b2c_ctx *ctx, int n, const int *bodies, const double *points, const double *normals,
+                     const double *radii, double *out_xyz, int cap, int *offsets, int *npoints);
+
 typedef struct b2c_obb {
   double t[3];
   double q_wxyz[4];

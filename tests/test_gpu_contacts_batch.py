@@ -109,3 +109,46 @@ def test_contacts_batch_matches_single_pose_path_and_reference(closed):
     # raw candidates are a superset of the processed contacts
     raw = eng.contacts_batch(rid, js[:8], THR, input_mode=B2C_INPUT_JOINTS, raw=True)
     assert len(raw["contacts"]) >= res["offsets"][8]
+
+
+def test_region_batch_matches_single_queries_and_reference():
+    """neighbourhoods of every contact of a batch of closed human hands (elastic fingertips): the batched bodyRegion returns
+    exactly what one b2c_region call per contact returns, which equals the reference's bodyRegion as a set"""
+    from graspit_b200 import engine as E
+    from tests.common import aa_to_raw_states, sample_aa_states
+    sc = load_pack("humanhand_flask")
+    eng = Engine(0)
+    sb = SceneBinding(eng, sc)
+    osc = OracleScene(sc, nthreads=1)
+    rid, obj = sb.robot_ids[0], sb.body_ids[object_body(sc)]
+    r = sc.robots[0]
+    pos, _ = sample_aa_states(sc, 400, seed=41, strata=("near",))
+    rest = np.clip(r.dof_default, r.dof_min, r.dof_max)
+    raw = aa_to_raw_states(sc, pos, np.tile(rest[None, :], (len(pos), 1)).astype(np.float32))
+    raw = raw[eng.eval_batch(rid, obj, raw)["legal"] == 1][:24]
+    ag = eng.auto_grasp(rid, r, raw)
+    ok = (ag["status"] & AG_INTERP_ERROR) == 0
+    js = np.concatenate([raw[ok, :7].astype(np.float64), ag["joints"][ok]], axis=1)
+    res = eng.contacts_batch(rid, js, THR, input_mode=B2C_INPUT_JOINTS)
+    assert len(res["contacts"]) > 40
+    pairs = eng.robot_pairs(rid)
+    inv = {v: k for k, v in sb.body_ids.items()}
+    bodies, points, normals, radii = [], [], [], []
+    for c, q in zip(res["contacts"], res["pair"]):
+        a, b = pairs[q]
+        if max(sc.bodies[inv[a]].youngs, sc.bodies[inv[b]].youngs) <= 0:
+            continue                      # rigid pair: addContacts takes the point-contact branch, no neighbourhoods
+        rad = E.soft_neighborhood_radius(sc.bodies[inv[a]].youngs, sc.bodies[inv[b]].youngs)
+        bodies += [a, b]; points += [c[0:3], c[3:6]]; normals += [c[6:9], c[9:12]]; radii += [rad, rad]
+    got = eng.body_region_batch(bodies, points, normals, radii)
+    assert len(got) == len(bodies) and len(bodies) >= 20
+    nonempty = 0
+    for i in range(0, len(bodies), 7):
+        one = eng.body_region(bodies[i], points[i], normals[i], radii[i])
+        assert np.array_equal(got[i], one), i
+        ref_pts = osc.w.region(osc.ids[inv[bodies[i]]], points[i], normals[i], radii[i])
+        assert {tuple(x) for x in ref_pts} == {tuple(x) for x in got[i]}
+        nonempty += len(one) > 1
+    assert nonempty > 5
+    # the last point of every list is the query point itself
+    assert all(np.array_equal(g[-1], np.asarray(p, dtype=np.float64)) for g, p in zip(got, points))

@@ -44,6 +44,24 @@ def main():
     fixed = res["contacts"]
     wr = E.point_contact_wrenches(fixed[:20000], 1, 0.5, [0.0, 0.0, 0.0], 100.0) if len(fixed) else None
     t_w = (time.perf_counter() - t0) * (len(fixed) / max(1, min(len(fixed), 20000)))
+    # neighbourhoods of both sides of every contact on an elastic body (findSoftNeighborhoods), one batched call
+    pairs = eng.robot_pairs(rid)
+    inv_b = {v: k for k, v in sb.body_ids.items()}
+    y = np.array([[sc.bodies[inv_b[a]].youngs, sc.bodies[inv_b[b]].youngs] for a, b in pairs])
+    soft = y.max(axis=1)[res["pair"]] > 0
+    cs, pq = res["contacts"][soft], res["pair"][soft]
+    pa = np.array(pairs)[pq]
+    rad = np.array([E.soft_neighborhood_radius(*y[q]) for q in pq])
+    qb = np.stack([pa[:, 0], pa[:, 1]], 1).reshape(-1)
+    qp = np.stack([cs[:, 0:3], cs[:, 3:6]], 1).reshape(-1, 3)
+    qn = np.stack([cs[:, 6:9], cs[:, 9:12]], 1).reshape(-1, 3)
+    qr = np.repeat(rad, 2)
+    eng.body_region_batch(qb[:512], qp[:512], qn[:512], qr[:512])
+    t0 = time.perf_counter()
+    ngh = eng.body_region_batch(qb, qp, qn, qr)
+    t_r = time.perf_counter() - t0
+    region = {"queries": int(len(qb)), "seconds": t_r, "queries_per_s": float(len(qb) / t_r) if len(qb) else 0.0,
+              "mean_points": float(np.mean([len(g) for g in ngh])) if ngh else 0.0}
     # CPU baseline (reported, not a target): the reference's own allContacts on the same link poses, one thread, 64 poses
     cpu = None
     try:
@@ -68,7 +86,7 @@ def main():
                       "contacts_total": int(len(fixed)), "contacts_per_pose": float(per_pose.mean()),
                       "poses_with_contacts": float((per_pose > 0).mean()),
                       "autograsp_seconds": t_ag, "autograsps_per_s": float(len(raw) / t_ag), "autograsp_rounds": ag["rounds"],
-                      "cone_wrenches_seconds_est": t_w, "active_pairs": len(eng.robot_pairs(rid)), "cpu_baseline": cpu}))
+                      "cone_wrenches_seconds_est": t_w, "active_pairs": len(eng.robot_pairs(rid)), "region_batch": region, "cpu_baseline": cpu}))
 
 
 if __name__ == "__main__":
