@@ -121,6 +121,7 @@ struct b2c_ctx {
   size_t h_contacts_cap = 0;
   int stage_nodes = 128;           // object-tree nodes staged in shared memory by the energy kernel
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int last_counters[4] = {0, 0, 0, 0};
   int eval_warps_per_block = 8;
   int eval_blocks_per_sm = 0;      // 0 = derive from shared memory
   cudaStream_t own_stream = nullptr;
@@ -990,9 +991,10 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   }
   CU(cudaMemcpyAsync(ctx->last_stats, ctx->d_stats.p, sizeof ctx->last_stats, cudaMemcpyDeviceToHost, ctx->stream));
   if (!dev) {
+    // the queue counters ride along with the results: one synchronisation, no second round trip
+    int *amb = ctx->last_counters;
+    CU(cudaMemcpyAsync(amb, ctx->d_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    int amb[4];
-    CU(cudaMemcpy(amb, ctx->d_counters.p, sizeof amb, cudaMemcpyDeviceToHost));
     if (amb[1] > (int)ctx->d_ambig.cap || amb[3] > (int)ctx->d_ambig.cap)
       return fail(ctx, B2C_ECAPACITY, "eval_batch: recheck queue overflow (%d entries)", std::max(amb[1], amb[3]));
   }

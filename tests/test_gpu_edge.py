@@ -133,3 +133,45 @@ def test_config5_full_size_properties():
     e1, e2 = ref_small["energy"][m].astype(np.float64), whole["energy"][idx][m].astype(np.float64)
     assert (np.abs(e1 - e2) <= REL * np.abs(e1) + 1e-4).all()
     assert (whole["energy"][whole["legal"] == 0] == 0).all()
+
+
+def test_batched_grasp_entry_points_edge_cases(ctx):
+    """autograsp / contacts / region batches: empty inputs, argument errors, a batch of one equals its row of a larger batch"""
+    from graspit_b200.engine import AG_INTERP_ERROR, B2C_INPUT_JOINTS
+    from tests.common import aa_to_raw_states
+    eng, sc, rid = ctx["eng"], ctx["sc"], ctx["rid"]
+    r = sc.robots[0]
+    pos, dofs = sample_aa_states(sc, 64, seed=9, strata=("near",))
+    dofs = dofs.copy(); dofs[:, 1:] = 0.0
+    raw = aa_to_raw_states(sc, pos, dofs)
+    # empty batches
+    out0 = eng.auto_grasp(rid, r, raw[:0])
+    assert out0["dof"].shape == (0, r.n_dof) and out0["rounds"] == 0
+    c0 = eng.contacts_batch(rid, raw[:0], 0.2)
+    assert len(c0["contacts"]) == 0 and list(c0["offsets"]) == [0]
+    assert eng.body_region_batch([], np.zeros((0, 3)), np.zeros((0, 3)), []) == []
+    # errors are reported, the context survives
+    with pytest.raises(B2CError):
+        eng.auto_grasp(99, r, raw)
+    with pytest.raises(B2CError):
+        eng.contacts_batch(rid, raw[:, :8], 0.2)                                   # stride too small
+    with pytest.raises(B2CError):
+        eng.contacts_batch(rid, np.zeros((4, 9)), 0.2, input_mode=B2C_INPUT_JOINTS)  # 7 + 8 joints needed
+    with pytest.raises(B2CError):
+        eng.body_region_batch([12345], np.zeros((1, 3)), np.array([[0, 0, 1.0]]), [3.0])
+    # a batch of one = its row of the batch of 64 (poses never interact)
+    full = eng.auto_grasp(rid, r, raw)
+    for i in (0, 17, 63):
+        one = eng.auto_grasp(rid, r, raw[i:i + 1])
+        assert np.array_equal(one["dof"][0], full["dof"][i]) and one["status"][0] == full["status"][i]
+        assert np.array_equal(one["joints"][0], full["joints"][i]) and one["iters"][0] == full["iters"][i]
+    ok = (full["status"] & AG_INTERP_ERROR) == 0
+    js = np.concatenate([raw[ok, :7].astype(np.float64), full["joints"][ok]], axis=1)
+    call = eng.contacts_batch(rid, js, 0.2, input_mode=B2C_INPUT_JOINTS)
+    for i in (0, 5, len(js) - 1):
+        one = eng.contacts_batch(rid, js[i:i + 1], 0.2, input_mode=B2C_INPUT_JOINTS)
+        lo, hi = call["offsets"][i], call["offsets"][i + 1]
+        assert np.array_equal(one["contacts"], call["contacts"][lo:hi]) and np.array_equal(one["pair"], call["pair"][lo:hi])
+    # truncation: a small cap still reports the full count through offsets (the wrapper retries with the right size)
+    small = eng.contacts_batch(rid, js, 0.2, input_mode=B2C_INPUT_JOINTS, cap_contacts=3)
+    assert np.array_equal(small["contacts"], call["contacts"])
