@@ -267,15 +267,21 @@ def main():
     # N > 1: every step ends with the all-gather of each rank's BEST_LIST_SIZE best (state || energy) rows.  The rows
     # come from the engine's incremental best list (one-warp kernel over the chains that improved this step), so the
     # exchange costs one tiny kernel + one 720-byte-per-rank NCCL all-gather
-    rows = torch.empty((BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) if anneal else None
-    gathered = torch.empty((world * BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) if world > 1 else None
+    # The exchange of step s overlaps the kernels of step s + 1: the all-gather is asynchronous, and a rank
+    # only waits for it -- on the stream, not on the host -- after it has enqueued its next step.  Rows and results are
+    # double-buffered; the merged list trails the chains by one step, which the planner's best-list rule does not mind.
+    rows = [torch.empty((BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) for _ in range(2)] if anneal else None
+    gathered = [torch.empty((world * BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    pending = [None]
 
     def step_device(i):
         if anneal:
             an.step(1)
             if world > 1:
-                an.best_rows(BEST_LIST_SIZE, rows.data_ptr())
-                dist.all_gather_into_tensor(gathered, rows)
+                if pending[0] is not None:
+                    pending[0].wait()
+                an.best_rows(BEST_LIST_SIZE, rows[i & 1].data_ptr())
+                pending[0] = dist.all_gather_into_tensor(gathered[i & 1], rows[i & 1], async_op=True)
         else:
             st = dev_batches[i]
             eng.eval_batch_device(rid, oid, st.data_ptr(), npose, nvar, legal_d.data_ptr(), energy_d.data_ptr(),
@@ -285,6 +291,9 @@ def main():
                 exchange_best(local_best_rows(st, e, BEST_LIST_SIZE))
 
     def sync_all():
+        if pending[0] is not None:
+            pending[0].wait()
+            pending[0] = None
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
