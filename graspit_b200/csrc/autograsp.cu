@@ -67,7 +67,7 @@ __device__ bool begin_jump(const AgDesc &D, AgState &S) {
   }
   if (!moving) return false;
   // interest list: links whose last joint is not stopped (robot.cpp:1623-1631) -> active pairs touching one of them
-  for (int w = 0; w < AG_MW; w++) { S.interest[w] = 0; S.late[w] = 0; }
+  for (int w = 0; w < D.mask_words; w++) { S.interest[w] = 0; S.late[w] = 0; }
   for (int p = 0; p < D.npairs; p++) {
     int la = D.pair_link_a[p], lb = D.pair_link_b[p];
     bool in = (la >= 0 && !S.stopped[D.link_last_joint[la]]) || (lb >= 0 && !S.stopped[D.link_last_joint[lb]]);
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(128) autograsp_step_kernel(AgParams p) {
       S.desired[d] = des; S.step[d] = st;
     }
     S.iters = 1; S.status = 0; S.ncols = 0; S.t = 0; S.deltat = 1;
-    for (int w = 0; w < AG_MW; w++) S.late[w] = S.col[w] = S.interest[w] = 0;
+    for (int w = 0; w < D.mask_words; w++) S.late[w] = S.col[w] = S.interest[w] = 0;
     S.phase = begin_jump(D, S) ? AG_CHECK : AG_DONE;
   } else if (S.phase != AG_DONE) {
     const float *dist = p.dist + (size_t)pose * D.npairs;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(128) autograsp_step_kernel(AgParams p) {
       }
       if (done) {
         // lateContacts = colReport; DOF targets interpolated; the loop of jumpDOFToContact checks collisions again
-        for (int w = 0; w < AG_MW; w++) S.late[w] = S.col[w];
+        for (int w = 0; w < D.mask_words; w++) S.late[w] = S.col[w];
         for (int d = 0; d < D.ndof; d++) S.new_dof[d] = S.new_dof[d] * S.t + S.initial_dof[d] * (1.0 - S.t);
         check = true;
       } else if (S.deltat > 1.0e-20 && S.t >= 0) {
@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(128) autograsp_step_kernel(AgParams p) {
     if (check && S.phase != AG_DONE) {
       const unsigned long long *pm = p.pair_mask + (size_t)pose * p.mask_words;
       bool any = false;
-      for (int w = 0; w < AG_MW; w++) {
-        S.col[w] = (w < p.mask_words ? pm[w] : 0ull) & S.interest[w];
+      for (int w = 0; w < D.mask_words; w++) {
+        S.col[w] = pm[w] & S.interest[w];
         any |= S.col[w] != 0ull;
       }
       if (any) {
@@ -198,13 +198,13 @@ __global__ void __launch_bounds__(128) autograsp_step_kernel(AgParams p) {
     }
   }
   for (int w = 0; w < p.mask_words; w++)
-    p.pair_enable[(size_t)pose * p.mask_words + w] = (S.phase != AG_DONE && w < AG_MW) ? S.interest[w] : 0ull;
+    p.pair_enable[(size_t)pose * p.mask_words + w] = S.phase != AG_DONE ? S.interest[w] : 0ull;
   if (S.phase != AG_DONE) {
     for (int j = 0; j < D.nj; j++) js[7 + j] = S.jv[j];
     atomicAdd(&p.counters[0], 1);
     if (S.phase == AG_INTERP) {
       int n = 0;
-      for (int w = 0; w < AG_MW; w++) n += __popcll(S.col[w]);
+      for (int w = 0; w < D.mask_words; w++) n += __popcll(S.col[w]);
       int at = atomicAdd(&p.counters[1], n);
       for (int q = 0; q < D.npairs; q++)
         if (bit(S.col, q)) { if (at < p.wcap) p.wlist[at] = pose * D.npairs + q; at++; }

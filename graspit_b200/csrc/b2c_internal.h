@@ -311,11 +311,12 @@ size_t energy_block_smem_bytes(int stage_nodes);
 
 // ---- batched autograsp (autograsp.cu): Robot::moveDOFToContacts for a batch of poses ----------------------------
 namespace b2c {
-constexpr int AG_MAXD = 32, AG_MAXJ = 32, AG_MAXL = 32, AG_MAXP = 256, AG_MW = AG_MAXP / 64;
+constexpr int AG_MAXD = 32, AG_MAXJ = 32, AG_MAXL = 32, AG_MAXP = 512, AG_MW = AG_MAXP / 64;
 enum { AG_CHECK = 1, AG_INTERP = 2, AG_DONE = 3 };
 enum { AG_ST_MOVED = 1, AG_ST_INTERP_ERROR = 2, AG_ST_FAILSAFE = 4, AG_ST_STOPPED_AT_CONTACT = 8 };
 struct AgDesc {
   int ndof, nj, nlinks, npairs;
+  int mask_words;                  // 64-bit words of a pair mask: (npairs + 63) / 64
   int one_step;                    // desiredSteps == NULL: WorldElement::ONE_STEP for every DOF
   int stop_at_contact;
   int max_iters;                   // moveDOFToContacts failsafe (500)

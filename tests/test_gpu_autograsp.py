@@ -170,3 +170,28 @@ def test_autograsp_opening_direction(barrett):
     assert exact >= 12
     # an unobstructed finger opens all the way to its lower limit
     assert (np.abs(out["dof"][:, 1:] - r.dof_min[None, 1:]) < 1e-9).any()
+
+
+def test_autograsp_of_a_hand_mounted_on_an_arm():
+    """staubli_barrett: the Barrett hand is a child robot of the arm (b2c_robot_desc.parent_robot >= 0); closing it at the
+    arm's rest pose with the arm links, table, shelf and floor as static bodies (100+ active pairs)"""
+    sc = load_pack("staubli_barrett")
+    eng = Engine(0)
+    sb = SceneBinding(eng, sc)
+    osc = OracleScene(sc, nthreads=1)
+    hand = sc.robots[1]
+    rid = sb.robot_ids[1]
+    assert len(eng.robot_pairs(rid)) > 64
+    q, t = sc.body_tran[hand.base_body]
+    spreads = np.linspace(0.0, float(hand.dof_max[0]), 6)
+    raw = np.zeros((len(spreads), 7 + hand.n_dof), dtype=np.float32)
+    raw[:, 0:4] = q; raw[:, 4:7] = t; raw[:, 7] = spreads
+    out = eng.auto_grasp(rid, hand, raw)
+    ag = AutoGraspOracle(sc, 1, osc.w, osc.ids)
+    for k in range(len(raw)):
+        o = ag.auto_grasp((raw[k, 0:4].astype(np.float64), raw[k, 4:7].astype(np.float64)), raw[k, 7:].astype(np.float64))
+        assert bool(int(out["status"][k]) & AG_INTERP_ERROR) == o["error"]
+        assert bool(int(out["status"][k]) & AG_MOVED) == o["moved"]
+        if not o["error"]:
+            assert np.abs(out["dof"][k] - o["dof"]).max() < 2e-2, (k, out["dof"][k], o["dof"])
+            assert (out["stopped"][k] != 0).any() == (o["stopped"] != 0).any()
