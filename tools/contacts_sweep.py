@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Parity sweep of the batched contacts against the reference's own allContacts.
+  GPU box:   python tools/contacts_sweep.py gpu N out.npz   (hands closed by the batched autograsp, b2c_contacts_batch)
+  anywhere:  python tools/contacts_sweep.py cpu out.npz     (GraspitCollision::allContacts at the same joint values, one JSON line)"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from graspit_b200.formats.scenepack import load_pack                            # noqa: E402
+from tests.common import aa_to_raw_states, object_body, sample_aa_states        # noqa: E402
+
+THR = 0.2
+
+
+def gpu(n, out):
+    from graspit_b200.engine import AG_INTERP_ERROR, B2C_INPUT_JOINTS, Engine, SceneBinding
+    sc = load_pack("barrett_mug")
+    eng = Engine(0)
+    sb = SceneBinding(eng, sc)
+    rid, oid = sb.robot_ids[0], sb.body_ids[object_body(sc)]
+    pos, dofs = sample_aa_states(sc, 4 * n, seed=888, strata=("near",))
+    dofs = dofs.copy(); dofs[:, 1:] = 0.0
+    raw = aa_to_raw_states(sc, pos, dofs)
+    raw = raw[eng.eval_batch(rid, oid, raw)["legal"] == 1][:n]
+    ag = eng.auto_grasp(rid, sc.robots[0], raw)
+    ok = (ag["status"] & AG_INTERP_ERROR) == 0
+    js = np.concatenate([raw[ok, :7].astype(np.float64), ag["joints"][ok]], axis=1)
+    res = eng.contacts_batch(rid, js, THR, input_mode=B2C_INPUT_JOINTS)
+    inv = {v: k for k, v in sb.body_ids.items()}
+    pairs = np.array([[inv[a], inv[b]] for a, b in eng.robot_pairs(rid)])        # scene body indices
+    np.savez_compressed(out, js=js, contacts=res["contacts"], pose=res["pose"], pair=res["pair"], offsets=res["offsets"], pairs=pairs)
+    print("wrote", out, len(js), "poses", len(res["contacts"]), "contacts")
+
+
+def cpu(path):
+    from oracle.port.autograsp import AutoGraspOracle
+    from tests.common import OracleScene
+    z = np.load(path)
+    sc = load_pack("barrett_mug")
+    osc = OracleScene(sc, nthreads=1)
+    ag = AutoGraspOracle(sc, 0, osc.w, osc.ids)
+    inv = {v: k for k, v in osc.ids.items()}
+    hand = [osc.ids[b] for b in sc.robots[0].body_list()]
+    js, pairs = z["js"], z["pairs"]
+    npose = len(js)
+    same_pairs = groups = exact = cluster_ok = counts_equal = 0
+    worst = 0.0
+    for p in range(npose):
+        ag.set_joints((js[p, 0:4], js[p, 4:7]), js[p, 7:])
+        refc = {}
+        for (a, b), cs in osc.w.all_contacts(THR, interest=hand):
+            ia, ib = inv[a], inv[b]
+            c = np.array(cs).reshape(-1, 13)
+            if ia > ib:
+                c = c[:, [3, 4, 5, 0, 1, 2, 9, 10, 11, 6, 7, 8, 12]]; ia, ib = ib, ia
+            refc[(ia, ib)] = c
+        lo, hi = z["offsets"][p], z["offsets"][p + 1]
+        mine = {}
+        for c, q in zip(z["contacts"][lo:hi], z["pair"][lo:hi]):
+            ia, ib = pairs[q]
+            if ia > ib:
+                c = c[[3, 4, 5, 0, 1, 2, 9, 10, 11, 6, 7, 8, 12]]; ia, ib = ib, ia
+            mine.setdefault((int(ia), int(ib)), []).append(c)
+        mine = {k: np.array(v) for k, v in mine.items()}
+        same_pairs += set(mine) == set(refc)
+        for key in set(mine) & set(refc):
+            groups += 1
+            a, b = mine[key], refc[key]
+            counts_equal += len(a) == len(b)
+            if len(a) == len(b) and {tuple(np.round(r[:6], 5)) for r in a} == {tuple(np.round(r[:6], 5)) for r in b}:
+                exact += 1
+            d = max(min(np.linalg.norm(a[:, :3] - r[:3], axis=1)) for r in b)
+            worst = max(worst, float(d))
+            cluster_ok += d < 6.0
+    print(json.dumps({"what": "b2c_contacts_batch vs GraspitCollision::allContacts(0.2, hand) on hands closed by the batched autograsp (Barrett vs mug)",
+                      "poses": int(npose), "poses_with_identical_contacting_pair_sets": int(same_pairs), "pair_groups": int(groups),
+                      "groups_with_identical_contact_sets": int(exact), "groups_with_equal_contact_count": int(counts_equal),
+                      "groups_whose_contacts_fall_in_the_same_3mm_clusters": int(cluster_ok), "worst_nearest_contact_distance_mm": worst}))
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "gpu":
+        gpu(int(sys.argv[2]), sys.argv[3])
+    else:
+        cpu(sys.argv[2])
