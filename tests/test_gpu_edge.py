@@ -175,3 +175,21 @@ def test_batched_grasp_entry_points_edge_cases(ctx):
     # truncation: a small cap still reports the full count through offsets (the wrapper retries with the right size)
     small = eng.contacts_batch(rid, js, 0.2, input_mode=B2C_INPUT_JOINTS, cap_contacts=3)
     assert np.array_equal(small["contacts"], call["contacts"])
+
+
+def test_two_devices_in_one_process():
+    """one process may hold a context per GPU (dynamic shared-memory opt-in is per device): same results on both"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sc = load_pack("barrett_mug")
+    obj = object_body(sc)
+    st = _states(sc, 512, 11)
+    out = []
+    for dev in (1, 0):                       # the second device first: nothing may depend on device 0 having run
+        eng = Engine(dev)
+        sb = SceneBinding(eng, sc)
+        out.append(eng.eval_batch(sb.robot_ids[0], sb.body_ids[obj], st, input_mode=B2C_INPUT_AA_EIGEN, ref_tran=sc.body_tran[obj],
+                                  live=True, link_dist=True))
+    assert (out[0]["legal"] == out[1]["legal"]).all() and np.array_equal(out[0]["energy"], out[1]["energy"])
+    assert np.array_equal(out[0]["link_dist"], out[1]["link_dist"])
