@@ -34,8 +34,12 @@ m = (ll == 1) & (live["legal"] == 1)
 e = rel(live["energy"][m], el[m])
 ld = live["link_dist"].astype(np.float64); both = (dl >= 0) & (ld >= 0)
 d = rel(ld[both], dl[both])
-print("LIVE n=%d legal mismatches=%d  energy rel err: max %.3g  >1e-4: %d | link dist sign mismatches=%d rel err max %.3g >1e-4: %d" % (
-    nlive, int((ll != live["legal"]).sum()), e.max(), int((e > 1e-4).sum()), int(((dl < 0) != (ld < 0)).sum()), d.max(), int((d > 1e-4).sum())))
+dabs = np.abs(ld[both] - dl[both])
+# relative error is meaningless for micro-distances (a 1e-9 relative difference of the link pose is 4e-7 mm): report those apart
+big = dl[both] >= 0.05
+print("LIVE n=%d legal mismatches=%d  energy rel err: max %.3g  >1e-4: %d | link dist sign mismatches=%d rel err max %.3g >1e-4: %d | d >= 0.05 mm: rel err max %.3g; d < 0.05 mm: abs err max %.3g mm" % (
+    nlive, int((ll != live["legal"]).sum()), e.max(), int((e > 1e-4).sum()), int(((dl < 0) != (ld < 0)).sum()), d.max(), int((d > 1e-4).sum()),
+    d[big].max(), dabs[~big].max() if (~big).any() else 0.0))
 # single-pose pointToBodyDistance: closest points (not only distances) against the reference
 w = osc.w
 w.set_transform(osc.ids[obj], *sc.body_tran[obj]); eng.set_body_transform(sb.body_ids[obj], *sc.body_tran[obj])
