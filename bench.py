@@ -269,19 +269,20 @@ def main():
     # exchange costs one tiny kernel + one 720-byte-per-rank NCCL all-gather
     # The exchange of step s overlaps the kernels of step s + 1: the all-gather is asynchronous, and a rank
     # only waits for it -- on the stream, not on the host -- after it has enqueued its next step.  Rows and results are
-    # double-buffered; the merged list trails the chains by one step, which the planner's best-list rule does not mind.
-    rows = [torch.empty((BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) for _ in range(2)] if anneal else None
-    gathered = [torch.empty((world * BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
-    pending = [None]
+    # kept in a ring of three; the merged list trails the chains by up to two steps, which the planner's best-list rule does not mind.
+    DEPTH = 3                                   # exchanges in flight: a rank never waits for a gather younger than two steps
+    rows = [torch.empty((BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) for _ in range(DEPTH)] if anneal else None
+    gathered = [torch.empty((world * BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) for _ in range(DEPTH)] if world > 1 else None
+    pending = []
 
     def step_device(i):
         if anneal:
             an.step(1)
             if world > 1:
-                if pending[0] is not None:
-                    pending[0].wait()
-                an.best_rows(BEST_LIST_SIZE, rows[i & 1].data_ptr())
-                pending[0] = dist.all_gather_into_tensor(gathered[i & 1], rows[i & 1], async_op=True)
+                if len(pending) >= DEPTH - 1:
+                    pending.pop(0).wait()
+                an.best_rows(BEST_LIST_SIZE, rows[i % DEPTH].data_ptr())
+                pending.append(dist.all_gather_into_tensor(gathered[i % DEPTH], rows[i % DEPTH], async_op=True))
         else:
             st = dev_batches[i]
             eng.eval_batch_device(rid, oid, st.data_ptr(), npose, nvar, legal_d.data_ptr(), energy_d.data_ptr(),
@@ -291,9 +292,8 @@ def main():
                 exchange_best(local_best_rows(st, e, BEST_LIST_SIZE))
 
     def sync_all():
-        if pending[0] is not None:
-            pending[0].wait()
-            pending[0] = None
+        while pending:
+            pending.pop(0).wait()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
