@@ -35,7 +35,7 @@ __device__ __forceinline__ const double *c_body_xf(const Xf *fk, const Xf *stati
                     : reinterpret_cast<const double *>(static_xf + (body - nrb));
 }
 
-__device__ void emit_contact(const ContactParams &p, int w, int ta, int tb, int feature, d3 p1, d3 p2,
+__device__ __noinline__ void emit_contact(const ContactParams &p, int w, int ta, int tb, int feature, d3 p1, d3 p2,
                              const double *XA, const double *XB) {
   int slot = atomicAdd(p.out_count, 1);
   atomicAdd(&p.per_query[w], 1);
@@ -57,32 +57,44 @@ __device__ void emit_contact(const ContactParams &p, int w, int ta, int tb, int 
   p.out[slot] = r;
 }
 
+__device__ __noinline__ d3 closest_pt_triangle_dd(d3 a, d3 b, d3 c, d3 q, int *region) {
+  return closest_pt_triangle<double>(a, b, c, q, region);
+}
+__device__ __noinline__ double seg_seg_dist2_dd(d3 p1, d3 q1, d3 p2, d3 q2, d3 &c1, d3 &c2, double *s, double *t) {
+  return seg_seg_dist2<double>(p1, q1, p2, q2, c1, c2, s, t);
+}
+
 // all contacts of one triangle pair (a* already in B's frame)
 __device__ __noinline__ void tri_pair_contacts(const ContactParams &p, int w, int ta, int tb, d3 a1, d3 a2, d3 a3,
                                                d3 b1, d3 b2, d3 b3, double thr2, const double *XA, const double *XB) {
   if (tri_tri_intersect_exact(a1, a2, a3, b1, b2, b3)) return;      // "Collision found when looking for contacts"
   d3 av[3] = {a1, a2, a3}, bv[3] = {b1, b2, b3};
+  // The loops stay rolled and the helpers out of line: unrolled, this routine was several tens of KB of fp64 code and the
+  // kernel spent its time waiting for instructions (ncu r01g: 4.5 warps stalled on "no instruction" per issue, 188 registers).
   // vertices of triangle 2 against face 1
+#pragma unroll 1
   for (int k = 0; k < 3; k++) {
-    d3 q = closest_pt_triangle<double>(a1, a2, a3, bv[k]);
+    d3 q = closest_pt_triangle_dd(a1, a2, a3, bv[k], nullptr);
     d3 d = bv[k] - q;
     if (dot(d, d) < thr2) emit_contact(p, w, ta, tb, k, q, bv[k], XA, XB);
   }
   // vertices of triangle 1 against face 2, unless the foot is a vertex of triangle 2 (already reported)
+#pragma unroll 1
   for (int k = 0; k < 3; k++) {
     int region = 6;
-    d3 q = closest_pt_triangle<double>(b1, b2, b3, av[k], &region);
+    d3 q = closest_pt_triangle_dd(b1, b2, b3, av[k], &region);
     d3 d = q - av[k];
     if (dot(d, d) < thr2 && region > 2) emit_contact(p, w, ta, tb, 3 + k, av[k], q, XA, XB);
   }
   // nine edge-edge pairs, unless a foot is an endpoint
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) {
-      d3 c1, c2;
-      double s, t;
-      double dd = seg_seg_dist2<double>(av[i], av[(i + 1) % 3], bv[j], bv[(j + 1) % 3], c1, c2, &s, &t);
-      if (dd < thr2 && s != 0.0 && s != 1.0 && t != 0.0 && t != 1.0) emit_contact(p, w, ta, tb, 6 + 3 * i + j, c1, c2, XA, XB);
-    }
+#pragma unroll 1
+  for (int ij = 0; ij < 9; ij++) {
+    const int i = ij / 3, j = ij - 3 * i;
+    d3 c1, c2;
+    double s, t;
+    double dd = seg_seg_dist2_dd(av[i], av[(i + 1) % 3], bv[j], bv[(j + 1) % 3], c1, c2, &s, &t);
+    if (dd < thr2 && s != 0.0 && s != 1.0 && t != 0.0 && t != 1.0) emit_contact(p, w, ta, tb, 6 + ij, c1, c2, XA, XB);
+  }
 }
 
 constexpr int CSTACK_CAP = 448, CSTACK_PHYS = 512, CLEAF_CAP = 96;
@@ -104,7 +116,10 @@ __device__ __forceinline__ void c_make_pair_xf(const double *XA, const double *X
   o.pad[0] = o.pad[1] = 0.f;
 }
 
-__global__ void __launch_bounds__(256) contact_kernel(ContactParams p) {
+#ifndef CONTACT_MIN_BLOCKS
+#define CONTACT_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, CONTACT_MIN_BLOCKS) contact_kernel(ContactParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
