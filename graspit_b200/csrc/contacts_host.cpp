@@ -341,23 +341,30 @@ static inline double d2(const double a[3], const double b[3]) {
 }
 
 void remove_contact_duplicates(std::vector<b2c_contact> &c, double thr) {
+  // The reference erases from its list while it scans (collisionInterface.cpp:254-287); the same scan over "alive" flags
+  // visits the same elements in the same order and compacts once at the end (erasing 104-byte records from the middle of a
+  // vector was the bulk of the batched post-processing time).
   const double t2 = thr * thr;
-  size_t i = 0;
-  while (i < c.size()) {
-    bool remove_me = false;
-    size_t j = i + 1;
-    while (j < c.size()) {
-      if (d2(c[j].b1_pos, c[i].b1_pos) > t2 || d2(c[j].b2_pos, c[i].b2_pos) > t2) {
-        j++;
-      } else if (c[i].distSq < c[j].distSq) {
-        c.erase(c.begin() + j);
+  const size_t n = c.size();
+  if (n < 2) return;
+  std::vector<unsigned char> alive(n, 1);
+  for (size_t i = 0; i < n; i++) {
+    if (!alive[i]) continue;
+    for (size_t j = i + 1; j < n; j++) {
+      if (!alive[j]) continue;
+      if (d2(c[j].b1_pos, c[i].b1_pos) > t2 || d2(c[j].b2_pos, c[i].b2_pos) > t2) continue;
+      if (c[i].distSq < c[j].distSq) {
+        alive[j] = 0;
       } else {
-        remove_me = true;
+        alive[i] = 0;
         break;
       }
     }
-    if (remove_me) c.erase(c.begin() + i); else i++;
   }
+  size_t k = 0;
+  for (size_t i = 0; i < n; i++)
+    if (alive[i]) { if (k != i) c[k] = c[i]; k++; }
+  c.resize(k);
 }
 
 namespace {
