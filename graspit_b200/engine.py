@@ -417,7 +417,7 @@ class Engine:
         self._ck(self.L.b2c_region(self.h, body, _dp(p), _dp(nn), float(radius), _dp(out), cap, C.byref(n)))
         return out[: 3 * min(n.value, cap)].reshape(-1, 3).copy()
 
-    def body_region_batch(self, bodies, points, normals, radii, cap=None):
+    def body_region_batch(self, bodies, points, normals, radii, cap=None, flat=False):
         """bodyRegion for n (body, point, normal, radius) queries in one call: list of (k_i, 3) arrays"""
         b = np.ascontiguousarray(bodies, dtype=np.int32)
         n = b.size
@@ -429,7 +429,9 @@ class Engine:
         tot = C.c_int(0)
         self._ck(self.L.b2c_region_batch(self.h, n, _ip(b), _dp(p), _dp(nn), _dp(r), _dp(out), cap, _ip(off), C.byref(tot)))
         if tot.value > cap:
-            return self.body_region_batch(bodies, points, normals, radii, cap=tot.value)
+            return self.body_region_batch(bodies, points, normals, radii, cap=tot.value, flat=flat)
+        if flat:
+            return out[:tot.value].copy(), off          # ragged form of the C ABI: points back to back + offsets[n + 1]
         return [out[off[i]:off[i + 1]].copy() for i in range(n)]
 
     def get_bounding_volumes(self, body: int, depth: int, cap=1 << 16):

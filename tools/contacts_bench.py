@@ -58,10 +58,10 @@ def main():
     qr = np.repeat(rad, 2)
     eng.body_region_batch(qb[:512], qp[:512], qn[:512], qr[:512])
     t0 = time.perf_counter()
-    ngh = eng.body_region_batch(qb, qp, qn, qr)
+    flat, off = eng.body_region_batch(qb, qp, qn, qr, flat=True)
     t_r = time.perf_counter() - t0
     region = {"queries": int(len(qb)), "seconds": t_r, "queries_per_s": float(len(qb) / t_r) if len(qb) else 0.0,
-              "mean_points": float(np.mean([len(g) for g in ngh])) if ngh else 0.0}
+              "mean_points": float(np.diff(off).mean()) if len(qb) else 0.0}
     # CPU baseline (reported, not a target): the reference's own allContacts on the same link poses, one thread, 64 poses
     cpu = None
     try:
