@@ -80,7 +80,7 @@ struct Plan {
   int object_e = -1;
   int ndof_total = 0;
   int nvc = 0;
-  int nhand = 0;                    // bodies of the root robot only (LIVE contacts / link_dist)
+  int nhand = 0;                    // finger links + palm of the root robot (LIVE contacts / link_dist); the mount is not one
   // device copies
   DevBuf<FkRobot> d_robots; DevBuf<FkChain> d_chains; DevBuf<FkJoint> d_joints; DevBuf<FkLink> d_links;
   DevBuf<double> d_eg; DevBuf<int> d_body_mesh; DevBuf<int2> d_pairs; DevBuf<VcDev> d_vcs; DevBuf<int2> d_queries;
@@ -94,6 +94,9 @@ struct Plan {
 };
 
 } // namespace
+
+struct AnnealHost;      // anneal_api.inc
+namespace { struct AgScratch; }       // autograsp_api.inc
 
 struct b2c_ctx {
   int device = 0;
@@ -119,12 +122,20 @@ struct b2c_ctx {
   DevBuf<unsigned char> d_cubtemp;
   std::vector<int> h_coffsets;
   size_t h_contacts_cap = 0;
+  Xf *h_fk = nullptr;               // pinned copy of the link transforms (reference-order replay of contact candidates)
+  size_t h_fk_cap = 0;
   int stage_nodes = 128;           // object-tree nodes staged in shared memory by the energy kernel
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int last_counters[4] = {0, 0, 0, 0};
   int eval_warps_per_block = 8;
   int eval_blocks_per_sm = 0;      // 0 = derive from shared memory
   cudaStream_t own_stream = nullptr;
+  // per-context annealers and autograsp scratch (contexts are independent: one per GPU, possibly one host thread each)
+  std::vector<AnnealHost *> anneals;
+  AgScratch *autograsp = nullptr;
+  // sticky overflow word on the device: bit 0 = legality recheck queue, bit 1 = distance recheck queue, bit 2 = broad-phase
+  // work-item list.  Kernels that drop an entry set it (and answer conservatively: "collides"); synchronising calls report it.
+  DevBuf<int> d_sticky;
   bool profiling = false;
   cudaEvent_t ev[16] = {};
   bool ev_used[8] = {};
@@ -213,6 +224,10 @@ void active_pairs(const b2c_ctx *c, const std::set<int> *interest, std::vector<s
 }
 
 int ensure_scratch(b2c_ctx *ctx) {
+  if (!ctx->d_sticky.p) {
+    CU(ctx->d_sticky.reserve(4));
+    CU(cudaMemsetAsync(ctx->d_sticky.p, 0, 4 * sizeof(int), ctx->stream));
+  }
   CU(ctx->d_counters.reserve(16));
   CU(ctx->d_stats.reserve(8));
   CU(ctx->d_ambig.reserve(1 << 20));
@@ -262,7 +277,7 @@ int run_static_collisions(b2c_ctx *ctx, const std::vector<std::pair<int, int>> &
   ep.body_mesh = d_bm; ep.meshes = ctx->d_meshes.p; ep.pairs = d_pairs; ep.vcs = nullptr;
   ep.legal = ctx->d_legal.p; ep.energy = nullptr; ep.pair_mask = ctx->d_mask.p;
   ep.pose_counter = ctx->d_counters.p; ep.ambig = ctx->d_ambig.p; ep.ambig_count = ctx->d_counters.p + 1;
-  ep.ambig_cap = (int)ctx->d_ambig.cap; ep.stats = nullptr;
+  ep.ambig_cap = (int)ctx->d_ambig.cap; ep.stats = nullptr; ep.overflow = ctx->d_sticky.p;
   CU(ctx->d_items.reserve((size_t)np + 32));
   ep.items = ctx->d_items.p; ep.item_count = ctx->d_counters.p + 8; ep.item_cap = (int)ctx->d_items.cap;
   CU(launch_collide(ep, 1, ctx->stream)); ctx->launches += 2;
@@ -302,7 +317,7 @@ int run_static_distance(b2c_ctx *ctx, int a, int b, double *dist, double pa[3], 
   dp.npose = 1; dp.nrb = 0; dp.nb = 2; dp.nq = 1; dp.queries = d_q; dp.fk = nullptr;
   dp.static_xf = reinterpret_cast<const Xf *>(ctx->d_misc.p); dp.body_mesh = d_bm; dp.meshes = ctx->d_meshes.p;
   dp.legal = nullptr; dp.dist = ctx->d_dist.p; dp.pts = ctx->d_pts.p; dp.work_counter = ctx->d_counters.p;
-  dp.ambig = ctx->d_ambig.p; dp.ambig_count = ctx->d_counters.p + 1; dp.ambig_cap = (int)ctx->d_ambig.cap; dp.stats = nullptr;
+  dp.ambig = ctx->d_ambig.p; dp.ambig_count = ctx->d_counters.p + 1; dp.ambig_cap = (int)ctx->d_ambig.cap; dp.stats = nullptr; dp.overflow = ctx->d_sticky.p;
   dp.near_dir = ctx->d_near_dir.p; dp.near_ent = ctx->d_near_ent.p; dp.near_count = ctx->d_counters.p + 5;
   dp.near_cap_dir = (int)ctx->d_near_dir.cap; dp.near_cap_ent = (int)ctx->d_near_ent.cap;
   CU(launch_dist(dp, 1, ctx->stream)); ctx->launches += 2;
@@ -395,10 +410,11 @@ int b2c_last_kernel_ms(b2c_ctx *ctx, float ms[8]) {
 void b2c_destroy(b2c_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  cudaDeviceSynchronize();         // ctx->stream may be a caller-owned stream that no longer exists (b2c_set_stream)
   anneal_release_all(ctx);
   autograsp_release_all(ctx);
   if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
+  if (ctx->h_fk) cudaFreeHost(ctx->h_fk);
   invalidate_plans(ctx);
   for (auto &m : ctx->meshes) {
     if (m.d_nodes) cudaFree(m.d_nodes);
@@ -408,6 +424,7 @@ void b2c_destroy(b2c_ctx *ctx) {
   ctx->d_meshes.release(); ctx->d_states.release(); ctx->d_fk.release(); ctx->d_fkqt.release(); ctx->d_legal.release();
   ctx->d_energy.release(); ctx->d_mask.release(); ctx->d_ambig.release(); ctx->d_counters.release(); ctx->d_stats.release();
   ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release(); ctx->d_legal_list.release(); ctx->d_items.release(); ctx->d_contacts.release(); ctx->d_flags.release(); ctx->d_terms.release(); ctx->d_near_dir.release(); ctx->d_near_ent.release();
+  ctx->d_contacts2.release(); ctx->d_coffsets.release(); ctx->d_cubtemp.release(); ctx->d_sticky.release();
   for (int i = 0; i < 16; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -626,6 +643,27 @@ int b2c_robot_define(b2c_ctx *ctx, const b2c_robot_desc *d, int *robot_id) {
   if (!ctx || !d || !robot_id) return fail(ctx, B2C_EINVAL, "robot_define: bad arguments");
   if (!body_ok(ctx, d->base_body)) return fail(ctx, B2C_EINVAL, "robot_define: unknown base body %d", d->base_body);
   if (d->ndof > FK_MAX_DOF_HOST) return fail(ctx, B2C_ECAPACITY, "robot_define: more than %d DOFs", FK_MAX_DOF_HOST);
+  if (d->ndof < 0 || d->nchains < 0 || d->njoints < 0 || d->nlinks < 0 || (d->ndof > 0 && (!d->dof_min || !d->dof_max)) ||
+      (d->nchains > 0 && !d->chains) || (d->njoints > 0 && !d->joints) || (d->nlinks > 0 && (!d->link_body || !d->link_last_joint)))
+    return fail(ctx, B2C_EINVAL, "robot_define: inconsistent counts / null tables");
+  if (d->mount_body >= 0 && !body_ok(ctx, d->mount_body)) return fail(ctx, B2C_EINVAL, "robot_define: unknown mount body %d", d->mount_body);
+  for (int c = 0; c < d->nchains; c++) {
+    const b2c_chain_desc &cd = d->chains[c];
+    if (cd.first_joint < 0 || cd.njoints < 0 || cd.first_joint + cd.njoints > d->njoints || cd.first_link < 0 || cd.nlinks < 1 ||
+        cd.first_link + cd.nlinks > d->nlinks)
+      return fail(ctx, B2C_EINVAL, "robot_define: chain %d: joint / link range outside the tables", c);
+    for (int l = 0; l < cd.nlinks; l++) {
+      const int lj = d->link_last_joint[cd.first_link + l];
+      if (lj < 0 || lj >= cd.njoints) return fail(ctx, B2C_EINVAL, "robot_define: chain %d link %d: last joint %d outside the chain", c, l, lj);
+    }
+  }
+  for (int j = 0; j < d->njoints; j++)
+    if (d->joints[j].dof < 0 || d->joints[j].dof >= d->ndof) return fail(ctx, B2C_EINVAL, "robot_define: joint %d: DOF %d outside [0, %d)", j, d->joints[j].dof, d->ndof);
+  if (d->parent_robot >= 0) {
+    if (d->parent_robot >= (int)ctx->robots.size()) return fail(ctx, B2C_EINVAL, "robot_define: parent robot %d not defined yet", d->parent_robot);
+    if (d->parent_chain < 0 || d->parent_chain >= ctx->robots[d->parent_robot].d.nchains)
+      return fail(ctx, B2C_EINVAL, "robot_define: parent chain %d outside the parent robot's %d chains", d->parent_chain, ctx->robots[d->parent_robot].d.nchains);
+  }
   RobotHost r;
   r.d = *d;
   r.dof_min.assign(d->dof_min, d->dof_min + d->ndof);
@@ -674,11 +712,20 @@ int build_plan(b2c_ctx *ctx, int robot, int object, Plan **out) {
   Plan *P = new Plan();
   P->robot = robot; P->object = object;
   collect_robots(ctx, robot, P->robots);
+  if ((int)P->robots.size() > FK_MAX_ROBOTS) { delete P; return fail(ctx, B2C_ECAPACITY, "more than %d robots in one kinematic tree", FK_MAX_ROBOTS); }
+  for (int rr : P->robots) {
+    std::vector<int> own;
+    robot_own_bodies(ctx->robots[rr], own);
+    for (int b : own)
+      if (!body_ok(ctx, b)) { delete P; return fail(ctx, B2C_EINVAL, "robot %d refers to body %d, which was removed", rr, b); }
+  }
   std::map<int, int> slot_of;
   for (size_t i = 0; i < P->robots.size(); i++) {
     std::vector<int> own;
     robot_own_bodies(ctx->robots[P->robots[i]], own);
-    if (i == 0) P->nhand = (int)own.size();
+    // LIVE contacts and link distances cover the finger links and the palm of the hand only -- not the mount piece
+    // (World::findVirtualContacts, reference world.cpp:1619-1639); they are the first nlinks + 1 slots
+    if (i == 0) P->nhand = (int)ctx->robots[P->robots[i]].link_body.size() + 1;
     for (int b : own) { slot_of[b] = (int)P->slots.size(); P->slots.push_back(b); }
   }
   // FK program
@@ -761,16 +808,18 @@ int build_plan(b2c_ctx *ctx, int robot, int object, Plan **out) {
   }
   P->object_e = object >= 0 ? eb(object) : -1;
   // virtual contacts of the root robot (Grasp::collectVirtualContacts order is irrelevant to the mean)
+  // (for an arm with a hand attached the contacts are the hand's: every robot of the tree contributes its own)
   std::vector<VcDev> vcs;
-  for (auto &v : ctx->robots[robot].vcs) {
-    VcDev d;
-    memset(&d, 0, sizeof d);
-    auto f = eidx.find(v.body);
-    if (f == eidx.end()) continue;
-    d.body = f->second;
-    for (int k = 0; k < 3; k++) { d.loc[k] = v.loc[k]; d.normal[k] = v.normal[k]; }
-    vcs.push_back(d);
-  }
+  for (int rr : P->robots)
+    for (auto &v : ctx->robots[rr].vcs) {
+      VcDev d;
+      memset(&d, 0, sizeof d);
+      auto f = eidx.find(v.body);
+      if (f == eidx.end()) continue;
+      d.body = f->second;
+      for (int k = 0; k < 3; k++) { d.loc[k] = v.loc[k]; d.normal[k] = v.normal[k]; }
+      vcs.push_back(d);
+    }
   P->nvc = (int)vcs.size();
   std::vector<int> bm(P->ebodies.size());
   for (size_t i = 0; i < bm.size(); i++) bm[i] = ctx->bodies[P->ebodies[i]].mesh;
@@ -855,6 +904,8 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   if (a->stride < min_stride) return fail(ctx, B2C_EINVAL, "eval_batch: stride %d < %d", a->stride, min_stride);
   if (a->input_mode == B2C_INPUT_AA_EIGEN && root.d.neg <= 0) return fail(ctx, B2C_EINVAL, "eval_batch: robot has no eigengrasps");
   if ((live || want_dist) && a->object < 0) return fail(ctx, B2C_EINVAL, "eval_batch: LIVE / LINKDIST need an object");
+  if ((live || want_dist) && P->robots.size() > 1)
+    return fail(ctx, B2C_EINVAL, "eval_batch: LIVE / LINKDIST are defined over the hand's own links and palm; evaluate the hand robot, not the arm it is attached to");
   const int nrb = (int)P->slots.size(), nb = (int)P->ebodies.size(), np = (int)P->pairs.size();
   const int mw = std::max(1, (np + 63) / 64);
 
@@ -901,7 +952,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   ep.fk = ctx->d_fk.p; ep.static_xf = P->d_static.p; ep.body_mesh = P->d_body_mesh.p; ep.meshes = ctx->d_meshes.p;
   ep.pairs = P->d_pairs.p; ep.vcs = P->d_vcs.p; ep.legal = d_legal; ep.energy = d_energy; ep.pair_mask = d_mask;
   ep.pose_counter = ctx->d_counters.p; ep.ambig = ctx->d_ambig.p; ep.ambig_count = ctx->d_counters.p + 1;
-  ep.ambig_cap = (int)ctx->d_ambig.cap; ep.stats = ctx->d_stats.p;
+  ep.ambig_cap = (int)ctx->d_ambig.cap; ep.stats = ctx->d_stats.p; ep.overflow = ctx->d_sticky.p;
   const bool want_energy = a->object >= 0 && (live || P->nvc > 0);
   if (want_energy) {
     CU(ctx->d_legal_list.reserve(npose));
@@ -962,7 +1013,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
     dp.static_xf = P->d_static.p; dp.body_mesh = P->d_body_mesh.p; dp.meshes = ctx->d_meshes.p;
     dp.legal = want_dist ? nullptr : d_legal;       // LIVE alone only needs legal poses
     dp.dist = d_dist; dp.pts = ctx->d_pts.p; dp.work_counter = ctx->d_counters.p + 2;
-    dp.ambig = ctx->d_ambig.p; dp.ambig_count = ctx->d_counters.p + 3; dp.ambig_cap = (int)ctx->d_ambig.cap; dp.stats = ctx->d_stats.p;
+    dp.ambig = ctx->d_ambig.p; dp.ambig_count = ctx->d_counters.p + 3; dp.ambig_cap = (int)ctx->d_ambig.cap; dp.stats = ctx->d_stats.p; dp.overflow = ctx->d_sticky.p;
     // near-ties and tiny distances are settled in fp64 (dist_refine_kernel): the closest POINTS feed CONTACT_LIVE
     dp.near_dir = ctx->d_near_dir.p; dp.near_ent = ctx->d_near_ent.p; dp.near_count = ctx->d_counters.p + 5;
     dp.near_cap_dir = (int)ctx->d_near_dir.cap; dp.near_cap_ent = (int)ctx->d_near_ent.cap;
@@ -991,14 +1042,26 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   }
   CU(cudaMemcpyAsync(ctx->last_stats, ctx->d_stats.p, sizeof ctx->last_stats, cudaMemcpyDeviceToHost, ctx->stream));
   if (!dev) {
-    // the queue counters ride along with the results: one synchronisation, no second round trip
-    int *amb = ctx->last_counters;
-    CU(cudaMemcpyAsync(amb, ctx->d_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (amb[1] > (int)ctx->d_ambig.cap || amb[3] > (int)ctx->d_ambig.cap)
-      return fail(ctx, B2C_ECAPACITY, "eval_batch: recheck queue overflow (%d entries)", std::max(amb[1], amb[3]));
+    // host buffers: the call synchronises anyway, so a queue overflow is reported right here.  With device pointers the
+    // call stays asynchronous; the kernels have answered fail-safe ("collides") and set the sticky word, which the next
+    // synchronising call (b2c_check_overflow, b2c_anneal_read) turns into B2C_ECAPACITY.
+    return b2c_check_overflow(ctx);
   }
   return B2C_OK;
+}
+
+int b2c_check_overflow(b2c_ctx *ctx) {
+  if (!ctx) return B2C_EINVAL;
+  cudaSetDevice(ctx->device);
+  if (!ctx->d_sticky.p) { CU(cudaStreamSynchronize(ctx->stream)); return B2C_OK; }
+  int word = 0;
+  CU(cudaMemcpyAsync(&word, ctx->d_sticky.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (!word) return B2C_OK;
+  CU(cudaMemsetAsync(ctx->d_sticky.p, 0, sizeof(int), ctx->stream));
+  return fail(ctx, B2C_ECAPACITY, "queue overflow since the last check:%s%s%s -- the affected poses were reported as colliding; split the batch",
+              (word & OVF_COLLIDE_QUEUE) ? " legality recheck queue" : "", (word & OVF_DIST_QUEUE) ? " distance recheck queue" : "",
+              (word & OVF_ITEMS) ? " broad-phase work list" : "");
 }
 
 } // extern "C"

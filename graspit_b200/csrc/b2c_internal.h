@@ -102,7 +102,9 @@ struct EvalParams {
   int2 *items;
   int *item_count;
   int item_cap;
+  int *overflow;           // sticky device word (b2c_ctx::d_sticky): OVF_* bits set when a queue drops an entry
 };
+enum { OVF_COLLIDE_QUEUE = 1, OVF_DIST_QUEUE = 2, OVF_ITEMS = 4 };
 
 // LIVE contacts / generic point-energy input: per pose, per contact: world location + world normal
 struct LiveContact {
@@ -135,6 +137,7 @@ struct DistParams {
   int *near_count;         // [0] segments, [1] entries
   int near_cap_dir, near_cap_ent;
   unsigned long long *stats;
+  int *overflow;           // sticky device word, see EvalParams
 };
 
 enum { STAT_BOX = 0, STAT_TRI = 1, STAT_PBOX = 2, STAT_PTRI = 3, STAT_AMBIG = 4, STAT_DBOX = 5, STAT_DTRI = 6, STAT_HITFIX = 7 };

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(256) broad_kernel(EvalParams p) {
     if (ov) {
       int at = base + __popc(m & ((1u << lane) - 1u));
       if (at < p.item_cap) p.items[at] = make_int2(pose, pi);
+      else if (p.overflow) atomicOr(p.overflow, OVF_ITEMS);      // cannot happen while item_cap >= npose * npairs; reported if it does
     }
   }
   if (p.stats) {
@@ -188,6 +189,11 @@ __global__ void __launch_bounds__(256, NARROW_MIN_BLOCKS) narrow_kernel(EvalPara
         int4 mt = S.meta[slot];
         int at = atomicAdd(p.ambig_count, 1);
         if (at < p.ambig_cap) { Ambig a; a.pose = mt.x; a.pair = mt.y; a.tri_a = ta; a.tri_b = tb; p.ambig[at] = a; }
+        else {
+          // the fp64 recheck queue is full: fail safe (an undecided pair counts as a collision) and say so
+          res = TT_HIT;
+          if (p.overflow) atomicOr(p.overflow, OVF_COLLIDE_QUEUE);
+        }
       }
       if (res == TT_HIT) {
         int4 mt = S.meta[slot];

@@ -154,12 +154,16 @@ struct ObbNode {
   P3 center;
   P3 half;
   int child[2] = {-1, -1};
+  int tri = -1;               // leaf: its triangle
+  int leaf_lo = 0, leaf_hi = 0;   // leaves below this node, as a range of depth-first leaf positions
+  M3 Rq;                      // R after the round trip through the unit quaternion transf stores (BoundingBox::setTran)
 };
 
 } // namespace
 
 struct ObbTree {
   std::vector<ObbNode> nodes;
+  std::vector<int> tri_pos;   // triangle -> depth-first position of its leaf
 };
 
 namespace {
@@ -231,7 +235,7 @@ void fit_obb(const std::vector<TriD> &tris, const std::vector<int> &idx, ObbNode
 }
 
 void split_node(ObbTree &T, const std::vector<TriD> &tris, int node, std::vector<int> idx) {
-  if ((int)idx.size() <= 1) return;
+  if ((int)idx.size() <= 1) { T.nodes[node].tri = idx.empty() ? -1 : idx[0]; return; }
   ObbNode nd = T.nodes[node];
   P3 xA = nd.R.col(0), yA = nd.R.col(1), zA = nd.R.col(2);
   if (nd.half.y > nd.half.x + 1.0e-5) { std::swap(xA, yA); yA = -1.0 * yA; }
@@ -320,7 +324,185 @@ ObbTree *obb_tree_build(const float *tri9, int ntri) {
     n.center = {0, 0, 0};
     n.half = {kPad, kPad, kPad};
   }
+  // depth-first leaf positions (explicit stack: degenerate meshes give deep trees) and the rotation each box really
+  // carries: BoundingBox keeps a transf, i.e. the unit quaternion of R (bBox.h:38-59)
+  T->tri_pos.assign(std::max(ntri, 1), 0);
+  {
+    int next = 0;
+    std::vector<std::pair<int, int>> st;      // (node, state)
+    st.push_back({0, 0});
+    while (!st.empty()) {
+      auto &top = st.back();
+      ObbNode &n = T->nodes[top.first];
+      if (n.child[0] < 0) {
+        n.leaf_lo = next; n.leaf_hi = next + 1;
+        if (n.tri >= 0) T->tri_pos[n.tri] = next;
+        next++;
+        st.pop_back();
+      } else if (top.second == 0) {
+        n.leaf_lo = next; top.second = 1; st.push_back({n.child[0], 0});
+      } else if (top.second == 1) {
+        top.second = 2; st.push_back({n.child[1], 0});
+      } else {
+        n.leaf_hi = next; st.pop_back();
+      }
+    }
+  }
+  for (ObbNode &n : T->nodes) {
+    double q[4];
+    matrix_to_quat(n.R, q);
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    n.Rq.m[0][0] = 1 - (tyy + tzz); n.Rq.m[0][1] = txy - twz; n.Rq.m[0][2] = txz + twy;
+    n.Rq.m[1][0] = txy + twz; n.Rq.m[1][1] = 1 - (txx + tzz); n.Rq.m[1][2] = tyz - twx;
+    n.Rq.m[2][0] = txz - twy; n.Rq.m[2][1] = tyz + twx; n.Rq.m[2][2] = 1 - (txx + tyy);
+  }
   return T;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Reference visit order of contact candidates.
+//
+// ContactCallback appends contacts in the order its dual-tree recursion reaches the leaf pairs
+// (collisionAlgorithms.cpp:42-130), and removeContactDuplicates / compactContactSet depend on that order
+// (collisionInterface.cpp:74-287: the survivor of a 3 mm cluster, first-group-wins).  The engine finds the
+// candidate triangle pairs on the device in no particular order; this replays the reference's recursion over
+// the reference-style OBB trees, restricted to node pairs that are ancestors of a candidate:
+//   * the node that is split: the one that is not a leaf; of two branches the one with the larger box
+//     volume (product of half sizes), ties -> the second model's (collisionAlgorithms.cpp:60-79);
+//   * the child visited first: the one with the smaller bboxDistanceSq to the other node, ties -> child1
+//     (collisionAlgorithms.cpp:90-101; bboxDistanceSq, bbox_inl.h:269-413, returns -1 for overlapping boxes).
+// The box distance is only evaluated where BOTH children hold candidates (elsewhere the order is forced).
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+struct RelXf {            // model 2 -> model 1 (RecursionCallback::mTran2To1)
+  M3 R;
+  P3 t;
+};
+
+// bboxDistanceSq(bb1, bb2, tran2To1) (bbox_inl.h:269-413), same operation order per axis
+double obb_distance_sq(const ObbNode &n1, const ObbNode &n2, const RelXf &x) {
+  // BtoA = bb1.TranInv % tran2To1 % bb2.Tran
+  M3 R1t;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R1t.m[i][j] = n1.Rq.m[j][i];
+  const M3 Bm = matmul(matmul(R1t, x.R), n2.Rq);
+  const P3 c2 = x.R.mul(n2.center) + x.t;
+  const P3 Tv = R1t.mul(c2 - n1.center);
+  const double T[3] = {Tv.x, Tv.y, Tv.z};
+  const double a[3] = {n1.half.x, n1.half.y, n1.half.z}, b[3] = {n2.half.x, n2.half.y, n2.half.z};
+  double B[3][3], Bf[3][3];
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { B[i][k] = Bm.m[i][k]; Bf[i][k] = std::fabs(B[i][k]) + 1e-6; }
+  double ga[3], gb[3];
+  for (int i = 0; i < 3; i++) {
+    double d = std::fabs(T[i]) - (a[i] + b[0] * Bf[i][0] + b[1] * Bf[i][1] + b[2] * Bf[i][2]);
+    d = std::max(0.0, d);
+    ga[i] = d * d;
+  }
+  for (int j = 0; j < 3; j++) {
+    double s = T[0] * B[0][j] + T[1] * B[1][j] + T[2] * B[2][j];
+    double d = std::fabs(s) - (b[j] + a[0] * Bf[0][j] + a[1] * Bf[1][j] + a[2] * Bf[2][j]);
+    d = std::max(0.0, d);
+    gb[j] = d * d;
+  }
+  double maxD = std::max(ga[0] + ga[1] + ga[2], gb[0] + gb[1] + gb[2]);
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    const int alo = std::min(i1, i2), ahi = std::max(i1, i2);
+    for (int j = 0; j < 3; j++) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const int blo = std::min(j1, j2), bhi = std::max(j1, j2);
+      double s = T[i2] * B[i1][j] - T[i1] * B[i2][j];
+      // a[alo] pairs with the row of the OTHER index and vice versa, likewise for b (bbox_inl.h:341-409)
+      double d = std::fabs(s) - (a[alo] * Bf[ahi][j] + a[ahi] * Bf[alo][j] + b[blo] * Bf[i][bhi] + b[bhi] * Bf[i][blo]);
+      d = std::max(0.0, d);
+      d *= d;
+      maxD = std::max(maxD, std::max(ga[i] + d, gb[j] + d));
+    }
+  }
+  if (maxD == 0.0) return -1;
+  return maxD;
+}
+
+struct VisitCtx {
+  const ObbTree *A, *B;
+  RelXf x;
+  const int *ta, *tb;
+  std::vector<int> *out;
+  std::vector<int> scratch;
+};
+
+inline double box_volume(const ObbNode &n) { return n.half.x * n.half.y * n.half.z; }
+
+// idx[lo, hi): candidates below the node pair (n1, n2)
+void visit_pair(VisitCtx &c, int n1, int n2, int *idx, int lo, int hi) {
+  while (true) {
+    if (hi <= lo) return;
+    const ObbNode &N1 = c.A->nodes[n1], &N2 = c.B->nodes[n2];
+    const bool l1 = N1.child[0] < 0, l2 = N2.child[0] < 0;
+    if (l1 && l2) {
+      for (int i = lo; i < hi; i++) c.out->push_back(idx[i]);
+      return;
+    }
+    bool split1;             // true: recurse on model 1's node (nodeSwap == false)
+    if (l1) split1 = false;
+    else if (l2) split1 = true;
+    else split1 = box_volume(N1) > box_volume(N2);
+    const ObbNode &R = split1 ? N1 : N2;
+    const ObbTree *T = split1 ? c.A : c.B;
+    const int *tri = split1 ? c.ta : c.tb;
+    const ObbNode &C0 = T->nodes[R.child[0]];
+    // stable split of the candidates between the two children
+    if ((int)c.scratch.size() < hi - lo) c.scratch.resize(hi - lo);
+    int k0 = lo, k1 = 0;
+    for (int i = lo; i < hi; i++) {
+      const int pos = T->tri_pos[tri[idx[i]]];
+      if (pos >= C0.leaf_lo && pos < C0.leaf_hi) idx[k0++] = idx[i]; else c.scratch[k1++] = idx[i];
+    }
+    for (int i = 0; i < k1; i++) idx[k0 + i] = c.scratch[i];
+    const int mid = k0;
+    int first = 0;
+    if (mid > lo && mid < hi) {
+      double d0, d1;
+      if (split1) { d0 = obb_distance_sq(C0, N2, c.x); d1 = obb_distance_sq(T->nodes[R.child[1]], N2, c.x); }
+      else { d0 = obb_distance_sq(N1, C0, c.x); d1 = obb_distance_sq(N1, T->nodes[R.child[1]], c.x); }
+      if (d1 < d0) first = 1;
+    } else if (mid == lo) {
+      first = 1;            // everything sits under child2
+    }
+    // recurse on one side, loop on the other (keeps the native stack shallow on degenerate trees)
+    const int f_lo = first == 0 ? lo : mid, f_hi = first == 0 ? mid : hi;
+    const int s_lo = first == 0 ? mid : lo, s_hi = first == 0 ? hi : mid;
+    const int fc = R.child[first], sc = R.child[1 - first];
+    if (f_hi > f_lo && s_hi > s_lo) {
+      if (split1) visit_pair(c, fc, n2, idx, f_lo, f_hi); else visit_pair(c, n1, fc, idx, f_lo, f_hi);
+      if (split1) n1 = sc; else n2 = sc;
+      lo = s_lo; hi = s_hi;
+    } else if (f_hi > f_lo) {
+      if (split1) n1 = fc; else n2 = fc;
+      lo = f_lo; hi = f_hi;
+    } else {
+      if (split1) n1 = sc; else n2 = sc;
+      lo = s_lo; hi = s_hi;
+    }
+  }
+}
+
+} // namespace
+
+void obb_visit_order(const ObbTree *A, const ObbTree *B, const double R21[9], const double t21[3], const int *tri_a,
+                     const int *tri_b, int n, std::vector<int> &order) {
+  order.clear();
+  if (n <= 0) return;
+  order.reserve(n);
+  VisitCtx c;
+  c.A = A; c.B = B; c.ta = tri_a; c.tb = tri_b; c.out = &order;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c.x.R.m[i][j] = R21[3 * i + j];
+  c.x.t = {t21[0], t21[1], t21[2]};
+  std::vector<int> idx(n);
+  for (int i = 0; i < n; i++) idx[i] = i;
+  visit_pair(c, 0, 0, idx.data(), 0, n);
 }
 
 void obb_tree_free(ObbTree *t) { delete t; }

@@ -9,6 +9,7 @@
 namespace b2c {
 
 constexpr int FK_MAX_DOF_HOST = 32;
+constexpr int FK_MAX_ROBOTS = 4;     // robots in one kinematic tree (fk_kernel keeps their parents' last-link poses in registers)
 
 struct ObbBox {
   double t[3];
@@ -27,6 +28,13 @@ void obb_tree_free(ObbTree *t);
 // Node::getBVRecurse / Branch::getBVRecurse (collisionModel.cpp:437-456): boxes at `depth`, plus
 // leaves that end above it, in depth-first order.
 void obb_tree_level(const ObbTree *t, int depth, std::vector<ObbBox> &out);
+
+// Reference visit order of candidate triangle pairs (tri_a[i] of tree A, tri_b[i] of tree B): the order in which
+// ContactCallback's recursion reaches their leaf pairs (collisionAlgorithms.cpp:42-130).  R21 (row-major), t21:
+// transform from model 2's frame to model 1's (mTran2To1).  `order` = indices into the candidate arrays; candidates
+// of one leaf pair keep their input order.
+void obb_visit_order(const ObbTree *A, const ObbTree *B, const double R21[9], const double t21[3], const int *tri_a,
+                     const int *tri_b, int n, std::vector<int> &order);
 
 // CollisionInterface::removeContactDuplicates (collisionInterface.cpp:254-287)
 void remove_contact_duplicates(std::vector<b2c_contact> &contacts, double duplicate_threshold);

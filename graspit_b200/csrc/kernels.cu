@@ -74,11 +74,11 @@ __global__ void __launch_bounds__(128) fk_kernel(FkParams p) {
     }
   };
   // last-link transforms of chains that carry an attached robot are re-read from this small table
-  Qt lastlink[4];
+  Qt lastlink[4];                  // FK_MAX_ROBOTS (build_plan rejects larger trees)
   for (int ri = 0; ri < g.nrobots; ri++) {
     const FkRobot &r = g.robots[ri];
     Qt rb = base;
-    if (r.parent >= 0) rb = q_compose(lastlink[ri & 3], r.parent_offset);
+    if (r.parent >= 0) rb = q_compose(lastlink[ri], r.parent_offset);
     emit(r.base_slot, rb);
     emit(r.mount_slot, rb);
     for (int ci = 0; ci < r.nchains; ci++) {
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) fk_kernel(FkParams p) {
       // children attached to this chain's end: remember the last link pose for them
       for (int rj = ri + 1; rj < g.nrobots; rj++)
         if (g.robots[rj].parent == ri && g.robots[rj].parent_last_slot == g.links[c.first_link + c.nlinks - 1].out_slot)
-          lastlink[rj & 3] = total;
+          lastlink[rj] = total;
     }
   }
 }
@@ -617,6 +617,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
         if (res == TT_AMBIG) {
           int slot = atomicAdd(p.ambig_count, 1);
           if (slot < p.ambig_cap) { Ambig a; a.pose = pose; a.pair = qi; a.tri_a = ta; a.tri_b = tb; p.ambig[slot] = a; }
+          else { res = TT_HIT; if (p.overflow) atomicOr(p.overflow, OVF_DIST_QUEUE); }     // fail safe: undecided = interpenetrating
         }
         if (__any_sync(FULL, res == TT_HIT)) { hit = true; break; }
         // warp arg-min

@@ -32,6 +32,7 @@ EXPORTS = [
     "b2c_pair_is_active", "b2c_body_set_thread", "b2c_set_thread", "b2c_all_collisions", "b2c_body_distance", "b2c_point_distance", "b2c_contacts",
     "b2c_all_contacts", "b2c_region", "b2c_bounding_volumes", "b2c_robot_define", "b2c_eval_batch",
     "b2c_robot_bodies", "b2c_robot_pairs", "b2c_last_stats", "b2c_obb_hierarchy", "b2c_contacts_postprocess",
+    "b2c_contact_visit_order", "b2c_check_overflow",
     "b2c_anneal_create", "b2c_anneal_destroy", "b2c_anneal_step", "b2c_anneal_read", "b2c_anneal_device_ptrs",
     "b2c_anneal_propose", "b2c_anneal_write", "b2c_anneal_best_rows",
     "b2c_check_contact_normals", "b2c_contact_frames", "b2c_point_contact_wrenches",
@@ -190,6 +191,8 @@ def load_library():
     L.b2c_last_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     L.b2c_obb_hierarchy.argtypes = [C.POINTER(C.c_float), ci, ci, C.POINTER(Obb), ci, ip]
     L.b2c_contacts_postprocess.argtypes = [C.POINTER(Contact), ip, C.c_double, ci]
+    L.b2c_check_overflow.argtypes = [vp]
+    L.b2c_contact_visit_order.argtypes = [C.POINTER(C.c_float), ci, C.POINTER(C.c_float), ci, dp, dp, dp, dp, ip, ip, ci, ip]
     _lib = L
     return L
 
@@ -230,6 +233,25 @@ def obb_hierarchy(tris, depth: int, cap=1 << 16):
     for i in range(out.shape[0]):
         out[i, 0:3] = buf[i].t[:]; out[i, 3:7] = buf[i].q_wxyz[:]; out[i, 7:10] = buf[i].half[:]
     return out
+
+
+def contact_visit_order(tris_a, tris_b, tf_a, tf_b, ta, tb):
+    """Host-only: the order in which the reference's ContactCallback reaches the triangle pairs (ta[i], tb[i]) of two
+    models with world transforms tf_a / tf_b = (q wxyz, t) -> permutation of range(len(ta)) (b2c_contact_visit_order)."""
+    L = load_library()
+    A = np.ascontiguousarray(np.asarray(tris_a, dtype=np.float32).reshape(-1, 9))
+    B = np.ascontiguousarray(np.asarray(tris_b, dtype=np.float32).reshape(-1, 9))
+    ia = np.ascontiguousarray(ta, dtype=np.int32); ib = np.ascontiguousarray(tb, dtype=np.int32)
+    assert ia.shape == ib.shape
+    order = np.zeros(max(1, ia.size), dtype=np.int32)
+    qa = (C.c_double * 4)(*[float(v) for v in tf_a[0]]); pa = (C.c_double * 3)(*[float(v) for v in tf_a[1]])
+    qb = (C.c_double * 4)(*[float(v) for v in tf_b[0]]); pb = (C.c_double * 3)(*[float(v) for v in tf_b[1]])
+    fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int)
+    rc = L.b2c_contact_visit_order(A.ctypes.data_as(fp), A.shape[0], B.ctypes.data_as(fp), B.shape[0], qa, pa, qb, pb,
+                                   ia.ctypes.data_as(ip), ib.ctypes.data_as(ip), ia.size, order.ctypes.data_as(ip))
+    if rc != 0:
+        raise B2CError(f"b2c_contact_visit_order failed: {rc}")
+    return order[: ia.size].copy()
 
 
 def contacts_postprocess(contacts, duplicate_threshold=3.0, compact=True):
@@ -505,6 +527,10 @@ class Engine:
         out = np.zeros(2 * 65536, dtype=np.int32); n = C.c_int(0)
         self._ck(self.L.b2c_robot_pairs(self.h, robot, _ip(out), 65536, C.byref(n)))
         return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(n.value)]
+
+    def check_overflow(self):
+        """synchronise and raise if a device-pointer evaluation overflowed an internal queue since the last check"""
+        self._ck(self.L.b2c_check_overflow(self.h))
 
     def last_stats(self) -> dict:
         st = (C.c_ulonglong * 8)()
@@ -846,4 +872,4 @@ class SceneBinding:
                         off = o
             rid = engine.define_robot(r, self.body_ids, parent_id, off)
             self.robot_ids[ri] = rid
-            engine._nroot[rid] = len(r.body_list())
+            engine._nroot[rid] = sum(len(c.link_bodies) for c in r.chains) + 1      # finger links + palm (no mount)

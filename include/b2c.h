@@ -151,6 +151,18 @@ int b2c_bounding_volumes(b2c_ctx *ctx, int body, int depth, b2c_obb *out, int ca
 int b2c_obb_hierarchy(const float *tri9, int ntri, int depth, b2c_obb *out, int cap, int *nboxes);
 int b2c_contacts_postprocess(b2c_contact *contacts, int *n, double duplicate_threshold, int compact);
 
+/* Order in which the reference's ContactCallback reaches a set of triangle pairs (ta[i] of model 1, tb[i] of model 2):
+ * its dual-tree recursion over the two OBB hierarchies splits the node with the larger box volume and descends first
+ * into the child with the smaller bboxDistanceSq (reference src/Collision/Graspit/collisionAlgorithms.cpp:42-130,
+ * include/graspit/bbox_inl.h:269-413).  removeContactDuplicates and compactContactSet depend on this order
+ * (src/Collision/collisionInterface.cpp:74-287), so b2c_contacts / b2c_all_contacts / b2c_contacts_batch put the
+ * device's candidates into it before post-processing; this context-free entry point exposes the replay for tests.
+ * q*, t*: world transforms of the two models.  order[n] receives indices into (ta, tb); entries that share a triangle
+ * pair keep their input order. */
+int b2c_contact_visit_order(const float *tri9_a, int ntri_a, const float *tri9_b, int ntri_b, const double qa_wxyz[4],
+                            const double ta_xyz[3], const double qb_wxyz[4], const double tb_xyz[3], const int *ta,
+                            const int *tb, int n, int *order);
+
 /* Contact frames and point-contact friction cones, the last step of World::findAllContacts -> addContacts
  * (reference src/contactSetting.cpp:193-221).  Context-free host utilities (closed form, a few hundred flops per contact).
  * side = 1: the contact as seen from body 1 (b1_pos, b1_normal), side = 2: its mate on body 2.
@@ -292,7 +304,8 @@ typedef struct b2c_eval_args {
   uint8_t *legal;            /* [npose] 1 = no collision among pairs touching the robot */
   float *energy;             /* [npose] CONTACT_ENERGY; 0 when illegal */
   uint64_t *pair_mask;       /* [npose x mask_words] bit i = i-th active pair collides (B2C_EVAL_PAIRMASK) */
-  float *link_dist;          /* [npose x nbodies] (B2C_EVAL_LINKDIST), robot body order of b2c_robot_bodies */
+  float *link_dist;          /* [npose x (nlinks + 1)] (B2C_EVAL_LINKDIST): finger links chain-major, then the palm -- the
+                              * first nlinks + 1 entries of b2c_robot_bodies (the mount piece carries no contact) */
   double *body_tf;           /* optional [npose x nbodies x 7]: FK result (q wxyz, t), host or device */
 } b2c_eval_args;
 
@@ -301,6 +314,13 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *args);
 /* bodies moved by a robot (and robots attached to it) in the order used by link_dist / body_tf:
  * finger links chain-major, then the base, then the mount piece (World::findVirtualContacts order,
  * reference world.cpp:1623-1639), children appended after their parent. */
+/* Batched calls with B2C_EVAL_DEVICE_PTRS (and the annealer built on them) stay asynchronous, so they cannot return a
+ * queue overflow themselves.  The kernels answer fail-safe -- a triangle pair the fp32 filter could not decide and that
+ * no longer fits the fp64 recheck queue counts as a COLLISION -- and set a sticky word on the device; this call
+ * synchronises the context's stream, returns B2C_ECAPACITY (and clears the word) if any queue overflowed since the last
+ * check, B2C_OK otherwise.  Host-buffer b2c_eval_batch, b2c_anneal_read and b2c_autograsp_batch call it themselves. */
+int b2c_check_overflow(b2c_ctx *ctx);
+
 int b2c_robot_bodies(b2c_ctx *ctx, int robot, int *bodies, int cap, int *nbodies);
 /* the active pairs (a,b) that a batched evaluation of `robot` tests, in pair_mask bit order */
 int b2c_robot_pairs(b2c_ctx *ctx, int robot, int *pairs, int cap, int *npairs);

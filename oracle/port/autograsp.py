@@ -100,8 +100,10 @@ class AutoGraspOracle:
         """KinematicChain::fwdKinematics from explicit joint values -> link poses into the reference world"""
         r = self.r
         b = (np.asarray(base[0], dtype=np.float64)[None], np.asarray(base[1], dtype=np.float64)[None])
+        self.last_tf = {r.base_body: (b[0][0].copy(), b[1][0].copy())}      # scene body -> (q wxyz, t) as pushed to the world
         self.w.set_transform(self.ids[r.base_body], b[0][0], b[1][0])
         if r.mount_body >= 0:
+            self.last_tf[r.mount_body] = self.last_tf[r.base_body]
             self.w.set_transform(self.ids[r.mount_body], b[0][0], b[1][0])
         for ci, c in enumerate(r.chains):
             total = T.compose(b, ofk._b(c.tran, 1))
@@ -110,6 +112,7 @@ class AutoGraspOracle:
                 total = T.compose(total, ofk.joint_transf(jd, np.array([jv[self.jnum[ci][j]]])))
                 if l < len(c.link_bodies) and c.last_joint[l] == j:
                     self.w.set_transform(self.ids[c.link_bodies[l]], total[0][0], total[1][0])
+                    self.last_tf[c.link_bodies[l]] = (total[0][0].copy(), total[1][0].copy())
                     l += 1
         self.jv = list(jv)
 

@@ -53,6 +53,8 @@ def lib():
         L.ref_point_distance.restype = C.c_double
         L.ref_contact.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_int]
         L.ref_contact_raw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
+        L.ref_contact_trace.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_int,
+                                        C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double), C.c_int]
         L.ref_all_contacts.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int),
                                        C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double), C.c_int]
         L.ref_region.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
@@ -165,6 +167,18 @@ class RefWorld:
         st = np.zeros(3, dtype=np.int32)
         n = self.L.ref_contact_raw(self.h, a, b, float(thr), _dp(out), cap, _ip(st))
         return out[: 13 * min(n, cap)].reshape(-1, 13).copy(), st
+
+    def contact_trace(self, a, b, thr, tris_a, tris_b, cap_visits=1 << 16, cap_contacts=1 << 17):
+        """leaf pairs in the reference's visit order that appended contacts: (n,3) rows (triangle of a, triangle of b,
+        contacts appended) + the raw report in the same order"""
+        ta = _d(np.asarray(tris_a, dtype=np.float64)); tb = _d(np.asarray(tris_b, dtype=np.float64))
+        vis = np.zeros(3 * cap_visits, dtype=np.int32)
+        out = np.zeros(13 * cap_contacts)
+        n = self.L.ref_contact_trace(self.h, a, b, float(thr), _dp(ta), ta.size // 9, _dp(tb), tb.size // 9,
+                                     _ip(vis), cap_visits, _dp(out), cap_contacts)
+        assert n <= cap_visits
+        vis = vis[: 3 * n].reshape(-1, 3).copy()
+        return vis, out[: 13 * int(vis[:, 2].sum())].reshape(-1, 13).copy()
 
     def all_contacts(self, thr, interest: Optional[Sequence[int]] = None, cap_pairs=1024, cap_contacts=65536):
         il = np.ascontiguousarray(np.asarray(interest if interest is not None else [], dtype=np.int32))

@@ -15,6 +15,7 @@
 //     src/world.cpp:1478-1508,1539-1549,1618-1651, src/contact/virtualContact.cpp:75-124),
 //     which is Qt-bound in the reference and therefore restated.
 #include <vector>
+#include <array>
 #include <map>
 #include <thread>
 #include <cstring>
@@ -56,6 +57,19 @@ struct StatClosest : public Collision::ClosestPtCallback {
 struct StatContact : public Collision::ContactCallback {
   StatContact(double thr, const CollisionModel *a, const CollisionModel *b) : ContactCallback(thr, a, b) {}
   void stats(int *s) const { s[0] = mNumQuickTests; s[1] = mNumLeafTests; s[2] = mNumTriangleTests; }
+};
+
+// Records which leaf pairs the reference's contact recursion reaches, in order, and how many contacts each appended
+// (ContactCallback::leafTest, collisionAlgorithms_inl.h:96-133): the ground truth for the product's visit-order replay.
+struct TraceContact : public Collision::ContactCallback {
+  struct Visit { const Collision::Leaf *l1, *l2; int added; };
+  std::vector<Visit> visits;
+  TraceContact(double thr, const CollisionModel *a, const CollisionModel *b) : ContactCallback(thr, a, b) {}
+  virtual void leafTest(const Collision::Leaf *l1, const Collision::Leaf *l2) {
+    const size_t before = getReport().size();
+    Collision::ContactCallback::leafTest(l1, l2);
+    visits.push_back(Visit{l1, l2, (int)(getReport().size() - before)});
+  }
 };
 
 struct RefWorld {
@@ -219,6 +233,41 @@ int ref_contact_raw(void *wv, int a, int b, double thr, double *out13, int cap, 
   for (int i = 0; i < (int)rep.size() && i < cap; i++) writeContact(rep[i], out13 + 13 * i);
   if (stats3) cc.stats(stats3);
   return (int)rep.size();
+}
+
+// Leaf pairs in the order the reference's ContactCallback visits them, restricted to those that appended contacts:
+// visits3 = (triangle of a, triangle of b, contacts appended) per visit, triangles identified by their position in the
+// lists the bodies were created from (tri9_a / tri9_b: the same arrays given to ref_add_body).  out13 (optional): the raw
+// report in the same order.  Returns the number of such visits.
+int ref_contact_trace(void *wv, int a, int b, double thr, const double *tri9_a, int ntri_a, const double *tri9_b, int ntri_b,
+                      int *visits3, int cap_visits, double *out13, int cap_contacts) {
+  RefWorld *w = (RefWorld *)wv;
+  if (!w->get(a) || !w->get(b)) return 0;
+  typedef std::array<double, 9> Key;
+  std::map<Key, int> ida, idb;
+  for (int i = ntri_a - 1; i >= 0; i--) { Key k; for (int j = 0; j < 9; j++) k[j] = tri9_a[9 * i + j]; ida[k] = i; }
+  for (int i = ntri_b - 1; i >= 0; i--) { Key k; for (int j = 0; j < 9; j++) k[j] = tri9_b[9 * i + j]; idb[k] = i; }
+  TraceContact cc(thr, w->gc.getModel(w->get(a)), w->gc.getModel(w->get(b)));
+  Collision::startRecursion(w->gc.getModel(w->get(a)), w->gc.getModel(w->get(b)), &cc);
+  auto key_of = [](const Collision::Leaf *l) {
+    const Triangle &t = l->getTriangles()->front();
+    Key k = {t.v1.x(), t.v1.y(), t.v1.z(), t.v2.x(), t.v2.y(), t.v2.z(), t.v3.x(), t.v3.y(), t.v3.z()};
+    return k;
+  };
+  int n = 0;
+  for (auto &v : cc.visits) {
+    if (v.added <= 0) continue;
+    if (n < cap_visits) {
+      auto fa = ida.find(key_of(v.l1)), fb = idb.find(key_of(v.l2));
+      visits3[3 * n] = fa == ida.end() ? -1 : fa->second;
+      visits3[3 * n + 1] = fb == idb.end() ? -1 : fb->second;
+      visits3[3 * n + 2] = v.added;
+    }
+    n++;
+  }
+  const ContactReport &rep = cc.getReport();
+  if (out13) for (int i = 0; i < (int)rep.size() && i < cap_contacts; i++) writeContact(rep[i], out13 + 13 * i);
+  return n;
 }
 
 // allContacts(): pair_ids gets (id1,id2) per reported pair, counts the contacts per pair,

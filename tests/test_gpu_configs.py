@@ -194,7 +194,8 @@ def test_config3_allcontacts_with_region(human):
             re = eng.body_region(sb.body_ids[obj], cpos, cnrm, 3.5)
             assert {tuple(r) for r in ro} == {tuple(r) for r in re}
     assert done >= 10 and npairs >= done and ncontacts >= done
-    assert exact >= 0.7 * npairs
+    print('config 3: identical contact sets in', exact, 'of', npairs, 'contacting pairs')
+    assert exact >= 0.99 * npairs
     assert ncones >= 5
     print('soft contacts checked:', nsoft)
 

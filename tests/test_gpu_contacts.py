@@ -45,7 +45,7 @@ def worlds():
 
 def test_contact_candidates_and_processed_sets(worlds):
     sc, eng, w, (mug_e, palm_e), (mug_o, palm_o) = worlds
-    exact = 0
+    exact = same_order = 0
     poses = _near_poses(w, mug_o, palm_o, 30)
     for q, t in poses:
         w.set_transform(palm_o, q, t); w.set_transform(mug_o, [1, 0, 0, 0], [0, 0, 0])
@@ -55,20 +55,33 @@ def test_contact_candidates_and_processed_sets(worlds):
         assert len(raw_o) > 0
         # candidate point pairs: equal as sets (the reference may hold endpoint duplicates, Appendix A.16)
         assert _rows(raw_e) == _rows(raw_o)
+        # ... and in the reference's own visit order (csrc/contacts_host.cpp obb_visit_order): compare the sequences of
+        # first occurrences (the reference's endpoint duplicates repeat a row, they never introduce one)
+        def firsts(a):
+            seen, out = set(), []
+            for r in a:
+                k = tuple(np.round(r[:6], 6))
+                if k not in seen:
+                    seen.add(k); out.append(k)
+            return out
+        same_order += firsts(raw_e) == firsts(raw_o)
         # every candidate obeys the reference's conventions
         for r in raw_e:
             assert np.linalg.norm(r[6:9]) == pytest.approx(1.0, abs=1e-9)
         full_o = w.contact(palm_o, mug_o, THR)
         full_e = eng.contact(palm_e, mug_e, THR)
         assert len(full_e) >= 1
-        # processed contact sets agree as clusters (the 3 mm duplicate removal is order dependent)
+        # processed contact sets: the 3 mm duplicate removal and the perimeter compaction are order dependent, the
+        # candidates arrive in the reference's order, so the sets are the reference's
         for r in full_o:
             assert min(np.linalg.norm(full_e[:, :3] - r[:3], axis=1)) <= 3.0
         for r in full_e:
             assert min(np.linalg.norm(full_o[:, :3] - r[:3], axis=1)) <= 3.0
         if len(full_e) == len(full_o) and _rows(full_e, 5) == _rows(full_o, 5):
             exact += 1
-    assert exact >= 0.8 * len(poses)
+    print("contact(): identical processed sets", exact, "of", len(poses), "; candidate sequences identical", same_order)
+    assert same_order >= 0.9 * len(poses)
+    assert exact >= 0.97 * len(poses)
 
 
 def test_no_contacts_when_far_or_interpenetrating(worlds):

@@ -90,6 +90,10 @@ def test_contacts_batch_matches_single_pose_path_and_reference(closed):
                     assert min(np.linalg.norm(mine[key][:, :3] - r[:3], axis=1)) < 6.0, (p, key)
         # (2) the reference backend at the same joint values: same contacting pairs, same clusters
         ag.set_joints((js[p, 0:4], js[p, 4:7]), js[p, 7:])
+        for k, b in enumerate(bodies):      # joint-level FK of the engine == the restated fwdKinematics feeding the reference
+            qo, to = ag.last_tf[inv_e[b]]
+            assert np.abs(tf[p, k, 4:] - to).max() < 1e-9, (p, k, tf[p, k, 4:] - to)
+            assert min(np.abs(tf[p, k, :4] - qo).max(), np.abs(tf[p, k, :4] + qo).max()) < 1e-12, (p, k)
         ref_pairs = {}
         for (a, b), cs in osc.w.all_contacts(THR, interest=interest_o):
             ref_pairs[tuple(sorted((inv_o[a], inv_o[b])))] = (inv_o[a] > inv_o[b], np.array(cs).reshape(-1, 13))

@@ -36,6 +36,24 @@ def gpu(n, out):
     print("wrote", out, len(js), "poses", len(res["contacts"]), "contacts")
 
 
+TOL = 1.0e-4     # mm: the two forward kinematics differ by ~2e-6 mm at the fingertips (fp32-rounded base quaternion, normalised
+                 # by each side in its own way); contact coordinates are compared to north_star's 1e-4
+
+
+def _same_set(a, b):
+    """same number of contacts and a one-to-one pairing with every coordinate of b1_pos / b2_pos within TOL"""
+    if len(a) != len(b):
+        return False
+    left = list(range(len(b)))
+    for r in a:
+        d = [np.abs(b[j][:6] - r[:6]).max() for j in left]
+        k = int(np.argmin(d))
+        if d[k] > TOL:
+            return False
+        left.pop(k)
+    return True
+
+
 def cpu(path):
     from oracle.port.autograsp import AutoGraspOracle
     from tests.common import OracleScene
@@ -49,15 +67,20 @@ def cpu(path):
     npose = len(js)
     same_pairs = groups = exact = cluster_ok = counts_equal = 0
     worst = 0.0
+    differing = []
     for p in range(npose):
         ag.set_joints((js[p, 0:4], js[p, 4:7]), js[p, 7:])
+        # GraspitCollision::allContacts runs ContactCallback(model1, model2) with the models in ADDRESS order
+        # (graspitCollision.cpp:229), and the contact set depends on which model comes first; the engine's pairs are in
+        # body-id order, so the reference is asked pair by pair in that order (GraspitCollision::contact, :407-433: the
+        # same callback, duplicate removal and compaction)
         refc = {}
-        for (a, b), cs in osc.w.all_contacts(THR, interest=hand):
-            ia, ib = inv[a], inv[b]
-            c = np.array(cs).reshape(-1, 13)
-            if ia > ib:
-                c = c[:, [3, 4, 5, 0, 1, 2, 9, 10, 11, 6, 7, 8, 12]]; ia, ib = ib, ia
-            refc[(ia, ib)] = c
+        for ia, ib in pairs:
+            c = osc.w.contact(osc.ids[int(ia)], osc.ids[int(ib)], THR)
+            if len(c):
+                if ia > ib:
+                    c = c[:, [3, 4, 5, 0, 1, 2, 9, 10, 11, 6, 7, 8, 12]]; ia, ib = ib, ia
+                refc[(int(ia), int(ib))] = c
         lo, hi = z["offsets"][p], z["offsets"][p + 1]
         mine = {}
         for c, q in zip(z["contacts"][lo:hi], z["pair"][lo:hi]):
@@ -71,15 +94,17 @@ def cpu(path):
             groups += 1
             a, b = mine[key], refc[key]
             counts_equal += len(a) == len(b)
-            if len(a) == len(b) and {tuple(np.round(r[:6], 5)) for r in a} == {tuple(np.round(r[:6], 5)) for r in b}:
+            if _same_set(a, b):
                 exact += 1
+            elif len(differing) < 40:
+                differing.append({"pose": int(p), "pair": [int(key[0]), int(key[1])], "engine": int(len(a)), "reference": int(len(b))})
             d = max(min(np.linalg.norm(a[:, :3] - r[:3], axis=1)) for r in b)
             worst = max(worst, float(d))
             cluster_ok += d < 6.0
     print(json.dumps({"what": "b2c_contacts_batch vs GraspitCollision::allContacts(0.2, hand) on hands closed by the batched autograsp (Barrett vs mug)",
                       "poses": int(npose), "poses_with_identical_contacting_pair_sets": int(same_pairs), "pair_groups": int(groups),
                       "groups_with_identical_contact_sets": int(exact), "groups_with_equal_contact_count": int(counts_equal),
-                      "groups_whose_contacts_fall_in_the_same_3mm_clusters": int(cluster_ok), "worst_nearest_contact_distance_mm": worst}))
+                      "groups_whose_contacts_fall_in_the_same_3mm_clusters": int(cluster_ok), "worst_nearest_contact_distance_mm": worst, "first_differing_groups": differing}))
 
 
 if __name__ == "__main__":
