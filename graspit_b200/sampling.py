@@ -1,7 +1,7 @@
 """Seeded synthetic pose batches of the benchmark configurations; numpy only, no geometry.
 
-Used by bench.py, the tools and the tests alike, so that the product side of a measurement never has to import
-anything from tests/ or oracle/."""
+Used by bench.py, the tools and the tests alike, so that the product side of a measurement depends on nothing
+outside this package."""
 from __future__ import annotations
 
 import numpy as np
