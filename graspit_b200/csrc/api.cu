@@ -35,6 +35,10 @@ struct MeshHost {
   int depth = 0;
   float extent = 0.f;
   ObbTree *obb = nullptr;         // lazily built reference-style hierarchy (getBoundingVolumes)
+  int *d_seed = nullptr;          // lazily built closest-point seed grid (meshes used as the energy object)
+  float g0[3] = {0, 0, 0}, ginv[3] = {0, 0, 0};
+  int gres[3] = {0, 0, 0};
+  float root_c[3] = {0, 0, 0}, root_h[3] = {0, 0, 0};
 };
 
 struct BodyHost {
@@ -125,6 +129,7 @@ struct b2c_ctx {
   Xf *h_fk = nullptr;               // pinned copy of the link transforms (reference-order replay of contact candidates)
   size_t h_fk_cap = 0;
   int stage_nodes = 128;           // object-tree nodes staged in shared memory by the energy kernel
+  int seed_res = 64;               // cells along the longest side of a closest-point seed grid (0 = no seeding)
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int last_counters[4] = {0, 0, 0, 0};
   int eval_warps_per_block = 8;
@@ -182,6 +187,8 @@ int sync_meshes(b2c_ctx *ctx) {
     md[i].nnodes = (int)m.nodes.size(); md[i].ntri = m.ntri;
     md[i].extent = m.extent; md[i].depth = m.depth;
     for (int k = 0; k < 3; k++) { md[i].q0[k] = m.quant.q0[k]; md[i].qs[k] = m.quant.qs[k]; }
+    md[i].seed = m.d_seed;
+    for (int k = 0; k < 3; k++) { md[i].g0[k] = m.g0[k]; md[i].ginv[k] = m.ginv[k]; md[i].gres[k] = m.gres[k]; }
   }
   CU(ctx->d_meshes.reserve(md.size() + 1));
   if (!md.empty()) CU(cudaMemcpyAsync(ctx->d_meshes.p, md.data(), md.size() * sizeof(MeshDev), cudaMemcpyHostToDevice, ctx->stream));
@@ -221,6 +228,32 @@ void active_pairs(const b2c_ctx *c, const std::set<int> *interest, std::vector<s
       out.push_back({a, b});
     }
   }
+}
+
+// Closest-point seed grid of the mesh an energy evaluation queries (built once per mesh, on the device): the mesh's
+// bounding box grown by a quarter of its longest side, cubic cells, seed_res cells along the longest side.
+int ensure_seed_grid(b2c_ctx *ctx, int mesh) {
+  MeshHost &m = ctx->meshes[mesh];
+  if (m.d_seed || ctx->seed_res <= 0 || m.ntri <= 0) return B2C_OK;
+  const float longest = 2.f * std::max(m.root_h[0], std::max(m.root_h[1], m.root_h[2]));
+  const float margin = 0.25f * longest;
+  const float cell = (longest + 2.f * margin) / (float)ctx->seed_res;
+  size_t cells = 1;
+  for (int k = 0; k < 3; k++) {
+    const float side = 2.f * m.root_h[k] + 2.f * margin;
+    m.gres[k] = std::max(1, (int)std::ceil(side / cell));
+    m.g0[k] = m.root_c[k] - 0.5f * (float)m.gres[k] * cell;
+    m.ginv[k] = 1.f / cell;
+    cells *= (size_t)m.gres[k];
+  }
+  CU(cudaMalloc(&m.d_seed, cells * sizeof(int)));
+  MeshDev md;
+  memset(&md, 0, sizeof md);
+  md.nodes = m.d_nodes; md.tris = m.d_tris; md.nnodes = (int)m.nodes.size(); md.ntri = m.ntri; md.extent = m.extent; md.depth = m.depth;
+  for (int k = 0; k < 3; k++) { md.q0[k] = m.quant.q0[k]; md.qs[k] = m.quant.qs[k]; md.g0[k] = m.g0[k]; md.ginv[k] = m.ginv[k]; md.gres[k] = m.gres[k]; }
+  CU(launch_seed_grid(md, m.d_seed, ctx->stream)); ctx->launches++;
+  ctx->meshes_dirty = true;
+  return B2C_OK;
 }
 
 int ensure_scratch(b2c_ctx *ctx) {
@@ -369,6 +402,7 @@ int b2c_create(int device, b2c_ctx **out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (const char *e = getenv("B2C_STAGE_NODES")) ctx->stage_nodes = std::max(0, atoi(e));
+  if (const char *e = getenv("B2C_SEED_RES")) ctx->seed_res = std::max(0, std::min(256, atoi(e)));
   if (const char *e = getenv("B2C_EVAL_WARPS")) ctx->eval_warps_per_block = std::max(1, std::min(32, atoi(e)));
   ctx->own_stream = ctx->stream;
   *out = ctx;
@@ -419,6 +453,7 @@ void b2c_destroy(b2c_ctx *ctx) {
   for (auto &m : ctx->meshes) {
     if (m.d_nodes) cudaFree(m.d_nodes);
     if (m.d_tris) cudaFree(m.d_tris);
+    if (m.d_seed) cudaFree(m.d_seed);
     if (m.obb) obb_tree_free(m.obb);
   }
   ctx->d_meshes.release(); ctx->d_states.release(); ctx->d_fk.release(); ctx->d_fkqt.release(); ctx->d_legal.release();
@@ -447,6 +482,7 @@ int b2c_mesh_create(b2c_ctx *ctx, const float *tri9, int ntri, int *mesh_id) {
   Node r;
   build_bvh(m.tri9.data(), ntri, m.nodes, &m.quant, &m.depth, &r);
   m.extent = ntri > 0 ? std::fabs(r.cx) + std::fabs(r.cy) + std::fabs(r.cz) + r.hx + r.hy + r.hz : 0.f;
+  m.root_c[0] = r.cx; m.root_c[1] = r.cy; m.root_c[2] = r.cz; m.root_h[0] = r.hx; m.root_h[1] = r.hy; m.root_h[2] = r.hz;
   std::vector<Tri> tris(std::max(ntri, 1));
   // an empty mesh is one far-away degenerate triangle (its leaf box sits at the same place): every query answers
   // "no collision, nothing near" without special cases in the kernels
@@ -472,6 +508,7 @@ int b2c_mesh_destroy(b2c_ctx *ctx, int mesh_id) {
   cudaStreamSynchronize(ctx->stream);
   MeshHost &m = ctx->meshes[mesh_id];
   cudaFree(m.d_nodes); cudaFree(m.d_tris);
+  if (m.d_seed) cudaFree(m.d_seed);
   if (m.obb) obb_tree_free(m.obb);
   m = MeshHost();
   ctx->meshes_dirty = true;
@@ -611,7 +648,7 @@ int b2c_point_distance(b2c_ctx *ctx, int body, const double point[3], double *di
   const MeshHost &m = ctx->meshes[ctx->bodies[body].mesh];
   pp.mesh.nodes = m.d_nodes; pp.mesh.tris = m.d_tris; pp.mesh.nnodes = (int)m.nodes.size(); pp.mesh.ntri = m.ntri;
   for (int k = 0; k < 3; k++) { pp.mesh.q0[k] = m.quant.q0[k]; pp.mesh.qs[k] = m.quant.qs[k]; }
-  pp.mesh.extent = m.extent; pp.mesh.depth = m.depth;
+  pp.mesh.extent = m.extent; pp.mesh.depth = m.depth; pp.mesh.seed = nullptr;
   pp.out = d_o;
   CU(launch_point(pp, ctx->stream)); ctx->launches++;
   double o[7];
@@ -705,6 +742,19 @@ void robot_own_bodies(const RobotHost &r, std::vector<int> &out) {
   if (r.d.mount_body >= 0) out.push_back(r.d.mount_body);
 }
 
+// floats (doubles for JOINTS) one pose occupies at least, per input mode
+int input_min_stride(int mode, int ndof_total, int njoints_total, int ndof_root, int neg) {
+  switch (mode) {
+    case B2C_INPUT_RAW: return 7 + ndof_total;
+    case B2C_INPUT_AA_EIGEN: return 6 + neg;
+    case B2C_INPUT_JOINTS: return 7 + njoints_total;
+    case B2C_INPUT_ELLIPSOID_EIGEN: return 4 + neg;
+    case B2C_INPUT_APPROACH_EIGEN: return 3 + neg;
+    default: return 7 + ndof_root;      // B2C_INPUT_COMPLETE_DOF
+  }
+}
+bool input_needs_eigen(int mode) { return mode == B2C_INPUT_AA_EIGEN || mode == B2C_INPUT_ELLIPSOID_EIGEN || mode == B2C_INPUT_APPROACH_EIGEN; }
+
 int build_plan(b2c_ctx *ctx, int robot, int object, Plan **out) {
   auto key = std::make_pair(robot, object);
   auto it = ctx->plans.find(key);
@@ -749,7 +799,8 @@ int build_plan(b2c_ctx *ctx, int robot, int object, Plan **out) {
     }
     R.dof_ofs = dof_ofs; R.ndof = r.d.ndof;
     R.first_chain = (int)fc.size(); R.nchains = r.d.nchains;
-    R.approach_inv = q_inverse(make_qt(r.d.approach_q, r.d.approach_t));
+    R.approach = make_qt(r.d.approach_q, r.d.approach_t);
+    R.approach_inv = q_inverse(R.approach);
     R.neg = r.d.neg;
     R.eg_ofs = (int)eg.size();
     if (r.d.neg > 0) {
@@ -883,7 +934,9 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   if (a->npose < 0 || !a->states) return fail(ctx, B2C_EINVAL, "eval_batch: bad pose batch");
   if (a->npose == 0) return B2C_OK;
   cudaSetDevice(ctx->device);
-  int rc = sync_meshes(ctx); if (rc) return rc;
+  int rc = B2C_OK;
+  if (a->object >= 0) { rc = ensure_seed_grid(ctx, ctx->bodies[a->object].mesh); if (rc) return rc; }
+  rc = sync_meshes(ctx); if (rc) return rc;
   rc = ensure_scratch(ctx); if (rc) return rc;
   Plan *P;
   rc = build_plan(ctx, a->robot, a->object, &P); if (rc) return rc;
@@ -899,10 +952,10 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   const bool joints_in = a->input_mode == B2C_INPUT_JOINTS;
   int njoints_total = 0;
   for (int r : P->robots) njoints_total += ctx->robots[r].d.njoints;
-  int min_stride = joints_in ? 7 + njoints_total : (a->input_mode == B2C_INPUT_RAW ? 7 + P->ndof_total : 6 + root.d.neg);
-  if (a->input_mode < 0 || a->input_mode > B2C_INPUT_JOINTS) return fail(ctx, B2C_EINVAL, "eval_batch: unknown input mode %d", a->input_mode);
+  if (a->input_mode < 0 || a->input_mode > B2C_INPUT_COMPLETE_DOF) return fail(ctx, B2C_EINVAL, "eval_batch: unknown input mode %d", a->input_mode);
+  const int min_stride = input_min_stride(a->input_mode, P->ndof_total, njoints_total, root.d.ndof, root.d.neg);
   if (a->stride < min_stride) return fail(ctx, B2C_EINVAL, "eval_batch: stride %d < %d", a->stride, min_stride);
-  if (a->input_mode == B2C_INPUT_AA_EIGEN && root.d.neg <= 0) return fail(ctx, B2C_EINVAL, "eval_batch: robot has no eigengrasps");
+  if (input_needs_eigen(a->input_mode) && root.d.neg <= 0) return fail(ctx, B2C_EINVAL, "eval_batch: robot has no eigengrasps");
   if ((live || want_dist) && a->object < 0) return fail(ctx, B2C_EINVAL, "eval_batch: LIVE / LINKDIST need an object");
   if ((live || want_dist) && P->robots.size() > 1)
     return fail(ctx, B2C_EINVAL, "eval_batch: LIVE / LINKDIST are defined over the hand's own links and palm; evaluate the hand robot, not the arm it is attached to");
@@ -939,6 +992,13 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   fp.prog = P->prog; fp.npose = npose; fp.input_mode = a->input_mode; fp.stride = a->stride; fp.states = d_states;
   fp.jstates = joints_in ? reinterpret_cast<const double *>(d_states) : nullptr;
   fp.ref = make_qt(a->ref_q, a->ref_t);
+  {
+    // PositionStateEllipsoid's parameters (searchStateImpl.cpp:212-215); all zero = the reference's defaults
+    const bool unset = a->position_params[0] == 0.0 && a->position_params[1] == 0.0 && a->position_params[2] == 0.0;
+    fp.pos_params[0] = unset ? 80.0 : a->position_params[0];
+    fp.pos_params[1] = unset ? 80.0 : a->position_params[1];
+    fp.pos_params[2] = unset ? 160.0 : a->position_params[2];
+  }
   fp.out = ctx->d_fk.p;
   fp.out_qt = want_tf ? (dev ? a->body_tf : ctx->d_fkqt.p) : nullptr;
   PROF_BEGIN(0); CU(launch_fk(fp, ctx->stream)); ctx->launches++; PROF_END(0);

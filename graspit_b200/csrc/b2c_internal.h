@@ -20,6 +20,11 @@ struct MeshDev {
   float extent;      // |root centre|_1 + |root half|_1 : coordinate scale of the mesh
   int depth;
   float q0[3], qs[3]; // quantisation grid of the stored boxes (bvh.h)
+  // closest-point seed grid (optional, built lazily for meshes used as the energy object): cell -> the triangle
+  // closest to the cell's centre.  A query starts from the exact distance to that triangle instead of +inf.
+  const int *seed;
+  float g0[3], ginv[3];
+  int gres[3];
 };
 
 // ---- forward-kinematics program ----------------------------------------
@@ -46,6 +51,7 @@ struct FkRobot {
   int dof_ofs, ndof;
   int first_chain, nchains;
   Qt approach_inv;
+  Qt approach;           // Robot::getApproachTran (SPACE_APPROACH needs it un-inverted too)
   int neg;
   int eg_ofs;            // offset into eg arrays: eg[neg*ndof], origin[ndof], norm[ndof], min[ndof], max[ndof]
 };
@@ -146,7 +152,8 @@ enum { STAT_BOX = 0, STAT_TRI = 1, STAT_PBOX = 2, STAT_PTRI = 3, STAT_AMBIG = 4,
 struct FkParams {
   FkProgram prog;
   int npose;
-  int input_mode;          // B2C_INPUT_RAW = 0, B2C_INPUT_AA_EIGEN = 1
+  int input_mode;          // B2C_INPUT_* (include/b2c.h)
+  double pos_params[3];    // SPACE_ELLIPSOID: a, b, c
   int stride;
   const float *states;
   const double *jstates;   // input_mode 2: per pose base (q wxyz, t) + one value per joint (program joint order), fp64
@@ -277,7 +284,10 @@ cudaError_t launch_anneal_propose(const AnnealParams &p, cudaStream_t s);
 cudaError_t launch_anneal_accept(const AnnealParams &p, cudaStream_t s);
 
 constexpr int DSTACK_CAP = 448, DSTACK_PHYS = 512, DLEAF_CAP = 96;
-constexpr int DNEAR_CAP = 64, DCONF_CAP = 64;
+#ifndef DNEAR_CAP_N
+#define DNEAR_CAP_N 64
+#endif
+constexpr int DNEAR_CAP = DNEAR_CAP_N, DCONF_CAP = 64;
 constexpr int DIST_WARP_SMEM = DSTACK_PHYS * 8 + DLEAF_CAP * 8 + 3 * 96 + 96 + DNEAR_CAP * 8 + DCONF_CAP * 8 + DNEAR_CAP * 8 + 32;
 
 // narrow phase of the legality test: per-warp shared memory = 32 fp64 relative transforms, 32 pair transforms,
@@ -308,6 +318,7 @@ cudaError_t launch_recheck(const RecheckParams &p, cudaStream_t s);
 cudaError_t launch_point(const PointParams &p, cudaStream_t s);
 cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s);
 cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s);
+cudaError_t launch_seed_grid(const MeshDev &m, int *seed, cudaStream_t s);
 size_t energy_block_smem_bytes(int stage_nodes);
 
 } // namespace b2c

@@ -30,6 +30,12 @@ template <typename T> __host__ __device__ __forceinline__ V3<T> cross(V3<T> a, V
 }
 template <typename T> __host__ __device__ __forceinline__ T min3(T a, T b, T c) { return fmin(a, fmin(b, c)); }
 template <typename T> __host__ __device__ __forceinline__ T max3(T a, T b, T c) { return fmax(a, fmax(b, c)); }
+// Eigen's normalized(): divides by the norm, leaves a zero vector alone
+__host__ __device__ __forceinline__ d3 d_normalized(d3 a) {
+  const double n2 = a.x * a.x + a.y * a.y + a.z * a.z;
+  if (n2 > 0.0) { const double n = sqrt(n2); return mk<double>(a.x / n, a.y / n, a.z / n); }
+  return a;
+}
 __host__ __device__ __forceinline__ f3 tof(d3 a) { return mk<float>((float)a.x, (float)a.y, (float)a.z); }
 __host__ __device__ __forceinline__ d3 tod(f3 a) { return mk<double>((double)a.x, (double)a.y, (double)a.z); }
 
@@ -95,6 +101,34 @@ __host__ __device__ __forceinline__ Qt q_inverse(const Qt &a) {
   d3 t = q_rot(r, mk<double>(a.tx, a.ty, a.tz));
   q_normalize(r);
   r.tx = -t.x; r.ty = -t.y; r.tz = -t.z;
+  return r;
+}
+// rotation matrix (row-major) -> unit quaternion: Eigen's trace-branch algorithm, what transf::set(mat3, vec3) stores
+// (include/graspit/transform.h:52-57); translation left at zero
+__host__ __device__ __forceinline__ Qt q_from_matrix(const double *m) {
+  double c[4];   // x y z w
+  double t = m[0] + m[4] + m[8];
+  if (t > 0.0) {
+    t = sqrt(t + 1.0);
+    c[3] = 0.5 * t;
+    t = 0.5 / t;
+    c[0] = (m[7] - m[5]) * t; c[1] = (m[2] - m[6]) * t; c[2] = (m[3] - m[1]) * t;
+  } else {
+    int i = 0;
+    if (m[4] > m[0]) i = 1;
+    if (m[8] > m[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(m[4 * i] - m[4 * j] - m[4 * k] + 1.0);
+    c[i] = 0.5 * t;
+    t = 0.5 / t;
+    c[3] = (m[3 * k + j] - m[3 * j + k]) * t;
+    c[j] = (m[3 * j + i] + m[3 * i + j]) * t;
+    c[k] = (m[3 * k + i] + m[3 * i + k]) * t;
+  }
+  Qt r;
+  r.w = c[3]; r.x = c[0]; r.y = c[1]; r.z = c[2];
+  r.tx = r.ty = r.tz = 0.0;
+  q_normalize(r);
   return r;
 }
 __host__ __device__ __forceinline__ Qt q_identity() { Qt r; r.w = 1; r.x = r.y = r.z = 0; r.tx = r.ty = r.tz = 0; return r; }

@@ -43,25 +43,69 @@ __global__ void __launch_bounds__(128) fk_kernel(FkParams p) {
     q_normalize(base);
     for (int d = 0; d < g.ndof_total && d < FK_MAX_DOF; d++) dof[d] = (double)s[7 + d];
   } else {
+    // search-state input (HandObjectState::execute, searchState.cpp:515-527): hand transform = mRefTran % coreTran(position
+    // variables), posture from the remaining variables.  coreTran per position type: searchStateImpl.cpp:125-135 (COMPLETE),
+    // :156-168 (AXIS_ANGLE), :218-252 (ELLIPSOID), :266-274 (APPROACH)
     const FkRobot &r0 = g.robots[0];
-    double tx = s[0], ty = s[1], tz = s[2], th = s[3], ph = s[4], al = s[5];
-    double sth, cth, sph, cph;
-    sincos(th, &sth, &cth);
-    sincos(ph, &sph, &cph);
-    Qt tr = q_identity(); tr.tx = tx; tr.ty = ty; tr.tz = tz;
-    Qt core = q_compose(tr, q_axis_angle(al, sth * cph, sth * sph, cth));
-    core = q_compose(core, r0.approach_inv);
-    base = q_compose(p.ref, core);
-    const double *eg = g.egdata + r0.eg_ofs;
-    const double *origin = eg + r0.neg * r0.ndof, *norm = origin + r0.ndof, *mn = norm + r0.ndof, *mx = mn + r0.ndof;
-    for (int d = 0; d < r0.ndof && d < FK_MAX_DOF; d++) {
-      double x = 0.0;
-      for (int e = 0; e < r0.neg; e++) x += eg[e * r0.ndof + d] * (double)s[6 + e];
-      double v = x * norm[d] + origin[d];
-      v = v > mx[d] ? mx[d] : (v < mn[d] ? mn[d] : v);
-      dof[d] = v;
+    Qt core;
+    int npos;
+    if (p.input_mode == 1) {
+      double tx = s[0], ty = s[1], tz = s[2], th = s[3], ph = s[4], al = s[5];
+      double sth, cth, sph, cph;
+      sincos(th, &sth, &cth);
+      sincos(ph, &sph, &cph);
+      Qt tr = q_identity(); tr.tx = tx; tr.ty = ty; tr.tz = tz;
+      core = q_compose(tr, q_axis_angle(al, sth * cph, sth * sph, cth));
+      core = q_compose(core, r0.approach_inv);
+      npos = 6;
+    } else if (p.input_mode == 3) {
+      const double a = p.pos_params[0], b = p.pos_params[1], c = p.pos_params[2];
+      double sb, cb, sg, cg;
+      sincos((double)s[0], &sb, &cb);
+      sincos((double)s[1], &sg, &cg);
+      const double tau = s[2], dist = s[3];
+      d3 pt = mk<double>(a * cb * cg, b * cb * sg, c * sb);
+      d3 n1 = d_normalized(mk<double>(-a * sb * cg, -b * sb * sg, c * cb));
+      d3 n2 = d_normalized(mk<double>(-a * cb * sg, b * cb * cg, 0.0));
+      d3 normal = cross(n1, n2);                       // NOT unit length unless a == b; the reference uses it as it is
+      d3 ydir = cross(normal, mk<double>(1.0, 0.0, 0.0));
+      d3 xdir = cross(ydir, normal);
+      d3 cx = d_normalized(xdir), cy = d_normalized(ydir), cz = d_normalized(normal);
+      const double m[9] = {cx.x, cy.x, cz.x, cx.y, cy.y, cz.y, cx.z, cy.z, cz.z};      // columns = x, y, normal
+      Qt hand = q_from_matrix(m);
+      hand.tx = pt.x - dist * normal.x; hand.ty = pt.y - dist * normal.y; hand.tz = pt.z - dist * normal.z;
+      Qt zrot = q_identity();                          // Eigen::AngleAxisd(tau, z) -> Quaternion: no small-angle snap here
+      sincos(0.5 * tau, &zrot.z, &zrot.w);
+      core = q_compose(q_compose(hand, zrot), r0.approach_inv);
+      npos = 4;
+    } else if (p.input_mode == 4) {
+      Qt hand = q_identity(); hand.tz = s[0];
+      hand = q_compose(q_compose(q_axis_angle((double)s[2], 0.0, 1.0, 0.0), q_axis_angle((double)s[1], 1.0, 0.0, 0.0)), hand);
+      core = q_compose(q_compose(r0.approach, hand), r0.approach_inv);
+      npos = 3;
+    } else {
+      core.w = s[3]; core.x = s[4]; core.y = s[5]; core.z = s[6];
+      core.tx = s[0]; core.ty = s[1]; core.tz = s[2];
+      q_normalize(core);
+      npos = 7;
     }
-    for (int d = r0.ndof; d < g.ndof_total && d < FK_MAX_DOF; d++) dof[d] = 0.0;
+    base = q_compose(p.ref, core);
+    if (p.input_mode == 5) {
+      // POSE_DOF (PostureStateDOF::getHandDOF, searchStateImpl.cpp:44-49): the variables are the DOF values
+      for (int d = 0; d < g.ndof_total && d < FK_MAX_DOF; d++) dof[d] = d < r0.ndof ? (double)s[npos + d] : 0.0;
+    } else {
+      // POSE_EIGEN (PostureStateEigen::getHandDOF, :83-95; EigenGraspInterface::toDOFSpace, eigenGrasp.cpp:638-646; checkSetDOFVals)
+      const double *eg = g.egdata + r0.eg_ofs;
+      const double *origin = eg + r0.neg * r0.ndof, *norm = origin + r0.ndof, *mn = norm + r0.ndof, *mx = mn + r0.ndof;
+      for (int d = 0; d < r0.ndof && d < FK_MAX_DOF; d++) {
+        double x = 0.0;
+        for (int e = 0; e < r0.neg; e++) x += eg[e * r0.ndof + d] * (double)s[npos + e];
+        double v = x * norm[d] + origin[d];
+        v = v > mx[d] ? mx[d] : (v < mn[d] ? mn[d] : v);
+        dof[d] = v;
+      }
+      for (int d = r0.ndof; d < g.ndof_total && d < FK_MAX_DOF; d++) dof[d] = 0.0;
+    }
   }
   Xf *out = p.out + (size_t)pose * g.nslots;
   double *oq = p.out_qt ? p.out_qt + (size_t)pose * g.nslots * 7 : nullptr;
@@ -830,6 +874,17 @@ __device__ __forceinline__ unsigned long long eq_entry(float lb, int q, int idx)
   return ((unsigned long long)__float_as_uint(lb) << 32) | ((unsigned long long)(unsigned)q << 24) | (unsigned long long)(unsigned)idx;
 }
 
+// exact test of one triangle for one query -> key = squared distance | 8-bit hash of the closest point (1/64 mm grid) |
+// triangle.  Triangles that share the closest vertex return bit-identical points: same hash, one solution, nothing to arbitrate.
+__device__ __forceinline__ unsigned long long point_tri_key(const MeshDev &mo, d3 q, int tri) {
+  d3 a = tri_vertex(mo.tris, tri, 0) - q, b = tri_vertex(mo.tris, tri, 1) - q, cc = tri_vertex(mo.tris, tri, 2) - q;
+  f3 v = closest_pt_triangle<float>(tof(a), tof(b), tof(cc), mk<float>(0.f, 0.f, 0.f));
+  float d2 = dot(v, v);
+  const unsigned h = ((unsigned)__float2int_rd(v.x * 64.f) * 73856093u ^ (unsigned)__float2int_rd(v.y * 64.f) * 19349663u ^
+                      (unsigned)__float2int_rd(v.z * 64.f) * 83492791u) & 0xffu;
+  return ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)h << 24) | (unsigned)tri;
+}
+
 // One warp = 32 closest-point queries (contacts of consecutive legal poses) traversed TOGETHER through one
 // shared work stack: every lane pops one (query, child-pair, lower bound) entry, loads the 64-byte pair of
 // sibling boxes, and pushes the children that can still beat the query's best distance (far first, near on
@@ -897,6 +952,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
     bool valid = qid < nquery;
     int pose = -1, c = 0;
     f3 cnl = mk<float>(0.f, 0.f, 0.f);
+    unsigned long long seedkey = EQ_NONE;
     if (valid) {
       int li = qid / nc;
       c = qid - li * nc;
@@ -924,8 +980,18 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
       cnl = tof(xf_rot_t(XO, cnw));
       qd[3 * lane] = q.x; qd[3 * lane + 1] = q.y; qd[3 * lane + 2] = q.z;
       qf[lane] = make_float4((float)q.x, (float)q.y, (float)q.z, 0.f);
+      if (mo.seed) {
+        // start from a real candidate: the triangle closest to the centre of the query's grid cell (clamped into the
+        // grid for far queries), tested exactly like any leaf.  Its key is what the traversal would have produced had it
+        // met that triangle first, so the result is unchanged; what changes is how much of the tree survives the bound.
+        const int ix = min(max(__float2int_rd(((float)q.x - mo.g0[0]) * mo.ginv[0]), 0), mo.gres[0] - 1);
+        const int iy = min(max(__float2int_rd(((float)q.y - mo.g0[1]) * mo.ginv[1]), 0), mo.gres[1] - 1);
+        const int iz = min(max(__float2int_rd(((float)q.z - mo.g0[2]) * mo.ginv[2]), 0), mo.gres[2] - 1);
+        const int tri = __ldg(&mo.seed[(iz * mo.gres[1] + iy) * mo.gres[0] + ix]);
+        if (tri >= 0) { seedkey = point_tri_key(mo, q, tri); ntr++; }
+      }
     }
-    bestkey[lane] = EQ_NONE;
+    bestkey[lane] = seedkey;
     secondkey[lane] = EQ_NONE;
     int sp = 0, lq = 0;
     {
@@ -949,15 +1015,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
           float best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
           if (lb <= best * NEAR_BAND + 1.0e-12f) {
             ntr++;
-            d3 q = mk<double>(qd[3 * qi], qd[3 * qi + 1], qd[3 * qi + 2]);
-            d3 a = tri_vertex(mo.tris, tri, 0) - q, b = tri_vertex(mo.tris, tri, 1) - q, cc = tri_vertex(mo.tris, tri, 2) - q;
-            f3 v = closest_pt_triangle<float>(tof(a), tof(b), tof(cc), mk<float>(0.f, 0.f, 0.f));
-            float d2 = dot(v, v);
-            // key = squared distance | 8-bit hash of the closest point (1/64 mm grid) | triangle.  Triangles that share the
-            // closest vertex return bit-identical points: same hash, one solution, nothing to arbitrate.
-            const unsigned h = ((unsigned)__float2int_rd(v.x * 64.f) * 73856093u ^ (unsigned)__float2int_rd(v.y * 64.f) * 19349663u ^
-                                (unsigned)__float2int_rd(v.z * 64.f) * 83492791u) & 0xffu;
-            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)h << 24) | (unsigned)tri;
+            const unsigned long long key = point_tri_key(mo, mk<double>(qd[3 * qi], qd[3 * qi + 1], qd[3 * qi + 2]), tri);
             const unsigned long long old = atomicMin(&bestkey[qi], key);
             // runner-up with a DIFFERENT closest point: fp32 cannot order two candidates whose distances agree to 1e-4,
             // and the energy depends on which closest point wins (its direction enters the normal term); the final stage
@@ -1057,6 +1115,26 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
     v = nbx; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PBOX], v);
     v = ntr; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PTRI], v);
   }
+}
+
+// closest-point seed grid of a mesh: one thread per cell, the triangle closest to the cell's centre (per-lane traversal,
+// run once per mesh)
+__global__ void __launch_bounds__(128) seed_grid_kernel(MeshDev m, int *seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = m.gres[0] * m.gres[1] * m.gres[2];
+  if (i >= n) return;
+  const int ix = i % m.gres[0], iy = (i / m.gres[0]) % m.gres[1], iz = i / (m.gres[0] * m.gres[1]);
+  d3 q = mk<double>((double)m.g0[0] + ((double)ix + 0.5) / (double)m.ginv[0], (double)m.g0[1] + ((double)iy + 0.5) / (double)m.ginv[1],
+                    (double)m.g0[2] + ((double)iz + 0.5) / (double)m.ginv[2]);
+  f3 v; int bt = -1; unsigned nb = 0, nt = 0;
+  closest_point_query(m, nullptr, 0, q, v, bt, nb, nt);
+  seed[i] = bt;
+}
+cudaError_t launch_seed_grid(const MeshDev &m, int *seed, cudaStream_t s) {
+  const int n = m.gres[0] * m.gres[1] * m.gres[2];
+  if (n <= 0) return cudaSuccess;
+  seed_grid_kernel<<<(n + 127) / 128, 128, 0, s>>>(m, seed);
+  return cudaGetLastError();
 }
 
 // fixed-order sum of the per-contact terms of every legal pose (ContactEnergy::energy's division by the

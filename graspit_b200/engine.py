@@ -21,6 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2C_LIB") or os.path.join(_HERE, "libb2c.so")
 
 B2C_INPUT_RAW, B2C_INPUT_AA_EIGEN, B2C_INPUT_JOINTS = 0, 1, 2
+B2C_INPUT_ELLIPSOID_EIGEN, B2C_INPUT_APPROACH_EIGEN, B2C_INPUT_COMPLETE_DOF = 3, 4, 5
 B2C_EVAL_PRESET, B2C_EVAL_LIVE, B2C_EVAL_PAIRMASK, B2C_EVAL_LINKDIST, B2C_EVAL_DEVICE_PTRS = 0, 1, 2, 4, 8
 FAST_COLLISION, ALL_COLLISIONS = 0, 1
 
@@ -92,7 +93,7 @@ class EvalArgs(C.Structure):
                 ("states", C.c_void_p), ("stride", C.c_int),
                 ("ref_q", C.c_double * 4), ("ref_t", C.c_double * 3), ("flags", C.c_int),
                 ("legal", C.c_void_p), ("energy", C.c_void_p), ("pair_mask", C.c_void_p),
-                ("link_dist", C.c_void_p), ("body_tf", C.c_void_p)]
+                ("link_dist", C.c_void_p), ("body_tf", C.c_void_p), ("position_params", C.c_double * 3)]
 
 
 class ContactsBatchArgs(C.Structure):
@@ -540,7 +541,7 @@ class Engine:
         return {k: int(st[i]) for i, k in enumerate(names)}
 
     def eval_batch(self, robot: int, obj: int, states, input_mode=B2C_INPUT_RAW, ref_tran=None, live=False,
-                   pair_mask=False, link_dist=False, body_tf=False):
+                   pair_mask=False, link_dist=False, body_tf=False, position_params=None):
         """Host-buffer batched evaluation.  states: (npose, stride) float32.
         Returns dict(legal, energy[, pair_mask, link_dist, body_tf])."""
         st = np.ascontiguousarray(states, dtype=np.float64 if input_mode == B2C_INPUT_JOINTS else np.float32)
@@ -550,6 +551,8 @@ class Engine:
         a.states, a.stride = st.ctypes.data, stride
         rq, rt = ref_tran if ref_tran is not None else (np.array([1.0, 0, 0, 0]), np.zeros(3))
         a.ref_q[:] = list(rq); a.ref_t[:] = list(rt)
+        if position_params is not None:
+            a.position_params[:] = [float(v) for v in position_params]
         flags = (B2C_EVAL_LIVE if live else 0) | (B2C_EVAL_PAIRMASK if pair_mask else 0) | (B2C_EVAL_LINKDIST if link_dist else 0)
         a.flags = flags
         legal = np.zeros(npose, dtype=np.uint8); energy = np.zeros(npose, dtype=np.float32)

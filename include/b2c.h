@@ -278,10 +278,16 @@ enum {
                               then attached robots' DOFs in robot id order); stride = 7 + total dofs */
   B2C_INPUT_AA_EIGEN = 1,  /* per pose: Tx Ty Tz theta phi alpha + neg eigengrasp amplitudes
                               (SPACE_AXIS_ANGLE + POSE_EIGEN, searchStateImpl.cpp:83-95,156-168) */
-  B2C_INPUT_JOINTS = 2     /* per pose: base (qw qx qy qz tx ty tz) + one value per JOINT (chain-major, the order of
+  B2C_INPUT_JOINTS = 2,    /* per pose: base (qw qx qy qz tx ty tz) + one value per JOINT (chain-major, the order of
                               b2c_robot_desc.joints), as DOUBLES: `states` points to doubles, stride counts doubles.
                               For postures whose joints no longer equal ratio x DOF (break-away fingers after
                               b2c_autograsp_batch: feed joint_out) */
+  /* the other search-state layouts of HandObjectState (reference src/EGPlanner/searchStateImpl.cpp): position variables first,
+   * posture variables after them; hand transform = mRefTran % getCoreTran() (searchState.cpp:515-527) */
+  B2C_INPUT_ELLIPSOID_EIGEN = 3,  /* SPACE_ELLIPSOID (:218-252): beta gamma tau dist, then neg eigengrasp amplitudes;
+                                     ellipsoid parameters a b c in b2c_eval_args.position_params */
+  B2C_INPUT_APPROACH_EIGEN = 4,   /* SPACE_APPROACH (:266-274): dist, wrist 1, wrist 2, then neg eigengrasp amplitudes */
+  B2C_INPUT_COMPLETE_DOF = 5      /* SPACE_COMPLETE + POSE_DOF (:44-49,125-135): Tx Ty Tz Qw Qx Qy Qz, then the root robot's DOFs */
 };
 
 enum {
@@ -307,6 +313,7 @@ typedef struct b2c_eval_args {
   float *link_dist;          /* [npose x (nlinks + 1)] (B2C_EVAL_LINKDIST): finger links chain-major, then the palm -- the
                               * first nlinks + 1 entries of b2c_robot_bodies (the mount piece carries no contact) */
   double *body_tf;           /* optional [npose x nbodies x 7]: FK result (q wxyz, t), host or device */
+  double position_params[3]; /* B2C_INPUT_ELLIPSOID_EIGEN: a, b, c (all zero = the reference's 80, 80, 160) */
 } b2c_eval_args;
 
 int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *args);

@@ -124,3 +124,72 @@ def complete_state_to_base(ref_tran, pos7):
     n = pos7.shape[0]
     core = T.make(pos7[:, 3:7], pos7[:, 0:3])
     return T.compose(_b(ref_tran, n), core)
+
+
+def _quat_from_matrix(m):
+    """rotation matrix (N,3,3) -> unit quaternion wxyz, Eigen's trace-branch algorithm (what transf::set(mat3, vec3) stores,
+    include/graspit/transform.h:52-57)"""
+    m = np.asarray(m, dtype=np.float64)
+    out = np.zeros((m.shape[0], 4))
+    for k in range(m.shape[0]):
+        M = m[k]
+        t = np.trace(M)
+        c = np.zeros(4)                      # x y z w
+        if t > 0:
+            t = np.sqrt(t + 1.0)
+            c[3] = 0.5 * t
+            t = 0.5 / t
+            c[0] = (M[2, 1] - M[1, 2]) * t; c[1] = (M[0, 2] - M[2, 0]) * t; c[2] = (M[1, 0] - M[0, 1]) * t
+        else:
+            i = 0
+            if M[1, 1] > M[0, 0]:
+                i = 1
+            if M[2, 2] > M[i, i]:
+                i = 2
+            j = (i + 1) % 3; kk = (j + 1) % 3
+            t = np.sqrt(M[i, i] - M[j, j] - M[kk, kk] + 1.0)
+            c[i] = 0.5 * t
+            t = 0.5 / t
+            c[3] = (M[kk, j] - M[j, kk]) * t; c[j] = (M[j, i] + M[i, j]) * t; c[kk] = (M[kk, i] + M[i, kk]) * t
+        out[k] = [c[3], c[0], c[1], c[2]]
+    return out / np.linalg.norm(out, axis=1, keepdims=True)
+
+
+def _unit(v):
+    n = np.linalg.norm(v, axis=1, keepdims=True)
+    return np.where(n > 0, v / np.where(n > 0, n, 1.0), v)       # Eigen normalized(): unchanged at zero
+
+
+def ellipsoid_state_to_base(robot, ref_tran, pos4, abc=(80.0, 80.0, 160.0)):
+    """SPACE_ELLIPSOID (PositionStateEllipsoid::getCoreTran, searchStateImpl.cpp:218-252): beta gamma tau dist; the hand sits
+    on the ellipsoid (a, b, c), z along the (inward) normal, rolled by tau, `dist` back along the un-normalised normal."""
+    pos4 = np.asarray(pos4, dtype=np.float64)
+    n = pos4.shape[0]
+    a, b, c = abc
+    be, ga, tau, dist = [pos4[:, i] for i in range(4)]
+    p = np.stack([a * np.cos(be) * np.cos(ga), b * np.cos(be) * np.sin(ga), c * np.sin(be)], 1)
+    n1 = np.stack([-a * np.sin(be) * np.cos(ga), -b * np.sin(be) * np.sin(ga), c * np.cos(be)], 1)
+    n2 = np.stack([-a * np.cos(be) * np.sin(ga), b * np.cos(be) * np.cos(ga), np.zeros(n)], 1)
+    normal = np.cross(_unit(n1), _unit(n2))
+    xdir = np.tile(np.array([[1.0, 0.0, 0.0]]), (n, 1))
+    ydir = np.cross(normal, _unit(xdir))
+    xdir = np.cross(ydir, normal)
+    r = np.stack([_unit(xdir), _unit(ydir), _unit(normal)], 2)          # columns
+    hand = (_quat_from_matrix(r), p - dist[:, None] * normal)
+    zrot = (np.stack([np.cos(0.5 * tau), np.zeros(n), np.zeros(n), np.sin(0.5 * tau)], 1), np.zeros((n, 3)))   # plain AngleAxisd: no snap
+    hand = T.compose(hand, T.make(zrot[0], zrot[1]))
+    core = T.compose(hand, _b(T.inverse(_b(robot.approach, 1)), n))
+    return T.compose(_b(ref_tran, n), core)
+
+
+def approach_state_to_base(robot, ref_tran, pos3):
+    """SPACE_APPROACH (PositionStateApproach::getCoreTran, searchStateImpl.cpp:266-274): dist, wrist 1, wrist 2:
+    approach % [ R(ry, y) % R(rx, x) % T(0, 0, dist) ] % approach^-1."""
+    pos3 = np.asarray(pos3, dtype=np.float64)
+    n = pos3.shape[0]
+    dist, rx, ry = pos3[:, 0], pos3[:, 1], pos3[:, 2]
+    hand = T.translation(np.stack([np.zeros(n), np.zeros(n), dist], 1))
+    hand = T.compose(T.compose(T.axis_angle_rotation(ry, np.array([0.0, 1.0, 0.0])), T.axis_angle_rotation(rx, np.array([1.0, 0.0, 0.0]))), hand)
+    ap = _b(robot.approach, n)
+    core = T.compose(T.compose(ap, hand), _b(T.inverse(_b(robot.approach, 1)), n))
+    return T.compose(_b(ref_tran, n), core)

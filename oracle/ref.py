@@ -53,6 +53,12 @@ def lib():
         L.ref_point_distance.restype = C.c_double
         L.ref_contact.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_int]
         L.ref_contact_raw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
+        L.ref_fk_chain.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.ref_fk_child_base.argtypes = [C.POINTER(C.c_double)] * 3
+        L.ref_state_to_base.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 5
+        L.ref_brute_distance.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ref_brute_distance.restype = C.c_double
         L.ref_contact_trace.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_int,
                                         C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double), C.c_int]
         L.ref_all_contacts.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int),
@@ -151,6 +157,13 @@ class RefWorld:
         p1 = np.zeros(3); p2 = np.zeros(3)
         d = self.L.ref_body_distance(self.h, a, b, _dp(p1), _dp(p2))
         return d, p1, p2
+
+    def brute_distance(self, a, b):
+        """exhaustive minimum over every triangle pair with the reference's leaf arithmetic (no tree): (dist, mP1 in a's
+        frame, mP2 in b's frame, (triangle of a, triangle of b))"""
+        p1 = np.zeros(3); p2 = np.zeros(3); tp = np.zeros(2, dtype=np.int32)
+        d = self.L.ref_brute_distance(self.h, a, b, _dp(p1), _dp(p2), _ip(tp))
+        return d, p1, p2, (int(tp[0]), int(tp[1]))
 
     def point_distance(self, body, p):
         pp = _d(p, 3); cp = np.zeros(3); cn = np.zeros(3)
@@ -302,6 +315,57 @@ def eval_batch(worlds: Sequence[RefWorld], hand_ids, object_id, tf7, vc_link, vc
                      _dp(vloc), _dp(vn), int(mode), int(bool(want_dist)),
                      legal.ctypes.data_as(C.POINTER(C.c_ubyte)), _dp(energy), _dp(dist) if want_dist else None)
     return legal, energy, dist
+
+
+# --- FK and state -> pose through the reference's own lines (oracle/ref_fk.cpp) ----------------------------------------
+
+def _t7(tr):
+    return np.ascontiguousarray(np.concatenate([np.asarray(tr[0], dtype=np.float64).ravel(), np.asarray(tr[1], dtype=np.float64).ravel()]))
+
+
+def state_to_base(kind, variables, ref_tran, approach, params=(80.0, 80.0, 160.0)):
+    """HandObjectState::execute with the reference's PositionState*::getCoreTran: kind 0 COMPLETE, 1 AXIS_ANGLE, 2 ELLIPSOID,
+    3 APPROACH -> (q wxyz, t)"""
+    v = _d(variables); pr = _d(params); r7 = _t7(ref_tran); a7 = _t7(approach); out = np.zeros(7)
+    rc = lib().ref_state_to_base(int(kind), _dp(v), _dp(pr), _dp(r7), _dp(a7), _dp(out))
+    assert rc == 0
+    return out[:4].copy(), out[4:].copy()
+
+
+def forward_kinematics(robots, ridx, base, dofs_by_robot, joint_values=None, out=None):
+    """One pose through KinematicChain::fwdKinematics (the reference's lines) for robot ``ridx`` and the robots attached
+    to it.  robots: scene RobotDesc list; base = (q, t); dofs_by_robot: {robot: (nDOF,)}; joint_values (optional):
+    {robot: per-chain lists of joint values} overriding ratio * dof.  Returns {scene body: (q, t)}."""
+    L = lib()
+    if out is None:
+        out = {}
+    r = robots[ridx]
+    out[r.base_body] = (np.asarray(base[0], dtype=np.float64).copy(), np.asarray(base[1], dtype=np.float64).copy())
+    if getattr(r, "mount_body", -1) >= 0:
+        out[r.mount_body] = out[r.base_body]
+    owner7 = _t7(base)
+    for ci, c in enumerate(r.chains):
+        nj, nl = len(c.joints), len(c.link_bodies)
+        j6 = np.zeros((max(nj, 1), 6))
+        for j, jd in enumerate(c.joints):
+            # JointDesc folds the DOF-expression offset c into theta (revolute) / d (prismatic): undo that, the reference keeps them apart
+            j6[j] = [1.0, jd.theta - jd.offset, jd.d, jd.a, jd.alpha, jd.offset] if jd.revolute else [0.0, jd.theta, jd.d - jd.offset, jd.a, jd.alpha, jd.offset]
+        if joint_values is not None and ridx in joint_values:
+            jv = np.ascontiguousarray(joint_values[ridx][ci], dtype=np.float64)
+        else:
+            d = np.asarray(dofs_by_robot[ridx], dtype=np.float64)
+            jv = np.ascontiguousarray([d[jd.dof] * jd.ratio for jd in c.joints], dtype=np.float64)
+        lj = np.ascontiguousarray(c.last_joint, dtype=np.int32)
+        o7 = np.zeros((nl, 7))
+        j6 = np.ascontiguousarray(j6)
+        L.ref_fk_chain(_dp(owner7), _dp(_t7(c.tran)), nj, _dp(j6), _dp(jv if nj else np.zeros(1)), nl, _ip(lj), _dp(o7))
+        for l, b in enumerate(c.link_bodies):
+            out[b] = (o7[l, :4].copy(), o7[l, 4:].copy())
+        for (child, off) in getattr(c, "children", []):
+            cb = np.zeros(7)
+            L.ref_fk_child_base(_dp(np.ascontiguousarray(o7[nl - 1])), _dp(_t7(off)), _dp(cb))
+            forward_kinematics(robots, child, (cb[:4].copy(), cb[4:].copy()), dofs_by_robot, joint_values, out)
+    return out
 
 
 def hardware_threads() -> int:

@@ -270,6 +270,37 @@ int ref_contact_trace(void *wv, int a, int b, double thr, const double *tri9_a, 
   return n;
 }
 
+// Exhaustive body-body distance: the reference's own leaf arithmetic (DistanceCallback::leafTest,
+// collisionAlgorithms_inl.h:176-204: t1.applyTransform(mTran1To2), triangleTriangleDistanceSq) over EVERY triangle pair,
+// no hierarchy and no pruning -- the arbiter when the engine's and the reference's tree searches disagree about which
+// pair is closest.  p1 (body-a frame) and p2 (body-b frame) are the callback's mP1 / mP2, i.e. WITHOUT the extra inverse
+// bodyToBodyDistance applies afterwards; tri_pair = the winning triangles.  Returns the distance, -1 on intersection.
+double ref_brute_distance(void *wv, int a, int b, double *p1o, double *p2o, int *tri_pair) {
+  RefWorld *w = (RefWorld *)wv;
+  if (!w->get(a) || !w->get(b)) return 0.0;
+  std::vector<Triangle> ta, tb;
+  w->get(a)->getGeometryTriangles(&ta);
+  w->get(b)->getGeometryTriangles(&tb);
+  const transf t1 = w->get(a)->getTran(), t2 = w->get(b)->getTran();
+  const transf tran2To1 = t1.inverse() % t2, tran1To2 = t2.inverse() % t1;     // RecursionCallback ctor
+  double best = 1.0e300;
+  position bp1(0, 0, 0), bp2(0, 0, 0);
+  int bi = -1, bj = -1;
+  for (size_t i = 0; i < ta.size() && best >= 0.0; i++) {
+    Triangle t(ta[i]);
+    t.applyTransform(tran1To2);
+    for (size_t j = 0; j < tb.size() && best >= 0.0; j++) {
+      position p1(0, 0, 0), p2(0, 0, 0);
+      double d = triangleTriangleDistanceSq(t, tb[j], p1, p2);
+      if (d < best) { best = d; bp1 = tran2To1 * p1; bp2 = p2; bi = (int)i; bj = (int)j; }
+    }
+  }
+  if (best < 0.0) { bp1 = bp2 = position(0, 0, 0); }
+  for (int k = 0; k < 3; k++) { if (p1o) p1o[k] = bp1[k]; if (p2o) p2o[k] = bp2[k]; }
+  if (tri_pair) { tri_pair[0] = bi; tri_pair[1] = bj; }
+  return best < 0.0 ? -1.0 : sqrt(best);
+}
+
 // allContacts(): pair_ids gets (id1,id2) per reported pair, counts the contacts per pair,
 // out13 the contacts of all pairs back to back.  Returns number of pairs.
 int ref_all_contacts(void *wv, double thr, const int *interest, int ninterest,

@@ -15,5 +15,7 @@ struct SoSFVec3fShim {
 struct SoTransform {
   SoSFRotationShim rotation;
   SoSFVec3fShim translation;
+  void ref() {}          // Coin reference counting (Joint::Joint, joint.h:206): nothing to count here
+  void unref() {}
 };
 #endif

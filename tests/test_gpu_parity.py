@@ -111,6 +111,54 @@ def test_search_state_input_matches_raw_input(ctx):
     assert relerr(res["energy"][m], energy_o[m]).max() < REL
 
 
+@pytest.mark.parametrize("kind", ["ellipsoid", "ellipsoid_abc", "approach", "complete_dof"])
+def test_other_search_state_layouts(ctx, kind):
+    """A12: SPACE_ELLIPSOID / SPACE_APPROACH + POSE_EIGEN and SPACE_COMPLETE + POSE_DOF mapped on the device; the oracle is
+    the numpy restatement, itself pinned to the reference's own getCoreTran lines (tests/test_oracle_fk_pinned.py)."""
+    from graspit_b200.engine import B2C_INPUT_APPROACH_EIGEN, B2C_INPUT_COMPLETE_DOF, B2C_INPUT_ELLIPSOID_EIGEN
+    from oracle.port import fk as ofk
+    sc, e, o = ctx["sc"], ctx["eng"], ctx["osc"]
+    r = sc.robots[0]
+    ref_tran = sc.body_tran[ctx["obj"]]
+    rng = np.random.default_rng(17)
+    n = 400
+    amps = rng.uniform(-4, 4, size=(n, r.eg.shape[0]))
+    params = None
+    if kind.startswith("ellipsoid"):
+        pos = np.stack([rng.uniform(-np.pi / 2, np.pi / 2, n), rng.uniform(-np.pi, np.pi, n), rng.uniform(-np.pi, np.pi, n), rng.uniform(-50, 100, n)], 1)
+        params = (60.0, 90.0, 120.0) if kind == "ellipsoid_abc" else None
+        states = np.concatenate([pos, amps], 1).astype(np.float32)
+        s64 = states.astype(np.float64)
+        base = ofk.ellipsoid_state_to_base(r, ref_tran, s64[:, :4], abc=params or (80.0, 80.0, 160.0))
+        dofs = ofk.eigen_to_dof(r, s64[:, 4:]); mode = B2C_INPUT_ELLIPSOID_EIGEN
+    elif kind == "approach":
+        pos = np.stack([rng.uniform(-30, 200, n), rng.uniform(-np.pi / 3, np.pi / 3, n), rng.uniform(-np.pi / 3, np.pi / 3, n)], 1)
+        pos[0, 1] = 0.0; pos[1, 2] = 2.0e-4                       # below the AXIS_ANGLE_ROTATION identity snap
+        states = np.concatenate([pos, amps], 1).astype(np.float32)
+        s64 = states.astype(np.float64)
+        base = ofk.approach_state_to_base(r, ref_tran, s64[:, :3])
+        dofs = ofk.eigen_to_dof(r, s64[:, 3:]); mode = B2C_INPUT_APPROACH_EIGEN
+    else:
+        q = rng.uniform(-5, 5, size=(n, 4))
+        pos = np.concatenate([rng.uniform(-250, 250, (n, 2)), rng.uniform(-150, 350, (n, 1)), q], 1)
+        d = rng.uniform(r.dof_min, r.dof_max, size=(n, r.n_dof))
+        states = np.concatenate([pos, d], 1).astype(np.float32)
+        s64 = states.astype(np.float64)
+        base = ofk.complete_state_to_base(ref_tran, s64[:, :7])
+        dofs = s64[:, 7:]; mode = B2C_INPUT_COMPLETE_DOF
+    raw64 = np.concatenate([base[0], base[1], dofs], 1)
+    legal_o, energy_o, _, order, tf7 = o.eval(0, ctx["obj"], raw64, mode=0)
+    res = e.eval_batch(ctx["rid"], ctx["sb"].body_ids[ctx["obj"]], states, input_mode=mode, ref_tran=ref_tran, body_tf=True,
+                       position_params=params)
+    assert np.abs(res["body_tf"][:, :, 4:7] - tf7[:, :, 4:7]).max() < 1e-8
+    dq = np.minimum(np.abs(res["body_tf"][:, :, 0:4] - tf7[:, :, 0:4]).max(-1), np.abs(res["body_tf"][:, :, 0:4] + tf7[:, :, 0:4]).max(-1))
+    assert dq.max() < 1e-11
+    assert (res["legal"] == legal_o).all()
+    m = legal_o == 1
+    assert m.sum() > 10
+    assert relerr(res["energy"][m], energy_o[m]).max() < REL
+
+
 def test_reference_collision_tests_through_the_abi(ctx):
     """test/graspit_collision_tests.cpp, all three tests, against the CUDA backend."""
     sc = ctx["sc"]
