@@ -6,20 +6,30 @@ EGPlanner's SimAnnPlanner with CONTACT_ENERGY: 65 536 independent annealing chai
 default state layout (SPACE_AXIS_ANGLE position + POSE_EIGEN posture = 8 fp32 variables), SimAnnParams
 ANNEAL_DEFAULT.  One step = one annealing step of every chain = one pass of the hot path over one batch:
     neighbour generation (Philox-keyed Ingber distribution) -> FK -> legality over the 35 active pairs ->
-    [CONTACT_LIVE: 9 body-body distances] -> CONTACT_ENERGY -> Metropolis accept,
+    [CONTACT_LIVE: 9 body-body distances] -> CONTACT_ENERGY -> Metropolis accept -> best-list update + exchange,
 all on the device with the chain states resident in HBM (`value`).  `e2e` is the same batches evaluated through the
-C ABI with HOST buffers (b2c_eval_batch: pinned H2D of the neighbour states, kernels, D2H of legal + energy) -- the
-call a GraspIt!-side batched SearchEnergy makes.  Chains start uniformly inside the planner's search box.
+C ABI with HOST buffers (b2c_eval_batch: H2D of the neighbour states, kernels, D2H of legal + energy, then the best-row
+exchange) -- the call a GraspIt!-side batched SearchEnergy makes.  Chains start uniformly inside the planner's search box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode preset|live] [--impl reference] [--workload anneal|random]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode preset|live] [--workload anneal|config5|random]
+                    [--exchange peer|nccl] [--no-sub] [--impl reference]
 
-N > 1 is launched by torchrun (one rank per GPU); chains shard across ranks with no data-path collective, and each
-step ends with the small NCCL all-gather of every rank's best (state || energy) rows that the planner's best-list
-merge needs.  Prints ONE JSON line on rank 0.
+N > 1 is launched by torchrun (one rank per GPU); chains shard across ranks with no data-path collective.  The planner's
+exchange -- every rank's BEST_LIST_SIZE best (state || energy) rows, merged into the best list on the host -- runs every
+step inside the timed region, at N = 1 too (there it is the planner's own best-list upkeep): by default through the
+engine's collective-free peer exchange (rows stored straight into the peers' HBM over NVLink by the kernel that updates
+the best list), `--exchange nccl` keeps the NCCL all-gather as the checked alternative.
+
+Besides the headline line the default run adds two sub-records measured the same way (`--no-sub` skips them):
+    "live"     CONTACT_LIVE annealing steps of the same chains,
+    "config5"  BASELINE.json configs[4]: 1 048 576 chains in total (strong scaling: / N per GPU) against the mug
+               subdivided to 220 800 triangles.
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -34,30 +44,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "hand-pose evals/sec (collision+contact+energy)"
 UNIT = "poses/s"
-BEST_LIST_SIZE = 20          # SimAnnPlanner BEST_LIST_SIZE, reference src/EGPlanner/simAnnPlanner.cpp:36
-ALGO_BYTES_EVAL_PER_POSE = 9 * 96 + 1 + 4     # eval kernel: 9 link transforms (12 fp64) in, legal + energy out
-ALGO_BYTES_STEP_PER_POSE = 8 * 4 + 1 + 4 + 2 * 9 * 96   # whole step: states in, legal+energy out, transforms written+read
-
-
-def sample_states(scene, n, seed):
-    """(n, 8) float32 planner states: Tx Ty Tz theta phi alpha + 2 eigengrasp amplitudes."""
-    from tests.common import sample_aa_states
-    pos, _ = sample_aa_states(scene, n, seed=seed)
-    rng = np.random.default_rng(seed + 7919)
-    neg = scene.robots[0].eg.shape[0]
-    amps = rng.uniform(-4.0, 4.0, size=(n, neg)).astype(np.float32)
-    return np.ascontiguousarray(np.concatenate([pos, amps], 1).astype(np.float32))
-
-
-def states_to_raw(scene, states):
-    """oracle-side state -> (base, dofs) mapping (fp64 on the widened fp32 states)"""
-    from oracle.port import fk as ofk
-    from tests.common import object_body
-    r = scene.robots[0]
-    s = states.astype(np.float64)
-    base = ofk.aa_state_to_base(r, scene.body_tran[object_body(scene)], s[:, :6])
-    dofs = ofk.eigen_to_dof(r, s[:, 6:])
-    return np.concatenate([base[0], base[1], dofs], 1)
+CONFIG5_TOTAL = 1048576
 
 
 class ClockSampler:
@@ -106,6 +93,18 @@ def start_states(sv, n, seed):
     return rng.uniform(sv.vmin, sv.vmax, size=(n, len(sv.vmin))).astype(np.float32)
 
 
+# ----------------------------------------------------------------------------------------------------- reference arm
+def states_to_raw(scene, states):
+    """oracle-side state -> (base, dofs) mapping (fp64 on the widened fp32 states)"""
+    from graspit_b200.sampling import object_body
+    from oracle.port import fk as ofk
+    r = scene.robots[0]
+    s = states.astype(np.float64)
+    base = ofk.aa_state_to_base(r, scene.body_tran[object_body(scene)], s[:, :6])
+    dofs = ofk.eigen_to_dof(r, s[:, 6:])
+    return np.concatenate([base[0], base[1], dofs], 1)
+
+
 def cpu_neighbour_batch(sv, params, n, step, seed, chain_offset=0):
     """a batch of annealing neighbours made on the CPU (oracle port of SimAnn::variableNeighbor) from the start states:
     the same distribution the device annealer evaluates in its first steps"""
@@ -119,7 +118,8 @@ class CpuReference:
     instance per host thread) evaluating planner states; FK is precomputed outside the timed call"""
 
     def __init__(self, scene, threads):
-        from tests.common import OracleScene, object_body
+        from graspit_b200.sampling import object_body
+        from tests.common import OracleScene
         self.scene, self.osc, self.obj = scene, OracleScene(scene, nthreads=threads), object_body(scene)
 
     def time(self, states, mode):
@@ -137,7 +137,13 @@ class CpuReference:
 
 
 def cpu_sample_size(args):
+    if args.workload == "config5":
+        return max(256, args.cpu_sample // 8)
     return args.cpu_sample if args.mode != "live" else max(256, args.cpu_sample // 16)
+
+
+def scene_name(args):
+    return "barrett_mug_200k" if args.workload == "config5" else "barrett_mug"
 
 
 def run_reference_arm(args):
@@ -146,8 +152,9 @@ def run_reference_arm(args):
         return
     from graspit_b200.formats.scenepack import load_pack
     from graspit_b200.planner import SearchVariables, SimAnnParams
+    from graspit_b200.sampling import sample_planner_states
     from oracle import ref
-    scene = load_pack("barrett_mug")
+    scene = load_pack(scene_name(args))
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgraspit_ref.so missing"}))
         return
@@ -159,16 +166,19 @@ def run_reference_arm(args):
     cpu = CpuReference(scene, threads)
     times = []
     for step in range(args.warmup + args.steps):
-        st = cpu_neighbour_batch(sv, params, sample, step, 1234) if args.workload == "anneal" else sample_states(scene, sample, 1234 + step)
+        if args.workload == "anneal":
+            st = cpu_neighbour_batch(sv, params, sample, step, 1234)
+        else:
+            st = sample_planner_states(scene, sample, 1234 + step)
         dt = cpu.time(st, mode)
         if step >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, args.poses),
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.workload == "config5" else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, poses_per_gpu(args, max(1, args.gpus))),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
                              "sample": f"{sample} neighbour states per step of the same workload (reference GraspitCollision compiled "
                                        "verbatim, -O3, one instance per thread; FK precomputed outside the timed call)"},
@@ -176,17 +186,278 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_config(args, poses):
-    mode = "CONTACT_LIVE" if args.mode == "live" else "CONTACT_PRESET"
-    if args.workload == "anneal":
-        w = ("Barrett hand vs mug (worlds/plannerMug.xml), EGPlanner SimAnnPlanner CONTACT_ENERGY " + mode +
+def poses_per_gpu(args, world):
+    return CONFIG5_TOTAL // world if args.workload == "config5" else args.poses
+
+
+def workload_config(args, poses, mode=None, workload=None):
+    mode = mode or args.mode
+    workload = workload or args.workload
+    m = "CONTACT_LIVE" if mode == "live" else "CONTACT_PRESET"
+    if workload == "anneal":
+        w = ("Barrett hand vs mug (worlds/plannerMug.xml), EGPlanner SimAnnPlanner CONTACT_ENERGY " + m +
              f", {poses} annealing chains per GPU, one neighbour per chain per step (SimAnnParams ANNEAL_DEFAULT, "
              "SPACE_AXIS_ANGLE + POSE_EIGEN = 8 fp32 variables, Philox seed 1234, chains started uniformly in the planner's box)")
+    elif workload == "config5":
+        w = (f"BASELINE.json configs[4]: Barrett hand vs the mug subdivided to 220 800 triangles, {CONFIG5_TOTAL} annealing chains in total "
+             f"({poses} per GPU, strong scaling), CONTACT_ENERGY " + m + ", one neighbour per chain per step, chains started on the config-1 "
+             "strata (planner box / 150 mm ball), best-row exchange every step")
     else:
-        w = ("Barrett hand vs mug (worlds/plannerMug.xml), CONTACT_ENERGY " + mode + f", {poses} random planner states per step per GPU "
+        w = ("Barrett hand vs mug (worlds/plannerMug.xml), CONTACT_ENERGY " + m + f", {poses} random planner states per step per GPU "
              "(SPACE_AXIS_ANGLE + POSE_EIGEN, 8 fp32 variables; 50% planner-box / 50% within 150 mm strata)")
-    return {"workload": w, "poses_per_step_per_gpu": poses, "mode": args.mode, "kind": args.workload,
-            "l2": "flushed between timed steps (256 MiB write); per-step inputs 2 MiB"}
+    return {"workload": w, "poses_per_step_per_gpu": poses, "mode": mode, "kind": workload,
+            "l2": "flushed between timed steps (256 MiB write); per-step inputs 32 B / pose"}
+
+
+# ------------------------------------------------------------------------------------------------------- product arm
+class Bench:
+    """torch / distributed plumbing shared by the headline run and the sub-records"""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        # one explicit stream for torch ops, the engine's kernels and the timing events
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(self.stream)
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        if self.world == 1:
+            return [float(v) for v in values]
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+
+def run_workload(B: Bench, scene_id: str, workload: str, npose: int, K: int, W: int, live: bool, exchange: str, e2e_steps: int):
+    """One measured workload on this rank's GPU.  Returns a dict of timings (already max-reduced over the ranks) and
+    explanatory numbers.  `workload`: anneal | config5 (annealing chains resident on the device) | random (fresh states)."""
+    torch, dist = B.torch, B.dist
+    from graspit_b200.engine import B2C_EVAL_LIVE, B2C_INPUT_AA_EIGEN, Annealer, Engine, EvalArgs, SceneBinding
+    from graspit_b200.formats.scenepack import load_pack
+    from graspit_b200.planner import BEST_LIST_SIZE, BestList, PeerExchange, SearchVariables, SimAnnParams
+    from graspit_b200.sampling import object_body, sample_planner_states
+
+    rank, world, dev, stream = B.rank, B.world, B.dev, B.stream
+    scene = load_pack(scene_id)
+    obj = object_body(scene)
+    eng = Engine(B.local_rank)
+    sb = SceneBinding(eng, scene)
+    rid, oid = sb.robot_ids[0], sb.body_ids[obj]
+    ref_tran = scene.body_tran[obj]
+    neg = scene.robots[0].eg.shape[0]
+    nvar = 6 + neg
+    sv = SearchVariables.axis_angle_eigen(neg)
+    params = SimAnnParams.ANNEAL_DEFAULT()
+    eng.set_stream(stream.cuda_stream)
+    anneal = workload in ("anneal", "config5")
+
+    # ---- device-resident annealing: chains [rank * npose, (rank + 1) * npose) of world * npose, chains never migrate
+    if workload == "config5":
+        init = sample_planner_states(scene, npose, 1234 + rank)                    # config-1 strata
+    else:
+        init = start_states(sv, npose, 1234 + rank)
+    an = Annealer(eng, rid, oid, sv, params, init, ref_tran, seed=1234, chain_offset=rank * npose, live=live)
+    best_list = BestList(ref_tran)
+    # exchange of the best rows: "peer" = stores into the peers' rings by the best-list kernel (no collective);
+    # "nccl" = all-gather of the rows (the checked alternative).  At N = 1 the same calls keep the planner's own best list.
+    px = PeerExchange(eng, an, rank, world, rows=BEST_LIST_SIZE, depth=4, device=dev)
+    RING = 3
+    host_rows = [torch.zeros((world, BEST_LIST_SIZE, nvar + 1), dtype=torch.float32).pin_memory() for _ in range(RING)]
+    host_ev = [torch.cuda.Event() for _ in range(RING)]
+    rows_d = [torch.empty((BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) for _ in range(RING)]
+    gathered = [torch.empty((world, BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) for _ in range(RING)]
+    pending = {}
+    merged = {"offers": 0}
+
+    def merge_host(slot):
+        r = host_rows[slot].numpy().reshape(-1, nvar + 1)
+        e = r[:, -1]
+        m = e < min(best_list.worst_energy(), 1.0e7)
+        if m.any():
+            merged["offers"] += int(m.sum())
+            best_list.merge(r[m, :-1], e[m])
+
+    def exchange_step(i):
+        """issue the exchange of step i; merge (on the host) the rows collected at step i - 1, which have long landed"""
+        slot = i % RING
+        if exchange == "peer":
+            an.publish()
+            eng.exchange_collect(host_rows[slot].data_ptr(), 0, True)
+        else:
+            an.best_rows(BEST_LIST_SIZE, rows_d[slot].data_ptr())
+            if world > 1:
+                # asynchronous all-gather of this step's rows; the rows gathered at the PREVIOUS step go to the host now
+                # (the stream waits for that gather only: one step of slack between the ranks)
+                pending[i] = dist.all_gather_into_tensor(gathered[slot].view(-1, nvar + 1), rows_d[slot], async_op=True)
+                if (i - 1) in pending:
+                    pending.pop(i - 1).wait()
+                    host_rows[slot].copy_(gathered[(i - 1) % RING], non_blocking=True)
+            else:
+                host_rows[slot][0].copy_(rows_d[slot], non_blocking=True)
+        host_ev[slot].record(stream)
+        prev = (i - 1) % RING
+        if i >= 1:
+            host_ev[prev].synchronize()                    # one step behind the GPU: never idles it
+            merge_host(prev)
+
+    # host copies of the neighbour batches of the end-to-end leg, taken from the same chains
+    host_batches = []
+    if anneal:
+        for _ in range(e2e_steps + min(W, 3)):
+            host_batches.append(an.propose())
+            an.step(1)
+    else:
+        host_batches = [sample_planner_states(scene, npose, 1234 + 1000 * rank + s) for s in range(K + W)]
+    dev_batches = None if anneal else [torch.from_numpy(b).to(dev) for b in host_batches]
+    legal_d = torch.zeros(npose, dtype=torch.uint8, device=dev)
+    energy_d = torch.zeros(npose, dtype=torch.float32, device=dev)
+    eng.set_profiling(True)
+
+    def step_device(i):
+        if anneal:
+            an.step(1)
+            exchange_step(i)
+        else:
+            st = dev_batches[i]
+            eng.eval_batch_device(rid, oid, st.data_ptr(), npose, nvar, legal_d.data_ptr(), energy_d.data_ptr(),
+                                  input_mode=B2C_INPUT_AA_EIGEN, ref_tran=ref_tran, live=live)
+
+    def drain():
+        for h in list(pending.values()):
+            h.wait()
+        pending.clear()
+        B.barrier()
+
+    for i in range(W):
+        step_device(i)
+    drain()
+
+    launches0 = eng.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kernel_ms = []
+    drain()
+    for s in range(K):
+        B.flush.fill_(s & 0xff)                     # L2 flush, outside the event bracket
+        ev[s][0].record(stream)
+        step_device(W + s)
+        ev[s][1].record(stream)
+        kernel_ms.append(eng.last_kernel_ms())      # synchronises; after the bracket
+    drain()
+    eng.check_overflow()
+    launches = eng.launch_count - launches0
+    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    stats = eng.last_stats()
+    d = an.read() if anneal else None
+    anneal_info = None
+    if anneal:
+        anneal_info = {"steps_taken": d["steps"], "neighbours_evaluated": d["evaluated"], "legal_fraction": d["legal_neighbours"] / max(1, d["evaluated"]),
+                       "jump_fraction": d["jumps"] / max(1, d["evaluated"]), "best_energy_min": float(d["best_energy"].min()),
+                       "best_energy_median": float(np.median(d["best_energy"])), "best_list": len(best_list.states),
+                       "best_list_energy": [round(float(x), 4) for x in best_list.energies[:3]], "rows_offered_to_best_list": merged["offers"]}
+
+    # ---- end to end through the C ABI with host buffers: H2D + kernels + D2H + exchange inside the timed region
+    eng.set_profiling(False)
+    KE = min(e2e_steps, len(host_batches) - min(W, 3)) if anneal else min(e2e_steps, K)
+    WE = min(W, 3)
+
+    def e2e_leg(pinned: bool):
+        if pinned:
+            bufs = [torch.from_numpy(b).pin_memory() for b in host_batches[: WE + KE]]
+            lg = torch.zeros(npose, dtype=torch.uint8).pin_memory()
+            en = torch.zeros(npose, dtype=torch.float32).pin_memory()
+        else:                                       # what a GraspIt!-side std::vector is: pageable
+            bufs = [torch.from_numpy(np.array(b, copy=True)) for b in host_batches[: WE + KE]]
+            lg = torch.zeros(npose, dtype=torch.uint8)
+            en = torch.zeros(npose, dtype=torch.float32)
+
+        def step_host(i):
+            a = EvalArgs()
+            a.robot, a.object, a.npose, a.input_mode = rid, oid, npose, B2C_INPUT_AA_EIGEN
+            a.states, a.stride = bufs[i].data_ptr(), nvar
+            a.ref_q[:] = list(ref_tran[0]); a.ref_t[:] = list(ref_tran[1])
+            a.flags = B2C_EVAL_LIVE if live else 0
+            a.legal, a.energy = lg.data_ptr(), en.data_ptr()
+            eng._ck(eng.L.b2c_eval_batch(eng.h, C.byref(a)))
+            if anneal:
+                # the planner's exchange belongs to the step: publish + collect + merge, synchronously
+                an.publish()
+                eng.exchange_collect(host_rows[0].data_ptr(), 0, False)
+                merge_host(0)
+
+        for i in range(WE):
+            step_host(i)
+        B.barrier()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KE)]
+        for s in range(KE):
+            B.flush.fill_(s & 0xff)
+            ev2[s][0].record(stream)
+            step_host(WE + s)
+            ev2[s][1].record(stream)
+        B.barrier()
+        return float(sum(a.elapsed_time(b) for a, b in ev2)), int(lg.sum().item())
+
+    e2e_ms, nlegal = e2e_leg(True)
+    e2e_pg_ms, _ = e2e_leg(False)
+    total_ms, e2e_ms, e2e_pg_ms = B.max_over_ranks([total_ms, e2e_ms, e2e_pg_ms])
+    kms = {k: float(np.mean([x[k] for x in kernel_ms])) for k in kernel_ms[0]}
+    out = dict(ms_per_step=total_ms / K, value=world * npose / (total_ms / K / 1e3), kernel_ms=kms, launches=int(launches), stats=stats,
+               anneal=anneal_info, e2e_ms=e2e_ms / KE, e2e_value=world * npose / (e2e_ms / KE / 1e3), e2e_steps=KE,
+               e2e_pageable_value=world * npose / (e2e_pg_ms / KE / 1e3), nlegal_last=nlegal, npose=npose, nvar=nvar, steps=K,
+               scene=scene, host_batches=host_batches, WE=WE, triangles=int(sum(len(b.tris) for b in scene.bodies)))
+    an.close()
+    eng.exchange_destroy()
+    eng.close()
+    return out
+
+
+def roofline(res, mode, root):
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(root, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kms, npose, nvar, nlegal = res["kernel_ms"], res["npose"], res["nvar"], res["nlegal_last"]
+    dom = max(kms, key=kms.get)
+    dom_ms = kms[dom]
+    # algorithmic DRAM bytes per launch (DESIGN.md section 5): what the kernel must read and write once
+    algo = {"eval": (9 * 96 + 1 + 4) * npose,                 # 9 link transforms in, legal + energy(0) out
+            "energy": nlegal * (9 * 96 + 4 + 4) + npose,      # legal list + transforms in, energy out
+            "dist": nlegal * 9 * (2 * 96 + 4 + 48),           # per (legal pose, link): 2 transforms in, dist + 2 points out
+            "fk": npose * (nvar * 4 + 9 * 96), "recheck": 0}
+    algo_bytes = algo.get(dom, 0)
+    achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(root, "profiles", "traffic.json")))
+        traffic = tr.get(mode, {}).get(f"{dom}_kernel")
+    except Exception:
+        pass
+    return {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": algo_bytes,
+            "kernel_ms_all": kms, "legal_fraction_last_step": nlegal / npose,
+            "note": "working set is L2-resident by design: compulsory HBM traffic only (SURVEY.md 8(d)); the kernel is "
+                    "bound by instruction issue under divergence, see profiles/; traffic = dram bytes of one ncu "
+                    "capture (profiles/traffic.json); traversal work of the last step: " + json.dumps(res["stats"])}
 
 
 def main():
@@ -196,228 +467,73 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="preset", choices=["preset", "live"])
-    ap.add_argument("--workload", default="anneal", choices=["anneal", "random"])
+    ap.add_argument("--workload", default="anneal", choices=["anneal", "random", "config5"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--poses", type=int, default=65536)
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the LIVE and config-5 sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
 
-    import torch
-    import torch.distributed as dist
-    from graspit_b200.engine import B2C_EVAL_LIVE, B2C_INPUT_AA_EIGEN, Annealer, Engine, EvalArgs, SceneBinding
-    from graspit_b200.formats.scenepack import load_pack
-    from graspit_b200.planner import BEST_LIST_SIZE, SearchVariables, SimAnnParams, exchange_best, local_best_rows
-    from tests.common import object_body
-    import ctypes as C
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    scene = load_pack("barrett_mug")
-    obj = object_body(scene)
-    eng = Engine(local_rank)
-    sb = SceneBinding(eng, scene)
-    rid, oid = sb.robot_ids[0], sb.body_ids[obj]
-    ref_tran = scene.body_tran[obj]
+    B = Bench(args)
+    world, rank = B.world, B.rank
     live = args.mode == "live"
-    npose, K, W = args.poses, args.steps, args.warmup
-    nvar = 6 + scene.robots[0].eg.shape[0]
-    sv = SearchVariables.axis_angle_eigen(scene.robots[0].eg.shape[0])
-    params = SimAnnParams.ANNEAL_DEFAULT()
+    npose = poses_per_gpu(args, world)
+    K, W = args.steps, args.warmup
+    if args.workload == "config5":
+        K, W = min(K, 10), min(W, 3)                 # 1 M chains: a step is ~0.1 s of kernels at N = 1
 
-    # one explicit stream for torch ops, the engine's kernels and the timing events
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.synchronize()
-    torch.cuda.set_stream(stream)
-    eng.set_stream(stream.cuda_stream)
-
-    anneal = args.workload == "anneal"
-    an = None
-    if anneal:
-        # chains [rank * npose, (rank + 1) * npose) of world * npose: weak scaling, chains never migrate
-        an = Annealer(eng, rid, oid, sv, params, start_states(sv, npose, 1234 + rank), ref_tran, seed=1234,
-                      chain_offset=rank * npose, live=live)
-        views = an.torch_views(dev)
-        # host copies of the neighbour batches of K + W consecutive annealing steps, for the end-to-end leg
-        host_batches = []
-        for _ in range(K + W):
-            host_batches.append(an.propose())
-            an.step(1)
-    else:
-        host_batches = [sample_states(scene, npose, 1234 + 1000 * rank + s) for s in range(K + W)]
-    pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
-    dev_batches = None if anneal else [p.to(dev, non_blocking=True) for p in pinned]
-    legal_d = torch.zeros(npose, dtype=torch.uint8, device=dev)
-    energy_d = torch.zeros(npose, dtype=torch.float32, device=dev)
-    legal_h = torch.zeros(npose, dtype=torch.uint8).pin_memory()
-    energy_h = torch.zeros(npose, dtype=torch.float32).pin_memory()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    eng.set_profiling(True)
-
-    # N > 1: every step ends with the all-gather of each rank's BEST_LIST_SIZE best (state || energy) rows.  The rows
-    # come from the engine's incremental best list (one-warp kernel over the chains that improved this step), so the
-    # exchange costs one tiny kernel + one 720-byte-per-rank NCCL all-gather
-    # The exchange of step s overlaps the kernels of step s + 1: the all-gather is asynchronous, and a rank
-    # only waits for it -- on the stream, not on the host -- after it has enqueued its next step.  Rows and results are
-    # kept in a ring of three; the merged list trails the chains by up to two steps, which the planner's best-list rule does not mind.
-    DEPTH = 3                                   # exchanges in flight: a rank never waits for a gather younger than two steps
-    rows = [torch.empty((BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) for _ in range(DEPTH)] if anneal else None
-    gathered = [torch.empty((world * BEST_LIST_SIZE, nvar + 1), dtype=torch.float32, device=dev) for _ in range(DEPTH)] if world > 1 else None
-    pending = []
-
-    def step_device(i):
-        if anneal:
-            an.step(1)
-            if world > 1:
-                if len(pending) >= DEPTH - 1:
-                    pending.pop(0).wait()
-                an.best_rows(BEST_LIST_SIZE, rows[i % DEPTH].data_ptr())
-                pending.append(dist.all_gather_into_tensor(gathered[i % DEPTH], rows[i % DEPTH], async_op=True))
-        else:
-            st = dev_batches[i]
-            eng.eval_batch_device(rid, oid, st.data_ptr(), npose, nvar, legal_d.data_ptr(), energy_d.data_ptr(),
-                                  input_mode=B2C_INPUT_AA_EIGEN, ref_tran=ref_tran, live=live)
-            if world > 1:
-                e = torch.where(legal_d.bool(), energy_d, torch.full_like(energy_d, 3.0e38))
-                exchange_best(local_best_rows(st, e, BEST_LIST_SIZE))
-
-    def sync_all():
-        while pending:
-            pending.pop(0).wait()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(W):
-        step_device(i)
-    sync_all()
-
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(B.local_rank)
     sampler.start()
-    launches0 = eng.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kernel_ms = []
-    sync_all()
-    for s in range(K):
-        flush.fill_(s & 0xff)                      # L2 flush, outside the event bracket
-        ev[s][0].record(stream)
-        step_device(W + s)
-        ev[s][1].record(stream)
-        kernel_ms.append(eng.last_kernel_ms())     # synchronises; after the bracket
-    sync_all()
-    launches = eng.launch_count - launches0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms))
-    stats = eng.last_stats()
-    anneal_info = None
-    if anneal:
-        d = an.read()
-        anneal_info = {"steps_taken": d["steps"], "neighbours_evaluated": d["evaluated"], "legal_fraction": d["legal_neighbours"] / max(1, d["evaluated"]),
-                       "jump_fraction": d["jumps"] / max(1, d["evaluated"]),
-                       "best_energy_min": float(d["best_energy"].min()), "best_energy_median": float(np.median(d["best_energy"]))}
-
-    # end to end through the C ABI with host buffers (pinned), H2D + kernels + D2H inside the timed region
-    eng.set_profiling(False)
-
-    def step_host(i):
-        a = EvalArgs()
-        a.robot, a.object, a.npose, a.input_mode = rid, oid, npose, B2C_INPUT_AA_EIGEN
-        a.states, a.stride = pinned[i].data_ptr(), nvar
-        a.ref_q[:] = list(ref_tran[0]); a.ref_t[:] = list(ref_tran[1])
-        a.flags = B2C_EVAL_LIVE if live else 0
-        a.legal, a.energy = legal_h.data_ptr(), energy_h.data_ptr()
-        eng._ck(eng.L.b2c_eval_batch(eng.h, C.byref(a)))
-
-    for i in range(W):
-        step_host(i)
-    sync_all()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for s in range(K):
-        flush.fill_(s & 0xff)
-        ev2[s][0].record(stream)
-        step_host(W + s)
-        ev2[s][1].record(stream)
-    sync_all()
-    e2e_ms = float(sum(a.elapsed_time(b) for a, b in ev2))
-    nlegal = int(legal_h.sum().item())
+    res = run_workload(B, scene_name(args), args.workload, npose, K, W, live, args.exchange, e2e_steps=min(K, 20))
     clocks = sampler.stop()
 
-    # max over ranks
-    if world > 1:
-        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
-    ms_per_step = total_ms / K
-    value = world * npose / (ms_per_step / 1e3)
-    e2e_value = world * npose / (e2e_ms / K / 1e3)
+    sub = {}
+    if not args.no_sub and args.workload == "anneal" and not live:
+        r = run_workload(B, "barrett_mug", "anneal", npose, 3, 3, True, args.exchange, e2e_steps=3)
+        sub["live"] = {"config": workload_config(args, npose, mode="live"), "steps": 3, "warmup": 3, "ms_per_step": r["ms_per_step"], "value": r["value"],
+                       "unit": UNIT, "e2e": {"value": r["e2e_value"], "pageable_value": r["e2e_pageable_value"]}, "kernel_ms": r["kernel_ms"],
+                       "gpu_launches": r["launches"], "traversal": r["stats"]}
+        n5 = CONFIG5_TOTAL // world
+        r = run_workload(B, "barrett_mug_200k", "config5", n5, 3, 3, False, args.exchange, e2e_steps=3)
+        sub["config5"] = {"config": workload_config(args, n5, mode="preset", workload="config5"), "steps": 3, "warmup": 3, "scaling": "strong",
+                          "ms_per_step": r["ms_per_step"], "value": r["value"], "unit": UNIT,
+                          "e2e": {"value": r["e2e_value"], "pageable_value": r["e2e_pageable_value"]}, "kernel_ms": r["kernel_ms"],
+                          "gpu_launches": r["launches"], "object_triangles": 220800, "legal_fraction": r["anneal"]["legal_fraction"], "traversal": r["stats"]}
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        kms = {k: float(np.mean([x[k] for x in kernel_ms])) for k in kernel_ms[0]}
-        dom = max(kms, key=kms.get)
-        dom_ms = kms[dom]
-        # algorithmic DRAM bytes per launch: what the kernel must read and write once
-        algo = {"eval": (9 * 96 + 1 + 4) * npose,                 # 9 link transforms in, legal + energy(0) out
-                "energy": nlegal * (9 * 96 + 4 + 4) + npose,      # legal list + transforms in, energy out
-                "dist": nlegal * 9 * (2 * 96 + 4 + 48),           # per (legal pose, link): 2 transforms in, dist + 2 points out
-                "fk": npose * (nvar * 4 + 9 * 96), "recheck": 0}
-        algo_bytes = algo.get(dom, 0)
-        achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tr.get(args.mode, {}).get(f"{dom}_kernel")
-        except Exception:
-            pass
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": workload_config(args, npose),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": npose * nvar * 4,
-                        "d2h_bytes_per_step": npose * 5, "ms_per_step": e2e_ms / K},
-                "gpu_launches": int(launches),
-                "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": algo_bytes,
-                             "kernel_ms_all": kms, "legal_fraction_last_step": nlegal / npose,
-                             "note": "working set is L2-resident by design: compulsory HBM traffic only (SURVEY.md 8(d)); the kernel is "
-                                     "bound by instruction issue under divergence, see profiles/; traffic = dram bytes of one ncu "
-                                     "capture (profiles/traffic.json); traversal work of the last step: " + json.dumps(stats)},
-                }
-        if anneal_info:
-            line["anneal"] = anneal_info
+        nvar = res["nvar"]
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": res["steps"], "warmup": W,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.workload == "config5" else "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, npose),
+                "e2e": {"value": res["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": npose * nvar * 4, "d2h_bytes_per_step": npose * 5 + world * 20 * (nvar + 1) * 4,
+                        "ms_per_step": res["e2e_ms"], "steps": res["e2e_steps"], "host_buffers": "pinned", "pageable_value": res["e2e_pageable_value"],
+                        "includes": "b2c_eval_batch (H2D states, kernels, D2H legal + energy) + best-row exchange (publish, collect, host merge)"},
+                "gpu_launches": res["launches"], "clocks": clocks, "exchange": args.exchange,
+                "roofline": roofline(res, args.mode, ROOT)}
+        if res["anneal"]:
+            line["anneal"] = res["anneal"]
+        line.update(sub)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle import ref
                 threads = max(1, ref.hardware_threads())
                 sample = cpu_sample_size(args)
-                cpu = CpuReference(scene, threads)
-                cpu.time(host_batches[W][: max(64, sample // 8)], 1 if live else 0)            # warm-up
-                secs = min(cpu.time(host_batches[W][:sample], 1 if live else 0) for _ in range(3))
+                cpu = CpuReference(res["scene"], threads)
+                hb = res["host_batches"][res["WE"]]
+                cpu.time(hb[: max(64, sample // 8)], 1 if live else 0)            # warm-up
+                secs = min(cpu.time(hb[:sample], 1 if live else 0) for _ in range(3))
                 line["cpu_baseline"] = {"value": sample / secs, "unit": UNIT, "cores": threads, "kind": "reference",
-                                        "sample": f"first {sample} states of the first timed batch, best of 3 ({secs:.2f} s); reference "
+                                        "sample": f"first {sample} states of the first timed end-to-end batch, best of 3 ({secs:.2f} s); reference "
                                                   "GraspitCollision compiled verbatim (-O3), one instance per thread, FK precomputed"}
             except Exception as ex:   # the oracle is a checker, never a dependency of the measurement
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        B.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -114,8 +114,8 @@ __global__ void anneal_accept_kernel(AnnealParams p) {
 // Candidates are the chains whose best improved below the list's current worst entry since the last call.  A chain
 // already listed is updated in place; otherwise it replaces the worst entry if it beats it.  Then the rows
 // (state || energy) of the listed chains are written out for the all-gather.  Empty slots carry energy 3e38.
-__global__ void anneal_toplist_kernel(AnnealParams p, int k, float *rows) {
-  const int lane = threadIdx.x;
+__device__ __forceinline__ void toplist_update(const AnnealParams &p, int k, float *rows) {
+  const int lane = threadIdx.x & 31;
   int chain = lane < k ? p.top_chain[lane] : -2;
   float e = lane < k ? (chain >= 0 ? p.best_energy[chain] : 3.0e38f) : -3.0e38f;   // lanes >= k never count as worst
   int n = *p.cand_count;
@@ -148,8 +148,73 @@ __global__ void anneal_toplist_kernel(AnnealParams p, int k, float *rows) {
   if (lane == 0) { *p.top_thresh = w; *p.cand_count = 0; }
 }
 
+__global__ void anneal_toplist_kernel(AnnealParams p, int k, float *rows) { toplist_update(p, k, rows); }
+
+// Fused best-list update + all-gather: warp 0 brings the context's best list up to date and leaves its rows in shared
+// memory; then warp w stores them straight into rank w's ring slot (step % depth, this rank) over NVLink (peer-mapped
+// memory, plain stores) under a sequence lock: tag < 0 while writing, tag = step + 1 when complete.  No collective, no
+// rendezvous: a rank never waits for another one; readers take whatever step has landed (exchange_collect_kernel).
+__global__ void __launch_bounds__(32 * EX_MAX_WORLD) anneal_publish_kernel(AnnealParams p, ExchangeDev x, float *rows_local) {
+  extern __shared__ float srows[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nf = x.rows * x.row_floats;
+  if (warp == 0) {
+    toplist_update(p, x.rows, srows);
+    __syncwarp();
+    if (rows_local) for (int i = lane; i < nf; i += 32) rows_local[i] = srows[i];
+  }
+  __syncthreads();
+  if (warp >= x.world) return;
+  float *slot = x.ring[warp] + ((size_t)(p.step % x.depth) * x.world + x.rank) * x.slot_floats;
+  volatile int *tag = reinterpret_cast<volatile int *>(slot + nf);
+  if (lane == 0) { *tag = -(p.step + 1); __threadfence_system(); }
+  __syncwarp();
+  for (int i = lane; i < nf; i += 32) slot[i] = srows[i];
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0) *tag = p.step + 1;
+}
+
+// Reader side: one warp per source rank scans that rank's `depth` slots in the LOCAL ring, takes the newest complete one
+// (largest tag; re-checked after the copy: a slot that changed underneath is skipped) and copies its rows out.
+// steps[src] = step + 1 of what was taken, 0 if nothing has arrived yet.
+__global__ void __launch_bounds__(32 * EX_MAX_WORLD) exchange_collect_kernel(ExchangeDev x, float *out, int *steps) {
+  const int lane = threadIdx.x & 31, src = threadIdx.x >> 5;
+  if (src >= x.world) return;
+  const int nf = x.rows * x.row_floats;
+  const float *base = x.ring[x.rank];
+  int taken = 0;
+  for (int attempt = 0; attempt < x.depth && !taken; attempt++) {
+    // newest complete slot not yet rejected
+    int best = 0, bslot = -1;
+    for (int d = 0; d < x.depth; d++) {
+      const float *slot = base + ((size_t)d * x.world + src) * x.slot_floats;
+      const int t = *reinterpret_cast<const volatile int *>(slot + nf);
+      if (t > best) { best = t; bslot = d; }
+    }
+    if (bslot < 0) break;
+    const float *slot = base + ((size_t)bslot * x.world + src) * x.slot_floats;
+    for (int i = lane; i < nf; i += 32) out[(size_t)src * nf + i] = reinterpret_cast<const volatile float *>(slot)[i];
+    __threadfence();
+    const int t1 = *reinterpret_cast<const volatile int *>(slot + nf);
+    const bool okay = __all_sync(0xffffffffu, t1 == best);
+    if (okay) taken = best;
+  }
+  if (!taken) for (int i = lane; i < nf; i += 32) out[(size_t)src * nf + i] = (i % x.row_floats == x.row_floats - 1) ? 3.0e38f : 0.f;
+  if (lane == 0) steps[src] = taken;
+}
+
 cudaError_t launch_anneal_toplist(const AnnealParams &p, int k, float *rows, cudaStream_t s) {
   anneal_toplist_kernel<<<1, 32, 0, s>>>(p, k, rows);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_anneal_publish(const AnnealParams &p, const ExchangeDev &x, float *rows_local, cudaStream_t s) {
+  anneal_publish_kernel<<<1, 32 * (x.world < 1 ? 1 : x.world), sizeof(float) * (size_t)x.rows * x.row_floats, s>>>(p, x, rows_local);
+  return cudaGetLastError();
+}
+cudaError_t launch_exchange_collect(const ExchangeDev &x, float *out, int *steps, cudaStream_t s) {
+  exchange_collect_kernel<<<1, 32 * (x.world < 1 ? 1 : x.world), 0, s>>>(x, out, steps);
   return cudaGetLastError();
 }
 

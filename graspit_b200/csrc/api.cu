@@ -100,6 +100,7 @@ struct Plan {
 } // namespace
 
 struct AnnealHost;      // anneal_api.inc
+struct ExchangeHost;    // anneal_api.inc
 namespace { struct AgScratch; }       // autograsp_api.inc
 
 struct b2c_ctx {
@@ -137,6 +138,7 @@ struct b2c_ctx {
   cudaStream_t own_stream = nullptr;
   // per-context annealers and autograsp scratch (contexts are independent: one per GPU, possibly one host thread each)
   std::vector<AnnealHost *> anneals;
+  ExchangeHost *exchange = nullptr;       // best-row exchange with the other GPUs (b2c_exchange_*)
   AgScratch *autograsp = nullptr;
   // sticky overflow word on the device: bit 0 = legality recheck queue, bit 1 = distance recheck queue, bit 2 = broad-phase
   // work-item list.  Kernels that drop an entry set it (and answer conservatively: "collides"); synchronising calls report it.

@@ -280,6 +280,19 @@ struct AnnealParams {
   int *top_chain;                    // [32] listed chains, -1 = empty
 };
 cudaError_t launch_anneal_toplist(const AnnealParams &p, int k, float *rows, cudaStream_t s);
+
+// ---- best-row exchange between GPUs without a collective (anneal.cu) ---------------------------------------------------
+// Every rank owns a ring of slots ring[depth][world][slot_floats] in its own HBM, mapped into its peers (CUDA IPC between
+// processes, peer access inside one process).  A slot = rows x row_floats floats + a 16-byte tag field; tag = step + 1 of
+// the rows it holds, negative while a writer is inside (sequence lock).
+constexpr int EX_MAX_WORLD = 16;
+struct ExchangeDev {
+  float *ring[EX_MAX_WORLD];     // ring base of every rank, as seen from this device ([rank] = own ring)
+  int world, rank, depth;
+  int rows, row_floats, slot_floats;
+};
+cudaError_t launch_anneal_publish(const AnnealParams &p, const ExchangeDev &x, float *rows_local, cudaStream_t s);
+cudaError_t launch_exchange_collect(const ExchangeDev &x, float *out, int *steps, cudaStream_t s);
 cudaError_t launch_anneal_propose(const AnnealParams &p, cudaStream_t s);
 cudaError_t launch_anneal_accept(const AnnealParams &p, cudaStream_t s);
 

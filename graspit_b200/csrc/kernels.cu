@@ -438,7 +438,7 @@ __device__ __noinline__ void near_emit(const DistParams &p, const int2 *nearq, c
     if (i < nnear) {
       t = (nearq[i].y & NEAR_TINY_BIT) != 0;
       k = neard[i] <= best * (t ? 1.004f : NEAR_BAND) + 1.0e-9f;
-      differs = k && fabsf(nearf[i] - best_fp) > 0.05f + 1.0e-5f * fabsf(best_fp);
+      differs = k && __float_as_int(nearf[i]) != __float_as_int(best_fp);
     }
     km[r] = __ballot_sync(FULL, k);
     anytiny = anytiny || __any_sync(FULL, k && t);
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
   int2 *nearq = reinterpret_cast<int2 *>(xp + 1);
   unsigned long long *confq = reinterpret_cast<unsigned long long *>(nearq + DNEAR_CAP);   // [DCONF_CAP] pairs that passed the pre-filter
   float *neard = reinterpret_cast<float *>(confq + DCONF_CAP);                             // [DNEAR_CAP] fp32 squared distance of nearq entries
-  float *nearf = neard + DNEAR_CAP;                                                          // [DNEAR_CAP] fingerprint of their closest points
+  float *nearf = neard + DNEAR_CAP;                                                          // [DNEAR_CAP] fingerprint (hash bits) of their closest points
   unsigned n_box = 0, n_tri = 0;
 #ifdef DIST_DEBUG_STATS
   unsigned dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0;
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
     float udt = 0.f;
     bool hit = false;
     bool near_overflow = false;    // the near-minimum list lost entries: its fp64 minimum is no longer authoritative
-    float best_fp = 0.f;           // fingerprint (a fixed linear form) of the best pair's closest points
+    float best_fp = 0.f;           // fingerprint (hash bits carried in a float) of the best pair's closest points
     int sp = 0, lq = 0, cq = 0, nnear = 0;
     if (lane == 0) stack[0] = pack_dist_entry(0.f, 0, 0);
     sp = 1;
@@ -646,7 +646,16 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
           // them is made in fp64 by dist_refine_kernel.  `best` here is the value before this batch: a superset.
           // fingerprint of this pair's closest points (B's frame): pairs that share the closest vertex / edge tie exactly
           // but describe the SAME solution and need no arbitration
-          const float fpr = fpr_lane = ((float)P1.x + 2.f * (float)P1.y + 3.f * (float)P1.z) * 6.0f + (pa.x + 2.f * pa.y + 3.f * pa.z) + 5.f * (pb.x + 2.f * pb.y + 3.f * pb.z);
+          // (a hash of both closest points on a 1/512 mm grid in B's frame, carried as the bits of a float: two pairs hash
+          // alike only if they describe the same two points; a linear form of the coordinates, used before, let pairs
+          // 0.1 mm apart pass as one solution at 300 mm coordinates and left 4 of 43 000 LIVE energies 1e-4 .. 1.6e-3 off)
+          unsigned hsh = 2166136261u;
+          {
+            const double qx[6] = {P1.x + (double)pa.x, P1.y + (double)pa.y, P1.z + (double)pa.z, P1.x + (double)pb.x, P1.y + (double)pb.y, P1.z + (double)pb.z};
+#pragma unroll
+            for (int k6 = 0; k6 < 6; k6++) hsh = (hsh ^ (unsigned)__double2int_rd(qx[k6] * 512.0)) * 16777619u;
+          }
+          const float fpr = fpr_lane = __int_as_float((int)hsh);
           const bool cand = res != TT_HIT && d2 < 2.9e38f && (tiny || d2 <= best * NEAR_BAND + 1.0e-12f);
           const unsigned cm = __ballot_sync(FULL, cand);
           const int add = __popc(cm);

@@ -34,6 +34,7 @@ EXPORTS = [
     "b2c_all_contacts", "b2c_region", "b2c_bounding_volumes", "b2c_robot_define", "b2c_eval_batch",
     "b2c_robot_bodies", "b2c_robot_pairs", "b2c_last_stats", "b2c_obb_hierarchy", "b2c_contacts_postprocess",
     "b2c_contact_visit_order", "b2c_check_overflow",
+    "b2c_exchange_create", "b2c_exchange_connect", "b2c_anneal_publish", "b2c_exchange_collect", "b2c_exchange_destroy",
     "b2c_anneal_create", "b2c_anneal_destroy", "b2c_anneal_step", "b2c_anneal_read", "b2c_anneal_device_ptrs",
     "b2c_anneal_propose", "b2c_anneal_write", "b2c_anneal_best_rows",
     "b2c_check_contact_normals", "b2c_contact_frames", "b2c_point_contact_wrenches",
@@ -193,6 +194,11 @@ def load_library():
     L.b2c_obb_hierarchy.argtypes = [C.POINTER(C.c_float), ci, ci, C.POINTER(Obb), ci, ip]
     L.b2c_contacts_postprocess.argtypes = [C.POINTER(Contact), ip, C.c_double, ci]
     L.b2c_check_overflow.argtypes = [vp]
+    L.b2c_exchange_create.argtypes = [vp, ci, ci, ci, ci, ci, vp, C.POINTER(vp)]
+    L.b2c_exchange_connect.argtypes = [vp, vp, C.POINTER(vp), ip]
+    L.b2c_anneal_publish.argtypes = [vp, ci, vp]
+    L.b2c_exchange_collect.argtypes = [vp, vp, vp, ci]
+    L.b2c_exchange_destroy.argtypes = [vp]
     L.b2c_contact_visit_order.argtypes = [C.POINTER(C.c_float), ci, C.POINTER(C.c_float), ci, dp, dp, dp, dp, ip, ip, ci, ip]
     _lib = L
     return L
@@ -529,6 +535,31 @@ class Engine:
         self._ck(self.L.b2c_robot_pairs(self.h, robot, _ip(out), 65536, C.byref(n)))
         return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(n.value)]
 
+    # --- best-row exchange between GPUs (no collective) -------------------------------------------------------------------
+    def exchange_create(self, rank: int, world: int, rows: int, row_floats: int, depth: int = 4):
+        """returns (64-byte IPC handle as bytes, own ring device pointer)"""
+        h = (C.c_ubyte * 64)()
+        ring = C.c_void_p()
+        self._ck(self.L.b2c_exchange_create(self.h, rank, world, depth, rows, row_floats, h, C.byref(ring)))
+        self._xshape = (world, rows, row_floats)
+        return bytes(h), ring.value
+
+    def exchange_connect(self, ipc_handles: bytes = None, peer_rings=None, peer_devices=None):
+        if peer_rings is not None:
+            arr = (C.c_void_p * len(peer_rings))(*peer_rings)
+            dev = None if peer_devices is None else (C.c_int * len(peer_devices))(*peer_devices)
+            self._ck(self.L.b2c_exchange_connect(self.h, None, arr, dev))
+        else:
+            buf = (C.c_ubyte * len(ipc_handles)).from_buffer_copy(ipc_handles)
+            self._ck(self.L.b2c_exchange_connect(self.h, buf, None, None))
+
+    def exchange_collect(self, rows_host_ptr: int, steps_host_ptr: int = 0, asynchronous=False):
+        """newest complete rows of every rank -> host memory [world][rows][row_floats] (+ steps [world])"""
+        self._ck(self.L.b2c_exchange_collect(self.h, rows_host_ptr, steps_host_ptr or None, int(bool(asynchronous))))
+
+    def exchange_destroy(self):
+        self._ck(self.L.b2c_exchange_destroy(self.h))
+
     def check_overflow(self):
         """synchronise and raise if a device-pointer evaluation overflowed an internal queue since the last check"""
         self._ck(self.L.b2c_check_overflow(self.h))
@@ -819,6 +850,10 @@ class Annealer:
     def best_rows(self, k: int, rows_device_ptr: int):
         """this context's k best (state || energy) rows into device memory [k][nvar + 1]; asynchronous"""
         self.engine._ck(self.engine.L.b2c_anneal_best_rows(self.engine.h, self.id, k, rows_device_ptr))
+
+    def publish(self, rows_device_ptr: int = 0):
+        """fused best-list update + store of this rank's best rows into every peer's ring (b2c_anneal_publish); asynchronous"""
+        self.engine._ck(self.engine.L.b2c_anneal_publish(self.engine.h, self.id, rows_device_ptr or None))
 
     def torch_views(self, device):
         """torch tensors aliasing the annealer's device rows (no copy): best, best_energy, cur, cur_energy"""

@@ -218,6 +218,52 @@ def exchange_best(rows, group=None):
     return out
 
 
+class PeerExchange:
+    """The planner's multi-GPU exchange without a collective (b2c_exchange_*): every rank stores its BEST_LIST_SIZE best
+    (state || energy) rows straight into its peers' HBM rings over NVLink right after a step (one fused kernel, no NCCL
+    launch, no rendezvous); ``collect`` reads whatever has landed.  torch.distributed is used ONCE, to hand the 64-byte
+    CUDA IPC handles round (one rank per process); ``peers`` = the other engines when all contexts live in this process."""
+
+    def __init__(self, engine, annealer, rank: int, world: int, rows: int = BEST_LIST_SIZE, depth: int = 4, peers=None, device=None):
+        import torch
+        self.engine, self.annealer, self.rank, self.world, self.rows = engine, annealer, rank, world, rows
+        self.row_floats = annealer.nvar + 1
+        handle, self.ring = engine.exchange_create(rank, world, rows, self.row_floats, depth)
+        self._handle = handle
+        if peers is None and world > 1:
+            import torch.distributed as dist
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+            allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allh, mine)
+            engine.exchange_connect(ipc_handles=bytes(allh.cpu().numpy().tobytes()))
+        self.host_rows = torch.zeros((world, rows, self.row_floats), dtype=torch.float32).pin_memory() if torch.cuda.is_available() else torch.zeros((world, rows, self.row_floats))
+        self.host_steps = torch.zeros(world, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else torch.zeros(world, dtype=torch.int32)
+
+    @staticmethod
+    def connect_in_process(exchanges):
+        """all contexts in one process (one per device): plain peer access instead of IPC"""
+        rings = [x.ring for x in exchanges]
+        devs = [x.engine.device for x in exchanges]
+        for x in exchanges:
+            x.engine.exchange_connect(peer_rings=rings, peer_devices=devs)
+
+    def publish(self):
+        self.annealer.publish()
+
+    def collect(self, asynchronous=False):
+        """rows [world, rows, nvar + 1] and steps [world] (host tensors; with asynchronous=True valid after a stream sync)"""
+        self.engine.exchange_collect(self.host_rows.data_ptr(), self.host_steps.data_ptr(), asynchronous)
+        return self.host_rows, self.host_steps
+
+    def merge_into(self, best_list):
+        """offer the collected rows to a BestList (only rows that beat its current worst entry reach the distance test)"""
+        r = self.host_rows.numpy().reshape(-1, self.row_floats)
+        e = r[:, -1]
+        m = e < min(best_list.worst_energy(), 1.0e7)
+        if m.any():
+            best_list.merge(r[m, :-1], e[m])
+
+
 def shard(nchain_total: int, rank: int, world: int):
     """block partition of the chains over ranks: chains [lo, hi) live on `rank` and never migrate"""
     per = nchain_total // world

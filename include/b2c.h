@@ -437,6 +437,26 @@ int b2c_anneal_device_ptrs(b2c_ctx *ctx, int anneal_id, void **best, void **best
  * planner's best list (SimAnnPlanner::mainLoop, simAnnPlanner.cpp:126-143).  Always call it with the same k. */
 int b2c_anneal_best_rows(b2c_ctx *ctx, int anneal_id, int k, void *rows_device);
 /* test hooks: the neighbours the next step would draw (no state change), and overwriting chain state */
+/* Multi-GPU: exchange of every GPU's BEST_LIST_SIZE best (state || energy) rows for the planner's best-list merge
+ * (reference src/EGPlanner/egPlanner.cpp:527-557) WITHOUT a collective.  Every rank owns a small ring of
+ * slots in its own HBM which its peers map (CUDA IPC between processes, peer access inside one process); after a step
+ * b2c_anneal_publish brings the context's best list up to date and stores its rows straight into every peer's ring over
+ * NVLink under a sequence lock -- one kernel, no NCCL launch, no rendezvous, a rank never waits for another one.
+ * b2c_exchange_collect copies out, per source rank, the newest complete rows that have landed (steps[src] = annealing
+ * step + 1 they belong to, 0 = nothing yet).  Rows only ever improve, so a reader that is a step behind or ahead merges
+ * the same list a little earlier or later.
+ *   create:  one exchange per context; ipc_handle_out (64 bytes, optional) is what the other PROCESSES need,
+ *            ring_out (optional) what other contexts of THIS process need
+ *   connect: ipc_handles = world x 64 bytes (all ranks, own entry ignored), or peer_rings = world device pointers
+ *            (+ peer_devices to enable peer access) when all contexts live in one process
+ *   publish: rows_device (optional) also receives this rank's rows [rows x (nvar + 1)]
+ *   collect: rows = world x rows x (nvar + 1) floats on the host (pinned for async != 0: the copy is then only enqueued) */
+int b2c_exchange_create(b2c_ctx *ctx, int rank, int world, int depth, int rows, int row_floats, void *ipc_handle_out, void **ring_out);
+int b2c_exchange_connect(b2c_ctx *ctx, const void *ipc_handles, void *const *peer_rings, const int *peer_devices);
+int b2c_anneal_publish(b2c_ctx *ctx, int anneal_id, void *rows_device);
+int b2c_exchange_collect(b2c_ctx *ctx, float *rows, int *steps, int async);
+int b2c_exchange_destroy(b2c_ctx *ctx);
+
 int b2c_anneal_propose(b2c_ctx *ctx, int anneal_id, float *proposals);
 int b2c_anneal_write(b2c_ctx *ctx, int anneal_id, const float *cur, const float *cur_energy, const int *k, int step);
 
