@@ -443,7 +443,7 @@ int b2c_anneal_best_rows(b2c_ctx *ctx, int anneal_id, int k, void *rows_device);
  * b2c_anneal_publish brings the context's best list up to date and stores its rows straight into every peer's ring over
  * NVLink under a sequence lock -- one kernel, no NCCL launch, no rendezvous, a rank never waits for another one.
  * b2c_exchange_collect copies out, per source rank, the newest complete rows that have landed (steps[src] = annealing
- * step + 1 they belong to, 0 = nothing yet).  Rows only ever improve, so a reader that is a step behind or ahead merges
+ * steps that source had completed + 1, 0 = nothing yet).  Rows only ever improve, so a reader that is a step behind or ahead merges
  * the same list a little earlier or later.
  *   create:  one exchange per context; ipc_handle_out (64 bytes, optional) is what the other PROCESSES need,
  *            ring_out (optional) what other contexts of THIS process need

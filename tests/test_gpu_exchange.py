@@ -49,7 +49,7 @@ def test_peer_exchange_two_contexts():
             own.append(rows.cpu().numpy())
         for r in range(2):
             got, steps = xs[r].collect()
-            assert steps.tolist() == [step + 1, step + 1]                 # the newest complete slot of either source
+            assert steps.tolist() == [step + 2, step + 2]                 # tag = annealing steps completed + 1; newest complete slot of either source
             for src in range(2):
                 assert np.array_equal(got[src].numpy(), own[src]), (step, r, src)
     # rows are real: finite energies of legal states, sorted into a best list without error
@@ -71,4 +71,4 @@ def test_collect_before_anything_arrived_reports_step_zero():
     an.step(1)
     x.publish()
     rows, steps = x.collect()
-    assert steps.tolist() == [1]
+    assert steps.tolist() == [2]          # one step completed
