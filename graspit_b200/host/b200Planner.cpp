@@ -249,6 +249,110 @@ bool BatchedSimAnnPlanner::run(int nSteps)
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+static bool makeAnnealDesc(b2c_anneal_desc *d, int robot, int object, int nchain, const transf7 &refTran,
+                           const std::vector<SearchVariable> &variables, const SimAnnParams &params, unsigned long long seed,
+                           int chainOffset, bool contactLive, std::vector<double> *vmin, std::vector<double> *vmax,
+                           std::vector<double> *vjump, std::vector<unsigned char> *circ)
+{
+  const int nv = (int)variables.size();
+  vmin->resize(nv); vmax->resize(nv); vjump->resize(nv); circ->resize(nv);
+  for (int i = 0; i < nv; i++) {
+    (*vmin)[i] = variables[i].mMinVal; (*vmax)[i] = variables[i].mMaxVal; (*vjump)[i] = variables[i].mMaxJump;
+    (*circ)[i] = variables[i].mCircular ? 1 : 0;
+  }
+  memset(d, 0, sizeof *d);
+  d->robot = robot; d->object = object; d->nchain = nchain; d->nvar = nv;
+  d->vmin = vmin->data(); d->vmax = vmax->data(); d->vjump = vjump->data(); d->circular = circ->data();
+  for (int k = 0; k < 4; k++) {d->ref_q[k] = refTran.q[k];}
+  for (int k = 0; k < 3; k++) {d->ref_t[k] = refTran.t[k];}
+  d->YC = params.YC; d->HC = params.HC; d->NBR_ADJ = params.NBR_ADJ; d->ERR_ADJ = params.ERR_ADJ; d->T0 = params.DEF_T0;
+  d->YDIMS = params.YDIMS; d->HDIMS = params.HDIMS; d->K0 = params.DEF_K0;
+  d->seed = seed; d->chain_offset = chainOffset; d->flags = contactLive ? B2C_EVAL_LIVE : B2C_EVAL_PRESET;
+  return true;
+}
+
+MultiGpuSimAnnPlanner::MultiGpuSimAnnPlanner(const std::vector<b2c_ctx *> &contexts, const std::vector<int> &robots,
+                                             const std::vector<int> &objects, const transf7 &refTran,
+                                             const std::vector<SearchVariable> &variables, const SimAnnParams &params,
+                                             const std::vector<float> &initialStates, unsigned long long seed, bool contactLive,
+                                             double maxRadius)
+  : mCtx(contexts), mNumVars((int)variables.size()), mCurrentStep(params.DEF_K0), mChainsPerRank(0),
+    mBestList(refTran, maxRadius), mValid(false)
+{
+  const int world = (int)contexts.size();
+  if (world < 1 || (int)robots.size() != world || (int)objects.size() != world || mNumVars <= 0) {mError = "one robot and object id per context"; return;}
+  const size_t total = initialStates.size() / mNumVars;
+  if (total == 0 || total % world != 0) {mError = "the chain count must be a multiple of the context count"; return;}
+  mChainsPerRank = (int)(total / world);
+  mAnnealers.assign(world, -1);
+  std::vector<void *> rings(world, NULL);
+  std::vector<int> devices(world, 0);
+  for (int r = 0; r < world; r++) {
+    b2c_anneal_desc d;
+    std::vector<double> vmin, vmax, vjump; std::vector<unsigned char> circ;
+    makeAnnealDesc(&d, robots[r], objects[r], mChainsPerRank, refTran, variables, params, seed, r * mChainsPerRank, contactLive,
+                   &vmin, &vmax, &vjump, &circ);
+    if (b2c_anneal_create(mCtx[r], &d, initialStates.data() + (size_t)r * mChainsPerRank * mNumVars, &mAnnealers[r]) != B2C_OK ||
+        b2c_exchange_create(mCtx[r], r, world, 4, BEST_LIST_SIZE, mNumVars + 1, NULL, &rings[r]) != B2C_OK) {
+      mError = b2c_last_error(mCtx[r]); return;
+    }
+    devices[r] = b2c_device(mCtx[r]);
+  }
+  for (int r = 0; r < world; r++) {
+    if (b2c_exchange_connect(mCtx[r], NULL, rings.data(), devices.data()) != B2C_OK) {mError = b2c_last_error(mCtx[r]); return;}
+  }
+  mRows.assign((size_t)world * BEST_LIST_SIZE * (mNumVars + 1), 0.f);
+  mSteps.assign(world, 0);
+  mValid = true;
+}
+
+MultiGpuSimAnnPlanner::~MultiGpuSimAnnPlanner()
+{
+  for (size_t r = 0; r < mCtx.size(); r++) {
+    if (r < mAnnealers.size() && mAnnealers[r] >= 0) {b2c_anneal_destroy(mCtx[r], mAnnealers[r]);}
+    b2c_exchange_destroy(mCtx[r]);
+  }
+}
+
+bool MultiGpuSimAnnPlanner::collectAndMerge()
+{
+  if (b2c_exchange_collect(mCtx[0], mRows.data(), mSteps.data(), 0) != B2C_OK) {mError = b2c_last_error(mCtx[0]); return false;}
+  const int n = (int)mCtx.size() * BEST_LIST_SIZE, w = mNumVars + 1;
+  std::vector<int> order(n);
+  for (int i = 0; i < n; i++) {order[i] = i;}
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {return mRows[(size_t)a * w + mNumVars] < mRows[(size_t)b * w + mNumVars];});
+  for (int k = 0; k < n; k++) {
+    const float *r = &mRows[(size_t)order[k] * w];
+    if (!(r[mNumVars] < 1.0e7f) || !(r[mNumVars] < mBestList.worstEnergy())) {continue;}
+    PlannerState s;
+    s.vars.assign(r, r + mNumVars); s.energy = r[mNumVars]; s.itNumber = mCurrentStep;
+    mBestList.offer(s);
+  }
+  return true;
+}
+
+bool MultiGpuSimAnnPlanner::run(int nSteps)
+{
+  if (!mValid) {return false;}
+  for (int s = 0; s < nSteps; s++) {
+    // enqueue on every device (asynchronous: the GPUs run the step concurrently), each publishes into all rings
+    for (size_t r = 0; r < mCtx.size(); r++) {
+      if (b2c_anneal_step(mCtx[r], mAnnealers[r], 1) != B2C_OK || b2c_anneal_publish(mCtx[r], mAnnealers[r], NULL) != B2C_OK) {
+        mError = b2c_last_error(mCtx[r]); return false;
+      }
+    }
+    mCurrentStep++;
+    // merge what has landed on context 0 (waits for ITS stream only; peers that are behind are picked up next step)
+    if (!collectAndMerge()) {return false;}
+  }
+  // the end of a run is a synchronisation point: every GPU's last rows are in
+  for (size_t r = 0; r < mCtx.size(); r++) {
+    if (b2c_check_overflow(mCtx[r]) != B2C_OK) {mError = b2c_last_error(mCtx[r]); return false;}
+  }
+  return collectAndMerge();
+}
+
 bool listPlannerRun(b2c_ctx *ctx, int robot, int object, const transf7 &refTran, const std::vector<PlannerState> &states,
                     bool contactLive, std::vector<unsigned char> *legal, std::vector<float> *energy,
                     std::vector<PlannerState> *bestList, int nEG)

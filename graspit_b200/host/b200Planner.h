@@ -107,6 +107,41 @@ class BatchedSimAnnPlanner
     int annealer() const {return mAnnealer;}
 };
 
+//! SimAnnPlanner over several GPUs driven from ONE process: one context per device, the chains
+//! block-partitioned over them (chain g keeps its Philox stream wherever it runs, so the trajectories equal the
+//! single-GPU ones), no data-path collective.  After every step each context publishes its BEST_LIST_SIZE best rows
+//! straight into its peers' HBM rings (b2c_anneal_publish: peer access over NVLink, no NCCL, no rendezvous); the host
+//! merges what has landed on the first context into mBestList with the reference's rules
+//! (simAnnPlanner.cpp:111-148, egPlanner.cpp:527-557).  The contexts must hold the same world (bodies, robot, object).
+class MultiGpuSimAnnPlanner
+{
+    std::vector<b2c_ctx *> mCtx;
+    std::vector<int> mAnnealers;
+    int mNumVars, mCurrentStep, mChainsPerRank;
+    std::vector<float> mRows;           // [world][BEST_LIST_SIZE][nvars + 1] as collected on context 0
+    std::vector<int> mSteps;
+    BestList mBestList;
+    std::string mError;
+    bool mValid;
+    bool collectAndMerge();
+  public:
+    //! robots[i] / objects[i]: the ids inside contexts[i]; initialStates: all chains (a multiple of the context count)
+    MultiGpuSimAnnPlanner(const std::vector<b2c_ctx *> &contexts, const std::vector<int> &robots, const std::vector<int> &objects,
+                          const transf7 &refTran, const std::vector<SearchVariable> &variables, const SimAnnParams &params,
+                          const std::vector<float> &initialStates, unsigned long long seed = 1234, bool contactLive = false,
+                          double maxRadius = 200.0);
+    ~MultiGpuSimAnnPlanner();
+    bool valid() const {return mValid;}
+    const std::string &error() const {return mError;}
+    //! n annealing steps on every GPU (enqueued device by device, running concurrently), exchange + merge every step
+    bool run(int nSteps);
+    int getCurrentStep() const {return mCurrentStep;}
+    const std::vector<PlannerState> &getBestList() const {return mBestList.list();}
+    //! annealing steps each source rank had completed when its rows were last taken (+ 1; 0 = none seen)
+    const std::vector<int> &stepsSeen() const {return mSteps;}
+    int annealer(int rank) const {return mAnnealers[rank];}
+};
+
 //! ListPlanner: every input state evaluated in one call; legal ones enter the list while it has room or they beat its
 //! worst entry (no similarity pruning, as in the reference)
 bool listPlannerRun(b2c_ctx *ctx, int robot, int object, const transf7 &refTran, const std::vector<PlannerState> &states,

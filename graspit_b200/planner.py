@@ -105,46 +105,95 @@ def aa_state_pose(state, ref_tran):
     return _quat_mul(rq, q), rt + rot_t
 
 
+def _poses_of(states, ref_tran):
+    """aa_state_pose for a batch: (q (n,4), t (n,3))"""
+    st = np.asarray(states, dtype=np.float64).reshape(-1, np.asarray(states).shape[-1])
+    out_q = np.zeros((len(st), 4)); out_t = np.zeros((len(st), 3))
+    for i, s in enumerate(st):
+        out_q[i], out_t[i] = aa_state_pose(s, ref_tran)
+    return out_q, out_t
+
+
 class BestList:
-    """mBestList of SimAnnPlanner: at most BEST_LIST_SIZE states, sorted by energy, no two closer than 0.2."""
+    """mBestList of SimAnnPlanner: at most BEST_LIST_SIZE states, sorted by energy, no two closer than 0.2.
+    The poses of the listed states are cached, and a candidate is compared with the whole list in one numpy expression
+    (HandObjectState::distance, searchState.cpp:572-611): the merge runs inside the timed planner step."""
 
     def __init__(self, ref_tran, max_radius=200.0, size=BEST_LIST_SIZE, distance=0.2):
         self.ref_tran, self.max_radius, self.size, self.distance = ref_tran, max_radius, size, distance
         self.states: List[np.ndarray] = []
         self.energies: List[float] = []
+        self._q = np.zeros((0, 4)); self._t = np.zeros((0, 3))
+        self._seen = set()
 
     def worst_energy(self) -> float:
         return 1.0e5 if len(self.states) < self.size else self.energies[-1]      # simAnnPlanner.cpp:128-130
+
+    def _distances(self, pose):
+        """state_distance(pose, every listed pose)"""
+        if not self.states:
+            return np.zeros(0)
+        d = np.linalg.norm(self._t - pose[1][None, :], axis=1) / self.max_radius
+        qa = np.asarray(pose[0], dtype=np.float64)
+        qb = self._q
+        # q = qa * conj(qb), normalised, w >= 0; angle = 2 atan2(|xyz|, w)
+        w = qa[0] * qb[:, 0] + qa[1] * qb[:, 1] + qa[2] * qb[:, 2] + qa[3] * qb[:, 3]
+        x = -qa[0] * qb[:, 1] + qa[1] * qb[:, 0] - qa[2] * qb[:, 3] + qa[3] * qb[:, 2]
+        y = -qa[0] * qb[:, 2] + qa[1] * qb[:, 3] + qa[2] * qb[:, 0] - qa[3] * qb[:, 1]
+        z = -qa[0] * qb[:, 3] - qa[1] * qb[:, 2] + qa[2] * qb[:, 1] + qa[3] * qb[:, 0]
+        n = np.sqrt(w * w + x * x + y * y + z * z)
+        w, x, y, z = w / n, x / n, y / n, z / n
+        sgn = np.where(w < 0, -1.0, 1.0)
+        angle = 2.0 * np.arctan2(np.sqrt(x * x + y * y + z * z), w * sgn)
+        return np.maximum(d, 0.5 * np.abs(angle) / np.pi)
 
     def offer(self, state, energy) -> bool:
         """the JUMP branch of SimAnnPlanner::mainLoop (simAnnPlanner.cpp:131-143)"""
         if not energy < self.worst_energy():
             return False
         pose = aa_state_pose(state, self.ref_tran)
-        i, add = 0, True
-        while i < len(self.states):                                              # addToListOfUniqueSolutions
-            if abs(state_distance(pose, aa_state_pose(self.states[i], self.ref_tran), self.max_radius)) < self.distance:
-                if energy < self.energies[i]:
-                    del self.states[i]; del self.energies[i]
-                else:
-                    add = False
-                    break
+        # addToListOfUniqueSolutions (egPlanner.cpp:527-557): walk the list in order; a near entry with higher energy is
+        # erased, the first near entry with lower-or-equal energy rejects the candidate (entries erased before it stay erased)
+        near = np.abs(self._distances(pose)) < self.distance
+        keep = np.ones(len(self.states), dtype=bool)
+        add = True
+        for i in np.nonzero(near)[0]:
+            if energy < self.energies[i]:
+                keep[i] = False
             else:
-                i += 1
+                add = False
+                break
+        if not keep.all():
+            self.states = [s for s, k in zip(self.states, keep) if k]
+            self.energies = [e for e, k in zip(self.energies, keep) if k]
+            self._q, self._t = self._q[keep], self._t[keep]
         if not add:
             return False
         self.states.append(np.array(state, dtype=np.float32)); self.energies.append(float(energy))
-        order = np.argsort(np.array(self.energies), kind="stable")
-        self.states = [self.states[j] for j in order][: self.size]
-        self.energies = [self.energies[j] for j in order][: self.size]
+        self._q = np.concatenate([self._q, np.asarray(pose[0], dtype=np.float64)[None]], 0)
+        self._t = np.concatenate([self._t, np.asarray(pose[1], dtype=np.float64)[None]], 0)
+        order = np.argsort(np.array(self.energies), kind="stable")[: self.size]
+        self.states = [self.states[j] for j in order]
+        self.energies = [self.energies[j] for j in order]
+        self._q, self._t = self._q[order], self._t[order]
         return True
 
     def merge(self, states: Sequence, energies: Sequence):
-        """offer candidates in ascending energy (the order a single planner would have met the better ones)"""
+        """offer candidates in ascending energy (the order a single planner would have met the better ones).  Rows that were
+        offered before (the exchange repeats a GPU's best rows until they change) are skipped: offering a state twice
+        cannot change the list."""
         e = np.asarray(energies, dtype=np.float64)
+        st = np.asarray(states, dtype=np.float32)
         for j in np.argsort(e, kind="stable"):
-            if e[j] < 1.0e7:
-                self.offer(np.asarray(states[j]), float(e[j]))
+            if not e[j] < 1.0e7:
+                continue
+            key = (st[j].tobytes(), float(e[j]))
+            if key in self._seen:
+                continue
+            if len(self._seen) > 100000:
+                self._seen.clear()
+            self._seen.add(key)
+            self.offer(st[j], float(e[j]))
 
 
 def complete_dof_to_raw(states, ref_tran):

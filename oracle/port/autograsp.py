@@ -99,7 +99,9 @@ class AutoGraspOracle:
     def set_joints(self, base, jv):
         """KinematicChain::fwdKinematics from explicit joint values -> link poses into the reference world"""
         r = self.r
-        b = (np.asarray(base[0], dtype=np.float64)[None], np.asarray(base[1], dtype=np.float64)[None])
+        # transf(Quaternion, vec3) normalises its rotation (transform.h:46-48): a base quaternion that went through fp32 is
+        # 4e-8 off unit length, and an unnormalised one would leak into every link translation below
+        b = T.make(np.asarray(base[0], dtype=np.float64)[None], np.asarray(base[1], dtype=np.float64)[None])
         self.last_tf = {r.base_body: (b[0][0].copy(), b[1][0].copy())}      # scene body -> (q wxyz, t) as pushed to the world
         self.w.set_transform(self.ids[r.base_body], b[0][0], b[1][0])
         if r.mount_body >= 0:

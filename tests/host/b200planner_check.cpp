@@ -14,6 +14,8 @@
 
 #include "b200Planner.h"
 
+extern "C" int cudaGetDeviceCount(int *count);      // libcudart (no CUDA headers needed on the host side)
+
 using namespace b200;
 static int g_fail = 0, g_checks = 0;
 #define CHECK(cond, ...) do { g_checks++; if (!(cond)) { g_fail++; printf("FAIL %s:%d  %s  ", __FILE__, __LINE__, #cond); printf(__VA_ARGS__); printf("\n"); } } while (0)
@@ -84,11 +86,11 @@ struct Scene {
   std::vector<double> jointRatio;
 };
 
-static bool loadScene(const char *path, Scene *S)
+static bool loadScene(const char *path, Scene *S, int device = 0)
 {
   std::ifstream in(path);
   if (!in) return false;
-  if (b2c_create(0, &S->ctx) != B2C_OK) return false;
+  if (b2c_create(device, &S->ctx) != B2C_OK) return false;
   int nb; in >> nb;
   std::vector<int> ids(nb);
   for (int i = 0; i < nb; i++) {
@@ -237,6 +239,53 @@ static void gpuChecks(const char *scenePath)
   b2c_destroy(S.ctx);
 }
 
+// One process, several contexts (one per device; on a single-GPU box both on device 0): the chains are split over them,
+// trajectories equal the single-context run chain by chain, the best list is fed by the collective-free exchange.
+static void multiGpuChecks(const char *scenePath)
+{
+  int ndev = 0;
+  cudaGetDeviceCount(&ndev);
+  const int world = 2;
+  Scene S[2], One;
+  for (int r = 0; r < world; r++)
+    if (!loadScene(scenePath, &S[r], ndev > 1 ? r : 0)) { printf("FAIL cannot load the scene on rank %d\n", r); g_fail++; return; }
+  if (!loadScene(scenePath, &One, 0)) { g_fail++; return; }
+  std::vector<SearchVariable> vars = axisAngleEigenVariables(One.neg);
+  const int K = 4096, nv = (int)vars.size();
+  std::mt19937_64 rng(5);
+  std::vector<float> init((size_t)K * nv);
+  for (int c = 0; c < K; c++) for (int i = 0; i < nv; i++) init[(size_t)c * nv + i] = (float)std::uniform_real_distribution<double>(vars[i].mMinVal, vars[i].mMaxVal)(rng);
+  {
+    MultiGpuSimAnnPlanner multi({S[0].ctx, S[1].ctx}, {S[0].robot, S[1].robot}, {S[0].object, S[1].object}, One.ref, vars,
+                                SimAnnParams::ANNEAL_DEFAULT(), init, 1234);
+    BatchedSimAnnPlanner single(One.ctx, One.robot, One.object, One.ref, vars, SimAnnParams::ANNEAL_DEFAULT(), init, 1234);
+    CHECK(multi.valid() && single.valid(), "%s %s", multi.error().c_str(), single.error().c_str());
+    for (int it = 0; it < 3; it++) CHECK(multi.run(20), "%s", multi.error().c_str());
+    CHECK(single.run(60), "%s", single.error().c_str());
+    CHECK(multi.getCurrentStep() == 30060, "step counter %d", multi.getCurrentStep());
+    CHECK(multi.stepsSeen()[0] == 61 && multi.stepsSeen()[1] == 61, "rows seen from steps %d / %d", multi.stepsSeen()[0], multi.stepsSeen()[1]);
+    // chain by chain the same trajectories: best energies of the two halves == the single run's
+    std::vector<float> be(K), half(K / 2);
+    CHECK(b2c_anneal_read(One.ctx, single.annealer(), NULL, NULL, NULL, be.data(), NULL, NULL) == B2C_OK, "read");
+    int same = 0;
+    for (int r = 0; r < world; r++) {
+      CHECK(b2c_anneal_read(S[r].ctx, multi.annealer(r), NULL, NULL, NULL, half.data(), NULL, NULL) == B2C_OK, "read rank %d", r);
+      for (int c = 0; c < K / 2; c++) same += half[c] == be[(size_t)r * (K / 2) + c];
+    }
+    CHECK(same == K, "%d of %d chains end with the single-GPU best energy", same, K);
+    // the merged best list: sorted, distinct, and its head is the global minimum over all chains
+    const std::vector<PlannerState> &best = multi.getBestList();
+    CHECK(!best.empty() && (int)best.size() <= BEST_LIST_SIZE, "%zu solutions", best.size());
+    for (size_t i = 1; i < best.size(); i++) CHECK(best[i - 1].energy <= best[i].energy, "sorted");
+    float gmin = 3.0e38f;
+    for (float e : be) gmin = std::min(gmin, e);
+    CHECK(!best.empty() && (float)best[0].energy == gmin, "head %g vs global minimum %g", best.empty() ? 0.0 : best[0].energy, gmin);
+    printf("MultiGpuSimAnnPlanner: %d contexts on %d device(s), %zu solutions, best %g\n", world, ndev > 1 ? 2 : 1, best.size(), best.empty() ? 0.0 : best[0].energy);
+  }
+  for (int r = 0; r < world; r++) b2c_destroy(S[r].ctx);
+  b2c_destroy(One.ctx);
+}
+
 int main(int argc, char **argv)
 {
   if (argc < 2) { fprintf(stderr, "usage: %s cpu | gpu scene.txt\n", argv[0]); return 2; }
@@ -244,6 +293,7 @@ int main(int argc, char **argv)
   if (!strcmp(argv[1], "gpu")) {
     if (argc < 3) return 2;
     gpuChecks(argv[2]);
+    multiGpuChecks(argv[2]);
   }
   printf("%s: %d checks, %d failed\n", g_fail ? "FAILED" : "PASSED", g_checks, g_fail);
   return g_fail ? 1 : 0;

@@ -25,6 +25,22 @@ for p in range(len(js)):
         qo, to = ag.last_tf[inv_e[b]]
         worst_t[k] = max(worst_t[k], np.abs(tf[p, k, 4:] - to).max())
         worst_q[k] = max(worst_q[k], min(np.abs(tf[p, k, :4] - qo).max(), np.abs(tf[p, k, :4] + qo).max()))
+np.set_printoptions(linewidth=250)
 print("per body max |dt|", worst_t)
 print("per body max |dq|", worst_q)
 print("base q norm - 1:", np.abs(np.linalg.norm(js[:, :4], axis=1) - 1).max())
+
+# the same on the poses of the contact sweep, if present
+if os.path.exists("gpurun_out/contacts_sweep_r02d.npz") or os.path.exists("tools/diag/sweep_js.npz"):
+    pth = "tools/diag/sweep_js.npz" if os.path.exists("tools/diag/sweep_js.npz") else "gpurun_out/contacts_sweep_r02d.npz"
+    js2 = np.load(pth)["js"][:300]
+    tf2 = eng.eval_batch(rid, -1, js2, input_mode=B2C_INPUT_JOINTS, body_tf=True)["body_tf"]
+    wt = np.zeros(len(bodies)); wq = np.zeros(len(bodies))
+    for p in range(len(js2)):
+        ag.set_joints((js2[p, 0:4], js2[p, 4:7]), js2[p, 7:])
+        for k, b in enumerate(bodies):
+            qo, to = ag.last_tf[inv_e[b]]
+            wt[k] = max(wt[k], np.abs(tf2[p, k, 4:] - to).max())
+            wq[k] = max(wq[k], min(np.abs(tf2[p, k, :4] - qo).max(), np.abs(tf2[p, k, :4] + qo).max()))
+    print("sweep poses: per body max |dt|", wt)
+    print("sweep poses: per body max |dq|", wq)

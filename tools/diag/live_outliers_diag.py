@@ -40,6 +40,11 @@ for p in bad:
         dp = max(np.linalg.norm(l1 - mp1r), np.linalg.norm(l2 - mp2r))
         if dp > 1e-3:
             db, b1, b2, tp = w.brute_distance(osc.ids[b], osc.ids[obj])
+            # the exhaustive winner as a two-triangle world: does the engine's own leaf arithmetic agree with the reference's?
+            ta = eng.add_body(sc.bodies[b].tris[tp[0]:tp[0] + 1]); tb_ = eng.add_body(sc.bodies[obj].tris[tp[1]:tp[1] + 1])
+            eng.set_body_transform(ta, tf7[p, j, :4], tf7[p, j, 4:]); eng.set_body_transform(tb_, *sc.body_tran[obj])
+            dpair, q1, q2 = eng.body_to_body_distance(ta, tb_, local=True)
+            print("    engine on the exhaustive winner alone: %.10f (|pts - brute pts| %.3g)" % (dpair, max(np.linalg.norm(q1 - b1), np.linalg.norm(q2 - b2))))
             print("  pose %d link %d: ref %.10f engine %.10f brute %.10f | (ref-brute)/brute %.3g (engine-brute)/brute %.3g | batch link_dist %.8f | |engine pts - brute pts| %.4g, |ref pts - brute pts| %.4g, brute tris %s"
                   % (p, j, dr, de, db, (dr - db) / db, (de - db) / db, live["link_dist"][p, j],
                      max(np.linalg.norm(l1 - b1), np.linalg.norm(l2 - b2)), max(np.linalg.norm(mp1r - b1), np.linalg.norm(mp2r - b2)), tp))
