@@ -297,6 +297,8 @@ def run_workload(B: Bench, scene_id: str, workload: str, npose: int, K: int, W: 
     def exchange_step(i):
         """issue the exchange of step i; merge (on the host) the rows collected at step i - 1, which have long landed"""
         slot = i % RING
+        if exchange == "none":
+            return
         if exchange == "peer":
             an.publish()
             eng.exchange_collect(host_rows[slot].data_ptr(), 0, True)
@@ -468,7 +470,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="preset", choices=["preset", "live"])
     ap.add_argument("--workload", default="anneal", choices=["anneal", "random", "config5"])
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "none"], help="none: no best-list upkeep at all (diagnostic)")
     ap.add_argument("--poses", type=int, default=65536)
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")

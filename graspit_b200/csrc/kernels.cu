@@ -421,9 +421,12 @@ __device__ __noinline__ int near_compact(int2 *nearq, float *neard, float *nearf
   }
   return kept;
 }
-// pairs still within tolerance of the FINAL best go to the fp64 refinement kernel -- only when there is a decision to
-// make: two or more candidates with different closest points, or a distance fp32 could not resolve.  Candidates that tie
-// because they share the closest vertex or edge describe one solution: nothing to arbitrate.
+// Pairs still within tolerance of the FINAL best go to the fp64 refinement kernel.  All of them when there is a decision
+// to make: two or more candidates with different closest points, or a distance fp32 could not resolve.  Candidates that
+// tie because they share the closest vertex or edge describe one solution: then only the winner goes, so that the
+// closest POINTS reported for a query always come from fp64 arithmetic -- between nearly parallel features the location of
+// the closest points is ill-conditioned (fp32 on coordinates of a few hundred mm moved them by 0.1 mm while the distance
+// changed by 2e-8 relative), and CONTACT_LIVE builds its virtual contacts from those points.
 __device__ __noinline__ void near_emit(const DistParams &p, const int2 *nearq, const float *neard, const float *nearf, int nnear,
                                        float best, float best_fp, bool overflow, int w) {
   const int lane = threadIdx.x & 31;
@@ -445,7 +448,25 @@ __device__ __noinline__ void near_emit(const DistParams &p, const int2 *nearq, c
     anydiff = anydiff || __any_sync(FULL, differs);
     cnt += __popc(km[r]);
   }
-  if (!((cnt >= 2 && anydiff) || anytiny)) return;
+  if (cnt == 0) return;
+  const bool arbitrate = (cnt >= 2 && anydiff) || anytiny;
+  if (!arbitrate && !p.pts) return;          // distances only (autograsp work lists): fp32 is what the caller asked for
+  if (!arbitrate && cnt > 1) {
+    // no arbitration needed: keep the fp32 winner alone (smallest distance, lowest index on ties)
+    float bd = 3.0e38f; int bi = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < (DNEAR_CAP + 31) / 32; r++) {
+      const int i = r * 32 + lane;
+      if (((km[r] >> lane) & 1u) && (neard[i] < bd)) { bd = neard[i]; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(FULL, bd, o); const int oi = __shfl_xor_sync(FULL, bi, o);
+      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+#pragma unroll
+    for (int r = 0; r < (DNEAR_CAP + 31) / 32; r++) km[r] = (bi >> 5) == r ? (1u << (bi & 31)) : 0u;
+    cnt = 1;
+  }
   int seg = 0, ofs = 0;
   if (lane == 0) { seg = atomicAdd(p.near_count, 1); ofs = atomicAdd(p.near_count + 1, cnt); }
   seg = __shfl_sync(FULL, seg, 0); ofs = __shfl_sync(FULL, ofs, 0);
@@ -836,7 +857,9 @@ __global__ void __launch_bounds__(128) dist_refine_kernel(DistParams p) {
     // the list holds every pair within tolerance of the fp32 best (flag 1): its fp64 minimum IS the answer; if the list
     // overflowed (flag 0) the fp32 answer stands unless a refined pair beats it
     const float cur = p.dist[w];
-    const bool replace = d.w != 0 || sqrt(m) < (double)cur;
+    // (flag 0: the list lost entries, so its minimum only counts if it is the fp32 winner itself -- equal within fp32
+    // rounding -- or better)
+    const bool replace = d.w != 0 || sqrt(m) <= (double)cur * (1.0 + 1.0e-6);
     if (replace && lane == __ffs(who) - 1 && m < 1.0e299) {
       p.dist[w] = (float)sqrt(m);
       if (p.pts) {

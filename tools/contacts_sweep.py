@@ -68,6 +68,7 @@ def cpu(path):
     same_pairs = groups = exact = cluster_ok = counts_equal = 0
     worst = 0.0
     differing = []
+    near_ties = 0
     for p in range(npose):
         ag.set_joints((js[p, 0:4], js[p, 4:7]), js[p, 7:])
         # GraspitCollision::allContacts runs ContactCallback(model1, model2) with the models in ADDRESS order
@@ -96,15 +97,35 @@ def cpu(path):
             counts_equal += len(a) == len(b)
             if _same_set(a, b):
                 exact += 1
-            elif len(differing) < 40:
-                differing.append({"pose": int(p), "pair": [int(key[0]), int(key[1])], "engine": int(len(a)), "reference": int(len(b))})
+            else:
+                # Why can a group still differ?  removeContactDuplicates keeps, of two candidates within 3 mm, the one with the
+                # smaller distSq and, on a tie, the LATER one (collisionInterface.cpp:254-287); where the survivor sits in the
+                # list then decides what it meets next.  Candidates that describe the same contact through different triangle
+                # pairs carry distSq values equal to ~1e-9 relative: which way such a near-tie falls hangs on the last bits of
+                # the fp64 arithmetic, which cannot be made bit-identical between g++ and nvcc code (FMA contraction,
+                # composition order of the transforms).  Count the groups whose reference candidate list holds such a near-tie.
+                ia, ib = int(key[0]), int(key[1])
+                raw, _ = osc.w.contact_raw(osc.ids[ia], osc.ids[ib], THR)
+                tie = False
+                for i in range(len(raw)):
+                    dd = np.abs(raw[i + 1:, 12] - raw[i, 12]) <= 1.0e-6 * raw[i, 12]
+                    close = (np.linalg.norm(raw[i + 1:, 0:3] - raw[i, 0:3], axis=1) <= 3.0) & (np.linalg.norm(raw[i + 1:, 3:6] - raw[i, 3:6], axis=1) <= 3.0)
+                    same = np.abs(raw[i + 1:, :6] - raw[i, :6]).max(axis=1) == 0.0
+                    if (dd & close & ~same).any():
+                        tie = True
+                        break
+                near_ties += tie
+                if len(differing) < 40:
+                    differing.append({"pose": int(p), "pair": [ia, ib], "engine": int(len(a)), "reference": int(len(b)), "near_tie_in_reference_candidates": bool(tie)})
             d = max(min(np.linalg.norm(a[:, :3] - r[:3], axis=1)) for r in b)
             worst = max(worst, float(d))
             cluster_ok += d < 6.0
     print(json.dumps({"what": "b2c_contacts_batch vs GraspitCollision::allContacts(0.2, hand) on hands closed by the batched autograsp (Barrett vs mug)",
                       "poses": int(npose), "poses_with_identical_contacting_pair_sets": int(same_pairs), "pair_groups": int(groups),
                       "groups_with_identical_contact_sets": int(exact), "groups_with_equal_contact_count": int(counts_equal),
-                      "groups_whose_contacts_fall_in_the_same_3mm_clusters": int(cluster_ok), "worst_nearest_contact_distance_mm": worst, "first_differing_groups": differing}))
+                      "groups_whose_contacts_fall_in_the_same_3mm_clusters": int(cluster_ok), "worst_nearest_contact_distance_mm": worst,
+                      "differing_groups_with_a_distSq_near_tie_among_the_reference_candidates": int(near_ties),
+                      "coordinate_tolerance_mm": TOL, "first_differing_groups": differing}))
 
 
 if __name__ == "__main__":
