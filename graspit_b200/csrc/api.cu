@@ -89,6 +89,7 @@ struct Plan {
   DevBuf<FkRobot> d_robots; DevBuf<FkChain> d_chains; DevBuf<FkJoint> d_joints; DevBuf<FkLink> d_links;
   DevBuf<double> d_eg; DevBuf<int> d_body_mesh; DevBuf<int2> d_pairs; DevBuf<VcDev> d_vcs; DevBuf<int2> d_queries;
   DevBuf<Xf> d_static;
+  std::vector<Xf> static_cache;     // what d_static holds
   FkProgram prog;
   void release() {
     d_robots.release(); d_chains.release(); d_joints.release(); d_links.release(); d_eg.release();
@@ -120,7 +121,7 @@ struct b2c_ctx {
   // scratch
   DevBuf<float> d_states; DevBuf<Xf> d_fk; DevBuf<double> d_fkqt; DevBuf<uint8_t> d_legal; DevBuf<float> d_energy;
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
-  DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
+  DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent; DevBuf<int2> d_fix;
   ContactRec *h_contacts = nullptr; // pinned staging of contact candidates (b2c_contacts_batch)
   DevBuf<ContactRec> d_contacts2;   // the same records grouped by query
   DevBuf<int> d_coffsets;           // per query: first record, fill cursor
@@ -131,7 +132,7 @@ struct b2c_ctx {
   size_t h_fk_cap = 0;
   int stage_nodes = 128;           // object-tree nodes staged in shared memory by the energy kernel
   int seed_res = 64;               // cells along the longest side of a closest-point seed grid (0 = no seeding)
-  unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long *last_stats = nullptr;    // pinned: the per-call copy must not block the host (a pageable D2H does)
   int last_counters[4] = {0, 0, 0, 0};
   int eval_warps_per_block = 8;
   int eval_blocks_per_sm = 0;      // 0 = derive from shared memory
@@ -407,6 +408,8 @@ int b2c_create(int device, b2c_ctx **out) {
   if (const char *e = getenv("B2C_SEED_RES")) ctx->seed_res = std::max(0, std::min(256, atoi(e)));
   if (const char *e = getenv("B2C_EVAL_WARPS")) ctx->eval_warps_per_block = std::max(1, std::min(32, atoi(e)));
   ctx->own_stream = ctx->stream;
+  if (cudaMallocHost(&ctx->last_stats, 8 * sizeof(unsigned long long)) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return B2C_ENODEVICE; }
+  memset(ctx->last_stats, 0, 8 * sizeof(unsigned long long));
   *out = ctx;
   return B2C_OK;
 }
@@ -451,6 +454,7 @@ void b2c_destroy(b2c_ctx *ctx) {
   autograsp_release_all(ctx);
   if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
   if (ctx->h_fk) cudaFreeHost(ctx->h_fk);
+  if (ctx->last_stats) cudaFreeHost(ctx->last_stats);
   invalidate_plans(ctx);
   for (auto &m : ctx->meshes) {
     if (m.d_nodes) cudaFree(m.d_nodes);
@@ -460,7 +464,7 @@ void b2c_destroy(b2c_ctx *ctx) {
   }
   ctx->d_meshes.release(); ctx->d_states.release(); ctx->d_fk.release(); ctx->d_fkqt.release(); ctx->d_legal.release();
   ctx->d_energy.release(); ctx->d_mask.release(); ctx->d_ambig.release(); ctx->d_counters.release(); ctx->d_stats.release();
-  ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release(); ctx->d_legal_list.release(); ctx->d_items.release(); ctx->d_contacts.release(); ctx->d_flags.release(); ctx->d_terms.release(); ctx->d_near_dir.release(); ctx->d_near_ent.release();
+  ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release(); ctx->d_legal_list.release(); ctx->d_items.release(); ctx->d_contacts.release(); ctx->d_flags.release(); ctx->d_terms.release(); ctx->d_near_dir.release(); ctx->d_near_ent.release(); ctx->d_fix.release();
   ctx->d_contacts2.release(); ctx->d_coffsets.release(); ctx->d_cubtemp.release(); ctx->d_sticky.release();
   for (int i = 0; i < 16; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->own_stream);
@@ -925,6 +929,8 @@ int b2c_robot_pairs(b2c_ctx *ctx, int robot, int *pairs, int cap, int *npairs) {
 
 int b2c_last_stats(b2c_ctx *ctx, unsigned long long stats[8]) {
   if (!ctx || !stats) return B2C_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);       // the counters of the last call ride on its stream
   for (int i = 0; i < 8; i++) stats[i] = ctx->last_stats[i];
   return B2C_OK;
 }
@@ -984,7 +990,13 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   // static transforms
   std::vector<Xf> sx(nb - nrb);
   for (int i = nrb; i < nb; i++) sx[i - nrb] = qt_to_xf(ctx->bodies[P->ebodies[i]].tf);
-  if (!sx.empty()) CU(cudaMemcpyAsync(P->d_static.p, sx.data(), sx.size() * sizeof(Xf), cudaMemcpyHostToDevice, ctx->stream));
+  // uploaded only when a static body moved since the last call: a pageable H2D copy synchronises the stream first, which
+  // would tie the host to the GPU once per annealing step
+  if (!sx.empty() && (P->static_cache.size() != sx.size() || memcmp(P->static_cache.data(), sx.data(), sx.size() * sizeof(Xf)) != 0)) {
+    CU(cudaMemcpyAsync(P->d_static.p, sx.data(), sx.size() * sizeof(Xf), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    P->static_cache = sx;
+  }
   CU(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int), ctx->stream));
   CU(cudaMemsetAsync(ctx->d_stats.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
 
@@ -1055,11 +1067,15 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   if (want_energy) {
     CU(ctx->d_terms.reserve((size_t)npose * std::max(P->nvc, P->nhand) + 32));
     gp.terms = ctx->d_terms.p;
+    // contested closest-point queries (near-ties): a fraction of a percent of the queries; an overflowing list only means
+    // the remaining ones keep their two-candidate arbitration
+    CU(ctx->d_fix.reserve(std::max<size_t>(1 << 16, (size_t)npose * std::max(P->nvc, P->nhand) / 16)));
+    gp.fix_list = ctx->d_fix.p; gp.fix_count = ctx->d_counters.p + 10; gp.fix_cap = (int)std::min<size_t>(ctx->d_fix.cap, 0x7fffffff);
   }
   if (want_energy && !live) {
     if (P->nvc > 256) return fail(ctx, B2C_ECAPACITY, "eval_batch: more than 256 virtual contacts");
     gp.live = 0;
-    PROF_BEGIN(4); CU(launch_energy(gp, energy_blocks(P->nvc), ctx->stream)); ctx->launches += 2; PROF_END(4);
+    PROF_BEGIN(4); CU(launch_energy(gp, energy_blocks(P->nvc), ctx->stream)); ctx->launches += 3; PROF_END(4);
   }
 
   // K4 (+ LIVE energy)
@@ -1093,7 +1109,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
     CU(launch_recheck(rd, ctx->stream)); ctx->launches++;
     if (live) {
       gp.live = 1; gp.pts = ctx->d_pts.p;
-      PROF_BEGIN(4); CU(launch_energy(gp, energy_blocks(nq), ctx->stream)); ctx->launches += 2; PROF_END(4);
+      PROF_BEGIN(4); CU(launch_energy(gp, energy_blocks(nq), ctx->stream)); ctx->launches += 3; PROF_END(4);
     }
   }
 
@@ -1105,7 +1121,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
     if (want_dist) CU(cudaMemcpyAsync(a->link_dist, d_dist, (size_t)npose * nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (want_tf) CU(cudaMemcpyAsync(a->body_tf, ctx->d_fkqt.p, (size_t)npose * nrb * 7 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  CU(cudaMemcpyAsync(ctx->last_stats, ctx->d_stats.p, sizeof ctx->last_stats, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->last_stats, ctx->d_stats.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   if (!dev) {
     // host buffers: the call synchronises anyway, so a queue overflow is reported right here.  With device pointers the
     // call stays asynchronous; the kernels have answered fail-safe ("collides") and set the sticky word, which the next

@@ -917,6 +917,28 @@ __device__ __forceinline__ unsigned long long point_tri_key(const MeshDev &mo, d
   return ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)h << 24) | (unsigned)tri;
 }
 
+// contact c of a pose -> query point in the object's frame and contact normal in the object's frame (fp32)
+__device__ __forceinline__ void energy_contact(const EnergyParams &p, int pose, int c, d3 &q, f3 &cnl) {
+  const double *XO = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, p.object);
+  d3 pw, cnw;
+  if (p.live) {
+    const double *o = p.pts + ((size_t)pose * p.nq + c) * 6;
+    d3 mP1 = mk<double>(o[0], o[1], o[2]), mP2 = mk<double>(o[3], o[4], o[5]);
+    d3 n = mP1 - mP2;
+    double nn = sqrt(dot(n, n));
+    if (nn > 0.0) n = n * (1.0 / nn);
+    pw = mP1;
+    cnw = mk<double>(-n.x, -n.y, -n.z);
+  } else {
+    const VcDev &vc = p.vcs[c];
+    const double *XL = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, vc.body);
+    pw = xf_apply(XL, mk<double>(vc.loc[0], vc.loc[1], vc.loc[2]));
+    cnw = xf_rot(XL, mk<double>(vc.normal[0], vc.normal[1], vc.normal[2]));
+  }
+  q = xf_apply_inv(XO, pw);
+  cnl = tof(xf_rot_t(XO, cnw));
+}
+
 // One warp = 32 closest-point queries (contacts of consecutive legal poses) traversed TOGETHER through one
 // shared work stack: every lane pops one (query, child-pair, lower bound) entry, loads the 64-byte pair of
 // sibling boxes, and pushes the children that can still beat the query's best distance (far first, near on
@@ -991,25 +1013,9 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
       pose = p.legal_list ? p.legal_list[li] : li;
       if (p.legal && !p.legal[pose]) valid = false;
     }
+    d3 q = mk<double>(0, 0, 0);
     if (valid) {
-      const double *XO = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, p.object);
-      d3 pw, cnw;
-      if (p.live) {
-        const double *o = p.pts + ((size_t)pose * p.nq + c) * 6;
-        d3 mP1 = mk<double>(o[0], o[1], o[2]), mP2 = mk<double>(o[3], o[4], o[5]);
-        d3 n = mP1 - mP2;
-        double nn = sqrt(dot(n, n));
-        if (nn > 0.0) n = n * (1.0 / nn);
-        pw = mP1;
-        cnw = mk<double>(-n.x, -n.y, -n.z);
-      } else {
-        const VcDev &vc = p.vcs[c];
-        const double *XL = body_xf_ptr(p.fk, p.static_xf, p.nrb, pose, vc.body);
-        pw = xf_apply(XL, mk<double>(vc.loc[0], vc.loc[1], vc.loc[2]));
-        cnw = xf_rot(XL, mk<double>(vc.normal[0], vc.normal[1], vc.normal[2]));
-      }
-      d3 q = xf_apply_inv(XO, pw);
-      cnl = tof(xf_rot_t(XO, cnw));
+      energy_contact(p, pose, c, q, cnl);
       qd[3 * lane] = q.x; qd[3 * lane + 1] = q.y; qd[3 * lane + 2] = q.z;
       qf[lane] = make_float4((float)q.x, (float)q.y, (float)q.z, 0.f);
       if (mo.seed) {
@@ -1123,6 +1129,12 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
         const unsigned long long key2 = secondkey[lane];
         const bool contested = key2 != EQ_NONE && ((key2 ^ key) & 0xff000000ull) != 0ull &&
                                __uint_as_float((unsigned)(key2 >> 32)) <= d2 * NEAR_BAND + 1.0e-12f;
+        if (contested && p.fix_list) {
+          // two candidates fp32 cannot order are rarely alone (a point near the mug's axis ties with a whole circle of rim
+          // segments): the query is re-run in fp64 by energy_fix_kernel, which overwrites this term
+          const int at = atomicAdd(p.fix_count, 1);
+          if (at < p.fix_cap) p.fix_list[at] = make_int2(qid, tri);
+        }
         if (d2 < 1.0e-4f * sc * sc || contested) {
           d3 v64 = closest_pt_triangle_d(a, b, cc);
           if (contested) {
@@ -1146,6 +1158,35 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
     unsigned long long v;
     v = nbx; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PBOX], v);
     v = ntr; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PTRI], v);
+  }
+}
+
+// fp64 re-run of the contested closest-point queries (one thread each; they are a fraction of a percent): the fp32
+// winner's exact distance bounds an fp64 traversal that evaluates every candidate inside it in double and keeps the true
+// minimum -- what the reference's fp64 recursion finds (ClosestPtCallback, collisionAlgorithms_inl.h:210-238).
+__global__ void __launch_bounds__(128) energy_fix_kernel(EnergyParams p) {
+  const int nc = p.live ? p.nq : p.nvc;
+  int n = *p.fix_count;
+  if (n > p.fix_cap) n = p.fix_cap;
+  const MeshDev &mo = p.meshes[p.body_mesh[p.object]];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int2 e = p.fix_list[i];
+    const int qid = e.x, tri = e.y;
+    const int li = qid / nc, c = qid - li * nc;
+    const int pose = p.legal_list ? p.legal_list[li] : li;
+    d3 q; f3 cnl;
+    energy_contact(p, pose, c, q, cnl);
+    d3 a = tri_vertex(mo.tris, tri, 0) - q, b = tri_vertex(mo.tris, tri, 1) - q, cc = tri_vertex(mo.tris, tri, 2) - q;
+    d3 v64 = closest_pt_triangle_d(a, b, cc);
+    double dd = dot(v64, v64);
+    d3 cl;
+    const double d2r = closest_point_query_d(mo, q, dd * (1.0 + 1.0e-12), &cl);
+    if (d2r >= 0.0 && d2r < dd) { v64 = cl - q; dd = d2r; }
+    const f3 v = tof(v64);
+    const float d2 = (float)dd;
+    const float dist = sqrtf(d2);
+    const float inv = d2 > 0.f ? 1.0f / dist : 0.f;
+    p.terms[qid] = dist + (1.0f - (cnl.x * v.x + cnl.y * v.y + cnl.z * v.z) * inv) * 50.0f;
   }
 }
 
@@ -1222,6 +1263,11 @@ cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s) {
   energy_kernel<<<blocks, 256, smem, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (p.fix_list) {
+    energy_fix_kernel<<<64, 128, 0, s>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   energy_reduce_kernel<<<(p.npose + 255) / 256, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
