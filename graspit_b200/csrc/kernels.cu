@@ -190,6 +190,8 @@ __device__ __noinline__ float tri_tri_dist2_plain(f3 p2, f3 p3, f3 q1, f3 q2, f3
 // Candidates whose squared distance is within this factor of the best are ordered in fp64, not fp32.  Pruning uses the
 // same band, so every such candidate is visited whatever order the traversal takes (deterministic results).
 constexpr float NEAR_BAND = 1.0002f;
+// squared distances closer than this (relative) are beyond fp32 on re-centred coordinates (error ~2e-7 at 300 mm): 20x margin
+constexpr float AMBIG_BAND = 1.000004f;
 #define CPQ_STACK 64
 __device__ __forceinline__ float closest_point_query(const MeshDev &m, const NodeQ *top, int ntop, d3 q, f3 &bestv,
                                                      int &best_tri, unsigned &n_box, unsigned &n_tri, int *second_tri = nullptr) {
@@ -1129,9 +1131,11 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
         const unsigned long long key2 = secondkey[lane];
         const bool contested = key2 != EQ_NONE && ((key2 ^ key) & 0xff000000ull) != 0ull &&
                                __uint_as_float((unsigned)(key2 >> 32)) <= d2 * NEAR_BAND + 1.0e-12f;
-        if (contested && p.fix_list) {
-          // two candidates fp32 cannot order are rarely alone (a point near the mug's axis ties with a whole circle of rim
-          // segments): the query is re-run in fp64 by energy_fix_kernel, which overwrites this term
+        if (contested && p.fix_list && __uint_as_float((unsigned)(key2 >> 32)) <= d2 * AMBIG_BAND + 1.0e-12f) {
+          // the runner-up is inside fp32's own resolution of the winner: candidates fp32 cannot order are rarely just two (a
+          // point near the mug's axis ties with a whole circle of rim segments), so the query is re-run in fp64 by
+          // energy_fix_kernel, which overwrites this term.  (Runners-up further out -- most far queries have one within
+          // 1e-4 -- are ordered reliably by fp32; the two-candidate fp64 comparison below costs nothing and stays.)
           const int at = atomicAdd(p.fix_count, 1);
           if (at < p.fix_cap) p.fix_list[at] = make_int2(qid, tri);
         }
