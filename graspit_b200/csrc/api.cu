@@ -121,7 +121,7 @@ struct b2c_ctx {
   // scratch
   DevBuf<float> d_states; DevBuf<Xf> d_fk; DevBuf<double> d_fkqt; DevBuf<uint8_t> d_legal; DevBuf<float> d_energy;
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
-  DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent; DevBuf<int2> d_fix;
+  DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
   ContactRec *h_contacts = nullptr; // pinned staging of contact candidates (b2c_contacts_batch)
   DevBuf<ContactRec> d_contacts2;   // the same records grouped by query
   DevBuf<int> d_coffsets;           // per query: first record, fill cursor
@@ -464,7 +464,7 @@ void b2c_destroy(b2c_ctx *ctx) {
   }
   ctx->d_meshes.release(); ctx->d_states.release(); ctx->d_fk.release(); ctx->d_fkqt.release(); ctx->d_legal.release();
   ctx->d_energy.release(); ctx->d_mask.release(); ctx->d_ambig.release(); ctx->d_counters.release(); ctx->d_stats.release();
-  ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release(); ctx->d_legal_list.release(); ctx->d_items.release(); ctx->d_contacts.release(); ctx->d_flags.release(); ctx->d_terms.release(); ctx->d_near_dir.release(); ctx->d_near_ent.release(); ctx->d_fix.release();
+  ctx->d_dist.release(); ctx->d_pts.release(); ctx->d_misc.release(); ctx->d_imisc.release(); ctx->d_legal_list.release(); ctx->d_items.release(); ctx->d_contacts.release(); ctx->d_flags.release(); ctx->d_terms.release(); ctx->d_near_dir.release(); ctx->d_near_ent.release();
   ctx->d_contacts2.release(); ctx->d_coffsets.release(); ctx->d_cubtemp.release(); ctx->d_sticky.release();
   for (int i = 0; i < 16; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->own_stream);
@@ -1067,15 +1067,11 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   if (want_energy) {
     CU(ctx->d_terms.reserve((size_t)npose * std::max(P->nvc, P->nhand) + 32));
     gp.terms = ctx->d_terms.p;
-    // contested closest-point queries (near-ties): a fraction of a percent of the queries; an overflowing list only means
-    // the remaining ones keep their two-candidate arbitration
-    CU(ctx->d_fix.reserve(std::max<size_t>(1 << 16, (size_t)npose * std::max(P->nvc, P->nhand) / 16)));
-    gp.fix_list = ctx->d_fix.p; gp.fix_count = ctx->d_counters.p + 10; gp.fix_cap = (int)std::min<size_t>(ctx->d_fix.cap, 0x7fffffff);
   }
   if (want_energy && !live) {
     if (P->nvc > 256) return fail(ctx, B2C_ECAPACITY, "eval_batch: more than 256 virtual contacts");
     gp.live = 0;
-    PROF_BEGIN(4); CU(launch_energy(gp, energy_blocks(P->nvc), ctx->stream)); ctx->launches += 3; PROF_END(4);
+    PROF_BEGIN(4); CU(launch_energy(gp, energy_blocks(P->nvc), ctx->stream)); ctx->launches += 2; PROF_END(4);
   }
 
   // K4 (+ LIVE energy)
@@ -1109,7 +1105,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
     CU(launch_recheck(rd, ctx->stream)); ctx->launches++;
     if (live) {
       gp.live = 1; gp.pts = ctx->d_pts.p;
-      PROF_BEGIN(4); CU(launch_energy(gp, energy_blocks(nq), ctx->stream)); ctx->launches += 3; PROF_END(4);
+      PROF_BEGIN(4); CU(launch_energy(gp, energy_blocks(nq), ctx->stream)); ctx->launches += 2; PROF_END(4);
     }
   }
 

@@ -211,11 +211,6 @@ struct EnergyParams {
   float *terms;             // [legal poses x contacts] per-contact energy terms (scratch)
   int *work_counter;        // dynamic hand-out of 32-query groups (zeroed by the caller)
   unsigned long long *stats;
-  // queries whose fp32 traversal met two or more candidates it could not order (near-ties): (query id, fp32 winner),
-  // re-run in fp64 by energy_fix_kernel before the terms are summed
-  int2 *fix_list;
-  int *fix_count;
-  int fix_cap;
 };
 
 // ---- K6 / K7 ---------------------------------------------------------------------------------------

@@ -190,8 +190,6 @@ __device__ __noinline__ float tri_tri_dist2_plain(f3 p2, f3 p3, f3 q1, f3 q2, f3
 // Candidates whose squared distance is within this factor of the best are ordered in fp64, not fp32.  Pruning uses the
 // same band, so every such candidate is visited whatever order the traversal takes (deterministic results).
 constexpr float NEAR_BAND = 1.0002f;
-// squared distances closer than this (relative) are beyond fp32 on re-centred coordinates (error ~2e-7 at 300 mm): 20x margin
-constexpr float AMBIG_BAND = 1.000004f;
 #define CPQ_STACK 64
 __device__ __forceinline__ float closest_point_query(const MeshDev &m, const NodeQ *top, int ntop, d3 q, f3 &bestv,
                                                      int &best_tri, unsigned &n_box, unsigned &n_tri, int *second_tri = nullptr) {
@@ -1131,14 +1129,6 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
         const unsigned long long key2 = secondkey[lane];
         const bool contested = key2 != EQ_NONE && ((key2 ^ key) & 0xff000000ull) != 0ull &&
                                __uint_as_float((unsigned)(key2 >> 32)) <= d2 * NEAR_BAND + 1.0e-12f;
-        if (contested && p.fix_list && __uint_as_float((unsigned)(key2 >> 32)) <= d2 * AMBIG_BAND + 1.0e-12f) {
-          // the runner-up is inside fp32's own resolution of the winner: candidates fp32 cannot order are rarely just two (a
-          // point near the mug's axis ties with a whole circle of rim segments), so the query is re-run in fp64 by
-          // energy_fix_kernel, which overwrites this term.  (Runners-up further out -- most far queries have one within
-          // 1e-4 -- are ordered reliably by fp32; the two-candidate fp64 comparison below costs nothing and stays.)
-          const int at = atomicAdd(p.fix_count, 1);
-          if (at < p.fix_cap) p.fix_list[at] = make_int2(qid, tri);
-        }
         if (d2 < 1.0e-4f * sc * sc || contested) {
           d3 v64 = closest_pt_triangle_d(a, b, cc);
           if (contested) {
@@ -1162,35 +1152,6 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
     unsigned long long v;
     v = nbx; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PBOX], v);
     v = ntr; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PTRI], v);
-  }
-}
-
-// fp64 re-run of the contested closest-point queries (one thread each; they are a fraction of a percent): the fp32
-// winner's exact distance bounds an fp64 traversal that evaluates every candidate inside it in double and keeps the true
-// minimum -- what the reference's fp64 recursion finds (ClosestPtCallback, collisionAlgorithms_inl.h:210-238).
-__global__ void __launch_bounds__(128) energy_fix_kernel(EnergyParams p) {
-  const int nc = p.live ? p.nq : p.nvc;
-  int n = *p.fix_count;
-  if (n > p.fix_cap) n = p.fix_cap;
-  const MeshDev &mo = p.meshes[p.body_mesh[p.object]];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int2 e = p.fix_list[i];
-    const int qid = e.x, tri = e.y;
-    const int li = qid / nc, c = qid - li * nc;
-    const int pose = p.legal_list ? p.legal_list[li] : li;
-    d3 q; f3 cnl;
-    energy_contact(p, pose, c, q, cnl);
-    d3 a = tri_vertex(mo.tris, tri, 0) - q, b = tri_vertex(mo.tris, tri, 1) - q, cc = tri_vertex(mo.tris, tri, 2) - q;
-    d3 v64 = closest_pt_triangle_d(a, b, cc);
-    double dd = dot(v64, v64);
-    d3 cl;
-    const double d2r = closest_point_query_d(mo, q, dd * (1.0 + 1.0e-12), &cl);
-    if (d2r >= 0.0 && d2r < dd) { v64 = cl - q; dd = d2r; }
-    const f3 v = tof(v64);
-    const float d2 = (float)dd;
-    const float dist = sqrtf(d2);
-    const float inv = d2 > 0.f ? 1.0f / dist : 0.f;
-    p.terms[qid] = dist + (1.0f - (cnl.x * v.x + cnl.y * v.y + cnl.z * v.z) * inv) * 50.0f;
   }
 }
 
@@ -1267,11 +1228,6 @@ cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s) {
   energy_kernel<<<blocks, 256, smem, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (p.fix_list) {
-    energy_fix_kernel<<<64, 128, 0, s>>>(p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
   energy_reduce_kernel<<<(p.npose + 255) / 256, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
