@@ -1055,11 +1055,12 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
   memset(&gp, 0, sizeof gp);
   gp.npose = npose; gp.nrb = nrb; gp.nb = nb; gp.nvc = P->nvc; gp.nq = P->nhand; gp.object = P->object_e;
   gp.stage_nodes = ctx->stage_nodes;
+  gp.stack_entries = energy_stack_entries_for(a->object >= 0 ? ctx->meshes[ctx->bodies[a->object].mesh].depth : 0);
   gp.fk = ctx->d_fk.p; gp.static_xf = P->d_static.p; gp.body_mesh = P->d_body_mesh.p; gp.meshes = ctx->d_meshes.p;
   gp.vcs = P->d_vcs.p; gp.legal = d_legal; gp.legal_list = ctx->d_legal_list.p; gp.legal_count = ctx->d_counters.p + 4;
   gp.energy = d_energy; gp.stats = ctx->d_stats.p; gp.work_counter = ctx->d_counters.p + 9;
   auto energy_blocks = [&](int contacts) {
-    size_t smem = energy_block_smem_bytes(gp.stage_nodes);
+    size_t smem = energy_block_smem_bytes(gp.stage_nodes, gp.stack_entries);
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / smem));
     long long groups = ((long long)npose * contacts + 255) / 256;
     return (int)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * per_sm, groups));
@@ -1136,9 +1137,9 @@ int b2c_check_overflow(b2c_ctx *ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   if (!word) return B2C_OK;
   CU(cudaMemsetAsync(ctx->d_sticky.p, 0, sizeof(int), ctx->stream));
-  return fail(ctx, B2C_ECAPACITY, "queue overflow since the last check:%s%s%s -- the affected poses were reported as colliding; split the batch",
+  return fail(ctx, B2C_ECAPACITY, "queue overflow since the last check:%s%s%s%s -- the affected poses were reported as colliding; split the batch",
               (word & OVF_COLLIDE_QUEUE) ? " legality recheck queue" : "", (word & OVF_DIST_QUEUE) ? " distance recheck queue" : "",
-              (word & OVF_ITEMS) ? " broad-phase work list" : "");
+              (word & OVF_ITEMS) ? " broad-phase work list" : "", (word & OVF_STACK) ? " traversal stack" : "");
 }
 
 } // extern "C"

@@ -110,7 +110,7 @@ struct EvalParams {
   int item_cap;
   int *overflow;           // sticky device word (b2c_ctx::d_sticky): OVF_* bits set when a queue drops an entry
 };
-enum { OVF_COLLIDE_QUEUE = 1, OVF_DIST_QUEUE = 2, OVF_ITEMS = 4 };
+enum { OVF_COLLIDE_QUEUE = 1, OVF_DIST_QUEUE = 2, OVF_ITEMS = 4, OVF_STACK = 8 };
 
 // LIVE contacts / generic point-energy input: per pose, per contact: world location + world normal
 struct LiveContact {
@@ -198,6 +198,7 @@ struct EnergyParams {
   int object;
   int live;
   int stage_nodes;          // top-of-tree nodes of the object staged in shared memory by TMA (0 = off)
+  int stack_entries;        // capacity of each warp's shared work stack (sized from the object tree's depth)
   const Xf *fk;
   const Xf *static_xf;
   const int *body_mesh;
@@ -233,6 +234,7 @@ struct ContactParams {
   int *out_count;
   int *per_query;          // [npose * nq] contact candidates per query
   int *work_counter;
+  int *overflow;           // sticky device word, see EvalParams
 };
 struct RegionParams {
   MeshDev mesh;
@@ -332,7 +334,8 @@ cudaError_t launch_point(const PointParams &p, cudaStream_t s);
 cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s);
 cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s);
 cudaError_t launch_seed_grid(const MeshDev &m, int *seed, cudaStream_t s);
-size_t energy_block_smem_bytes(int stage_nodes);
+size_t energy_block_smem_bytes(int stage_nodes, int stack_entries);
+int energy_stack_entries_for(int depth);
 
 } // namespace b2c
 

@@ -221,6 +221,16 @@ __global__ void __launch_bounds__(256, NARROW_MIN_BLOCKS) narrow_kernel(EvalPara
     }
 
     int room = NSTACK_CAP - sp;
+    if (room <= -60) {
+      // the shared stack is about to outgrow its physical size (never seen: it would take a tree far deeper than 2^23
+      // triangles allow): give up on the open items LOUDLY -- they count as collisions and the sticky word reports it
+      if (p.overflow && lane == 0) atomicOr(p.overflow, OVF_STACK);
+      const int mypose = S.meta[lane].x;
+      if (cnt[lane] > 0 && p.legal) p.legal[mypose] = 0;
+      cnt[lane] = 0; sp = 0; lq = 0; done = 0xffffffffu;
+      __syncwarp();
+      continue;
+    }
     int k = sp < 32 ? sp : 32;
     if (k > room) k = room > 1 ? room : 1;
     bool have = lane < k;

@@ -175,6 +175,11 @@ __global__ void __launch_bounds__(256, CONTACT_MIN_BLOCKS) contact_kernel(Contac
       }
       if (sp == 0) break;
       int room = CSTACK_CAP - sp;
+      if (room <= -60) {
+        // about to outgrow the physical stack: drop the rest of this pair and report it
+        if (p.overflow && lane == 0) atomicOr(p.overflow, OVF_STACK);
+        break;
+      }
       int k = sp < 32 ? sp : 32;
       if (k > room) k = room > 1 ? room : 1;
       bool have = lane < k;

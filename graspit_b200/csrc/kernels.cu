@@ -719,6 +719,12 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
       }
       if (sp == 0) break;
       int room = DSTACK_CAP - sp;
+      if (room <= -60) {
+        // about to outgrow the physical stack: answer "interpenetrating" (fail safe) and report it
+        if (p.overflow && lane == 0) atomicOr(p.overflow, OVF_STACK);
+        hit = true;
+        break;
+      }
       int k = sp < 32 ? sp : 32;
       if (k > room) k = room > 1 ? room : 1;
       if (!seeded) k = 1;          // greedy descent: only the nearest open entry, until a first distance is known
@@ -898,9 +904,11 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 #ifndef EQ_LEAF_TRIGGER
 #define EQ_LEAF_TRIGGER 32      // queued leaves that start a batch of point-triangle tests
 #endif
-constexpr int EQ_STACK_PHYS = EQ_STACK_PHYS_N, EQ_STACK_CAP = EQ_STACK_PHYS_N - 64, EQ_LEAF_CAP = 96;
+constexpr int EQ_STACK_MIN = EQ_STACK_PHYS_N, EQ_LEAF_CAP = 96;     // stack entries per warp: at least this, more for deep trees
 constexpr unsigned long long EQ_NONE = 0x7f7fffffffffffffull;   // (FLT_MAX bits << 32) | no triangle
-constexpr int ENERGY_WARP_SMEM = EQ_STACK_PHYS * 8 + EQ_LEAF_CAP * 8 + 32 * 8 + 32 * 24 + 32 * 16 + 32 * 8;
+constexpr int ENERGY_WARP_FIXED = EQ_LEAF_CAP * 8 + 32 * 8 + 32 * 24 + 32 * 16 + 32 * 8;
+// 32 depth-first traversals keep about one open sibling per level each
+__host__ __device__ inline int energy_stack_entries(int depth) { int n = 32 * (depth + 3); n = (n + 63) & ~63; return n < EQ_STACK_MIN ? EQ_STACK_MIN : (n > 2048 ? 2048 : n); }
 
 __device__ __forceinline__ unsigned long long eq_entry(float lb, int q, int idx) {
   return ((unsigned long long)__float_as_uint(lb) << 32) | ((unsigned long long)(unsigned)q << 24) | (unsigned long long)(unsigned)idx;
@@ -939,6 +947,56 @@ __device__ __forceinline__ void energy_contact(const EnergyParams &p, int pose, 
   cnl = tof(xf_rot_t(XO, cnw));
 }
 
+// exact test of one leaf for query qi of the warp: best (distance, triangle) by 64-bit atomicMin; the best loser with a
+// DIFFERENT closest point inside the near-tie band is remembered for the fp64 arbitration of the final stage (fp32 cannot
+// order two candidates whose distances agree to 1e-4, and the energy depends on which closest point wins)
+__device__ __forceinline__ void eq_leaf_test(const MeshDev &mo, const double *qd, unsigned long long *bestkey, unsigned long long *secondkey,
+                                             int qi, int tri) {
+  const unsigned long long key = point_tri_key(mo, mk<double>(qd[3 * qi], qd[3 * qi + 1], qd[3 * qi + 2]), tri);
+  const unsigned long long old = atomicMin(&bestkey[qi], key);
+  const unsigned long long win = old < key ? old : key, lose = old < key ? key : old;
+  if (lose != EQ_NONE && ((win ^ lose) & 0xff000000ull) != 0ull &&
+      __uint_as_float((unsigned)(lose >> 32)) <= __uint_as_float((unsigned)(win >> 32)) * NEAR_BAND + 1.0e-12f)
+    atomicMin(&secondkey[qi], lose);
+}
+
+// The shared stack is full: one lane finishes the subtree of the top entry on a private stack (depth-first, nearer child
+// first, same pruning, same leaf test).  Rare -- 32 depth-first traversals keep about 32 x depth entries open and the stack
+// is sized for that -- but it makes the traversal exact whatever the tree depth and however the queries interleave.
+__device__ __noinline__ void energy_private_dfs(const MeshDev &mo, const NodeQ *top, int ntop, unsigned long long e, const double *qd,
+                                                const float4 *qf, unsigned long long *bestkey, unsigned long long *secondkey,
+                                                unsigned &nbx, unsigned &ntr) {
+  const int qi = (int)((e >> 24) & 0xffu);
+  int stk[64]; float stl[64];
+  int n = 0;
+  stk[n] = (int)(e & 0xffffffu); stl[n] = __uint_as_float((unsigned)(e >> 32)); n++;
+  const float4 qq = qf[qi];
+  while (n > 0) {
+    n--;
+    const int pair = stk[n];
+    float best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
+    if (stl[n] > best * NEAR_BAND + 1.0e-12f) continue;
+    uint4 w0, w1;
+    fetch_pair_raw(mo, top, ntop, pair, w0, w1);
+    float d0 = point_nodeq_dist2(w0, mo.q0, mo.qs, qq.x, qq.y, qq.z);
+    float d1 = point_nodeq_dist2(w1, mo.q0, mo.qs, qq.x, qq.y, qq.z);
+    nbx += 2;
+    const bool swap = d1 < d0;
+    const float dn = swap ? d1 : d0, df = swap ? d0 : d1;
+    const int lkn = (int)(swap ? w1.w : w0.w), lkf = (int)(swap ? w0.w : w1.w);
+    // far child first (deeper in the stack), leaves tested at once
+    if (df <= best * NEAR_BAND + 1.0e-12f) {
+      if (lkf < 0) { eq_leaf_test(mo, qd, bestkey, secondkey, qi, ~lkf); ntr++; }
+      else if (n < 64) { stk[n] = lkf; stl[n] = df; n++; }
+    }
+    best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
+    if (dn <= best * NEAR_BAND + 1.0e-12f) {
+      if (lkn < 0) { eq_leaf_test(mo, qd, bestkey, secondkey, qi, ~lkn); ntr++; }
+      else if (n < 64) { stk[n] = lkn; stl[n] = dn; n++; }
+    }
+  }
+}
+
 // One warp = 32 closest-point queries (contacts of consecutive legal poses) traversed TOGETHER through one
 // shared work stack: every lane pops one (query, child-pair, lower bound) entry, loads the 64-byte pair of
 // sibling boxes, and pushes the children that can still beat the query's best distance (far first, near on
@@ -954,9 +1012,10 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
   __shared__ __align__(8) unsigned long long bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  unsigned char *wbase = smem_raw + (size_t)p.stage_nodes * sizeof(NodeQ) + (size_t)warp * ENERGY_WARP_SMEM;
+  const int stack_cap = p.stack_entries;
+  unsigned char *wbase = smem_raw + (size_t)p.stage_nodes * sizeof(NodeQ) + (size_t)warp * (ENERGY_WARP_FIXED + 8 * stack_cap);
   unsigned long long *stack = reinterpret_cast<unsigned long long *>(wbase);
-  unsigned long long *leafq = stack + EQ_STACK_PHYS;
+  unsigned long long *leafq = stack + stack_cap;
   unsigned long long *bestkey = leafq + EQ_LEAF_CAP;                 // [32] (d2 bits << 32) | point hash << 24 | triangle
   double *qd = reinterpret_cast<double *>(bestkey + 32);              // [32][3] query point, object frame
   float4 *qf = reinterpret_cast<float4 *>(qd + 96);                   // [32] fp32 copy
@@ -1053,15 +1112,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
           float best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
           if (lb <= best * NEAR_BAND + 1.0e-12f) {
             ntr++;
-            const unsigned long long key = point_tri_key(mo, mk<double>(qd[3 * qi], qd[3 * qi + 1], qd[3 * qi + 2]), tri);
-            const unsigned long long old = atomicMin(&bestkey[qi], key);
-            // runner-up with a DIFFERENT closest point: fp32 cannot order two candidates whose distances agree to 1e-4,
-            // and the energy depends on which closest point wins (its direction enters the normal term); the final stage
-            // arbitrates in fp64
-            const unsigned long long win = old < key ? old : key, lose = old < key ? key : old;
-            if (lose != EQ_NONE && ((win ^ lose) & 0xff000000ull) != 0ull &&
-                __uint_as_float((unsigned)(lose >> 32)) <= __uint_as_float((unsigned)(win >> 32)) * NEAR_BAND + 1.0e-12f)
-              atomicMin(&secondkey[qi], lose);
+            eq_leaf_test(mo, qd, bestkey, secondkey, qi, tri);
           }
         }
         lq -= n;
@@ -1069,9 +1120,16 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
         continue;
       }
       if (sp == 0) break;
-      int room = EQ_STACK_CAP - sp;
+      // k entries popped push at most 2k: with k <= room the stack never outgrows its capacity
+      const int room = stack_cap - sp;
+      if (room <= 0) {
+        if (lane == 0) energy_private_dfs(mo, top, ntop, stack[sp - 1], qd, qf, bestkey, secondkey, nbx, ntr);
+        sp -= 1;
+        __syncwarp();
+        continue;
+      }
       int k = sp < 32 ? sp : 32;
-      if (k > room) k = room > 1 ? room : 1;
+      if (k > room) k = room;
       bool have = lane < k;
       unsigned long long e = have ? stack[sp - 1 - lane] : 0ull;
       sp -= k;
@@ -1222,7 +1280,7 @@ cudaError_t launch_dist(const DistParams &p, int blocks, cudaStream_t s) {
 
 cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s) {
   if (p.npose <= 0) return cudaSuccess;
-  size_t smem = energy_block_smem_bytes(p.stage_nodes);
+  size_t smem = energy_block_smem_bytes(p.stage_nodes, p.stack_entries);
   static size_t granted[64] = {};
   { cudaError_t e = ensure_dyn_smem((const void *)energy_kernel, smem, granted); if (e != cudaSuccess) return e; }
   energy_kernel<<<blocks, 256, smem, s>>>(p);
@@ -1232,6 +1290,9 @@ cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-size_t energy_block_smem_bytes(int stage_nodes) { return (size_t)stage_nodes * sizeof(NodeQ) + (size_t)8 * ENERGY_WARP_SMEM; }
+size_t energy_block_smem_bytes(int stage_nodes, int stack_entries) {
+  return (size_t)stage_nodes * sizeof(NodeQ) + (size_t)8 * (ENERGY_WARP_FIXED + 8 * (size_t)stack_entries);
+}
+int energy_stack_entries_for(int depth) { return energy_stack_entries(depth); }
 
 } // namespace b2c
