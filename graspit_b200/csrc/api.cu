@@ -1083,7 +1083,7 @@ int b2c_eval_batch(b2c_ctx *ctx, const b2c_eval_args *a) {
     CU(ctx->d_pts.reserve((size_t)npose * nq * 6));
     // every query hands at least its winning pair to the fp64 refinement
     CU(ctx->d_near_dir.reserve((size_t)npose * nq + 1024));
-    CU(ctx->d_near_ent.reserve(std::max<size_t>((size_t)1 << 21, 4 * (size_t)npose * nq)));
+    CU(ctx->d_near_ent.reserve(std::max<size_t>((size_t)1 << 21, 16 * (size_t)npose * nq)));     // lists of up to DNEAR_CAP pairs where fp32 ties
     d_dist = dev && want_dist ? a->link_dist : ctx->d_dist.p;
     DistParams dp;
     memset(&dp, 0, sizeof dp);

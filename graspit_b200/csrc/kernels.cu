@@ -470,7 +470,11 @@ __device__ __noinline__ void near_emit(const DistParams &p, const int2 *nearq, c
   int seg = 0, ofs = 0;
   if (lane == 0) { seg = atomicAdd(p.near_count, 1); ofs = atomicAdd(p.near_count + 1, cnt); }
   seg = __shfl_sync(FULL, seg, 0); ofs = __shfl_sync(FULL, ofs, 0);
-  if (seg >= p.near_cap_dir || ofs + cnt > p.near_cap_ent) return;
+  if (seg >= p.near_cap_dir || ofs + cnt > p.near_cap_ent) {
+    // no room for this query's fp64 pass: its fp32 answer stands, and the caller hears about it
+    if (p.overflow && lane == 0) atomicOr(p.overflow, OVF_DIST_QUEUE);
+    return;
+  }
   int at0 = 0;
 #pragma unroll
   for (int r = 0; r < (DNEAR_CAP + 31) / 32; r++) {
@@ -908,7 +912,7 @@ constexpr int EQ_STACK_MIN = EQ_STACK_PHYS_N, EQ_LEAF_CAP = 96;     // stack ent
 constexpr unsigned long long EQ_NONE = 0x7f7fffffffffffffull;   // (FLT_MAX bits << 32) | no triangle
 constexpr int ENERGY_WARP_FIXED = EQ_LEAF_CAP * 8 + 32 * 8 + 32 * 24 + 32 * 16 + 32 * 8;
 // 32 depth-first traversals keep about one open sibling per level each
-__host__ __device__ inline int energy_stack_entries(int depth) { int n = 32 * (depth + 3); n = (n + 63) & ~63; return n < EQ_STACK_MIN ? EQ_STACK_MIN : (n > 2048 ? 2048 : n); }
+__host__ __device__ inline int energy_stack_entries(int depth) { (void)depth; return EQ_STACK_MIN; }   // deeper trees measured slower with larger stacks (occupancy)
 
 __device__ __forceinline__ unsigned long long eq_entry(float lb, int q, int idx) {
   return ((unsigned long long)__float_as_uint(lb) << 32) | ((unsigned long long)(unsigned)q << 24) | (unsigned long long)(unsigned)idx;
@@ -1120,16 +1124,18 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
         continue;
       }
       if (sp == 0) break;
-      // k entries popped push at most 2k: with k <= room the stack never outgrows its capacity
-      const int room = stack_cap - sp;
-      if (room <= 0) {
+      // k entries popped push at most 2k.  Above the soft limit only one entry is popped per round (the depth-first order
+      // then shrinks the stack again); should it still reach the physical size, one lane finishes the top entry's subtree
+      // on a private stack, so the shared one is never outgrown
+      const int room = stack_cap - 64 - sp;
+      if (sp >= stack_cap - 2) {
         if (lane == 0) energy_private_dfs(mo, top, ntop, stack[sp - 1], qd, qf, bestkey, secondkey, nbx, ntr);
         sp -= 1;
         __syncwarp();
         continue;
       }
       int k = sp < 32 ? sp : 32;
-      if (k > room) k = room;
+      if (k > room) k = room > 1 ? room : 1;
       bool have = lane < k;
       unsigned long long e = have ? stack[sp - 1 - lane] : 0ull;
       sp -= k;
