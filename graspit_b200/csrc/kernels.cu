@@ -189,7 +189,10 @@ __device__ __noinline__ float tri_tri_dist2_plain(f3 p2, f3 p3, f3 q1, f3 q2, f3
 // ============================================================================================
 // Candidates whose squared distance is within this factor of the best are ordered in fp64, not fp32.  Pruning uses the
 // same band, so every such candidate is visited whatever order the traversal takes (deterministic results).
-constexpr float NEAR_BAND = 1.0002f;
+// fp32 on coordinates re-centred next to the query resolves squared distances to ~2e-7 relative at 300 mm; the band is
+// 100 x that.  (It was 2e-4 at first: on the 220 800-triangle mug every far query then met 64+ "ties" -- neighbours of
+// the closest triangle on the same facet -- and the fp64 lists overflowed.)
+constexpr float NEAR_BAND = 1.00002f;
 #define CPQ_STACK 64
 __device__ __forceinline__ float closest_point_query(const MeshDev &m, const NodeQ *top, int ntop, d3 q, f3 &bestv,
                                                      int &best_tri, unsigned &n_box, unsigned &n_tri, int *second_tri = nullptr) {
