@@ -189,10 +189,12 @@ __device__ __noinline__ float tri_tri_dist2_plain(f3 p2, f3 p3, f3 q1, f3 q2, f3
 // ============================================================================================
 // Candidates whose squared distance is within this factor of the best are ordered in fp64, not fp32.  Pruning uses the
 // same band, so every such candidate is visited whatever order the traversal takes (deterministic results).
-// fp32 on coordinates re-centred next to the query resolves squared distances to ~2e-7 relative at 300 mm; the band is
-// 100 x that.  (It was 2e-4 at first: on the 220 800-triangle mug every far query then met 64+ "ties" -- neighbours of
-// the closest triangle on the same facet -- and the fp64 lists overflowed.)
-constexpr float NEAR_BAND = 1.00002f;
+constexpr float NEAR_BAND = 1.0002f;
+// The same for the body-body distance, whose near-ties are LISTED for the fp64 pass: fp32 on coordinates re-centred next to
+// the query resolves squared distances to ~2e-7 relative at 300 mm; the band is 100 x that.  (With 2e-4 every far query
+// against the 220 800-triangle mug met 64+ "ties" -- neighbours of the closest triangle on the same facet -- and the
+// lists overflowed.)
+constexpr float DIST_BAND = 1.00002f;
 #define CPQ_STACK 64
 __device__ __forceinline__ float closest_point_query(const MeshDev &m, const NodeQ *top, int ntop, d3 q, f3 &bestv,
                                                      int &best_tri, unsigned &n_box, unsigned &n_tri, int *second_tri = nullptr) {
@@ -415,7 +417,7 @@ __device__ __noinline__ int near_compact(int2 *nearq, float *neard, float *nearf
   for (int b0 = 0; b0 < nnear; b0 += 32) {
     const int i = b0 + lane;
     bool k = false; int2 en = make_int2(0, 0); float dn = 0.f, fn = 0.f;
-    if (i < nnear) { en = nearq[i]; dn = neard[i]; fn = nearf[i]; k = dn <= best * ((en.y & NEAR_TINY_BIT) ? 1.004f : NEAR_BAND) + 1.0e-9f; }
+    if (i < nnear) { en = nearq[i]; dn = neard[i]; fn = nearf[i]; k = dn <= best * ((en.y & NEAR_TINY_BIT) ? 1.004f : DIST_BAND) + 1.0e-9f; }
     const unsigned km = __ballot_sync(FULL, k);
     __syncwarp();
     if (k) { const int at = kept + __popc(km & lt_mask); nearq[at] = en; neard[at] = dn; nearf[at] = fn; }
@@ -443,7 +445,7 @@ __device__ __noinline__ void near_emit(const DistParams &p, const int2 *nearq, c
     bool k = false, t = false, differs = false;
     if (i < nnear) {
       t = (nearq[i].y & NEAR_TINY_BIT) != 0;
-      k = neard[i] <= best * (t ? 1.004f : NEAR_BAND) + 1.0e-9f;
+      k = neard[i] <= best * (t ? 1.004f : DIST_BAND) + 1.0e-9f;
       differs = k && __float_as_int(nearf[i]) != __float_as_int(best_fp);
     }
     km[r] = __ballot_sync(FULL, k);
@@ -596,7 +598,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
         unsigned long long e = 0ull;
         if (lane < n) {
           e = leafq[lq - n + lane];
-          keep = entry_lb(e) <= best * NEAR_BAND + 1.0e-12f;
+          keep = entry_lb(e) <= best * DIST_BAND + 1.0e-12f;
           if (keep && seeded) {
             int ta = (int)((e >> 24) & 0xffffffu), tb = (int)(e & 0xffffffu);
             float amax = -3.0e38f, bmin = 3.0e38f;
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
         if (lane < n) {
           unsigned long long e = confq[cq - n + lane];
           ta = (int)((e >> 24) & 0xffffffu); tb = (int)(e & 0xffffffu);
-          if (entry_lb(e) <= best * NEAR_BAND + 1.0e-12f) {
+          if (entry_lb(e) <= best * DIST_BAND + 1.0e-12f) {
             n_tri++;
             d3 a1 = tri_vertex(ma.tris, ta, 0), a2 = tri_vertex(ma.tris, ta, 1), a3 = tri_vertex(ma.tris, ta, 2);
             d3 b1 = tri_vertex(mb.tris, tb, 0), b2 = tri_vertex(mb.tris, tb, 1), b3 = tri_vertex(mb.tris, tb, 2);
@@ -684,7 +686,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
             for (int k6 = 0; k6 < 6; k6++) hsh = (hsh ^ (unsigned)__double2int_rd(qx[k6] * 512.0)) * 16777619u;
           }
           const float fpr = fpr_lane = __int_as_float((int)hsh);
-          const bool cand = res != TT_HIT && d2 < 2.9e38f && (tiny || d2 <= best * NEAR_BAND + 1.0e-12f);
+          const bool cand = res != TT_HIT && d2 < 2.9e38f && (tiny || d2 <= best * DIST_BAND + 1.0e-12f);
           const unsigned cm = __ballot_sync(FULL, cand);
           const int add = __popc(cm);
           if (add) {
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
       __syncwarp();
       bool pn = false, pf = false, ln = false, lf = false;      // near / far child: push?, leaf pair?
       unsigned long long cn = 0ull, cf = 0ull;
-      if (have && entry_lb(e) <= best * NEAR_BAND + 1.0e-12f) {
+      if (have && entry_lb(e) <= best * DIST_BAND + 1.0e-12f) {
         int na = (int)((e >> 24) & 0xffffffu), nb = (int)(e & 0xffffffu);
         Node a = load_node(ma, na), b = load_node(mb, nb);
         bool la = a.child < 0, lb = b.child < 0;
@@ -783,7 +785,7 @@ __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p
           n_box += 2;
           bool swap = d1 < d0;
           float dn = swap ? d1 : d0, df = swap ? d0 : d1;
-          pn = dn <= best * NEAR_BAND + 1.0e-12f; pf = df <= best * NEAR_BAND + 1.0e-12f;
+          pn = dn <= best * DIST_BAND + 1.0e-12f; pf = df <= best * DIST_BAND + 1.0e-12f;
           ln = swap ? lf1 : lf0; lf = swap ? lf0 : lf1;
           cn = pack_dist_entry(dn, swap ? i1a : i0a, swap ? i1b : i0b);
           cf = pack_dist_entry(df, swap ? i0a : i1a, swap ? i0b : i1b);
