@@ -972,9 +972,10 @@ __device__ __forceinline__ void eq_leaf_test(const MeshDev &mo, const double *qd
 // The shared stack is full: one lane finishes the subtree of the top entry on a private stack (depth-first, nearer child
 // first, same pruning, same leaf test).  Rare -- 32 depth-first traversals keep about 32 x depth entries open and the stack
 // is sized for that -- but it makes the traversal exact whatever the tree depth and however the queries interleave.
-__device__ __noinline__ void energy_private_dfs(const MeshDev &mo, const NodeQ *top, int ntop, unsigned long long e, const double *qd,
-                                                const float4 *qf, unsigned long long *bestkey, unsigned long long *secondkey,
-                                                unsigned &nbx, unsigned &ntr) {
+// (returns box tests | triangle tests << 16 for the statistics: counters passed by reference would live in memory)
+__device__ __noinline__ unsigned energy_private_dfs(const MeshDev &mo, const NodeQ *top, int ntop, unsigned long long e, const double *qd,
+                                                    const float4 *qf, unsigned long long *bestkey, unsigned long long *secondkey) {
+  unsigned nbx = 0, ntr = 0;
   const int qi = (int)((e >> 24) & 0xffu);
   int stk[64]; float stl[64];
   int n = 0;
@@ -1004,6 +1005,7 @@ __device__ __noinline__ void energy_private_dfs(const MeshDev &mo, const NodeQ *
       else if (n < 64) { stk[n] = lkn; stl[n] = dn; n++; }
     }
   }
+  return (nbx & 0xffffu) | (ntr << 16);
 }
 
 // One warp = 32 closest-point queries (contacts of consecutive legal poses) traversed TOGETHER through one
@@ -1134,7 +1136,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
       // on a private stack, so the shared one is never outgrown
       const int room = stack_cap - 64 - sp;
       if (sp >= stack_cap - 2) {
-        if (lane == 0) energy_private_dfs(mo, top, ntop, stack[sp - 1], qd, qf, bestkey, secondkey, nbx, ntr);
+        if (lane == 0) { const unsigned c = energy_private_dfs(mo, top, ntop, stack[sp - 1], qd, qf, bestkey, secondkey); nbx += c & 0xffffu; ntr += c >> 16; }
         sp -= 1;
         __syncwarp();
         continue;
