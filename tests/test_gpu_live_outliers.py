@@ -71,4 +71,26 @@ def test_live_60k_sweep_outliers_sit_on_closest_pair_ties():
     assert (l2 == 1).all()
     rel2 = np.abs(sub["energy"] - e2) / np.maximum(np.abs(e2), 1e-9)
     print("  outliers", bad.tolist(), "rel err vs reference on restated FK", rel[bad], "on the engine's FK", rel2)
-    assert rel2.max() < TOL, (bad.tolist(), rel2)
+    # What is left are EXACT ties: a link whose closest point has two equally distant partners on the object (to the last
+    # digit of fp64).  Which one a search returns then depends on its visiting order -- the reference keeps the first pair
+    # its OBB recursion meets (strict <, collisionAlgorithms_inl.h:193) -- and the virtual contact's normal, hence the
+    # energy, differs while every DISTANCE is identical.  Checked through the single-pose interface on identical poses.
+    ties = 0
+    w = osc.w
+    for p, r2 in zip(bad, rel2):
+        if r2 < TOL:
+            continue
+        for j, b in enumerate(order):
+            w.set_transform(osc.ids[b], tf7[p, j, :4], tf7[p, j, 4:])
+            eng.set_body_transform(sb.body_ids[b], tf7[p, j, :4], tf7[p, j, 4:])
+        w.set_transform(osc.ids[obj], *sc.body_tran[obj]); eng.set_body_transform(sb.body_ids[obj], *sc.body_tran[obj])
+        moved = 0
+        for j, b in enumerate(order):
+            dr, p1r, p2r = w.body_distance(osc.ids[b], osc.ids[obj])
+            de, p1e, p2e = eng.body_to_body_distance(sb.body_ids[b], sb.body_ids[obj])
+            assert abs(de - dr) <= 1e-9 * max(1.0, dr), (p, j, de, dr)            # same distance on every link ...
+            moved += max(np.linalg.norm(p1e - p1r), np.linalg.norm(p2e - p2r)) > 1e-6
+        assert moved >= 1, (p, "energy differs although distances AND closest points agree")   # ... reached at another point
+        assert r2 < 1e-3, (p, r2)
+        ties += 1
+    assert ties <= 2, ties
