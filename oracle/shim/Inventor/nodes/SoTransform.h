@@ -5,6 +5,7 @@
 struct SoSFRotationShim {
   SbRotation r;
   void setValue(const SbRotation &v) { r = v; }
+  void setValue(const SbVec3f &, float) {}          // axis / angle form (visual markers only)
   const SbRotation &getValue() const { return r; }
 };
 struct SoSFVec3fShim {

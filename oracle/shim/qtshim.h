@@ -18,6 +18,10 @@ class QString {
     std::string toStdString() const { return s_; }
     const char *latin1() const { return s_.c_str(); }
     bool isNull() const { return s_.empty(); }
+    bool operator==(const QString &o) const { return s_ == o.s_; }
+    bool operator!=(const QString &o) const { return s_ != o.s_; }
+    QString operator+(const QString &o) const { return QString(s_ + o.s_); }
+    QString &setNum(int n) { s_ = std::to_string(n); return *this; }
 };
 class QTextStream {};
 class QPixmap {};
