@@ -20,7 +20,7 @@ def test_bindings_compile_against_reference_headers():
     assert os.path.exists(BIN), "run `make -C oracle` (needs /root/reference)"
     syms = subprocess.run(["nm", "-C", BIN], capture_output=True, text=True).stdout
     for s in ("B200ContactEnergy::analyzeStates", "B200SimAnnPlanner::mainLoop", "SimAnnPlanner::mainLoop", "SimAnn::iterate",
-              "EGPlanner::addToListOfUniqueSolutions", "GraspPlanningState::GraspPlanningState", "PositionStateAA::getCoreTran"):
+              "EGPlanner::addToListOfUniqueSolutions", "HandObjectState::HandObjectState", "PositionStateAA::getCoreTran"):
         assert s in syms, s
 
 

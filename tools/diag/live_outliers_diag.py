@@ -38,7 +38,7 @@ for p in bad:
         mp1r, mp2r = T.apply(tl, p1r[None])[0], T.apply(to, p2r[None])[0]
         de, l1, l2 = eng.body_to_body_distance(sb.body_ids[b], sb.body_ids[obj], local=True)
         dp = max(np.linalg.norm(l1 - mp1r), np.linalg.norm(l2 - mp2r))
-        if dp > 1e-3:
+        if dp > 1e-3 or abs(de - dr) > 1e-9 * max(1.0, dr):
             db, b1, b2, tp = w.brute_distance(osc.ids[b], osc.ids[obj])
             # the exhaustive winner as a two-triangle world: does the engine's own leaf arithmetic agree with the reference's?
             ta = eng.add_body(sc.bodies[b].tris[tp[0]:tp[0] + 1]); tb_ = eng.add_body(sc.bodies[obj].tris[tp[1]:tp[1] + 1])
