@@ -23,10 +23,24 @@ namespace {
 
 __device__ inline bool bit(const AgCol<unsigned long long> &m, int i) { return (m[i >> 6] >> (i & 63)) & 1ull; }
 
-// RigidDOF::accumulateMove (dof.cpp:500-514) / BreakAwayDOF::accumulateMove (dof.cpp:577-620)
+// RigidDOF::accumulateMove (dof.cpp:500-514) / BreakAwayDOF::accumulateMove (dof.cpp:577-620) /
+// CompliantDOF::accumulateMove (dof.cpp:830-856: every joint moves on its own unless IT is stopped in that direction;
+// joint_ratio holds CompliantDOF::getStaticRatio of the joint)
 __device__ bool accumulate_move(const AgDesc &D, const AgState &S, int d, double q1, double *jv) {
   const double q = S.q[d];
   if (fabs(q - q1) < 1.0e-5) return false;
+  if (D.dof_breakaway[d] == 2) {
+    bool movement = false;
+    for (int j = 0; j < D.nj; j++) {
+      if (D.joint_dof[j] != d) continue;
+      double nv = q1 * D.joint_ratio[j], ov = S.jv[j];
+      if (nv > ov && (S.stopped[j] & 1)) continue;
+      if (nv < ov && (S.stopped[j] & 2)) continue;
+      jv[j] = nv;
+      movement = true;
+    }
+    return movement;
+  }
   if (!D.dof_breakaway[d]) {
     for (int j = 0; j < D.nj; j++)
       if (D.joint_dof[j] == d && S.stopped[j]) return false;
@@ -98,7 +112,7 @@ __device__ void finish_jump(const AgDesc &D, AgState &S, const float *dist) {
   S.ncols = ncols;
   for (int d = 0; d < D.ndof; d++) {
     double q1 = S.new_dof[d];
-    if (D.dof_breakaway[d]) {            // BreakAwayDOF::updateVal (dof.cpp:622-648)
+    if (D.dof_breakaway[d] == 1) {       // BreakAwayDOF::updateVal (dof.cpp:622-648); Rigid / CompliantDOF::updateVal: q = q1
       for (int j = 0; j < D.nj; j++) {
         if (D.joint_dof[j] != d) continue;
         double jval = S.jv[j] / D.joint_ratio[j];

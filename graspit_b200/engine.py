@@ -664,7 +664,7 @@ class Engine:
         vel = np.asarray(robot_desc.dof_velocity, dtype=np.float64)
         desired = np.where(speed_factor * vel >= 0, robot_desc.dof_max, robot_desc.dof_min).astype(np.float64)
         steps = vel * speed_factor * AUTO_GRASP_TIME_STEP
-        brk = [1 if t == "b" else 0 for t in robot_desc.dof_type]
+        brk = [{"r": 0, "b": 1, "c": 2}[t] for t in robot_desc.dof_type]
         return self.move_dof_to_contacts(robot, states, desired, steps, brk, stop_at_contact, njoints=robot_desc.n_joints)
 
     def _root_bodies(self, robot: int) -> int:

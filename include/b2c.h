@@ -384,7 +384,9 @@ typedef struct b2c_autograsp_args {
   int stride;
   const double *desired;           /* [ndof] desiredVals */
   const double *steps;             /* [ndof] desiredSteps (0: the DOF does not move); NULL = WorldElement::ONE_STEP */
-  const unsigned char *dof_breakaway;  /* [ndof] 1 = BreakAwayDOF (<dof type="b">), 0 = RigidDOF */
+  const unsigned char *dof_breakaway;  /* [ndof] DOF type: 0 = RigidDOF (<dof type="r">), 1 = BreakAwayDOF ("b"), 2 = CompliantDOF ("c":
+                                       * every joint moves on its own, dof.cpp:830-856; the joints' `ratio` in b2c_robot_desc must
+                                       * then hold CompliantDOF::getStaticRatio, dof.cpp:779-795) */
   int stop_at_contact;
   double contact_threshold;        /* Contact::THRESHOLD; <= 0 selects the reference's 0.2 mm */
   int max_rounds;                  /* safety bound on host-loop rounds; <= 0 selects the default */

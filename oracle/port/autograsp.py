@@ -46,6 +46,17 @@ class _Dof:
     def accumulate_move(self, q1, jv, cur_jv, stopped):
         if abs(self.q - q1) < 1.0e-5:
             return False
+        if self.kind == "c":                                   # CompliantDOF::accumulateMove (dof.cpp:830-856)
+            movement = False
+            for j, r in zip(self.joints, self.ratios):
+                new, old = q1 * r, cur_jv[j]
+                if new > old and (stopped[j] & 1):
+                    continue
+                if new < old and (stopped[j] & 2):
+                    continue
+                jv[j] = new
+                movement = True
+            return movement
         if self.kind != "b":                                   # RigidDOF
             if any(stopped[j] for j in self.joints):
                 return False

@@ -195,3 +195,38 @@ def test_autograsp_of_a_hand_mounted_on_an_arm():
         if not o["error"]:
             assert np.abs(out["dof"][k] - o["dof"]).max() < 2e-2, (k, out["dof"][k], o["dof"])
             assert (out["stopped"][k] != 0).any() == (o["stopped"] != 0).any()
+
+
+def test_autograsp_compliant_dofs(barrett):
+    """CompliantDOF (dof.cpp:830-856: each joint of the DOF keeps moving until IT is stopped).  No benchmark hand of the
+    reference carries <dof type="c">, so the Barrett's three finger DOFs are retyped: the engine's state machine against the
+    restated control flow on the reference's collision backend, pose by pose."""
+    import copy
+    sc = copy.deepcopy(barrett["sc"])
+    sc.robots[0].dof_type = ["r", "c", "c", "c"]
+    eng, osc, rid = barrett["eng"], barrett["osc"], barrett["rid"]
+    raw = _open_hand_states(sc, 300, 33)
+    res = eng.eval_batch(rid, barrett["sb"].body_ids[barrett["obj"]], raw)
+    sel = np.nonzero(res["legal"])[0][:40]
+    out = eng.auto_grasp(rid, sc.robots[0], raw[sel])
+    ag = AutoGraspOracle(sc, 0, osc.w, osc.ids)
+    exact = distal_runs_on = 0
+    for k, p in enumerate(sel):
+        r = ag.auto_grasp((raw[p, 0:4].astype(np.float64), raw[p, 4:7].astype(np.float64)), raw[p, 7:].astype(np.float64))
+        st = int(out["status"][k])
+        assert bool(st & AG_INTERP_ERROR) == r["error"] and bool(st & AG_MOVED) == r["moved"], (p, st, r)
+        if r["error"]:
+            continue
+        err = np.abs(out["joints"][k] - r["joints"]).max()
+        assert err < 2e-2, (p, out["joints"][k], r["joints"])
+        if err < 1e-9:
+            exact += 1
+            assert (out["stopped"][k] == r["stopped"]).all() and int(out["iters"][k]) == r["iters"]
+        # the compliant signature: a proximal joint stopped by a contact while the distal joint of the same DOF went on
+        jd = [j for c in sc.robots[0].chains for j in c.joints]
+        for d in (1, 2, 3):
+            js = [i for i, j in enumerate(jd) if j.dof == d]
+            vals = [r["joints"][i] / jd[i].ratio for i in js]
+            distal_runs_on += (max(vals) - min(vals)) > 0.05
+    assert exact >= 0.9 * len(sel), exact
+    assert distal_runs_on >= 5
