@@ -8,7 +8,6 @@
 //   energy_kernel    K5+K8 CONTACT_ENERGY, PRESET or LIVE contacts, TMA-staged tree top (thread / pose,contact)
 //
 // See DESIGN.md for the data layout and the roofline that bounds each kernel.
-#include <cstdlib>
 #include "b2c_internal.h"
 #include "traverse.cuh"
 
@@ -1228,187 +1227,6 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
   }
 }
 
-// ============================================================================================
-// K5 + K8, per-lane variant: every lane owns one closest-point query and walks the tree depth-first (nearer child
-// first) on its own stack -- a column of a [depth][32] array in shared memory, so that the 32 lanes of a warp hit 32
-// different banks whatever their stack pointers are.  "while-while": a lane descends until it holds a leaf or has
-// nothing left; then every lane that holds a leaf runs the exact triangle test together.  No ballots, no compaction, no
-// atomics: best and runner-up keys live in registers.  The price is lane imbalance (a finished query idles its lane until
-// the warp's 32 queries are done); the 32 queries of a group are contacts of the same one or two hands, similar in cost.
-// Box tests work on the stored 16-bit corners directly: the query is moved onto the mesh's quantisation grid once
-// (floor and ceiling, each biased by 2^23 so that a corner becomes a float by ONE byte-permute: 0x4B000000 | corner
-// = 2^23 + corner exactly), a gap is one subtraction, and only the three positive gaps are scaled back to millimetres.
-// Rounding the query down for the low faces and up for the high faces keeps every bound conservative (by at most one
-// grid step, ~2 um).  Leaf arithmetic, keys, near-tie band and final stage are those of energy_kernel: same results.
-// ============================================================================================
-#ifndef EPL_DEPTH
-#define EPL_DEPTH 24            // stack entries per lane in shared memory; deeper paths continue in an overflow frame
-#endif
-constexpr int EPL_WARP_SMEM = EPL_DEPTH * 32 * 8;
-
-__device__ __forceinline__ float epl_gap2(uint4 w, const float *qlo, const float *qhi, const float *qs) {
-  // corner words: x = lo0 | lo1 << 16, y = lo2 | hi0 << 16, z = hi1 | hi2 << 16
-  const float L0 = __uint_as_float(0x4B000000u | (w.x & 0xffffu)), L1 = __uint_as_float(0x4B000000u | (w.x >> 16));
-  const float L2 = __uint_as_float(0x4B000000u | (w.y & 0xffffu)), H0 = __uint_as_float(0x4B000000u | (w.y >> 16));
-  const float H1 = __uint_as_float(0x4B000000u | (w.z & 0xffffu)), H2 = __uint_as_float(0x4B000000u | (w.z >> 16));
-  const float g0 = fmaxf(fmaxf(L0 - qhi[0], qlo[0] - H0), 0.f) * qs[0];
-  const float g1 = fmaxf(fmaxf(L1 - qhi[1], qlo[1] - H1), 0.f) * qs[1];
-  const float g2 = fmaxf(fmaxf(L2 - qhi[2], qlo[2] - H2), 0.f) * qs[2];
-  return g0 * g0 + g1 * g1 + g2 * g2;
-}
-
-__device__ __forceinline__ void epl_leaf(const MeshDev &mo, d3 q, int tri, unsigned long long &best, unsigned long long &second) {
-  const unsigned long long key = point_tri_key(mo, q, tri);
-  const unsigned long long win = best < key ? best : key, lose = best < key ? key : best;
-  if (lose != EQ_NONE && ((win ^ lose) & 0xff000000ull) != 0ull &&
-      __uint_as_float((unsigned)(lose >> 32)) <= __uint_as_float((unsigned)(win >> 32)) * NEAR_BAND + 1.0e-12f && lose < second)
-    second = lose;
-  best = win;
-}
-
-#ifndef EPL_MIN_BLOCKS
-#define EPL_MIN_BLOCKS 3
-#endif
-__global__ void __launch_bounds__(256, EPL_MIN_BLOCKS) energy_kernel_pl(EnergyParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned long long *stk = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)warp * EPL_WARP_SMEM) + lane;   // [depth * 32]
-  const int nc = p.live ? p.nq : p.nvc;
-  const MeshDev mo = p.meshes[p.body_mesh[p.object]];
-  const int nlegal = p.legal_count ? *p.legal_count : p.npose;
-  const int nquery = nlegal * nc;
-  const int ngroups = (nquery + 31) / 32;
-  unsigned nbx = 0, ntr = 0;
-  const int rootlink = (int)__ldg(reinterpret_cast<const uint4 *>(mo.nodes)).w;
-  const float inv_qs[3] = {1.0f / mo.qs[0], 1.0f / mo.qs[1], 1.0f / mo.qs[2]};
-
-  while (true) {
-    int g = 0;
-    if (lane == 0) g = atomicAdd(p.work_counter, 1);
-    g = __shfl_sync(FULL, g, 0);
-    if (g >= ngroups) break;
-    const int qid = g * 32 + lane;
-    bool valid = qid < nquery;
-    int pose = -1, c = 0;
-    f3 cnl = mk<float>(0.f, 0.f, 0.f);
-    if (valid) {
-      int li = qid / nc;
-      c = qid - li * nc;
-      pose = p.legal_list ? p.legal_list[li] : li;
-      if (p.legal && !p.legal[pose]) valid = false;
-    }
-    d3 q = mk<double>(0, 0, 0);
-    unsigned long long best = EQ_NONE, second = EQ_NONE;
-    float qlo[3] = {0.f, 0.f, 0.f}, qhi[3] = {0.f, 0.f, 0.f};
-    int cur = -1, leaf = -1, sp = 0;
-    float curlb = 0.f;
-    if (valid) {
-      energy_contact(p, pose, c, q, cnl);
-      // the query on the quantisation grid, rounded away from every face it can be compared with, biased by 2^23
-      // (clamped to +-4e6 grid steps so the biased sums stay exact integers; clamping only moves the query towards the boxes)
-      const float gx = fminf(fmaxf(((float)q.x - mo.q0[0]) * inv_qs[0], -4.0e6f), 4.0e6f);
-      const float gy = fminf(fmaxf(((float)q.y - mo.q0[1]) * inv_qs[1], -4.0e6f), 4.0e6f);
-      const float gz = fminf(fmaxf(((float)q.z - mo.q0[2]) * inv_qs[2], -4.0e6f), 4.0e6f);
-      qlo[0] = floorf(gx - 0.05f) + 8388608.f; qhi[0] = ceilf(gx + 0.05f) + 8388608.f;
-      qlo[1] = floorf(gy - 0.05f) + 8388608.f; qhi[1] = ceilf(gy + 0.05f) + 8388608.f;
-      qlo[2] = floorf(gz - 0.05f) + 8388608.f; qhi[2] = ceilf(gz + 0.05f) + 8388608.f;
-      if (mo.seed) {
-        const int ix = min(max(__float2int_rd(((float)q.x - mo.g0[0]) * mo.ginv[0]), 0), mo.gres[0] - 1);
-        const int iy = min(max(__float2int_rd(((float)q.y - mo.g0[1]) * mo.ginv[1]), 0), mo.gres[1] - 1);
-        const int iz = min(max(__float2int_rd(((float)q.z - mo.g0[2]) * mo.ginv[2]), 0), mo.gres[2] - 1);
-        const int tri = __ldg(&mo.seed[(iz * mo.gres[1] + iy) * mo.gres[0] + ix]);
-        if (tri >= 0) { best = point_tri_key(mo, q, tri); ntr++; }
-      }
-      if (rootlink >= 0) cur = rootlink; else leaf = ~rootlink;
-    }
-    // overflow frame for paths deeper than EPL_DEPTH (degenerate trees): a few entries in local memory
-    unsigned long long ovf[8];
-    int osp = 0;
-
-    while (true) {
-      // ---- descend until this lane holds a leaf or runs dry
-      while (cur >= 0) {
-        float bound = __uint_as_float((unsigned)(best >> 32)) * NEAR_BAND + 1.0e-12f;
-        if (curlb <= bound) {
-          unsigned r0, r1, r2, r3, r4, r5, r6, r7;
-          asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
-                       : "l"(mo.nodes + cur));
-          const float d0 = epl_gap2(make_uint4(r0, r1, r2, r3), qlo, qhi, mo.qs);
-          const float d1 = epl_gap2(make_uint4(r4, r5, r6, r7), qlo, qhi, mo.qs);
-          nbx += 2;
-          const bool swap = d1 < d0;
-          const float dn = swap ? d1 : d0, df = swap ? d0 : d1;
-          const int lkn = (int)(swap ? r7 : r3), lkf = (int)(swap ? r3 : r7);
-          if (df <= bound) {
-            // far child (inner node or leaf, told apart by the sign of its link) waits on the stack
-            const unsigned long long e = ((unsigned long long)__float_as_uint(df) << 32) | (unsigned)lkf;
-            if (sp < EPL_DEPTH) { stk[sp * 32] = e; sp++; }
-            else if (osp < 8) { ovf[osp++] = e; }
-            else {
-              // both frames full (a path > 32 unbalanced levels): finish the far subtree right here, on a tiny loop
-              // that revisits it from its root without a stack -- reached only on pathological trees
-              int stack2[48]; int n2 = 0; stack2[n2++] = lkf;
-              while (n2 > 0) {
-                const int lk = stack2[--n2];
-                if (lk < 0) { epl_leaf(mo, q, ~lk, best, second); ntr++; continue; }
-                uint4 a = __ldg(reinterpret_cast<const uint4 *>(mo.nodes + lk)), b = __ldg(reinterpret_cast<const uint4 *>(mo.nodes + lk + 1));
-                const float bb = __uint_as_float((unsigned)(best >> 32)) * NEAR_BAND + 1.0e-12f;
-                if (epl_gap2(a, qlo, qhi, mo.qs) <= bb && n2 < 48) stack2[n2++] = (int)a.w;
-                if (epl_gap2(b, qlo, qhi, mo.qs) <= bb && n2 < 48) stack2[n2++] = (int)b.w;
-                nbx += 2;
-              }
-            }
-          }
-          if (dn <= bound) {
-            if (lkn >= 0) { cur = lkn; curlb = dn; continue; }
-            leaf = ~lkn; cur = -1;
-            break;
-          }
-        }
-        // pop
-        cur = -1;
-        while (osp > 0 || sp > 0) {
-          unsigned long long e;
-          if (osp > 0) e = ovf[--osp]; else { sp--; e = stk[sp * 32]; }
-          const float lb = __uint_as_float((unsigned)(e >> 32));
-          bound = __uint_as_float((unsigned)(best >> 32)) * NEAR_BAND + 1.0e-12f;
-          if (lb > bound) continue;
-          const int lk = (int)(unsigned)e;
-          if (lk >= 0) { cur = lk; curlb = lb; } else leaf = ~lk;
-          break;
-        }
-        if (leaf >= 0) break;
-      }
-      // ---- every lane that holds a leaf tests it
-      const bool has = leaf >= 0;
-      if (!__any_sync(FULL, has || cur >= 0)) break;
-      if (has) {
-        epl_leaf(mo, q, leaf, best, second);
-        ntr++;
-        leaf = -1;
-        // next entry of this lane
-        while (osp > 0 || sp > 0) {
-          unsigned long long e;
-          if (osp > 0) e = ovf[--osp]; else { sp--; e = stk[sp * 32]; }
-          const float lb = __uint_as_float((unsigned)(e >> 32));
-          if (lb > __uint_as_float((unsigned)(best >> 32)) * NEAR_BAND + 1.0e-12f) continue;
-          const int lk = (int)(unsigned)e;
-          if (lk >= 0) { cur = lk; curlb = lb; } else leaf = ~lk;
-          break;
-        }
-      }
-    }
-    if (valid) p.terms[qid] = energy_term_from_keys(mo, q, cnl, best, second);
-    __syncwarp();
-  }
-  if (p.stats) {
-    unsigned long long v;
-    v = nbx; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PBOX], v);
-    v = ntr; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0 && v) atomicAdd(&p.stats[STAT_PTRI], v);
-  }
-}
-
 // closest-point seed grid of a mesh: one thread per cell, the triangle closest to the cell's centre (per-lane traversal,
 // run once per mesh)
 __global__ void __launch_bounds__(128) seed_grid_kernel(MeshDev m, int *seed) {
@@ -1479,15 +1297,7 @@ cudaError_t launch_energy(const EnergyParams &p, int blocks, cudaStream_t s) {
   size_t smem = energy_block_smem_bytes(p.stage_nodes, p.stack_entries);
   static size_t granted[64] = {};
   { cudaError_t e = ensure_dyn_smem((const void *)energy_kernel, smem, granted); if (e != cudaSuccess) return e; }
-  static const int variant = getenv("B2C_ENERGY_VARIANT") ? atoi(getenv("B2C_ENERGY_VARIANT")) : 0;
-  if (variant == 1) {
-    const size_t smem_pl = (size_t)8 * EPL_WARP_SMEM;
-    static size_t granted_pl[64] = {};
-    { cudaError_t e = ensure_dyn_smem((const void *)energy_kernel_pl, smem_pl, granted_pl); if (e != cudaSuccess) return e; }
-    energy_kernel_pl<<<blocks, 256, smem_pl, s>>>(p);
-  } else {
-    energy_kernel<<<blocks, 256, smem, s>>>(p);
-  }
+  energy_kernel<<<blocks, 256, smem, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   energy_reduce_kernel<<<(p.npose + 255) / 256, 256, 0, s>>>(p);
