@@ -8,6 +8,7 @@
 //   energy_kernel    K5+K8 CONTACT_ENERGY, PRESET or LIVE contacts, TMA-staged tree top (thread / pose,contact)
 //
 // See DESIGN.md for the data layout and the roofline that bounds each kernel.
+#include <cstdlib>
 #include "b2c_internal.h"
 #include "traverse.cuh"
 
@@ -915,7 +916,8 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 #endif
 constexpr int EQ_STACK_MIN = EQ_STACK_PHYS_N, EQ_LEAF_CAP = 96;     // stack entries per warp: at least this, more for deep trees
 constexpr unsigned long long EQ_NONE = 0x7f7fffffffffffffull;   // (FLT_MAX bits << 32) | no triangle
-constexpr int ENERGY_WARP_FIXED = EQ_LEAF_CAP * 8 + 32 * 8 + 32 * 24 + 32 * 16 + 32 * 8;
+// per warp: leaf queue, best and runner-up keys, and the 32 queries in fp32 form (EnergyQueries below)
+constexpr int ENERGY_WARP_FIXED = EQ_LEAF_CAP * 8 + 32 * 8 + 32 * 8 + 32 * 16 + 32 * 16 + 32 * 4;
 // 32 depth-first traversals keep about one open sibling per level each
 __host__ __device__ inline int energy_stack_entries(int depth) { (void)depth; return EQ_STACK_MIN; }   // deeper trees measured slower with larger stacks (occupancy)
 
@@ -932,6 +934,72 @@ __device__ __forceinline__ unsigned long long point_tri_key(const MeshDev &mo, d
   const unsigned h = ((unsigned)__float2int_rd(v.x * 64.f) * 73856093u ^ (unsigned)__float2int_rd(v.y * 64.f) * 19349663u ^
                       (unsigned)__float2int_rd(v.z * 64.f) * 83492791u) & 0xffu;
   return ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)h << 24) | (unsigned)tri;
+}
+
+// The 32 queries of a warp as the traversal reads them (shared memory).  A query point q (fp64, object frame) is held as
+// the fp32 pair qh + ql (qh = fl(q), ql = fl(q - qh)): a triangle vertex relative to it is (v - qh) - ql in two fp32
+// subtractions -- exact where it matters (v within a factor 2 of qh: Sterbenz), within half an ulp of the fp64
+// difference rounded to fp32 elsewhere -- instead of 9 fp32->fp64 conversions, 9 fp64 subtractions and 9 conversions back
+// on the quarter-rate pipe.  For the box tests the query also sits on the mesh's quantisation grid, rounded DOWN and
+// biased by 2^23 (glo); see eq_gap2.
+struct EnergyQueries {
+  float4 *hx;        // [32] qh.x qh.y qh.z ql.x
+  float4 *gl;        // [32] glo.x glo.y glo.z ql.y
+  float *lz;         // [32] ql.z
+};
+#ifndef EQ_SPLIT_SUB
+#define EQ_SPLIT_SUB 1
+#endif
+#ifndef EQ_GRID_GAP
+#define EQ_GRID_GAP 1
+#endif
+__device__ __forceinline__ unsigned long long point_tri_key_s(const MeshDev &mo, f3 qh, f3 ql, int tri) {
+#if EQ_SPLIT_SUB
+  const float4 v0 = __ldg(&mo.tris[tri].v[0]), v1 = __ldg(&mo.tris[tri].v[1]), v2 = __ldg(&mo.tris[tri].v[2]);
+  const f3 a = mk<float>((v0.x - qh.x) - ql.x, (v0.y - qh.y) - ql.y, (v0.z - qh.z) - ql.z);
+  const f3 b = mk<float>((v1.x - qh.x) - ql.x, (v1.y - qh.y) - ql.y, (v1.z - qh.z) - ql.z);
+  const f3 c = mk<float>((v2.x - qh.x) - ql.x, (v2.y - qh.y) - ql.y, (v2.z - qh.z) - ql.z);
+  f3 v = closest_pt_triangle<float>(a, b, c, mk<float>(0.f, 0.f, 0.f));
+  float d2 = dot(v, v);
+  const unsigned h = ((unsigned)__float2int_rd(v.x * 64.f) * 73856093u ^ (unsigned)__float2int_rd(v.y * 64.f) * 19349663u ^
+                      (unsigned)__float2int_rd(v.z * 64.f) * 83492791u) & 0xffu;
+  return ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)h << 24) | (unsigned)tri;
+#else
+  return point_tri_key(mo, mk<double>((double)qh.x + (double)ql.x, (double)qh.y + (double)ql.y, (double)qh.z + (double)ql.z), tri);
+#endif
+}
+// Squared distance from a query to a stored box, straight from the 16-bit corners: 0x4B000000 | corner is the float
+// 2^23 + corner (one byte permute, no integer-to-float conversion), the query's grid coordinate carries the same bias, so
+// a gap is ONE exact subtraction of integers; only the three clamped gaps are scaled to millimetres.  The query is rounded
+// down for the low faces and (glo + 2) up for the high faces, so the result never exceeds the true distance to the stored
+// box (it falls short of it by at most two grid steps, a few micrometres): a lower bound, which is all the pruning needs.
+__device__ __forceinline__ float eq_gap2(unsigned wx, unsigned wy, unsigned wz, float4 glo, const float *qs) {
+  const float L0 = __uint_as_float(__byte_perm(wx, 0x4B000000u, 0x7610)), L1 = __uint_as_float(__byte_perm(wx, 0x4B000000u, 0x7632));
+  const float L2 = __uint_as_float(__byte_perm(wy, 0x4B000000u, 0x7610)), H0 = __uint_as_float(__byte_perm(wy, 0x4B000000u, 0x7632));
+  const float H1 = __uint_as_float(__byte_perm(wz, 0x4B000000u, 0x7610)), H2 = __uint_as_float(__byte_perm(wz, 0x4B000000u, 0x7632));
+  const float g0 = fmaxf(fmaxf(L0 - (glo.x + 2.f), glo.x - H0), 0.f) * qs[0];
+  const float g1 = fmaxf(fmaxf(L1 - (glo.y + 2.f), glo.y - H1), 0.f) * qs[1];
+  const float g2 = fmaxf(fmaxf(L2 - (glo.z + 2.f), glo.z - H2), 0.f) * qs[2];
+  return g0 * g0 + g1 * g1 + g2 * g2;
+}
+__device__ __forceinline__ float eq_box_dist2(const MeshDev &mo, uint4 w, float4 hx, float4 gl) {
+#if EQ_GRID_GAP
+  return eq_gap2(w.x, w.y, w.z, gl, mo.qs);
+#else
+  return point_nodeq_dist2(w, mo.q0, mo.qs, hx.x, hx.y, hx.z);
+#endif
+}
+__device__ __forceinline__ void eq_store_query(const MeshDev &mo, const EnergyQueries &Q, int lane, d3 q) {
+  const float hx = (float)q.x, hy = (float)q.y, hz = (float)q.z;
+  const float lx = (float)(q.x - (double)hx), ly = (float)(q.y - (double)hy), lz = (float)(q.z - (double)hz);
+  // grid coordinate, clamped to +-4e6 steps so that the biased value stays an exact integer (clamping moves the query
+  // towards the boxes: still a lower bound), rounded down with a margin for the fp32 rounding of the division
+  const float gx = fminf(fmaxf((hx - mo.q0[0]) / mo.qs[0], -4.0e6f), 4.0e6f);
+  const float gy = fminf(fmaxf((hy - mo.q0[1]) / mo.qs[1], -4.0e6f), 4.0e6f);
+  const float gz = fminf(fmaxf((hz - mo.q0[2]) / mo.qs[2], -4.0e6f), 4.0e6f);
+  Q.hx[lane] = make_float4(hx, hy, hz, lx);
+  Q.gl[lane] = make_float4(floorf(gx - 0.5f) + 8388608.f, floorf(gy - 0.5f) + 8388608.f, floorf(gz - 0.5f) + 8388608.f, ly);
+  Q.lz[lane] = lz;
 }
 
 // contact c of a pose -> query point in the object's frame and contact normal in the object's frame (fp32)
@@ -988,9 +1056,10 @@ __device__ __forceinline__ float energy_term_from_keys(const MeshDev &mo, d3 q, 
 // exact test of one leaf for query qi of the warp: best (distance, triangle) by 64-bit atomicMin; the best loser with a
 // DIFFERENT closest point inside the near-tie band is remembered for the fp64 arbitration of the final stage (fp32 cannot
 // order two candidates whose distances agree to 1e-4, and the energy depends on which closest point wins)
-__device__ __forceinline__ void eq_leaf_test(const MeshDev &mo, const double *qd, unsigned long long *bestkey, unsigned long long *secondkey,
+__device__ __forceinline__ void eq_leaf_test(const MeshDev &mo, const EnergyQueries &Q, unsigned long long *bestkey, unsigned long long *secondkey,
                                              int qi, int tri) {
-  const unsigned long long key = point_tri_key(mo, mk<double>(qd[3 * qi], qd[3 * qi + 1], qd[3 * qi + 2]), tri);
+  const float4 hx = Q.hx[qi], gl = Q.gl[qi];
+  const unsigned long long key = point_tri_key_s(mo, mk<float>(hx.x, hx.y, hx.z), mk<float>(hx.w, gl.w, Q.lz[qi]), tri);
   const unsigned long long old = atomicMin(&bestkey[qi], key);
   const unsigned long long win = old < key ? old : key, lose = old < key ? key : old;
   if (lose != EQ_NONE && ((win ^ lose) & 0xff000000ull) != 0ull &&
@@ -1002,14 +1071,14 @@ __device__ __forceinline__ void eq_leaf_test(const MeshDev &mo, const double *qd
 // first, same pruning, same leaf test).  Rare -- 32 depth-first traversals keep about 32 x depth entries open and the stack
 // is sized for that -- but it makes the traversal exact whatever the tree depth and however the queries interleave.
 // (returns box tests | triangle tests << 16 for the statistics: counters passed by reference would live in memory)
-__device__ __noinline__ unsigned energy_private_dfs(const MeshDev &mo, const NodeQ *top, int ntop, unsigned long long e, const double *qd,
-                                                    const float4 *qf, unsigned long long *bestkey, unsigned long long *secondkey) {
+__device__ __noinline__ unsigned energy_private_dfs(const MeshDev &mo, const NodeQ *top, int ntop, unsigned long long e, const EnergyQueries &Q,
+                                                    unsigned long long *bestkey, unsigned long long *secondkey) {
   unsigned nbx = 0, ntr = 0;
   const int qi = (int)((e >> 24) & 0xffu);
   int stk[64]; float stl[64];
   int n = 0;
   stk[n] = (int)(e & 0xffffffu); stl[n] = __uint_as_float((unsigned)(e >> 32)); n++;
-  const float4 qq = qf[qi];
+  const float4 qhx = Q.hx[qi], qgl = Q.gl[qi];
   while (n > 0) {
     n--;
     const int pair = stk[n];
@@ -1017,20 +1086,20 @@ __device__ __noinline__ unsigned energy_private_dfs(const MeshDev &mo, const Nod
     if (stl[n] > best * NEAR_BAND + 1.0e-12f) continue;
     uint4 w0, w1;
     fetch_pair_raw(mo, top, ntop, pair, w0, w1);
-    float d0 = point_nodeq_dist2(w0, mo.q0, mo.qs, qq.x, qq.y, qq.z);
-    float d1 = point_nodeq_dist2(w1, mo.q0, mo.qs, qq.x, qq.y, qq.z);
+    float d0 = eq_box_dist2(mo, w0, qhx, qgl);
+    float d1 = eq_box_dist2(mo, w1, qhx, qgl);
     nbx += 2;
     const bool swap = d1 < d0;
     const float dn = swap ? d1 : d0, df = swap ? d0 : d1;
     const int lkn = (int)(swap ? w1.w : w0.w), lkf = (int)(swap ? w0.w : w1.w);
     // far child first (deeper in the stack), leaves tested at once
     if (df <= best * NEAR_BAND + 1.0e-12f) {
-      if (lkf < 0) { eq_leaf_test(mo, qd, bestkey, secondkey, qi, ~lkf); ntr++; }
+      if (lkf < 0) { eq_leaf_test(mo, Q, bestkey, secondkey, qi, ~lkf); ntr++; }
       else if (n < 64) { stk[n] = lkf; stl[n] = df; n++; }
     }
     best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
     if (dn <= best * NEAR_BAND + 1.0e-12f) {
-      if (lkn < 0) { eq_leaf_test(mo, qd, bestkey, secondkey, qi, ~lkn); ntr++; }
+      if (lkn < 0) { eq_leaf_test(mo, Q, bestkey, secondkey, qi, ~lkn); ntr++; }
       else if (n < 64) { stk[n] = lkn; stl[n] = dn; n++; }
     }
   }
@@ -1057,9 +1126,11 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
   unsigned long long *stack = reinterpret_cast<unsigned long long *>(wbase);
   unsigned long long *leafq = stack + stack_cap;
   unsigned long long *bestkey = leafq + EQ_LEAF_CAP;                 // [32] (d2 bits << 32) | point hash << 24 | triangle
-  double *qd = reinterpret_cast<double *>(bestkey + 32);              // [32][3] query point, object frame
-  float4 *qf = reinterpret_cast<float4 *>(qd + 96);                   // [32] fp32 copy
-  unsigned long long *secondkey = reinterpret_cast<unsigned long long *>(qf + 32);   // [32] best loser within 1e-4 of the winner
+  unsigned long long *secondkey = bestkey + 32;                       // [32] best loser within the near-tie band of the winner
+  EnergyQueries Q;
+  Q.hx = reinterpret_cast<float4 *>(secondkey + 32);
+  Q.gl = Q.hx + 32;
+  Q.lz = reinterpret_cast<float *>(Q.gl + 32);
   const int nc = p.live ? p.nq : p.nvc;
   const MeshDev mo = p.meshes[p.body_mesh[p.object]];
   const int ntop = p.stage_nodes < mo.nnodes ? p.stage_nodes : mo.nnodes;
@@ -1115,8 +1186,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
     d3 q = mk<double>(0, 0, 0);
     if (valid) {
       energy_contact(p, pose, c, q, cnl);
-      qd[3 * lane] = q.x; qd[3 * lane + 1] = q.y; qd[3 * lane + 2] = q.z;
-      qf[lane] = make_float4((float)q.x, (float)q.y, (float)q.z, 0.f);
+      eq_store_query(mo, Q, lane, q);
       if (mo.seed) {
         // start from a real candidate: the triangle closest to the centre of the query's grid cell (clamped into the
         // grid for far queries), tested exactly like any leaf.  Its key is what the traversal would have produced had it
@@ -1125,7 +1195,11 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
         const int iy = min(max(__float2int_rd(((float)q.y - mo.g0[1]) * mo.ginv[1]), 0), mo.gres[1] - 1);
         const int iz = min(max(__float2int_rd(((float)q.z - mo.g0[2]) * mo.ginv[2]), 0), mo.gres[2] - 1);
         const int tri = __ldg(&mo.seed[(iz * mo.gres[1] + iy) * mo.gres[0] + ix]);
-        if (tri >= 0) { seedkey = point_tri_key(mo, q, tri); ntr++; }
+        if (tri >= 0) {
+          const float4 hx = Q.hx[lane], gl = Q.gl[lane];
+          seedkey = point_tri_key_s(mo, mk<float>(hx.x, hx.y, hx.z), mk<float>(hx.w, gl.w, Q.lz[lane]), tri);
+          ntr++;
+        }
       }
     }
     bestkey[lane] = seedkey;
@@ -1152,7 +1226,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
           float best = __uint_as_float((unsigned)(bestkey[qi] >> 32));
           if (lb <= best * NEAR_BAND + 1.0e-12f) {
             ntr++;
-            eq_leaf_test(mo, qd, bestkey, secondkey, qi, tri);
+            eq_leaf_test(mo, Q, bestkey, secondkey, qi, tri);
           }
         }
         lq -= n;
@@ -1165,7 +1239,7 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
       // on a private stack, so the shared one is never outgrown
       const int room = stack_cap - 64 - sp;
       if (sp >= stack_cap - 2) {
-        if (lane == 0) { const unsigned c = energy_private_dfs(mo, top, ntop, stack[sp - 1], qd, qf, bestkey, secondkey); nbx += c & 0xffffu; ntr += c >> 16; }
+        if (lane == 0) { const unsigned c = energy_private_dfs(mo, top, ntop, stack[sp - 1], Q, bestkey, secondkey); nbx += c & 0xffffu; ntr += c >> 16; }
         sp -= 1;
         __syncwarp();
         continue;
@@ -1185,9 +1259,9 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
         if (lb <= best * NEAR_BAND + 1.0e-12f) {
           uint4 w0, w1;
           fetch_pair_raw(mo, top, ntop, pair, w0, w1);
-          float4 qq = qf[qi];
-          float d0 = point_nodeq_dist2(w0, mo.q0, mo.qs, qq.x, qq.y, qq.z);
-          float d1 = point_nodeq_dist2(w1, mo.q0, mo.qs, qq.x, qq.y, qq.z);
+          const float4 qhx = Q.hx[qi], qgl = Q.gl[qi];
+          float d0 = eq_box_dist2(mo, w0, qhx, qgl);
+          float d1 = eq_box_dist2(mo, w1, qhx, qgl);
           nbx += 2;
           bool swap = d1 < d0;
           float dn = swap ? d1 : d0, df = swap ? d0 : d1;
@@ -1215,8 +1289,10 @@ __global__ void __launch_bounds__(256, ENERGY_MIN_BLOCKS) energy_kernel(EnergyPa
 
     // ---- this lane's result: redo the winning triangle (fp64 when the distance is tiny against its extent)
     if (valid) {
-      const float term = energy_term_from_keys(mo, mk<double>(qd[3 * lane], qd[3 * lane + 1], qd[3 * lane + 2]), cnl, bestkey[lane], secondkey[lane]);
-      p.terms[qid] = term;
+      // qh + ql gives q back to 2^-48 of |q - qh| (~1e-20 mm): not worth six registers across the traversal
+      const float4 hx = Q.hx[lane], gl = Q.gl[lane];
+      const d3 qq = mk<double>((double)hx.x + (double)hx.w, (double)hx.y + (double)gl.w, (double)hx.z + (double)Q.lz[lane]);
+      p.terms[qid] = energy_term_from_keys(mo, qq, cnl, bestkey[lane], secondkey[lane]);
     }
     __syncwarp();
   }
