@@ -370,3 +370,77 @@ def forward_kinematics(robots, ridx, base, dofs_by_robot, joint_values=None, out
 
 def hardware_threads() -> int:
     return int(lib().ref_hardware_threads())
+
+
+# ---- contact set-up pinned to the reference's own lines (oracle/ref_contact.cpp -> oracle/_ref/libgraspit_ref_contact.so)
+CONTACT_LIB_PATH = os.path.join(_HERE, "_ref", "libgraspit_ref_contact.so")
+_clib = None
+
+
+def contact_lib():
+    global _clib
+    if _clib is None:
+        if not os.path.exists(CONTACT_LIB_PATH):
+            raise RuntimeError(f"oracle library missing: {CONTACT_LIB_PATH} (run `make -C oracle` where /root/reference exists)")
+        L = C.CDLL(CONTACT_LIB_PATH)
+        L.ref_soft_neighborhood_radius.restype = C.c_double
+        L.ref_soft_neighborhood_radius.argtypes = [C.c_double, C.c_double]
+        _clib = L
+    return _clib
+
+
+def _t7(tran):
+    return np.ascontiguousarray(np.concatenate([np.asarray(tran[0], dtype=np.float64), np.asarray(tran[1], dtype=np.float64)]))
+
+
+def point_contact(pos, normal, cof, cog, max_radius):
+    """PointContact::PointContact + computeWrenches: (frame q wxyz + t, edges (8, 6), wrenches (8, 6) = force, torque)"""
+    frame, edges, wr = np.zeros(7), np.zeros(48), np.zeros(48)
+    n = contact_lib().ref_point_contact(_dp(_d(pos, 3)), _dp(_d(normal, 3)), C.c_double(cof), _dp(_d(cog, 3)), C.c_double(max_radius),
+                                        _dp(frame), _dp(edges), _dp(wr))
+    return frame, edges.reshape(8, 6)[:n], wr.reshape(8, 6)[:n]
+
+
+def check_contact_normals_ref(row12, tran1, tran2):
+    """checkContactNormals (contactSetting.cpp:54-81): returns (row with possibly flipped normals, ok)"""
+    r = np.ascontiguousarray(np.asarray(row12, dtype=np.float64)[:12].copy())
+    ok = contact_lib().ref_check_contact_normals(_dp(_t7(tran1)), _dp(_t7(tran2)), _dp(r))
+    return r, bool(ok)
+
+
+def soft_neighborhood_radius_ref(y1, y2):
+    return float(contact_lib().ref_soft_neighborhood_radius(float(y1), float(y2)))
+
+
+def merge_soft_neighborhoods_ref(rows12, tran1, tran2, nghbd1, nghbd2):
+    """mergeSoftNeighborhoods (contactSetting.cpp:139-186): (surviving original indices, merged nghbd1 list, nghbd2 list)"""
+    rows = np.ascontiguousarray(np.asarray(rows12, dtype=np.float64)[:, :12])
+    n = len(rows)
+
+    def flat(lists):
+        off = np.zeros(n + 1, dtype=np.int32)
+        for i, a in enumerate(lists):
+            off[i + 1] = off[i] + len(np.asarray(a).reshape(-1, 3))
+        x = np.zeros((max(int(off[-1]), 1), 3))
+        for i, a in enumerate(lists):
+            x[off[i]:off[i + 1]] = np.asarray(a, dtype=np.float64).reshape(-1, 3)
+        return np.ascontiguousarray(x), off
+    x1, o1 = flat(nghbd1); x2, o2 = flat(nghbd2)
+    keep = np.zeros(n, dtype=np.int32)
+    out1, out2 = np.zeros((len(x1) + 1, 3)), np.zeros((len(x2) + 1, 3))
+    oo1, oo2 = np.zeros(n + 1, dtype=np.int32), np.zeros(n + 1, dtype=np.int32)
+    k = contact_lib().ref_merge_soft_neighborhoods(_dp(_t7(tran1)), _dp(_t7(tran2)), n, _dp(rows), _dp(x1), _ip(o1), _dp(x2), _ip(o2),
+                                                   _ip(keep), _dp(out1), _ip(oo1), _dp(out2), _ip(oo2))
+    return (keep[:k].copy(), [out1[oo1[i]:oo1[i + 1]].copy() for i in range(k)], [out2[oo2[i]:oo2[i + 1]].copy() for i in range(k)])
+
+
+def soft_contact_pair(tran1, tran2, pos1, nrm1, nghbd1, pos2, nrm2, nghbd2, y1, y2, cof, cog1, max_radius1):
+    """SoftContact + mate as addContacts builds them, setUpFrictionEdges + computeWrenches on side 1:
+    (wrenches (20, 6), info side 1, info side 2); info = majorAxis, minorAxis, relPhi, r1prime, r2prime, a, b, c, r1, r2"""
+    a = np.ascontiguousarray(np.asarray(nghbd1, dtype=np.float64).reshape(-1, 3)); b = np.ascontiguousarray(np.asarray(nghbd2, dtype=np.float64).reshape(-1, 3))
+    wr, i1, i2 = np.zeros(20 * 6), np.zeros(10), np.zeros(10)
+    n = contact_lib().ref_soft_contact_pair(_dp(_t7(tran1)), _dp(_t7(tran2)), _dp(_d(pos1, 3)), _dp(_d(nrm1, 3)), len(a), _dp(a if len(a) else np.zeros(3)),
+                                            _dp(_d(pos2, 3)), _dp(_d(nrm2, 3)), len(b), _dp(b if len(b) else np.zeros(3)),
+                                            C.c_double(y1), C.c_double(y2), C.c_double(cof), _dp(_d(cog1, 3)), C.c_double(max_radius1),
+                                            _dp(wr), _dp(i1), _dp(i2))
+    return wr.reshape(20, 6)[:n], i1, i2
