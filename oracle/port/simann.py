@@ -2,11 +2,11 @@
 of independent chains.  Follows src/EGPlanner/simAnn.cpp: cooling :218-227, prob :229-234, neighborDistribution
 :236-250, variableNeighbor :175-215 (no target state), iterate :96-158.
 
-Parity status: the reference draws from libc rand() seeded with time(NULL) (simAnn.cpp:85) and holds no golden
-vectors for this path, so the random stream is ours (Philox4x32-10, counter = (chain, step, draw block), shared
-with the CUDA kernels) and parity of trajectories is UNPINNED against the reference; the closed-form pieces
-(cooling, prob, the Ingber neighbour map) are pinned by tests/test_simann_port.py against values computed by hand
-from the reference's formulas.
+Parity status: PINNED.  The reference draws from libc rand() seeded with time(NULL) (simAnn.cpp:85); the product's
+stream is Philox4x32-10 (counter = (chain, step, draw block), shared with the CUDA kernels), so product trajectories are
+its own by design.  The restatement itself, though, takes its uniforms from any source (`draws=`, `U=`) and runs in
+fp64 on request (`dtype=`): fed libc's rand() stream it reproduces, call for call, the trajectory of the reference's
+own SimAnn::iterate compiled verbatim (oracle/ref_simann.cpp, tests/test_simann_port.py::test_port_reproduces_*).
 """
 from __future__ import annotations
 
@@ -70,13 +70,15 @@ def neighbor_distribution(T, u):
     return np.where(u < 0.5, -y, y)
 
 
-def propose(cur, k, variables, params, step, seed, chain_offset=0):
-    """one neighbour per chain (variableNeighbor).  cur: (n, nvar) float32 states; k: (n,) per-chain step counters."""
-    cur = np.asarray(cur, dtype=np.float32)
+def propose(cur, k, variables, params, step, seed, chain_offset=0, draws=None, dtype=np.float32):
+    """one neighbour per chain (variableNeighbor).  cur: (n, nvar) states; k: (n,) per-chain step counters.
+    draws: an object with next(mask) -> uniforms (default: the product's Philox stream); dtype: float32 as the engine
+    stores states, float64 to follow the reference's doubles."""
+    cur = np.asarray(cur, dtype=dtype)
     n, nvar = cur.shape
     T = cooling(params.T0, params.YC, k, params.YDIMS) * params.NBR_ADJ
-    rng = ChainDraws(np.arange(n) + chain_offset, step, seed)
-    out = np.zeros((n, nvar), dtype=np.float32)
+    rng = draws if draws is not None else ChainDraws(np.arange(n) + chain_offset, step, seed)
+    out = np.zeros((n, nvar), dtype=dtype)
     for i in range(nvar):
         vmin, vmax, jump = float(variables.vmin[i]), float(variables.vmax[i]), float(variables.vjump[i])
         rng_range = abs(vmax - vmin)
@@ -93,19 +95,21 @@ def propose(cur, k, variables, params, step, seed, chain_offset=0):
             cand = np.where((cand > vmax) & (cand - vmax < 1.0e-7), vmax, cand)
             cand = np.where((cand < vmin) & (cand - vmin > -1.0e-7), vmin, cand)
             v = np.where(todo, cand, v)
-        vf = v.astype(np.float32)
-        out[:, i] = np.minimum(np.maximum(vf, np.float32(vmin)), np.float32(vmax))
+        vf = v.astype(dtype)
+        out[:, i] = np.minimum(np.maximum(vf, dtype(vmin)), dtype(vmax))
     return out
 
 
-def accept(cur, cur_energy, k, prop, legal, energy, params, step, seed, chain_offset=0):
-    """Metropolis rule of SimAnn::iterate; returns (cur, cur_energy, k, jumped)"""
+def accept(cur, cur_energy, k, prop, legal, energy, params, step, seed, chain_offset=0, U=None):
+    """Metropolis rule of SimAnn::iterate; returns (cur, cur_energy, k, jumped).  U: the uniforms to compare P with
+    (default: the product's Philox stream)"""
     n = len(k)
     T = cooling(params.T0, params.HC, k, params.HDIMS)
     P = prob(params.ERR_ADJ * cur_energy.astype(np.float64), params.ERR_ADJ * energy.astype(np.float64), T)
-    w = philox4x32_10(np.arange(n, dtype=np.uint64) + np.uint64(chain_offset), np.uint64(step), np.uint64(0xFFFFFFFF), np.uint64(1),
-                      np.uint64(int(seed) & 0xFFFFFFFF), np.uint64((int(seed) >> 32) & 0xFFFFFFFF))
-    U = _to_unit(w[0])
+    if U is None:
+        w = philox4x32_10(np.arange(n, dtype=np.uint64) + np.uint64(chain_offset), np.uint64(step), np.uint64(0xFFFFFFFF), np.uint64(1),
+                          np.uint64(int(seed) & 0xFFFFFFFF), np.uint64((int(seed) >> 32) & 0xFFFFFFFF))
+        U = _to_unit(w[0])
     ok = legal.astype(bool)
     jump = ok & (P > U)
     cur = np.where(jump[:, None], prop, cur)

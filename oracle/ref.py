@@ -444,3 +444,26 @@ def soft_contact_pair(tran1, tran2, pos1, nrm1, nghbd1, pos2, nrm2, nghbd2, y1, 
                                             C.c_double(y1), C.c_double(y2), C.c_double(cof), _dp(_d(cog1, 3)), C.c_double(max_radius1),
                                             _dp(wr), _dp(i1), _dp(i2))
     return wr.reshape(20, 6)[:n], i1, i2
+
+
+# ---- simulated annealing pinned to the reference's own SimAnn (oracle/ref_simann.cpp -> libgraspit_ref_simann.so)
+SIMANN_LIB_PATH = os.path.join(_HERE, "_ref", "libgraspit_ref_simann.so")
+_slib = None
+
+
+def simann_run(neg, seed, preset, iters, start, w, c, cut, start_energy):
+    """`iters` calls of the reference's SimAnn::iterate on one SPACE_AXIS_ANGLE + POSE_EIGEN state after srand(seed), with
+    the closed-form energy of oracle/ref_simann.cpp.  Variables position first, then posture.  Returns dict(result
+    (0 FAIL, 1 JUMP, 2 KEEP), state (iters, nvar), energy, step, table (nvar, 4) = min, max, max jump, circular)."""
+    global _slib
+    if _slib is None:
+        if not os.path.exists(SIMANN_LIB_PATH):
+            raise RuntimeError(f"oracle library missing: {SIMANN_LIB_PATH} (run `make -C oracle` where /root/reference exists)")
+        _slib = C.CDLL(SIMANN_LIB_PATH)
+    nvar = 6 + neg
+    res = np.zeros(iters, dtype=np.int32); st = np.zeros((iters, nvar)); en = np.zeros(iters); stp = np.zeros(iters, dtype=np.int32)
+    table = np.zeros((nvar, 4))
+    rc = _slib.ref_simann_run(int(neg), C.c_uint(seed), int(preset), int(iters), _dp(_d(start, nvar)), _dp(_d(w, nvar)), _dp(_d(c, nvar)),
+                              C.c_double(cut), C.c_double(start_energy), _ip(res), _dp(st), _dp(en), _ip(stp), _dp(table))
+    assert rc == nvar, rc
+    return dict(result=res, state=st, energy=en, step=stp, table=table)

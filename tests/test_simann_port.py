@@ -1,6 +1,12 @@
-"""CPU: the annealing restatement (oracle/port/simann.py) against values worked out by hand from the reference's
-formulas (src/EGPlanner/simAnn.cpp:218-250), the Philox known-answer vectors, and the host-side planner logic."""
+"""CPU: the annealing restatement (oracle/port/simann.py) against the reference's own SimAnn compiled verbatim
+(oracle/ref_simann.cpp: same rand() stream, same trajectory), values worked out by hand from the reference's formulas
+(src/EGPlanner/simAnn.cpp:218-250), the Philox known-answer vectors, and the host-side planner logic."""
+import ctypes
+import os
+from types import SimpleNamespace
+
 import numpy as np
+import pytest
 
 from graspit_b200.planner import BestList, SearchVariables, SimAnnParams, shard, state_distance
 from oracle.port import simann
@@ -96,3 +102,75 @@ def test_shard_partition():
         assert parts[0][0] == 0 and parts[-1][1] == total
         assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
         assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
+
+
+# ---- the restatement against the reference's own SimAnn::iterate ---------------------------------------------------------
+class _LibcDraws:
+    """uniforms as the reference draws them: ((double) rand()) / RAND_MAX (simAnn.cpp:240,129)"""
+    RAND_MAX = 2147483647
+
+    def __init__(self, seed):
+        self.libc = ctypes.CDLL("libc.so.6")
+        self.libc.srand(ctypes.c_uint(seed))
+        self.count = 0
+
+    def one(self):
+        self.count += 1
+        return self.libc.rand() / self.RAND_MAX
+
+    def next(self, mask):
+        return np.array([self.one() if m else 0.5 for m in mask])
+
+
+def _closed_form_energy(x, w, c, cut):
+    e = 0.0
+    for i in range(len(x)):
+        d = float(x[i]) - c[i]
+        e += w[i] * d * d
+    legal = not (np.sin(3.0 * float(x[0])) * np.cos(2.0 * float(x[-1])) > cut)
+    return legal, e
+
+
+@pytest.mark.parametrize("preset,name,cut", [(0, "ANNEAL_DEFAULT", 0.3), (3, "ANNEAL_STRICT", 0.3), (4, "ANNEAL_ONLINE", -0.2),
+                                             (2, "ANNEAL_MODIFIED", 0.6)])
+def test_port_reproduces_the_reference_simann_trajectory(preset, name, cut):
+    from oracle import ref
+    if not os.path.exists(ref.SIMANN_LIB_PATH):
+        pytest.skip("oracle/_ref/libgraspit_ref_simann.so not built")
+    neg, iters, seed = 2, 400, 4242 + preset
+    nvar = 6 + neg
+    rng = np.random.default_rng(5 + preset)
+    start = np.array([10.0, -20.0, 30.0, 1.0, 0.5, 2.0, 0.3, -0.7])
+    w = rng.uniform(0.5, 2.0, nvar); c = np.array([40.0, 10.0, -15.0, 2.0, -1.0, 1.0, 1.0, -2.0])
+    _, e0 = _closed_form_energy(start, w, c, cut)
+    R = ref.simann_run(neg, seed, preset, iters, start, w, c, cut, e0)
+    # the reference's own variable table is the one the product ships
+    sv = SearchVariables.axis_angle_eigen(neg)
+    assert np.allclose(R["table"][:, 0], sv.vmin) and np.allclose(R["table"][:, 1], sv.vmax)
+    assert np.allclose(R["table"][:, 2], sv.vjump) and (R["table"][:, 3] == sv.circular).all()
+    p = getattr(SimAnnParams, name)()
+    variables = SimpleNamespace(vmin=R["table"][:, 0], vmax=R["table"][:, 1], vjump=R["table"][:, 2], circular=R["table"][:, 3].astype(int))
+    draws = _LibcDraws(seed)
+    cur = start[None, :].copy(); ce = np.array([e0]); k = np.array([p.K0])
+    results = {0: 0, 1: 0, 2: 0}
+    for it in range(iters):
+        # SimAnn::iterate: up to 11 neighbours until one is legal (simAnn.cpp:106-116)
+        legal, prop, e = False, None, 0.0
+        for attempt in range(11):
+            prop = simann.propose(cur, k, variables, p, step=0, seed=0, draws=draws, dtype=np.float64)
+            legal, e = _closed_form_energy(prop[0], w, c, cut)
+            if legal:
+                break
+        if not legal:
+            r = 0
+        else:
+            U = np.array([draws.one()])
+            cur, ce, k, j = simann.accept(cur, ce, k, prop, np.array([1], np.uint8), np.array([e]), p, step=0, seed=0, U=U)
+            r = 1 if j[0] else 2
+        results[r] += 1
+        assert r == R["result"][it], (it, r, R["result"][it])
+        assert int(k[0]) == R["step"][it]
+        assert np.allclose(cur[0], R["state"][it], rtol=1e-9, atol=1e-9), (it, cur[0], R["state"][it])
+        assert ce[0] == pytest.approx(R["energy"][it], rel=1e-9, abs=1e-9)
+    # the run exercised every outcome the rule has
+    assert results[1] > 3 and results[2] > 3, results
