@@ -54,6 +54,8 @@ class JointDesc:
     alpha: float
     min: float
     max: float
+    stiffness: float = 0.0                # <springStiffness> (joint.cpp:227,319); only CompliantDOF::getStaticRatio reads it
+    coupling: Optional[float] = None      # the DOF expression's ratio where `ratio` had to be replaced (CompliantDOF)
 
 
 @dataclass
@@ -254,9 +256,30 @@ def _parse_joint(e) -> JointDesc:
     if rev:
         c = c * math.pi / 180.0
         d = _get_double(e, "d", 0.0)
-        return JointDesc(dof, ratio, c, True, 0.0 + c, d, a, alpha, mn * math.pi / 180.0, mx * math.pi / 180.0)
+        return JointDesc(dof, ratio, c, True, 0.0 + c, d, a, alpha, mn * math.pi / 180.0, mx * math.pi / 180.0, _get_double(e, "springStiffness", 0.0))
     theta = _get_double(e, "theta", 0.0) * math.pi / 180.0
-    return JointDesc(dof, ratio, c, False, theta, 0.0 + c, a, alpha, mn, mx)
+    return JointDesc(dof, ratio, c, False, theta, 0.0 + c, a, alpha, mn, mx, _get_double(e, "springStiffness", 0.0))
+
+
+def apply_static_ratios(chains, dof_type):
+    """JointDesc.ratio is what the reference calls DOF::getStaticRatio(joint): joint value = ratio x DOF value.  For Rigid
+    and BreakAway DOFs that is the coupling ratio of the DOF expression (dof.cpp:484-487).  CompliantDOF::getStaticRatio
+    (dof.cpp:779-795) keeps the coupling ratio for joints number 0, 2, 4, 6 of the robot and gives every other joint
+    (ref / k) * tau1 * tau2 / (tau1 + tau2): tau1, ref = coupling ratio and spring stiffness of the DOF's first joint,
+    tau2, k = its own (k == 0 -> ref).  Joint numbers are chain-major (Joint::getNum)."""
+    joints = [j for c in chains for j in c.joints]
+    first = {}
+    for jn, j in enumerate(joints):
+        first.setdefault(j.dof, jn)
+    coupling = [j.ratio for j in joints]
+    for jn, j in enumerate(joints):
+        if dof_type[j.dof] != "c" or jn in (0, 2, 4, 6):
+            continue
+        f = first[j.dof]
+        ref = joints[f].stiffness if joints[f].stiffness != 0.0 else 1.0        # the reference asserts ref != 0
+        k = j.stiffness if j.stiffness != 0.0 else ref
+        j.coupling = coupling[jn]
+        j.ratio = (ref / k) * (coupling[f] * coupling[jn]) / (coupling[f] + coupling[jn])
 
 
 _DYN_STEP = {"Revolute": 1, "Ball": 3, "Universal": 2, "Prismatic": 1, "Fixed": 0}
@@ -312,6 +335,8 @@ def load_robot(scene: Scene, xml_path: str, tran: Transf, dof_values=None) -> in
                     scene.disable(bidx, tgt)
         chains.append(ChainDesc(ctran, joints, link_bodies, last_joint))
 
+    if "c" in dof_type:
+        apply_static_ratios(chains, dof_type)
     # DOF limits: intersection of joint ranges / ratio (DOF::updateMinMax, src/dof.cpp:93-121)
     dof_min = np.full(n_dof, -np.inf)
     dof_max = np.full(n_dof, np.inf)

@@ -268,6 +268,50 @@ class AutoGraspOracle:
         return self.move_dof_to_contacts(base, dof0, desired, steps, stop_at_contact)
 
 
+def compliant_static_ratios(robot, stiffness=None):
+    """CompliantDOF::getStaticRatio (dof.cpp:779-795) for every joint of `robot` (RobotDesc), in the robot's joint order
+    (chain-major = Joint::getNum): joints 0, 2, 4, 6 keep their coupling ratio; any other joint gets
+    (ref / k) * tau1 * tau2 / (tau1 + tau2) with tau1 the coupling ratio and ref the spring stiffness of the DOF's first
+    joint, tau2 / k its own (k == 0 -> ref).  Rigid and break-away DOFs: the coupling ratio (dof.cpp:484-487)."""
+    joints = [jd for c in robot.chains for jd in c.joints]
+    k_all = [1.0] * len(joints) if stiffness is None else list(stiffness)
+    first = {}
+    for jn, jd in enumerate(joints):
+        first.setdefault(jd.dof, jn)
+    out = []
+    for jn, jd in enumerate(joints):
+        if robot.dof_type[jd.dof] != "c" or jn in (0, 2, 4, 6):
+            out.append(jd.ratio)
+            continue
+        ref = k_all[first[jd.dof]]
+        k = k_all[jn] if k_all[jn] != 0.0 else ref
+        tau2, tau1 = jd.ratio, joints[first[jd.dof]].ratio
+        out.append((ref / k) * (tau1 * tau2) / (tau1 + tau2))
+    return out
+
+
+def with_static_ratios(scene, ridx=0, stiffness=None):
+    """copy of `scene` whose JointDesc.ratio hold DOF::getStaticRatio (what include/b2c.h asks a caller to put into
+    b2c_joint_desc.ratio for CompliantDOFs) and whose DOF limits follow DOF::updateMinMax (dof.cpp:92-119) on them"""
+    import copy
+    sc = copy.deepcopy(scene)
+    r = sc.robots[ridx]
+    ratios = compliant_static_ratios(r, stiffness)
+    joints = [jd for c in r.chains for jd in c.joints]
+    for jd, x in zip(joints, ratios):
+        jd.ratio = x
+    mn, mx = np.array(r.dof_min, dtype=np.float64), np.array(r.dof_max, dtype=np.float64)
+    for d in range(r.n_dof):
+        js = [jd for jd in joints if jd.dof == d]
+        lo, hi = [], []
+        for jd in js:
+            a, b = jd.min / jd.ratio, jd.max / jd.ratio
+            lo.append(min(a, b)); hi.append(max(a, b))
+        mn[d], mx[d] = max(lo), min(hi)
+    r.dof_min, r.dof_max = mn, mx
+    return sc
+
+
 def auto_grasp_targets(robot, speed_factor=1.0):
     """Hand::autoGrasp (static branch): per-DOF target and step"""
     vel = np.asarray(robot.dof_velocity, dtype=np.float64)

@@ -467,3 +467,72 @@ def simann_run(neg, seed, preset, iters, start, w, c, cut, start_energy):
                               C.c_double(cut), C.c_double(start_energy), _ip(res), _dp(st), _dp(en), _ip(stp), _dp(table))
     assert rc == nvar, rc
     return dict(result=res, state=st, energy=en, step=stp, table=table)
+
+
+# ---- autograsp pinned to the reference's own lines (oracle/ref_autograsp.cpp, inside libgraspit_ref.so) ------------------
+class RefAutoGrasp:
+    """One hand (no attached robots) and the rest of a scene inside the reference's collision backend, closed by the
+    reference's own Hand::autoGrasp / Robot::moveDOFToContacts / DOF::accumulateMove lines."""
+
+    DOF_TYPES = {"r": 0, "b": 1, "c": 2}
+
+    def __init__(self, scene, ridx=0, dof_type=None, stiffness=1.0):
+        L = lib()
+        L.ref_ag_create.restype = C.c_void_p
+        self.L, self.scene, self.r = L, scene, scene.robots[ridx]
+        r = self.r
+        assert not any(c.children for c in r.chains), "RefAutoGrasp: single-robot trees only"
+        self.h = C.c_void_p(L.ref_ag_create())
+        self.ids = {}
+        for i, b in enumerate(scene.bodies):
+            if b.robot == ridx and b.kind == "link":
+                chain, link = b.chain, b.link
+            elif b.robot == ridx:
+                chain, link = -1, 0                     # base / mount piece
+            else:
+                chain, link = -2, 0
+            tris = np.ascontiguousarray(b.tris.astype(np.float64).reshape(-1, 9))
+            self.ids[i] = L.ref_ag_add_body(self.h, _dp(tris), len(tris), chain, link)
+            L.ref_ag_set_transform(self.h, self.ids[i], _dp(_t7(scene.body_tran[i])))
+        for (a, b) in list(scene.disabled_pairs) + list(scene.touching_pairs):
+            L.ref_ag_activate_pair(self.h, self.ids[a], self.ids[b], 0)
+        nch = len(r.chains)
+        ctran = np.ascontiguousarray(np.stack([_t7(c.tran) for c in r.chains]))
+        cnj = np.ascontiguousarray([len(c.joints) for c in r.chains], dtype=np.int32)
+        cnl = np.ascontiguousarray([len(c.link_bodies) for c in r.chains], dtype=np.int32)
+        rows = []
+        for c in r.chains:
+            for jd in c.joints:
+                dh = [1.0, jd.theta - jd.offset, jd.d, jd.a, jd.alpha, jd.offset] if jd.revolute else [0.0, jd.theta, jd.d - jd.offset, jd.a, jd.alpha, jd.offset]
+                coupling = jd.coupling if getattr(jd, "coupling", None) is not None else jd.ratio
+                k = jd.stiffness if getattr(jd, "stiffness", 0.0) else stiffness
+                rows.append([jd.dof, coupling] + dh + [jd.min, jd.max, k])
+        joints = np.ascontiguousarray(np.array(rows, dtype=np.float64))
+        llj = np.ascontiguousarray([j for c in r.chains for j in c.last_joint], dtype=np.int32)
+        lbody = np.ascontiguousarray([self.ids[b] for c in r.chains for b in c.link_bodies], dtype=np.int32)
+        types = dof_type if dof_type is not None else r.dof_type
+        dtype_codes = np.ascontiguousarray([self.DOF_TYPES[t] for t in types], dtype=np.int32)
+        vel = np.ascontiguousarray(np.asarray(r.dof_velocity, dtype=np.float64))
+        self.dof_min, self.dof_max = np.zeros(r.n_dof), np.zeros(r.n_dof)
+        self.nj = L.ref_ag_define_hand(self.h, nch, _dp(ctran), _ip(cnj), _ip(cnl), _dp(joints), _ip(llj), _ip(lbody), r.n_dof, _ip(dtype_codes),
+                                       _dp(vel), self.ids[r.base_body], self.ids[r.mount_body] if r.mount_body >= 0 else -1,
+                                       _dp(self.dof_min), _dp(self.dof_max))
+
+    def auto_grasp(self, base, dof0, speed_factor=1.0, stop_at_contact=False):
+        """Hand::autoGrasp(false, speed_factor, stop_at_contact) from (base = (q, t), dof0): dict(dof, joints, stopped, moved,
+        jumps (successful jumpDOFToContact calls), error ("Interpolation failed!"), failsafe)"""
+        dof, jv, st, info = np.zeros(self.r.n_dof), np.zeros(self.nj), np.zeros(self.nj, dtype=np.int32), np.zeros(4, dtype=np.int32)
+        self.L.ref_ag_autograsp(self.h, _dp(_t7(base)), _dp(_d(dof0, self.r.n_dof)), C.c_double(speed_factor), int(stop_at_contact),
+                                _dp(dof), _dp(jv), _ip(st), _ip(info))
+        return dict(dof=dof, joints=jv, stopped=st, moved=bool(info[0]), jumps=int(info[1]), error=bool(info[2]), failsafe=bool(info[3]))
+
+    def close(self):
+        if self.h:
+            self.L.ref_ag_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -37,9 +37,7 @@
 #include "graspit/FitParabola.h"
 #include "graspit/debug.h"
 
-const double Contact::THRESHOLD = 0.1;
-const double Contact::INHERITANCE_THRESHOLD = 1;
-const double Contact::INHERITANCE_ANGULAR_THRESHOLD = 0.984;
+#include "extract/contact_constants.inc"        // contact.cpp:58-60: THRESHOLD, INHERITANCE_THRESHOLD, INHERITANCE_ANGULAR_THRESHOLD
 
 #include "extract/contact_ctor.inc"
 #include "extract/contact_wrenchFromFrictionEdge.inc"

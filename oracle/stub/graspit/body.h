@@ -10,6 +10,7 @@
 #include "graspit/matvec3D.h"
 #include "graspit/triangle.h"
 
+class WorldElement;
 class Body {
     std::vector<Triangle> tris_;
     transf tran_;
@@ -22,5 +23,8 @@ class Body {
     const transf &getTran() const { return tran_; }
     void setTranRaw(const transf &t) { tran_ = t; }
     QString getName() const { return QString(name_); }
+    // Body::getOwner (include/graspit/body.h): the robot a link belongs to; a free body owns itself.  Last in the class so
+    // that the stand-in's layout is the same for every translation unit (oracle/ref_autograsp.cpp overrides it in Link)
+    virtual WorldElement *getOwner() { return 0; }
 };
 #endif
