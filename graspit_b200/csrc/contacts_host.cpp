@@ -437,8 +437,17 @@ inline double box_volume(const ObbNode &n) { return n.half.x * n.half.y * n.half
 
 // idx[lo, hi): candidates below the node pair (n1, n2)
 void visit_pair(VisitCtx &c, int n1, int n2, int *idx, int lo, int hi) {
+  if (hi <= lo) return;
+  // leaf-position ranges of the candidates in both trees: "every candidate sits under the same child" is then two
+  // comparisons, so the long single-file descents between real branchings cost O(1) per level instead of a pass over
+  // the candidates (a group holds ~40 candidates under ~30 levels of which a handful branch)
+  int amin = 0x7fffffff, amax = -1, bmin = 0x7fffffff, bmax = -1;
+  for (int i = lo; i < hi; i++) {
+    const int pa = c.A->tri_pos[c.ta[idx[i]]], pb = c.B->tri_pos[c.tb[idx[i]]];
+    amin = std::min(amin, pa); amax = std::max(amax, pa);
+    bmin = std::min(bmin, pb); bmax = std::max(bmax, pb);
+  }
   while (true) {
-    if (hi <= lo) return;
     const ObbNode &N1 = c.A->nodes[n1], &N2 = c.B->nodes[n2];
     const bool l1 = N1.child[0] < 0, l2 = N2.child[0] < 0;
     if (l1 && l2) {
@@ -451,9 +460,18 @@ void visit_pair(VisitCtx &c, int n1, int n2, int *idx, int lo, int hi) {
     else split1 = box_volume(N1) > box_volume(N2);
     const ObbNode &R = split1 ? N1 : N2;
     const ObbTree *T = split1 ? c.A : c.B;
-    const int *tri = split1 ? c.ta : c.tb;
     const ObbNode &C0 = T->nodes[R.child[0]];
-    // stable split of the candidates between the two children
+    const int pmin = split1 ? amin : bmin, pmax = split1 ? amax : bmax;
+    if (pmin >= C0.leaf_lo && pmax < C0.leaf_hi) {           // everything sits under child 1: no order to decide
+      if (split1) n1 = R.child[0]; else n2 = R.child[0];
+      continue;
+    }
+    if (pmin >= C0.leaf_hi || pmax < C0.leaf_lo) {           // everything sits under child 2
+      if (split1) n1 = R.child[1]; else n2 = R.child[1];
+      continue;
+    }
+    // a real branching: stable split of the candidates between the two children
+    const int *tri = split1 ? c.ta : c.tb;
     if ((int)c.scratch.size() < hi - lo) c.scratch.resize(hi - lo);
     int k0 = lo, k1 = 0;
     for (int i = lo; i < hi; i++) {
@@ -462,30 +480,16 @@ void visit_pair(VisitCtx &c, int n1, int n2, int *idx, int lo, int hi) {
     }
     for (int i = 0; i < k1; i++) idx[k0 + i] = c.scratch[i];
     const int mid = k0;
-    int first = 0;
-    if (mid > lo && mid < hi) {
-      double d0, d1;
-      if (split1) { d0 = obb_distance_sq(C0, N2, c.x); d1 = obb_distance_sq(T->nodes[R.child[1]], N2, c.x); }
-      else { d0 = obb_distance_sq(N1, C0, c.x); d1 = obb_distance_sq(N1, T->nodes[R.child[1]], c.x); }
-      if (d1 < d0) first = 1;
-    } else if (mid == lo) {
-      first = 1;            // everything sits under child2
-    }
-    // recurse on one side, loop on the other (keeps the native stack shallow on degenerate trees)
+    double d0, d1;
+    if (split1) { d0 = obb_distance_sq(C0, N2, c.x); d1 = obb_distance_sq(T->nodes[R.child[1]], N2, c.x); }
+    else { d0 = obb_distance_sq(N1, C0, c.x); d1 = obb_distance_sq(N1, T->nodes[R.child[1]], c.x); }
+    const int first = d1 < d0 ? 1 : 0;
     const int f_lo = first == 0 ? lo : mid, f_hi = first == 0 ? mid : hi;
     const int s_lo = first == 0 ? mid : lo, s_hi = first == 0 ? hi : mid;
     const int fc = R.child[first], sc = R.child[1 - first];
-    if (f_hi > f_lo && s_hi > s_lo) {
-      if (split1) visit_pair(c, fc, n2, idx, f_lo, f_hi); else visit_pair(c, n1, fc, idx, f_lo, f_hi);
-      if (split1) n1 = sc; else n2 = sc;
-      lo = s_lo; hi = s_hi;
-    } else if (f_hi > f_lo) {
-      if (split1) n1 = fc; else n2 = fc;
-      lo = f_lo; hi = f_hi;
-    } else {
-      if (split1) n1 = sc; else n2 = sc;
-      lo = s_lo; hi = s_hi;
-    }
+    if (split1) { visit_pair(c, fc, n2, idx, f_lo, f_hi); visit_pair(c, sc, n2, idx, s_lo, s_hi); }
+    else { visit_pair(c, n1, fc, idx, f_lo, f_hi); visit_pair(c, n1, sc, idx, s_lo, s_hi); }
+    return;
   }
 }
 
