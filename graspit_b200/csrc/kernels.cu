@@ -498,7 +498,7 @@ __device__ __noinline__ void near_emit(const DistParams &p, const int2 *nearq, c
 #define DIST_MIN_BLOCKS 2
 #endif
 __global__ void __launch_bounds__(256, DIST_MIN_BLOCKS) dist_kernel(DistParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
