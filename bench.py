@@ -20,7 +20,9 @@ step inside the timed region, at N = 1 too (there it is the planner's own best-l
 engine's collective-free peer exchange (rows stored straight into the peers' HBM over NVLink by the kernel that updates
 the best list), `--exchange nccl` keeps the NCCL all-gather as the checked alternative.
 
-Besides the headline line the default run adds two sub-records measured the same way (`--no-sub` skips them):
+Besides the headline line the default run adds sub-records (`--no-sub` skips them).  At N = 1 only: "config3" (allContacts
+for 16 384 closed HumanHand poses), "config4" (allCollisions for 262 144 arm + hand configurations), "autograsp" (65 536
+hands closed in one call) -- one timed call each, host buffers.  At every N, measured like the headline:
     "live"     CONTACT_LIVE annealing steps of the same chains,
     "config5"  BASELINE.json configs[4]: 1 048 576 chains in total (strong scaling: / N per GPU) against the mug
                subdivided to 220 800 triangles.
@@ -462,6 +464,95 @@ def roofline(res, mode, root):
                     "capture (profiles/traffic.json); traversal work of the last step: " + json.dumps(res["stats"])}
 
 
+# ------------------------------------------------------------------------------------- secondary configurations (N = 1)
+def _rest_postures(eng, sb, sc, n, seed, strata=("near",)):
+    """n collision-free hand poses near the object with the DOFs at rest: RAW rows (base q, t + DOFs).  The base poses come
+    from the engine's own state mapping (body_tf of an AA + EIGEN evaluation), so nothing outside the product is involved."""
+    from graspit_b200.engine import B2C_INPUT_AA_EIGEN
+    from graspit_b200.sampling import hand_robot, object_body, sample_aa_states
+    ridx = hand_robot(sc)
+    r = sc.robots[ridx]
+    rid, obj = sb.robot_ids[ridx], sb.body_ids[object_body(sc)]
+    rest = np.clip(r.dof_default, r.dof_min, r.dof_max).astype(np.float32)
+    nlink = sum(len(c.link_bodies) for c in r.chains)
+    raw = np.zeros((0, 7 + r.n_dof), dtype=np.float32)
+    while len(raw) < n:
+        pos, _ = sample_aa_states(sc, 4 * n, seed=seed, strata=strata)
+        st = np.concatenate([pos, np.zeros((len(pos), r.eg.shape[0]), np.float32)], 1).astype(np.float32)
+        tf = eng.eval_batch(rid, obj, st, input_mode=B2C_INPUT_AA_EIGEN, ref_tran=sc.body_tran[object_body(sc)], body_tf=True)["body_tf"]
+        cand = np.concatenate([tf[:, nlink, :].astype(np.float32), np.tile(rest[None, :], (len(pos), 1))], 1)
+        raw = np.concatenate([raw, cand[eng.eval_batch(rid, obj, cand)["legal"] == 1]])[:n]
+        seed += 1
+    return raw
+
+
+def secondary_configs(device):
+    """BASELINE.json configs[2] (contacts of closed hands), configs[3] (arm + hand collisions) and the batched autograsp as
+    throughput sub-records: one timed call each after a warm-up call of the same size, host buffers, rank 0 at N = 1 only."""
+    import time
+    from graspit_b200.engine import AG_INTERP_ERROR, B2C_INPUT_JOINTS, Engine, SceneBinding
+    from graspit_b200.formats.scenepack import load_pack
+    out = {}
+    # ---- autograsp: Hand::autoGrasp to contact for 65 536 Barrett poses in one call
+    sc = load_pack("barrett_mug")
+    eng = Engine(device)
+    sb = SceneBinding(eng, sc)
+    rid = sb.robot_ids[0]
+    raw = _rest_postures(eng, sb, sc, 65536, 7)
+    raw[:, 8:] = 0.0                                       # fingers open, spread at rest
+    eng.auto_grasp(rid, sc.robots[0], raw)
+    l0 = eng.launch_count
+    t0 = time.perf_counter()
+    ag = eng.auto_grasp(rid, sc.robots[0], raw)
+    dt = time.perf_counter() - t0
+    out["autograsp"] = {"metric": "autograsps/s (Hand::autoGrasp to contact, Barrett vs mug, one b2c_autograsp_batch call, host buffers)",
+                        "npose": len(raw), "seconds": dt, "value": len(raw) / dt, "unit": "autograsps/s", "rounds": int(ag["rounds"]),
+                        "gpu_launches": int(eng.launch_count - l0), "mean_steps": float(ag["iters"].mean()),
+                        "errors": int(((ag["status"] & AG_INTERP_ERROR) != 0).sum())}
+    eng.close()
+    # ---- config 3: HumanHand20DOF vs flask, hands closed by the autograsp, allContacts(0.2) per pose in one call
+    sc = load_pack("humanhand_flask")
+    eng = Engine(device)
+    sb = SceneBinding(eng, sc)
+    rid = sb.robot_ids[0]
+    raw = _rest_postures(eng, sb, sc, 16384, 100)
+    ag = eng.auto_grasp(rid, sc.robots[0], raw)
+    ok = (ag["status"] & AG_INTERP_ERROR) == 0
+    js = np.concatenate([raw[ok, :7].astype(np.float64), ag["joints"][ok]], axis=1)
+    eng.contacts_batch(rid, js, 0.2, input_mode=B2C_INPUT_JOINTS)
+    l0 = eng.launch_count
+    t0 = time.perf_counter()
+    res = eng.contacts_batch(rid, js, 0.2, input_mode=B2C_INPUT_JOINTS)
+    dt = time.perf_counter() - t0
+    out["config3"] = {"metric": "poses/s: allContacts(0.2) per pose, HumanHand20DOF vs flask (BASELINE.json configs[2]), one b2c_contacts_batch call, host buffers",
+                      "npose": len(js), "seconds": dt, "value": len(js) / dt, "unit": "poses/s", "contacts_total": int(len(res["contacts"])),
+                      "contacts_per_pose": float(len(res["contacts"]) / max(1, len(js))), "active_pairs": len(eng.robot_pairs(rid)),
+                      "gpu_launches": int(eng.launch_count - l0)}
+    eng.close()
+    # ---- config 4: Staubli TX60L + Barrett vs obstacles, allCollisions(ALL) for 262 144 arm + hand configurations
+    sc = load_pack("staubli_barrett")
+    eng = Engine(device)
+    sb = SceneBinding(eng, sc)
+    arm, hand = sc.robots[0], sc.robots[1]
+    rng = np.random.default_rng(1234)
+    n = 262144
+    base = np.tile(np.concatenate([arm.tran[0], arm.tran[1]])[None, :], (n, 1))
+    dofs = np.concatenate([rng.uniform(arm.dof_min, arm.dof_max, size=(n, arm.n_dof)), rng.uniform(hand.dof_min, hand.dof_max, size=(n, hand.n_dof))], 1)
+    raw = np.concatenate([base, dofs], 1).astype(np.float32)
+    rid = sb.robot_ids[0]
+    eng.eval_batch(rid, -1, raw, pair_mask=True)
+    l0 = eng.launch_count
+    t0 = time.perf_counter()
+    res = eng.eval_batch(rid, -1, raw, pair_mask=True)
+    dt = time.perf_counter() - t0
+    out["config4"] = {"metric": "configurations/s: allCollisions(ALL, interest = robot), Staubli TX60L + Barrett vs obstacles (BASELINE.json configs[3]), host buffers",
+                      "n": n, "seconds": dt, "value": n / dt, "unit": "configurations/s", "collision_free": float(res["legal"].mean()),
+                      "active_pairs": len(eng.robot_pairs(rid)), "triangles": int(sum(len(b.tris) for b in sc.bodies)),
+                      "gpu_launches": int(eng.launch_count - l0)}
+    eng.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -505,6 +596,12 @@ def main():
                           "ms_per_step": r["ms_per_step"], "value": r["value"], "unit": UNIT,
                           "e2e": {"value": r["e2e_value"], "pageable_value": r["e2e_pageable_value"]}, "kernel_ms": r["kernel_ms"],
                           "gpu_launches": r["launches"], "object_triangles": 220800, "legal_fraction": r["anneal"]["legal_fraction"], "traversal": r["stats"]}
+
+    if not args.no_sub and world == 1 and args.workload == "anneal" and not live:
+        try:
+            sub.update(secondary_configs(B.local_rank))
+        except Exception as ex:          # secondary numbers never break the headline line
+            sub["secondary_error"] = str(ex)[:200]
 
     if rank == 0:
         nvar = res["nvar"]
