@@ -122,12 +122,13 @@ struct b2c_ctx {
   DevBuf<float> d_states; DevBuf<Xf> d_fk; DevBuf<double> d_fkqt; DevBuf<uint8_t> d_legal; DevBuf<float> d_energy;
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
   DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
-  ContactRec *h_contacts = nullptr; // pinned staging of contact candidates (b2c_contacts_batch)
+  ContactRec *h_contacts[2] = {nullptr, nullptr}; // pinned staging of contact candidates, double-buffered (b2c_contacts_batch)
+  cudaEvent_t ev_blocking = nullptr;               // blocking-sync event: waits that must not spin a host core
   DevBuf<ContactRec> d_contacts2;   // the same records grouped by query
   DevBuf<int> d_coffsets;           // per query: first record, fill cursor
   DevBuf<unsigned char> d_cubtemp;
-  std::vector<int> h_coffsets;
-  size_t h_contacts_cap = 0;
+  std::vector<int> h_coffsets[2];
+  size_t h_contacts_cap[2] = {0, 0};
   Xf *h_fk = nullptr;               // pinned copy of the link transforms (reference-order replay of contact candidates)
   size_t h_fk_cap = 0;
   int stage_nodes = 128;           // object-tree nodes staged in shared memory by the energy kernel
@@ -452,7 +453,8 @@ void b2c_destroy(b2c_ctx *ctx) {
   cudaDeviceSynchronize();         // ctx->stream may be a caller-owned stream that no longer exists (b2c_set_stream)
   anneal_release_all(ctx);
   autograsp_release_all(ctx);
-  if (ctx->h_contacts) cudaFreeHost(ctx->h_contacts);
+  for (int i = 0; i < 2; i++) if (ctx->h_contacts[i]) cudaFreeHost(ctx->h_contacts[i]);
+  if (ctx->ev_blocking) cudaEventDestroy(ctx->ev_blocking);
   if (ctx->h_fk) cudaFreeHost(ctx->h_fk);
   if (ctx->last_stats) cudaFreeHost(ctx->last_stats);
   invalidate_plans(ctx);
