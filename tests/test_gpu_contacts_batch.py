@@ -115,6 +115,29 @@ def test_contacts_batch_matches_single_pose_path_and_reference(closed):
     assert len(raw["contacts"]) >= res["offsets"][8]
 
 
+def test_chunked_pipeline_equals_one_chunk_calls(closed):
+    """b2c_contacts_batch sends a large batch through in chunks of poses, post-processing chunk c on the host cores while the
+    GPU works on chunk c + 1 (two pinned staging buffers): the result must be the concatenation of small one-chunk calls."""
+    eng, rid, js = closed["eng"], closed["rid"], closed["js"]
+    reps = 4500 // len(js) + 1
+    big = np.tile(js, (reps, 1))[:4500]                       # 4 500 poses -> chunks of 1 125
+    whole = eng.contacts_batch(rid, big, THR, input_mode=B2C_INPUT_JOINTS)
+    assert len(whole["contacts"]) > 1000
+    parts, at = [], 0
+    for lo in range(0, len(big), 700):                        # 700 < 1 024: always a single chunk
+        r = eng.contacts_batch(rid, big[lo:lo + 700], THR, input_mode=B2C_INPUT_JOINTS)
+        parts.append((r["contacts"], r["pose"] + lo, r["pair"]))
+    c = np.concatenate([p[0] for p in parts]); ps = np.concatenate([p[1] for p in parts]); pr = np.concatenate([p[2] for p in parts])
+    assert np.array_equal(whole["contacts"], c) and np.array_equal(whole["pose"], ps) and np.array_equal(whole["pair"], pr)
+    off = whole["offsets"]
+    assert off[0] == 0 and off[-1] == len(c) and (np.diff(off) >= 0).all()
+    # every repetition of the fixture's poses reports the same contacts
+    n0 = len(js)
+    first = whole["contacts"][(whole["pose"] < n0)]
+    second = whole["contacts"][(whole["pose"] >= n0) & (whole["pose"] < 2 * n0)]
+    assert np.array_equal(first, second)
+
+
 def test_region_batch_matches_single_queries_and_reference():
     """neighbourhoods of every contact of a batch of closed human hands (elastic fingertips): the batched bodyRegion returns
     exactly what one b2c_region call per contact returns, which equals the reference's bodyRegion as a set"""
