@@ -8,7 +8,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2c.so")
-SOURCES = ["api.cu", "kernels.cu", "collide.cu", "contacts.cu", "anneal.cu", "autograsp.cu", "bvh.cpp", "contacts_host.cpp", "soft_contact_host.cpp"]
+SOURCES = ["api.cu", "kernels.cu", "collide.cu", "contacts.cu", "contact_order.cu", "anneal.cu", "autograsp.cu", "bvh.cpp", "contacts_host.cpp", "soft_contact_host.cpp"]
+# contact_order.cu shares its arithmetic with the host replay (csrc/obb_order.h): no fused multiply-adds, so that both sides round alike
+EXTRA_FLAGS = {"contact_order.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xcompiler", "-O3"]
 
@@ -41,7 +43,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
     objs = []
     for s in SOURCES:
         o = os.path.join(objdir, os.path.splitext(s)[0] + ".o")
-        cmd = [_nvcc(), "-ccbin", ccbin, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [_nvcc(), "-ccbin", ccbin, *NVCC_FLAGS, *EXTRA_FLAGS.get(s, []), *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
             print(" ".join(cmd))

@@ -5,6 +5,7 @@
 #include "../../include/b2c.h"
 #include "b2c_internal.h"
 #include "contacts_host.h"
+#include "obb_order.h"
 
 #include <algorithm>
 #include <chrono>
@@ -24,6 +25,8 @@ using namespace b2c;
 
 namespace {
 
+constexpr int B2C_MAX_CHUNKS = 8;
+
 struct MeshHost {
   bool alive = false;
   int ntri = 0;
@@ -35,6 +38,8 @@ struct MeshHost {
   int depth = 0;
   float extent = 0.f;
   ObbTree *obb = nullptr;         // lazily built reference-style hierarchy (getBoundingVolumes)
+  OrderNode *d_order = nullptr;   // the same tree as the visit-order kernel reads it (contact_order.cu), uploaded on first use
+  int *d_tri_pos = nullptr;
   int *d_seed = nullptr;          // lazily built closest-point seed grid (meshes used as the energy object)
   float g0[3] = {0, 0, 0}, ginv[3] = {0, 0, 0};
   int gres[3] = {0, 0, 0};
@@ -123,7 +128,12 @@ struct b2c_ctx {
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
   DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
   ContactRec *h_contacts[2] = {nullptr, nullptr}; // pinned staging of contact candidates, double-buffered (b2c_contacts_batch)
-  cudaEvent_t ev_blocking = nullptr;               // blocking-sync event: waits that must not spin a host core
+  unsigned long long *h_okeys[2] = {nullptr, nullptr};   // pinned staging of their visit keys (2 words each) ...
+  int *h_odepth[2] = {nullptr, nullptr};                 // ... and path lengths
+  size_t h_okeys_cap[2] = {0, 0};
+  DevBuf<unsigned long long> d_okeys; DevBuf<int> d_odepth; DevBuf<unsigned long long> d_order_tab;
+  double contacts_per_pose_seen = 0.0;             // candidate records per pose of the densest batched contacts call so far
+  cudaEvent_t ev_chunk[B2C_MAX_CHUNKS] = {};       // one per chunk of a batched contacts call: "this chunk's copies have landed"
   DevBuf<ContactRec> d_contacts2;   // the same records grouped by query
   DevBuf<int> d_coffsets;           // per query: first record, fill cursor
   DevBuf<unsigned char> d_cubtemp;
@@ -454,7 +464,9 @@ void b2c_destroy(b2c_ctx *ctx) {
   anneal_release_all(ctx);
   autograsp_release_all(ctx);
   for (int i = 0; i < 2; i++) if (ctx->h_contacts[i]) cudaFreeHost(ctx->h_contacts[i]);
-  if (ctx->ev_blocking) cudaEventDestroy(ctx->ev_blocking);
+  for (int i = 0; i < 2; i++) { if (ctx->h_okeys[i]) cudaFreeHost(ctx->h_okeys[i]); if (ctx->h_odepth[i]) cudaFreeHost(ctx->h_odepth[i]); }
+  ctx->d_okeys.release(); ctx->d_odepth.release(); ctx->d_order_tab.release();
+  for (int i = 0; i < B2C_MAX_CHUNKS; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
   if (ctx->h_fk) cudaFreeHost(ctx->h_fk);
   if (ctx->last_stats) cudaFreeHost(ctx->last_stats);
   invalidate_plans(ctx);
@@ -462,6 +474,8 @@ void b2c_destroy(b2c_ctx *ctx) {
     if (m.d_nodes) cudaFree(m.d_nodes);
     if (m.d_tris) cudaFree(m.d_tris);
     if (m.d_seed) cudaFree(m.d_seed);
+    if (m.d_order) cudaFree(m.d_order);
+    if (m.d_tri_pos) cudaFree(m.d_tri_pos);
     if (m.obb) obb_tree_free(m.obb);
   }
   ctx->d_meshes.release(); ctx->d_states.release(); ctx->d_fk.release(); ctx->d_fkqt.release(); ctx->d_legal.release();
@@ -517,6 +531,8 @@ int b2c_mesh_destroy(b2c_ctx *ctx, int mesh_id) {
   MeshHost &m = ctx->meshes[mesh_id];
   cudaFree(m.d_nodes); cudaFree(m.d_tris);
   if (m.d_seed) cudaFree(m.d_seed);
+  if (m.d_order) cudaFree(m.d_order);
+  if (m.d_tri_pos) cudaFree(m.d_tri_pos);
   if (m.obb) obb_tree_free(m.obb);
   m = MeshHost();
   ctx->meshes_dirty = true;

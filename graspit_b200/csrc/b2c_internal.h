@@ -255,6 +255,20 @@ struct RegionBatchParams {
   int *out_count;
 };
 cudaError_t launch_region_batch(const RegionBatchParams &p, cudaStream_t s);
+// K6b (contact_order.cu): per-candidate visit keys
+struct OrderNode;
+struct OrderParams {
+  const ContactRec *recs;            // candidates grouped by query (local pose * np + pair)
+  int n, np, nrb;
+  const Xf *fk;                      // link transforms of the chunk's first pose onwards
+  const Xf *static_xf;
+  const int2 *pairs;
+  const OrderNode *const *nodes;     // [engine body] reference-style OBB tree as the order rule reads it (obb_order.h)
+  const int *const *tri_pos;         // [engine body] triangle -> depth-first leaf position
+  unsigned long long *keys;          // [n][2] out: path bits, most significant first
+  int *depth;                        // [n] out: path length (> 128: the key is truncated, the host replays the group)
+};
+cudaError_t launch_contact_order(const OrderParams &p, cudaStream_t s);
 size_t contact_group_temp_bytes(int nqueries);
 cudaError_t launch_contact_group(const ContactRec *in, int n, const int *per_query, int nqueries, int *offsets, int *cursor,
                                  ContactRec *out, void *temp, size_t temp_bytes, cudaStream_t s);

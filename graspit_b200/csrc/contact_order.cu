@@ -1,0 +1,52 @@
+// K6b: visit keys of contact candidates.  Compiled with -fmad=false (see obb_order.h).
+//
+// removeContactDuplicates depends on the order in which the reference's dual-tree recursion appends the candidates
+// (collisionInterface.cpp:254-287, collisionAlgorithms.cpp:42-130).  That order is a property of each candidate's own path
+// through the two reference-style OBB trees: at every node pair on the path the rule picks the node to split and visits the
+// child with the smaller bboxDistanceSq first, so "my child is visited second" is one bit per level, and the candidates of a
+// (pose, pair) group, sorted by these bit strings (then by feature code inside a triangle pair), stand in visit order.  One
+// thread per candidate walks its path (two box distances per level, fp64, the reference's operation order) and writes the
+// bits as a 128-bit key; the host sorts each group by it.  The host replay (contacts_host.cpp, obb_visit_order) evaluates
+// the same function only where a group's paths branch; it remains the fallback for paths longer than 128 levels.
+#include "b2c_internal.h"
+#include "obb_order.h"
+
+namespace b2c {
+
+__global__ void __launch_bounds__(128) contact_order_kernel(OrderParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const ContactRec &r = p.recs[i];
+  const int q = r.query;
+  const int lpose = q / p.np, pair = q - lpose * p.np;
+  const int2 ab = p.pairs[pair];
+  const double *X1 = ab.x < p.nrb ? reinterpret_cast<const double *>(p.fk + (size_t)lpose * p.nrb + ab.x)
+                                  : reinterpret_cast<const double *>(p.static_xf + (ab.x - p.nrb));
+  const double *X2 = ab.y < p.nrb ? reinterpret_cast<const double *>(p.fk + (size_t)lpose * p.nrb + ab.y)
+                                  : reinterpret_cast<const double *>(p.static_xf + (ab.y - p.nrb));
+  OrderXf x;
+  order_rel_xf(X1, X2, x);
+  const OrderNode *A = p.nodes[ab.x], *B = p.nodes[ab.y];
+  const int pa = p.tri_pos[ab.x][r.tri_a], pb = p.tri_pos[ab.y][r.tri_b];
+  unsigned long long hi = 0ull, lo = 0ull;
+  int depth = 0, n1 = 0, n2 = 0, second = 0;
+  while (order_step(A, B, x, n1, n2, pa, pb, &second)) {
+    if (second) {
+      if (depth < 64) hi |= 1ull << (63 - depth);
+      else if (depth < 128) lo |= 1ull << (127 - depth);
+    }
+    depth++;
+    if (depth > 4096) break;              // (a malformed tree cannot hang the kernel)
+  }
+  p.keys[2 * (size_t)i] = hi;
+  p.keys[2 * (size_t)i + 1] = lo;
+  p.depth[i] = depth;
+}
+
+cudaError_t launch_contact_order(const OrderParams &p, cudaStream_t s) {
+  if (p.n <= 0) return cudaSuccess;
+  contact_order_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+} // namespace b2c

@@ -1,5 +1,6 @@
 // Host-side, non-throughput parts of the CollisionInterface surface (see contacts_host.h).
 #include "contacts_host.h"
+#include "obb_order.h"
 
 #include <algorithm>
 #include <cmath>
@@ -164,6 +165,7 @@ struct ObbNode {
 struct ObbTree {
   std::vector<ObbNode> nodes;
   std::vector<int> tri_pos;   // triangle -> depth-first position of its leaf
+  std::vector<OrderNode> order;   // what the visit-order rule reads of every node (obb_order.h), same indices as nodes
 };
 
 namespace {
@@ -358,6 +360,15 @@ ObbTree *obb_tree_build(const float *tri9, int ntri) {
     n.Rq.m[1][0] = txy + twz; n.Rq.m[1][1] = 1 - (txx + tzz); n.Rq.m[1][2] = tyz - twx;
     n.Rq.m[2][0] = txz - twy; n.Rq.m[2][1] = tyz + twx; n.Rq.m[2][2] = 1 - (txx + tyy);
   }
+  T->order.resize(T->nodes.size());
+  for (size_t i = 0; i < T->nodes.size(); i++) {
+    const ObbNode &n = T->nodes[i];
+    OrderNode &o = T->order[i];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) o.Rq[r][c] = n.Rq.m[r][c];
+    o.center[0] = n.center.x; o.center[1] = n.center.y; o.center[2] = n.center.z;
+    o.half[0] = n.half.x; o.half[1] = n.half.y; o.half[2] = n.half.z;
+    o.child0 = n.child[0]; o.child1 = n.child[1]; o.leaf_lo = n.leaf_lo; o.leaf_hi = n.leaf_hi;
+  }
   return T;
 }
 
@@ -377,63 +388,13 @@ ObbTree *obb_tree_build(const float *tri9, int ntri) {
 // -------------------------------------------------------------------------------------------------
 namespace {
 
-struct RelXf {            // model 2 -> model 1 (RecursionCallback::mTran2To1)
-  M3 R;
-  P3 t;
-};
-
-// bboxDistanceSq(bb1, bb2, tran2To1) (bbox_inl.h:269-413), same operation order per axis
-double obb_distance_sq(const ObbNode &n1, const ObbNode &n2, const RelXf &x) {
-  // BtoA = bb1.TranInv % tran2To1 % bb2.Tran
-  M3 R1t;
-  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R1t.m[i][j] = n1.Rq.m[j][i];
-  const M3 Bm = matmul(matmul(R1t, x.R), n2.Rq);
-  const P3 c2 = x.R.mul(n2.center) + x.t;
-  const P3 Tv = R1t.mul(c2 - n1.center);
-  const double T[3] = {Tv.x, Tv.y, Tv.z};
-  const double a[3] = {n1.half.x, n1.half.y, n1.half.z}, b[3] = {n2.half.x, n2.half.y, n2.half.z};
-  double B[3][3], Bf[3][3];
-  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { B[i][k] = Bm.m[i][k]; Bf[i][k] = std::fabs(B[i][k]) + 1e-6; }
-  double ga[3], gb[3];
-  for (int i = 0; i < 3; i++) {
-    double d = std::fabs(T[i]) - (a[i] + b[0] * Bf[i][0] + b[1] * Bf[i][1] + b[2] * Bf[i][2]);
-    d = std::max(0.0, d);
-    ga[i] = d * d;
-  }
-  for (int j = 0; j < 3; j++) {
-    double s = T[0] * B[0][j] + T[1] * B[1][j] + T[2] * B[2][j];
-    double d = std::fabs(s) - (b[j] + a[0] * Bf[0][j] + a[1] * Bf[1][j] + a[2] * Bf[2][j]);
-    d = std::max(0.0, d);
-    gb[j] = d * d;
-  }
-  double maxD = std::max(ga[0] + ga[1] + ga[2], gb[0] + gb[1] + gb[2]);
-  for (int i = 0; i < 3; i++) {
-    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-    const int alo = std::min(i1, i2), ahi = std::max(i1, i2);
-    for (int j = 0; j < 3; j++) {
-      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-      const int blo = std::min(j1, j2), bhi = std::max(j1, j2);
-      double s = T[i2] * B[i1][j] - T[i1] * B[i2][j];
-      // a[alo] pairs with the row of the OTHER index and vice versa, likewise for b (bbox_inl.h:341-409)
-      double d = std::fabs(s) - (a[alo] * Bf[ahi][j] + a[ahi] * Bf[alo][j] + b[blo] * Bf[i][bhi] + b[bhi] * Bf[i][blo]);
-      d = std::max(0.0, d);
-      d *= d;
-      maxD = std::max(maxD, std::max(ga[i] + d, gb[j] + d));
-    }
-  }
-  if (maxD == 0.0) return -1;
-  return maxD;
-}
-
 struct VisitCtx {
   const ObbTree *A, *B;
-  RelXf x;
+  OrderXf x;
   const int *ta, *tb;
   std::vector<int> *out;
   std::vector<int> scratch;
 };
-
-inline double box_volume(const ObbNode &n) { return n.half.x * n.half.y * n.half.z; }
 
 // idx[lo, hi): candidates below the node pair (n1, n2)
 void visit_pair(VisitCtx &c, int n1, int n2, int *idx, int lo, int hi) {
@@ -447,9 +408,10 @@ void visit_pair(VisitCtx &c, int n1, int n2, int *idx, int lo, int hi) {
     amin = std::min(amin, pa); amax = std::max(amax, pa);
     bmin = std::min(bmin, pb); bmax = std::max(bmax, pb);
   }
+  const OrderNode *NA = c.A->order.data(), *NB = c.B->order.data();
   while (true) {
-    const ObbNode &N1 = c.A->nodes[n1], &N2 = c.B->nodes[n2];
-    const bool l1 = N1.child[0] < 0, l2 = N2.child[0] < 0;
+    const OrderNode &N1 = NA[n1], &N2 = NB[n2];
+    const bool l1 = N1.child0 < 0, l2 = N2.child0 < 0;
     if (l1 && l2) {
       for (int i = lo; i < hi; i++) c.out->push_back(idx[i]);
       return;
@@ -457,17 +419,18 @@ void visit_pair(VisitCtx &c, int n1, int n2, int *idx, int lo, int hi) {
     bool split1;             // true: recurse on model 1's node (nodeSwap == false)
     if (l1) split1 = false;
     else if (l2) split1 = true;
-    else split1 = box_volume(N1) > box_volume(N2);
-    const ObbNode &R = split1 ? N1 : N2;
-    const ObbTree *T = split1 ? c.A : c.B;
-    const ObbNode &C0 = T->nodes[R.child[0]];
+    else split1 = order_box_volume(N1) > order_box_volume(N2);
+    const OrderNode &R = split1 ? N1 : N2;
+    const OrderNode *T = split1 ? NA : NB;
+    const std::vector<int> &tpos = split1 ? c.A->tri_pos : c.B->tri_pos;
+    const OrderNode &C0 = T[R.child0];
     const int pmin = split1 ? amin : bmin, pmax = split1 ? amax : bmax;
     if (pmin >= C0.leaf_lo && pmax < C0.leaf_hi) {           // everything sits under child 1: no order to decide
-      if (split1) n1 = R.child[0]; else n2 = R.child[0];
+      if (split1) n1 = R.child0; else n2 = R.child0;
       continue;
     }
     if (pmin >= C0.leaf_hi || pmax < C0.leaf_lo) {           // everything sits under child 2
-      if (split1) n1 = R.child[1]; else n2 = R.child[1];
+      if (split1) n1 = R.child1; else n2 = R.child1;
       continue;
     }
     // a real branching: stable split of the candidates between the two children
@@ -475,18 +438,18 @@ void visit_pair(VisitCtx &c, int n1, int n2, int *idx, int lo, int hi) {
     if ((int)c.scratch.size() < hi - lo) c.scratch.resize(hi - lo);
     int k0 = lo, k1 = 0;
     for (int i = lo; i < hi; i++) {
-      const int pos = T->tri_pos[tri[idx[i]]];
+      const int pos = tpos[tri[idx[i]]];
       if (pos >= C0.leaf_lo && pos < C0.leaf_hi) idx[k0++] = idx[i]; else c.scratch[k1++] = idx[i];
     }
     for (int i = 0; i < k1; i++) idx[k0 + i] = c.scratch[i];
     const int mid = k0;
     double d0, d1;
-    if (split1) { d0 = obb_distance_sq(C0, N2, c.x); d1 = obb_distance_sq(T->nodes[R.child[1]], N2, c.x); }
-    else { d0 = obb_distance_sq(N1, C0, c.x); d1 = obb_distance_sq(N1, T->nodes[R.child[1]], c.x); }
+    if (split1) { d0 = order_distance_sq(C0, N2, c.x); d1 = order_distance_sq(T[R.child1], N2, c.x); }
+    else { d0 = order_distance_sq(N1, C0, c.x); d1 = order_distance_sq(N1, T[R.child1], c.x); }
     const int first = d1 < d0 ? 1 : 0;
     const int f_lo = first == 0 ? lo : mid, f_hi = first == 0 ? mid : hi;
     const int s_lo = first == 0 ? mid : lo, s_hi = first == 0 ? hi : mid;
-    const int fc = R.child[first], sc = R.child[1 - first];
+    const int fc = first == 0 ? R.child0 : R.child1, sc = first == 0 ? R.child1 : R.child0;
     if (split1) { visit_pair(c, fc, n2, idx, f_lo, f_hi); visit_pair(c, sc, n2, idx, s_lo, s_hi); }
     else { visit_pair(c, n1, fc, idx, f_lo, f_hi); visit_pair(c, n1, sc, idx, s_lo, s_hi); }
     return;
@@ -502,12 +465,15 @@ void obb_visit_order(const ObbTree *A, const ObbTree *B, const double R21[9], co
   order.reserve(n);
   VisitCtx c;
   c.A = A; c.B = B; c.ta = tri_a; c.tb = tri_b; c.out = &order;
-  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c.x.R.m[i][j] = R21[3 * i + j];
-  c.x.t = {t21[0], t21[1], t21[2]};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c.x.R[i][j] = R21[3 * i + j];
+  for (int i = 0; i < 3; i++) c.x.t[i] = t21[i];
   std::vector<int> idx(n);
   for (int i = 0; i < n; i++) idx[i] = i;
   visit_pair(c, 0, 0, idx.data(), 0, n);
 }
+
+const OrderNode *obb_order_nodes(const ObbTree *t, int *count) { if (count) *count = (int)t->order.size(); return t->order.data(); }
+const int *obb_tri_positions(const ObbTree *t, int *count) { if (count) *count = (int)t->tri_pos.size(); return t->tri_pos.data(); }
 
 void obb_tree_free(ObbTree *t) { delete t; }
 

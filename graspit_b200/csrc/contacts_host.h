@@ -25,6 +25,10 @@ struct ObbTree;
 // along x (median and alternating fallbacks), one triangle per leaf.
 ObbTree *obb_tree_build(const float *tri9, int ntri);
 void obb_tree_free(ObbTree *t);
+struct OrderNode;
+// the tree as the visit-order rule reads it (obb_order.h) and the triangle -> depth-first leaf position table: for the device
+const OrderNode *obb_order_nodes(const ObbTree *t, int *count);
+const int *obb_tri_positions(const ObbTree *t, int *count);
 // Node::getBVRecurse / Branch::getBVRecurse (collisionModel.cpp:437-456): boxes at `depth`, plus
 // leaves that end above it, in depth-first order.
 void obb_tree_level(const ObbTree *t, int depth, std::vector<ObbBox> &out);

@@ -138,6 +138,30 @@ def test_chunked_pipeline_equals_one_chunk_calls(closed):
     assert np.array_equal(first, second)
 
 
+def test_device_visit_keys_equal_host_replay(closed):
+    """The candidates' visit order comes from per-candidate keys computed on the device (csrc/contact_order.cu); the host
+    replay of the reference's recursion (B2C_CONTACT_ORDER=host), which tests/test_contact_order.py holds to the reference's
+    own contact trace, must give the same contacts, bit for bit -- raw (order itself) and post-processed."""
+    eng, rid, js = closed["eng"], closed["rid"], closed["js"]
+    big = np.tile(js, (3000 // len(js) + 1, 1))[:3000]
+    out = {}
+    for mode in ("device", "host"):
+        if mode == "host":
+            os.environ["B2C_CONTACT_ORDER"] = "host"
+        else:
+            os.environ.pop("B2C_CONTACT_ORDER", None)
+        try:
+            out[mode] = (eng.contacts_batch(rid, big, THR, input_mode=B2C_INPUT_JOINTS, raw=True),
+                         eng.contacts_batch(rid, big, THR, input_mode=B2C_INPUT_JOINTS))
+        finally:
+            os.environ.pop("B2C_CONTACT_ORDER", None)
+    for i in (0, 1):
+        a, b = out["device"][i], out["host"][i]
+        assert len(a["contacts"]) == len(b["contacts"]) > 1000
+        assert np.array_equal(a["pose"], b["pose"]) and np.array_equal(a["pair"], b["pair"])
+        assert np.array_equal(a["contacts"], b["contacts"])
+
+
 def test_region_batch_matches_single_queries_and_reference():
     """neighbourhoods of every contact of a batch of closed human hands (elastic fingertips): the batched bodyRegion returns
     exactly what one b2c_region call per contact returns, which equals the reference's bodyRegion as a set"""
