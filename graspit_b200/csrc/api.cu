@@ -128,10 +128,10 @@ struct b2c_ctx {
   DevBuf<unsigned long long> d_mask; DevBuf<Ambig> d_ambig; DevBuf<int> d_counters; DevBuf<unsigned long long> d_stats;
   DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
   ContactRec *h_contacts[2] = {nullptr, nullptr}; // pinned staging of contact candidates, double-buffered (b2c_contacts_batch)
-  unsigned long long *h_okeys[2] = {nullptr, nullptr};   // pinned staging of their visit keys (2 words each) ...
-  int *h_odepth[2] = {nullptr, nullptr};                 // ... and path lengths
-  size_t h_okeys_cap[2] = {0, 0};
-  DevBuf<unsigned long long> d_okeys; DevBuf<int> d_odepth; DevBuf<unsigned long long> d_order_tab;
+  DevBuf<unsigned long long> d_okeys; DevBuf<int> d_odepth; DevBuf<int> d_operm; DevBuf<unsigned long long> d_order_tab;
+  int *h_operm = nullptr; size_t h_operm_cap = 0;       // pinned: the candidates' order inside their groups
+  cudaStream_t copy_stream = nullptr;              // D2H copies of a batched contacts call, beside the compute stream
+  cudaEvent_t ev_keys = nullptr;
   double contacts_per_pose_seen = 0.0;             // candidate records per pose of the densest batched contacts call so far
   cudaEvent_t ev_chunk[B2C_MAX_CHUNKS] = {};       // one per chunk of a batched contacts call: "this chunk's copies have landed"
   DevBuf<ContactRec> d_contacts2;   // the same records grouped by query
@@ -464,9 +464,11 @@ void b2c_destroy(b2c_ctx *ctx) {
   anneal_release_all(ctx);
   autograsp_release_all(ctx);
   for (int i = 0; i < 2; i++) if (ctx->h_contacts[i]) cudaFreeHost(ctx->h_contacts[i]);
-  for (int i = 0; i < 2; i++) { if (ctx->h_okeys[i]) cudaFreeHost(ctx->h_okeys[i]); if (ctx->h_odepth[i]) cudaFreeHost(ctx->h_odepth[i]); }
-  ctx->d_okeys.release(); ctx->d_odepth.release(); ctx->d_order_tab.release();
+  ctx->d_okeys.release(); ctx->d_odepth.release(); ctx->d_operm.release(); ctx->d_order_tab.release();
+  if (ctx->h_operm) cudaFreeHost(ctx->h_operm);
   for (int i = 0; i < B2C_MAX_CHUNKS; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+  if (ctx->ev_keys) cudaEventDestroy(ctx->ev_keys);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->h_fk) cudaFreeHost(ctx->h_fk);
   if (ctx->last_stats) cudaFreeHost(ctx->last_stats);
   invalidate_plans(ctx);

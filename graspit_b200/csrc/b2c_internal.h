@@ -267,6 +267,10 @@ struct OrderParams {
   const int *const *tri_pos;         // [engine body] triangle -> depth-first leaf position
   unsigned long long *keys;          // [n][2] out: path bits, most significant first
   int *depth;                        // [n] out: path length (> 128: the key is truncated, the host replays the group)
+  // rank pass (optional): recs / keys / depth / perm point at record `base` of the grouped array
+  const int *offsets;                // [nqueries] first record of every query in the grouped array
+  int nqueries, total, base;
+  int *perm;                         // [n] out: perm[first of group - base + rank] = index inside the group; -1 = replay on the host
 };
 cudaError_t launch_contact_order(const OrderParams &p, cudaStream_t s);
 size_t contact_group_temp_bytes(int nqueries);

@@ -43,9 +43,36 @@ __global__ void __launch_bounds__(128) contact_order_kernel(OrderParams p) {
   p.depth[i] = depth;
 }
 
+// Rank of every candidate inside its (pose, pair) group by (visit key, feature code, arrival index): thread / candidate,
+// one pass over the keys of its group (a group holds ~40 candidates, a few hold thousands).  perm[first of the group + rank]
+// = the candidate's index inside the group, i.e. the group in the reference's visit order without a sort on the host.  A
+// candidate whose path was longer than the key writes nothing: the slot left at -1 tells the host to replay that group.
+__global__ void __launch_bounds__(256) contact_rank_kernel(OrderParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  if (p.depth[i] > 128) return;
+  const int q = p.recs[i].query;
+  const int lo = p.offsets[q] - p.base, hi = (q + 1 < p.nqueries ? p.offsets[q + 1] : p.total) - p.base;
+  const unsigned long long k0 = p.keys[2 * (size_t)i], k1 = p.keys[2 * (size_t)i + 1];
+  const int f = p.recs[i].feature;
+  int rank = 0;
+  for (int j = lo; j < hi; j++) {
+    const unsigned long long a0 = p.keys[2 * (size_t)j], a1 = p.keys[2 * (size_t)j + 1];
+    const int fj = p.recs[j].feature;
+    const bool less = a0 != k0 ? a0 < k0 : (a1 != k1 ? a1 < k1 : (fj != f ? fj < f : j < i));
+    rank += less ? 1 : 0;
+  }
+  p.perm[lo + rank] = i - lo;
+}
+
 cudaError_t launch_contact_order(const OrderParams &p, cudaStream_t s) {
   if (p.n <= 0) return cudaSuccess;
   contact_order_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !p.perm) return e;
+  e = cudaMemsetAsync(p.perm, 0xff, sizeof(int) * (size_t)p.n, s);
+  if (e != cudaSuccess) return e;
+  contact_rank_kernel<<<(p.n + 255) / 256, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
 
