@@ -8,6 +8,7 @@
 #include "obb_order.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <thread>
 #include <array>

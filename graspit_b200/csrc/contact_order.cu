@@ -27,10 +27,22 @@ __global__ void __launch_bounds__(128) contact_order_kernel(OrderParams p) {
   OrderXf x;
   order_rel_xf(X1, X2, x);
   const OrderNode *A = p.nodes[ab.x], *B = p.nodes[ab.y];
-  const int pa = p.tri_pos[ab.x][r.tri_a], pb = p.tri_pos[ab.y][r.tri_b];
+  const int *tpa = p.tri_pos[ab.x], *tpb = p.tri_pos[ab.y];
+  const int pa = tpa[r.tri_a], pb = tpb[r.tri_b];
+  // leaf positions spanned by the candidates of this (pose, pair) group: levels of the walk where the whole group sits
+  // under one child decide nothing and cost nothing (most of the upper levels: a group is one contact patch)
+  int range[4] = {pa, pa, pb, pb};
+  if (p.offsets) {
+    const int glo = p.offsets[q] - p.base, ghi = (q + 1 < p.nqueries ? p.offsets[q + 1] : p.total) - p.base;
+    for (int j = glo; j < ghi; j++) {
+      const int ja = tpa[p.recs[j].tri_a], jb = tpb[p.recs[j].tri_b];
+      range[0] = min(range[0], ja); range[1] = max(range[1], ja);
+      range[2] = min(range[2], jb); range[3] = max(range[3], jb);
+    }
+  }
   unsigned long long hi = 0ull, lo = 0ull;
   int depth = 0, n1 = 0, n2 = 0, second = 0;
-  while (order_step(A, B, x, n1, n2, pa, pb, &second)) {
+  while (order_step(A, B, x, n1, n2, pa, pb, &second, range)) {
     if (second) {
       if (depth < 64) hi |= 1ull << (63 - depth);
       else if (depth < 128) lo |= 1ull << (127 - depth);

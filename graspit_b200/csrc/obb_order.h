@@ -97,7 +97,11 @@ B2C_HD inline double order_distance_sq(const OrderNode &n1, const OrderNode &n2,
 // One step of the reference's dual recursion below the node pair (N1, N2), for a candidate whose triangles sit at leaf
 // positions pa / pb: which node is split, which child holds the candidate, and whether that child is visited first.
 //   returns false when both nodes are leaves (the walk is over)
-B2C_HD inline bool order_step(const OrderNode *A, const OrderNode *B, const OrderXf &x, int &n1, int &n2, int pa, int pb, int *second) {
+//   range (optional) = {amin, amax, bmin, bmax}: leaf positions spanned by the candidates whose order is being decided;
+//   where they all sit under one child of the split node nobody is on the other side, the bit cannot matter, and the two
+//   box distances are not evaluated
+B2C_HD inline bool order_step(const OrderNode *A, const OrderNode *B, const OrderXf &x, int &n1, int &n2, int pa, int pb, int *second,
+                              const int *range = nullptr) {
   const OrderNode &N1 = A[n1], &N2 = B[n2];
   const bool l1 = N1.child0 < 0, l2 = N2.child0 < 0;
   if (l1 && l2) return false;
@@ -110,6 +114,14 @@ B2C_HD inline bool order_step(const OrderNode *A, const OrderNode *B, const Orde
   const OrderNode &C0 = T[R.child0], &C1 = T[R.child1];
   const int pos = split1 ? pa : pb;
   const int mine = (pos >= C0.leaf_lo && pos < C0.leaf_hi) ? 0 : 1;
+  if (range) {
+    const int pmin = split1 ? range[0] : range[2], pmax = split1 ? range[1] : range[3];
+    if ((pmin >= C0.leaf_lo && pmax < C0.leaf_hi) || pmin >= C0.leaf_hi || pmax < C0.leaf_lo) {
+      *second = 0;
+      if (split1) n1 = mine ? R.child1 : R.child0; else n2 = mine ? R.child1 : R.child0;
+      return true;
+    }
+  }
   double d0, d1;
   if (split1) { d0 = order_distance_sq(C0, N2, x); d1 = order_distance_sq(C1, N2, x); }
   else { d0 = order_distance_sq(N1, C0, x); d1 = order_distance_sq(N1, C1, x); }
