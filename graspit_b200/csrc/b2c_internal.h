@@ -273,6 +273,9 @@ struct OrderParams {
   int *perm;                         // [n] out: perm[first of group - base + rank] = index inside the group; -1 = replay on the host
 };
 cudaError_t launch_contact_order(const OrderParams &p, cudaStream_t s);
+size_t region_sort_temp_bytes(int n, int query_bits);
+cudaError_t launch_region_sort(unsigned long long *pairs, unsigned long long *alt, int n, int query_bits, void *temp, size_t temp_bytes,
+                               unsigned long long **sorted, cudaStream_t s);
 size_t contact_group_temp_bytes(int nqueries);
 cudaError_t launch_contact_group(const ContactRec *in, int n, const int *per_query, int nqueries, int *offsets, int *cursor,
                                  ContactRec *out, void *temp, size_t temp_bytes, cudaStream_t s);

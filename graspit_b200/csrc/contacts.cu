@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) region_batch_kernel(RegionBatchParams p) 
         base = __shfl_sync(0xffffffffu, base, __ffs(mk_) - 1);
         if (flag) {
           const int at = base + __popc(mk_ & ((1u << lane) - 1u));
-          if (at < p.out_cap) p.out[at] = make_int2(q, t);
+          if (at < p.out_cap) p.out[at] = make_int2(t, q);      // (triangle, query): as one 64-bit word the query is the high half
         }
       }
     }
@@ -295,6 +295,22 @@ cudaError_t launch_region_batch(const RegionBatchParams &p, cudaStream_t s) {
   const int blocks = std::max(1, std::min((p.nquery + 7) / 8, 148 * 8));
   region_batch_kernel<<<blocks, 256, 0, s>>>(p);
   return cudaGetLastError();
+}
+
+// flagged (triangle, query) pairs -> sorted by query, triangles ascending inside a query (the order b2c_region visits them):
+// one radix sort of the pairs as 64-bit words
+size_t region_sort_temp_bytes(int n, int query_bits) {
+  size_t bytes = 0;
+  cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
+  cub::DeviceRadixSort::SortKeys(nullptr, bytes, k, n, 0, 32 + query_bits);
+  return bytes;
+}
+cudaError_t launch_region_sort(unsigned long long *pairs, unsigned long long *alt, int n, int query_bits, void *temp, size_t temp_bytes,
+                               unsigned long long **sorted, cudaStream_t s) {
+  cub::DoubleBuffer<unsigned long long> k(pairs, alt);
+  cudaError_t e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, k, n, 0, 32 + query_bits, s);
+  *sorted = k.Current();
+  return e;
 }
 
 cudaError_t launch_contacts(const ContactParams &p, int blocks, cudaStream_t s) {
