@@ -130,6 +130,9 @@ struct b2c_ctx {
   DevBuf<float> d_dist; DevBuf<double> d_pts; DevBuf<double> d_misc; DevBuf<int> d_imisc; DevBuf<int> d_legal_list; DevBuf<int2> d_items; DevBuf<ContactRec> d_contacts; DevBuf<unsigned char> d_flags; DevBuf<float> d_terms; DevBuf<int4> d_near_dir; DevBuf<int2> d_near_ent;
   ContactRec *h_contacts[2] = {nullptr, nullptr}; // pinned staging of contact candidates, double-buffered (b2c_contacts_batch)
   DevBuf<unsigned long long> d_okeys; DevBuf<int> d_odepth; DevBuf<int> d_operm; DevBuf<unsigned long long> d_order_tab;
+  DevBuf<int> d_nsurv, d_soff, d_dtotals, d_leader, d_leaders;                // device duplicate removal of a batched contacts call
+  int *h_nsurv = nullptr; size_t h_nsurv_cap = 0; int *h_dtotals = nullptr;   // pinned
+  cudaStream_t copy_stream2 = nullptr; cudaEvent_t ev_surv = nullptr;
   int2 *h_hits = nullptr; size_t h_hits_cap = 0;        // pinned: flagged (triangle, query) pairs of a region batch
   DevBuf<int2> d_items2;
   int *h_operm = nullptr; size_t h_operm_cap = 0;       // pinned: the candidates' order inside their groups
@@ -470,6 +473,11 @@ void b2c_destroy(b2c_ctx *ctx) {
   ctx->d_okeys.release(); ctx->d_odepth.release(); ctx->d_operm.release(); ctx->d_order_tab.release();
   if (ctx->h_operm) cudaFreeHost(ctx->h_operm);
   if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
+  if (ctx->h_nsurv) cudaFreeHost(ctx->h_nsurv);
+  if (ctx->h_dtotals) cudaFreeHost(ctx->h_dtotals);
+  if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
+  if (ctx->ev_surv) cudaEventDestroy(ctx->ev_surv);
+  ctx->d_nsurv.release(); ctx->d_soff.release(); ctx->d_dtotals.release(); ctx->d_leader.release(); ctx->d_leaders.release();
   ctx->d_items2.release();
   for (int i = 0; i < B2C_MAX_CHUNKS; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
   if (ctx->ev_keys) cudaEventDestroy(ctx->ev_keys);

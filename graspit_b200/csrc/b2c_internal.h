@@ -271,8 +271,31 @@ struct OrderParams {
   const int *offsets;                // [nqueries] first record of every query in the grouped array
   int nqueries, total, base;
   int *perm;                         // [n] out: perm[first of group - base + rank] = index inside the group; -1 = replay on the host
+  // leaders (optional, needs offsets): candidates of one triangle pair share a path; only the first of them walks it
+  int *leader;                       // [n] scratch: index of the candidate whose key this one copies (itself: a leader)
+  int *leaders;                      // [n] scratch: dense list of the leaders
+  int *nleaders;                     // [1] scratch
 };
 cudaError_t launch_contact_order(const OrderParams &p, cudaStream_t s);
+// K6d: removeContactDuplicates on the device, per (pose, pair) group in visit order, + the survivors gathered into a compact
+// array (contact_order.cu).  Queries [q0, q1) of the grouped array.
+struct DedupeParams {
+  const ContactRec *recs;            // grouped candidates (whole batch)
+  const int *offsets;                // [nqueries] first record of every query
+  int nqueries, total;
+  int q0, q1;                        // this launch's queries
+  int *perm;                         // [total] in: the group's visit order (index inside the group, -1 = unknown);
+                                     //         out: the survivors' indices at the front of the group's segment
+  int *nsurv;                        // [nqueries] out: survivors of the group; -1 = the host has to do this group
+  int *soff;                         // [nqueries] scratch: exclusive scan of max(nsurv, 0) over [q0, q1)
+  ContactRec *out;                   // survivors of [q0, q1), group after group, visit order inside a group
+  int *out_total;                    // their number
+  double thresh_sq;
+  void *temp; size_t temp_bytes;
+};
+size_t contact_dedupe_temp_bytes(int nqueries);
+cudaError_t launch_contact_dedupe(const DedupeParams &p, cudaStream_t s);
+cudaError_t launch_contact_gather(const DedupeParams &p, int r0, int r1, cudaStream_t s);
 size_t region_sort_temp_bytes(int n, int query_bits);
 cudaError_t launch_region_sort(unsigned long long *pairs, unsigned long long *alt, int n, int query_bits, void *temp, size_t temp_bytes,
                                unsigned long long **sorted, cudaStream_t s);
