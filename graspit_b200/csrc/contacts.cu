@@ -97,8 +97,34 @@ __device__ __noinline__ void tri_pair_contacts(const ContactParams &p, int w, in
   }
 }
 
-constexpr int CSTACK_CAP = 448, CSTACK_PHYS = 512, CLEAF_CAP = 96;
-constexpr int CONTACT_WARP_SMEM = CSTACK_PHYS * 8 + CLEAF_CAP * 8 + 2 * 96 + 96 + 32;
+constexpr int CSTACK_CAP = 448, CSTACK_PHYS = 512, CLEAF_CAP = 96, CEXACT_CAP = 64;
+constexpr int CONTACT_WARP_SMEM = CSTACK_PHYS * 8 + CLEAF_CAP * 8 + CEXACT_CAP * 8 + 2 * 96 + 96 + 32;
+
+// fp32 gate in front of the fp64 enumeration: the gap between the two triangles' projections on any axis is a lower
+// bound of their distance, so a pair with such a gap above threshold + rounding head-room can neither touch nor
+// intersect and the enumeration would emit nothing for it.  Axes: both face normals and the line of centroids.  Leaf
+// boxes are axis aligned in the body frames and loose around slanted triangles; with a 0.2 mm threshold most queued
+// pairs are of this kind (ncu r02g: 1 717 pairs enumerated per pose for 285 candidates).
+__device__ __forceinline__ bool c_axis_far(f3 n, const f3 *a, const f3 *b, float lim2) {
+  float a0 = dot(n, a[0]), a1 = dot(n, a[1]), a2 = dot(n, a[2]);
+  float b0 = dot(n, b[0]), b1 = dot(n, b[1]), b2 = dot(n, b[2]);
+  float gap = fmaxf(fminf(b0, fminf(b1, b2)) - fmaxf(a0, fmaxf(a1, a2)), fminf(a0, fminf(a1, a2)) - fmaxf(b0, fmaxf(b1, b2)));
+  return gap > 0.f && gap * gap > lim2 * dot(n, n);
+}
+__device__ __noinline__ bool tri_pair_far(const Tri *tris_a, const Tri *tris_b, int ta, int tb, const PairXf *xp, float lim2) {
+  f3 a[3], b[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float4 va = __ldg(&tris_a[ta].v[k]), vb = __ldg(&tris_b[tb].v[k]);
+    a[k] = mk<float>(va.x, va.y, va.z);
+    b[k] = mk<float>(xp->r[0] * vb.x + xp->r[1] * vb.y + xp->r[2] * vb.z + xp->t[0],
+                     xp->r[3] * vb.x + xp->r[4] * vb.y + xp->r[5] * vb.z + xp->t[1],
+                     xp->r[6] * vb.x + xp->r[7] * vb.y + xp->r[8] * vb.z + xp->t[2]);
+  }
+  if (c_axis_far(cross(a[1] - a[0], a[2] - a[0]), a, b, lim2)) return true;
+  if (c_axis_far(cross(b[1] - b[0], b[2] - b[0]), a, b, lim2)) return true;
+  return c_axis_far((b[0] + b[1] + b[2]) - (a[0] + a[1] + a[2]), a, b, lim2);
+}
 
 // same PairXf construction as the evaluation kernel (kept local to this translation unit)
 __device__ __forceinline__ void c_make_pair_xf(const double *XA, const double *XB, float extA, float extB, PairXf &o) {
@@ -126,9 +152,10 @@ __global__ void __launch_bounds__(256, CONTACT_MIN_BLOCKS) contact_kernel(Contac
   unsigned char *base = smem_raw + (size_t)warp * CONTACT_WARP_SMEM;
   unsigned long long *stack = reinterpret_cast<unsigned long long *>(base);
   unsigned long long *leafq = stack + CSTACK_PHYS;
-  double *XA = reinterpret_cast<double *>(leafq + CLEAF_CAP);
+  double *XA = reinterpret_cast<double *>(leafq + CLEAF_CAP + CEXACT_CAP);
   double *XB = XA + 12;
   PairXf *xp = reinterpret_cast<PairXf *>(XB + 12);
+  unsigned long long *exactq = leafq + CLEAF_CAP;
   const int total = p.npose * p.nq;
   const float thr = (float)p.threshold;
   // fp32 box bound with head-room so that the fp64 leaf test, not the culling, decides
@@ -154,14 +181,32 @@ __global__ void __launch_bounds__(256, CONTACT_MIN_BLOCKS) contact_kernel(Contac
     if (lane == 0) { PairXf x; c_make_pair_xf(XA, XB, ma.extent, mb.extent, x); *xp = x; }
     __syncwarp();
     const PairXf x = *xp;
-    int sp = 1, lq = 0;
+    int sp = 1, lq = 0, xq = 0;
+    // head-room: the gate works on fp32 vertices through the fp32 pair transform
+    const float far_lim = thr + 16.f * x.eps + 1.0e-3f, far_lim2 = far_lim * far_lim;
     if (lane == 0) stack[0] = 0ull;     // (nodeA = 0, nodeB = 0)
     __syncwarp();
     while (true) {
       if (lq >= 32 || (sp == 0 && lq > 0)) {
+        // gate a full warp of queued triangle pairs; the survivors are packed for the fp64 enumeration
         int n = lq < 32 ? lq : 32;
+        unsigned long long e = 0ull;
+        bool keep = false;
         if (lane < n) {
-          unsigned long long e = leafq[lq - n + lane];
+          e = leafq[lq - n + lane];
+          keep = !tri_pair_far(ma.tris, mb.tris, (int)((e >> 24) & 0xffffffu), (int)(e & 0xffffffu), xp, far_lim2);
+        }
+        unsigned km = __ballot_sync(FULL, keep);
+        if (keep) exactq[xq + __popc(km & lt_mask)] = e;
+        xq += __popc(km);
+        lq -= n;
+        __syncwarp();
+        if (xq < 32 && (sp > 0 || lq > 0)) continue;
+      }
+      if (xq >= 32 || (sp == 0 && lq == 0 && xq > 0)) {
+        int n = xq < 32 ? xq : 32;
+        if (lane < n) {
+          unsigned long long e = exactq[xq - n + lane];
           int ta = (int)((e >> 24) & 0xffffffu), tb = (int)(e & 0xffffffu);
           d3 a1 = xf_apply_inv(XB, xf_apply(XA, c_tri_vertex(ma.tris, ta, 0)));
           d3 a2 = xf_apply_inv(XB, xf_apply(XA, c_tri_vertex(ma.tris, ta, 1)));
@@ -169,7 +214,7 @@ __global__ void __launch_bounds__(256, CONTACT_MIN_BLOCKS) contact_kernel(Contac
           d3 b1 = c_tri_vertex(mb.tris, tb, 0), b2 = c_tri_vertex(mb.tris, tb, 1), b3 = c_tri_vertex(mb.tris, tb, 2);
           tri_pair_contacts(p, w, ta, tb, a1, a2, a3, b1, b2, b3, thr2, XA, XB);
         }
-        lq -= n;
+        xq -= n;
         __syncwarp();
         continue;
       }
@@ -180,53 +225,41 @@ __global__ void __launch_bounds__(256, CONTACT_MIN_BLOCKS) contact_kernel(Contac
         if (p.overflow && lane == 0) atomicOr(p.overflow, OVF_STACK);
         break;
       }
-      int k = sp < 32 ? sp : 32;
+      // Two lanes per popped node pair, one per child of the node that is split: with the 0.2 mm band the front of live
+      // node pairs is narrow (ncu r02g: 6 of 32 lanes in the box tests when one lane took a node pair and both children).
+      int k = sp < 16 ? sp : 16;
       if (k > room) k = room > 1 ? room : 1;
-      bool have = lane < k;
-      unsigned long long e = have ? stack[sp - 1 - lane] : 0ull;
+      const int ent = lane >> 1, side = lane & 1;
+      bool have = ent < k;
+      unsigned long long e = have ? stack[sp - 1 - ent] : 0ull;
       sp -= k;
       __syncwarp();
-      bool p0 = false, p1 = false, l0 = false, l1 = false;
-      unsigned long long c0 = 0ull, c1 = 0ull;
+      bool pp = false, ll = false;
+      unsigned long long c = 0ull;
       if (have) {
         int na = (int)((e >> 24) & 0xffffffu), nb = (int)(e & 0xffffffu);
         Node a = load_node(ma, na), b = load_node(mb, nb);
         bool la = a.child < 0, lb = b.child < 0;
         if (la && lb) {
-          p0 = l0 = a.tri >= 0 && b.tri >= 0;
-          c0 = ((unsigned long long)(unsigned)a.tri << 24) | (unsigned)b.tri;
+          pp = ll = side == 0 && a.tri >= 0 && b.tri >= 0;
+          c = ((unsigned long long)(unsigned)a.tri << 24) | (unsigned)b.tri;
         } else {
           bool splitA = lb || (!la && (a.hx * a.hy * a.hz > b.hx * b.hy * b.hz));
           float ca[3], ha[3], cb[3], hb[3];
-          if (splitA) {
-            Node a0, a1;
-            load_pair(ma, a.child, a0, a1);
-            c_node_ch(b, cb, hb);
-            c_node_ch(a0, ca, ha); p0 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
-            c_node_ch(a1, ca, ha); p1 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
-            l0 = p0 && lb && a0.child < 0; l1 = p1 && lb && a1.child < 0;
-            c0 = l0 ? (((unsigned long long)(unsigned)a0.tri << 24) | (unsigned)b.tri) : (((unsigned long long)(unsigned)a.child << 24) | (unsigned)nb);
-            c1 = l1 ? (((unsigned long long)(unsigned)a1.tri << 24) | (unsigned)b.tri) : (((unsigned long long)(unsigned)(a.child + 1) << 24) | (unsigned)nb);
-          } else {
-            Node b0, b1;
-            load_pair(mb, b.child, b0, b1);
-            c_node_ch(a, ca, ha);
-            c_node_ch(b0, cb, hb); p0 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
-            c_node_ch(b1, cb, hb); p1 = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
-            l0 = p0 && la && b0.child < 0; l1 = p1 && la && b1.child < 0;
-            c0 = l0 ? (((unsigned long long)(unsigned)a.tri << 24) | (unsigned)b0.tri) : (((unsigned long long)(unsigned)na << 24) | (unsigned)b.child);
-            c1 = l1 ? (((unsigned long long)(unsigned)a.tri << 24) | (unsigned)b1.tri) : (((unsigned long long)(unsigned)na << 24) | (unsigned)(b.child + 1));
-          }
+          if (splitA) { na = a.child + side; a = load_node(ma, na); }
+          else { nb = b.child + side; b = load_node(mb, nb); }
+          c_node_ch(a, ca, ha);
+          c_node_ch(b, cb, hb);
+          pp = box_dist_lb(ca, ha, cb, hb, x) <= bound2;
+          ll = pp && a.child < 0 && b.child < 0;
+          c = ll ? (((unsigned long long)(unsigned)a.tri << 24) | (unsigned)b.tri) : (((unsigned long long)(unsigned)na << 24) | (unsigned)nb);
         }
       }
-      unsigned s0 = __ballot_sync(FULL, p0 && !l0), s1 = __ballot_sync(FULL, p1 && !l1);
-      unsigned q0 = __ballot_sync(FULL, p0 && l0), q1 = __ballot_sync(FULL, p1 && l1);
-      if (p0 && !l0) stack[sp + __popc(s0 & lt_mask)] = c0;
-      if (p1 && !l1) stack[sp + __popc(s0) + __popc(s1 & lt_mask)] = c1;
-      sp += __popc(s0) + __popc(s1);
-      if (p0 && l0) leafq[lq + __popc(q0 & lt_mask)] = c0;
-      if (p1 && l1) leafq[lq + __popc(q0) + __popc(q1 & lt_mask)] = c1;
-      lq += __popc(q0) + __popc(q1);
+      unsigned s0 = __ballot_sync(FULL, pp && !ll), q0 = __ballot_sync(FULL, pp && ll);
+      if (pp && !ll) stack[sp + __popc(s0 & lt_mask)] = c;
+      sp += __popc(s0);
+      if (pp && ll) leafq[lq + __popc(q0 & lt_mask)] = c;
+      lq += __popc(q0);
       __syncwarp();
     }
     __syncwarp();
