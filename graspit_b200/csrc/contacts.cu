@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256, CONTACT_MIN_BLOCKS) contact_kernel(Contac
     __syncwarp();
     if (lane == 0) { PairXf x; c_make_pair_xf(XA, XB, ma.extent, mb.extent, x); *xp = x; }
     __syncwarp();
-    const PairXf x = *xp;
+    const PairXf &x = *xp;
     int sp = 1, lq = 0, xq = 0;
     // head-room: the gate works on fp32 vertices through the fp32 pair transform
     const float far_lim = thr + 16.f * x.eps + 1.0e-3f, far_lim2 = far_lim * far_lim;
