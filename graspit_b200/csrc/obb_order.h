@@ -100,34 +100,53 @@ B2C_HD inline double order_distance_sq(const OrderNode &n1, const OrderNode &n2,
 //   range (optional) = {amin, amax, bmin, bmax}: leaf positions spanned by the candidates whose order is being decided;
 //   where they all sit under one child of the split node nobody is on the other side, the bit cannot matter, and the two
 //   box distances are not evaluated
-B2C_HD inline bool order_step(const OrderNode *A, const OrderNode *B, const OrderXf &x, int &n1, int &n2, int pa, int pb, int *second,
-                              const int *range = nullptr) {
+// The step in two halves, so that a kernel can run the cheap half of many candidates up to their next deciding level and
+// then evaluate the box distances of all of them together.
+struct OrderPick {
+  int split1;              // 1: model 1's node is split (nodeSwap == false)
+  int c0, c1;              // its children
+  int mine;                // the child holding the candidate
+};
+//   0: both nodes are leaves (the walk is over);  1: the level decides nothing for this group;  2: the level decides
+B2C_HD inline int order_pick(const OrderNode *A, const OrderNode *B, int n1, int n2, int pa, int pb, const int *range, OrderPick &k) {
   const OrderNode &N1 = A[n1], &N2 = B[n2];
   const bool l1 = N1.child0 < 0, l2 = N2.child0 < 0;
-  if (l1 && l2) return false;
-  bool split1;             // true: recurse on model 1's node (nodeSwap == false)
+  if (l1 && l2) return 0;
+  bool split1;
   if (l1) split1 = false;
   else if (l2) split1 = true;
   else split1 = order_box_volume(N1) > order_box_volume(N2);
   const OrderNode &R = split1 ? N1 : N2;
   const OrderNode *T = split1 ? A : B;
-  const OrderNode &C0 = T[R.child0], &C1 = T[R.child1];
+  const OrderNode &C0 = T[R.child0];
   const int pos = split1 ? pa : pb;
-  const int mine = (pos >= C0.leaf_lo && pos < C0.leaf_hi) ? 0 : 1;
+  k.split1 = split1 ? 1 : 0;
+  k.c0 = R.child0; k.c1 = R.child1;
+  k.mine = (pos >= C0.leaf_lo && pos < C0.leaf_hi) ? 0 : 1;
   if (range) {
     const int pmin = split1 ? range[0] : range[2], pmax = split1 ? range[1] : range[3];
-    if ((pmin >= C0.leaf_lo && pmax < C0.leaf_hi) || pmin >= C0.leaf_hi || pmax < C0.leaf_lo) {
-      *second = 0;
-      if (split1) n1 = mine ? R.child1 : R.child0; else n2 = mine ? R.child1 : R.child0;
-      return true;
-    }
+    if ((pmin >= C0.leaf_lo && pmax < C0.leaf_hi) || pmin >= C0.leaf_hi || pmax < C0.leaf_lo) return 1;
   }
+  return 2;
+}
+//   which child the reference visits first
+B2C_HD inline int order_first(const OrderNode *A, const OrderNode *B, const OrderXf &x, int n1, int n2, const OrderPick &k) {
   double d0, d1;
-  if (split1) { d0 = order_distance_sq(C0, N2, x); d1 = order_distance_sq(C1, N2, x); }
-  else { d0 = order_distance_sq(N1, C0, x); d1 = order_distance_sq(N1, C1, x); }
-  const int first = d1 < d0 ? 1 : 0;
-  *second = mine != first ? 1 : 0;
-  if (split1) n1 = mine ? R.child1 : R.child0; else n2 = mine ? R.child1 : R.child0;
+  if (k.split1) { d0 = order_distance_sq(A[k.c0], B[n2], x); d1 = order_distance_sq(A[k.c1], B[n2], x); }
+  else { d0 = order_distance_sq(A[n1], B[k.c0], x); d1 = order_distance_sq(A[n1], B[k.c1], x); }
+  return d1 < d0 ? 1 : 0;
+}
+B2C_HD inline void order_advance(int &n1, int &n2, const OrderPick &k) {
+  if (k.split1) n1 = k.mine ? k.c1 : k.c0; else n2 = k.mine ? k.c1 : k.c0;
+}
+
+B2C_HD inline bool order_step(const OrderNode *A, const OrderNode *B, const OrderXf &x, int &n1, int &n2, int pa, int pb, int *second,
+                              const int *range = nullptr) {
+  OrderPick k;
+  const int st = order_pick(A, B, n1, n2, pa, pb, range, k);
+  if (st == 0) return false;
+  *second = st == 2 && k.mine != order_first(A, B, x, n1, n2, k) ? 1 : 0;
+  order_advance(n1, n2, k);
   return true;
 }
 
