@@ -143,7 +143,9 @@ struct b2c_ctx {
   DevBuf<ContactRec> d_contacts2;   // the same records grouped by query
   DevBuf<int> d_coffsets;           // per query: first record, fill cursor
   DevBuf<unsigned char> d_cubtemp;
-  std::vector<int> h_coffsets[2];
+  int *h_qoff = nullptr; size_t h_qoff_cap = 0;        // pinned: first record of every (pose, pair) query of a batched contacts call
+  int *h_qsmall = nullptr; size_t h_qsmall_cap = 0;    // pinned: chunk starts + pairs in use (contact_digest_kernel)
+  DevBuf<int> d_qsmall;
   size_t h_contacts_cap[2] = {0, 0};
   Xf *h_fk = nullptr;               // pinned copy of the link transforms (reference-order replay of contact candidates)
   size_t h_fk_cap = 0;
@@ -475,6 +477,9 @@ void b2c_destroy(b2c_ctx *ctx) {
   if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
   if (ctx->h_nsurv) cudaFreeHost(ctx->h_nsurv);
   if (ctx->h_dtotals) cudaFreeHost(ctx->h_dtotals);
+  if (ctx->h_qoff) cudaFreeHost(ctx->h_qoff);
+  if (ctx->h_qsmall) cudaFreeHost(ctx->h_qsmall);
+  ctx->d_qsmall.release();
   if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
   if (ctx->ev_surv) cudaEventDestroy(ctx->ev_surv);
   ctx->d_nsurv.release(); ctx->d_soff.release(); ctx->d_dtotals.release(); ctx->d_leader.release(); ctx->d_leaders.release();

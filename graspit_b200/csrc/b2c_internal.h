@@ -302,6 +302,7 @@ cudaError_t launch_region_sort(unsigned long long *pairs, unsigned long long *al
 size_t contact_group_temp_bytes(int nqueries);
 cudaError_t launch_contact_group(const ContactRec *in, int n, const int *per_query, int nqueries, int *offsets, int *cursor,
                                  ContactRec *out, void *temp, size_t temp_bytes, cudaStream_t s);
+cudaError_t launch_contact_digest(const int *per_query, const int *offsets, int nqueries, int np, int stride, int *out, int nslots, cudaStream_t s);
 
 // ---- batched annealing (anneal.cu) ------------------------------------------------------------------
 struct AnnealParams {

@@ -381,6 +381,22 @@ cudaError_t launch_contact_group(const ContactRec *in, int n, const int *per_que
   return cudaGetLastError();
 }
 
+// What the host needs of the grouping before it can enqueue the chunks: the first record of every chunk of poses and
+// which pairs of the plan hold candidates at all (their reference-style trees are built on first use).  The full offset
+// table follows on the copy stream.   out = [nslots chunk starts][np pair flags]
+__global__ void contact_digest_kernel(const int *per_query, const int *offsets, int nqueries, int np, int stride, int *out, int nslots) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nqueries) return;
+  if (per_query[q] > 0) out[nslots + q % np] = 1;
+  if (q % stride == 0 && q / stride < nslots) out[q / stride] = offsets[q];
+}
+cudaError_t launch_contact_digest(const int *per_query, const int *offsets, int nqueries, int np, int stride, int *out, int nslots, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(int) * (size_t)(nslots + np), s);
+  if (e != cudaSuccess || nqueries <= 0) return e;
+  contact_digest_kernel<<<(nqueries + 255) / 256, 256, 0, s>>>(per_query, offsets, nqueries, np, stride, out, nslots);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_region(const RegionParams &p, cudaStream_t s) {
   if (p.mesh.ntri <= 0) return cudaSuccess;
   region_kernel<<<(p.mesh.ntri + 255) / 256, 256, 0, s>>>(p);
