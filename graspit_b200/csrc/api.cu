@@ -143,6 +143,7 @@ struct b2c_ctx {
   DevBuf<ContactRec> d_contacts2;   // the same records grouped by query
   DevBuf<int> d_coffsets;           // per query: first record, fill cursor
   DevBuf<unsigned char> d_cubtemp;
+  std::vector<int> h_soff;
   int *h_qoff = nullptr; size_t h_qoff_cap = 0;        // pinned: first record of every (pose, pair) query of a batched contacts call
   int *h_qsmall = nullptr; size_t h_qsmall_cap = 0;    // pinned: chunk starts + pairs in use (contact_digest_kernel)
   DevBuf<int> d_qsmall;

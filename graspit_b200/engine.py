@@ -628,7 +628,8 @@ class Engine:
         if n.value > cap:
             return self.contacts_batch(robot, states, threshold, input_mode, ref_tran, raw, cap_contacts=n.value)
         k = n.value
-        return {"contacts": buf[:k].copy(), "pose": cpose[:k].copy(), "pair": cpair[:k].copy(), "offsets": off}
+        # (views of this call's own buffers: the untouched tail of the capacity estimate never becomes resident)
+        return {"contacts": buf[:k], "pose": cpose[:k], "pair": cpair[:k], "offsets": off}
 
     def move_dof_to_contacts(self, robot: int, states, desired, steps, dof_breakaway, stop_at_contact=False,
                              contact_threshold=0.2, njoints=None):
