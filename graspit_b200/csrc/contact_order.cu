@@ -10,6 +10,9 @@
 // the same function only where a group's paths branch; it remains the fallback for paths longer than 128 levels.
 #include <cub/cub.cuh>
 #include "b2c_internal.h"
+// the box distance stays out of line in the visit-key kernel: inlined twice per level it took 166 registers and the warps
+// waited on instruction fetch (ncu r02i); out of line 128 registers and 6 % off the whole batched call
+#define B2C_ORDER_DIST_ATTR __noinline__
 #include "obb_order.h"
 
 namespace b2c {

@@ -51,7 +51,10 @@ B2C_HD inline void order_matmul(const double a[3][3], const double b[3][3], doub
 }
 
 // bboxDistanceSq(bb1, bb2, tran2To1); -1 for boxes the separating-axis bounds cannot tell apart
-B2C_HD inline double order_distance_sq(const OrderNode &n1, const OrderNode &n2, const OrderXf &x) {
+#ifndef B2C_ORDER_DIST_ATTR
+#define B2C_ORDER_DIST_ATTR
+#endif
+B2C_HD B2C_ORDER_DIST_ATTR inline double order_distance_sq(const OrderNode &n1, const OrderNode &n2, const OrderXf &x) {
   // BtoA = bb1.TranInv % tran2To1 % bb2.Tran
   double R1t[3][3], M[3][3], B[3][3], Bf[3][3];
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R1t[i][j] = n1.Rq[j][i];
