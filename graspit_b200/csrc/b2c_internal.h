@@ -235,6 +235,8 @@ struct ContactParams {
   int *per_query;          // [npose * nq] contact candidates per query
   int *work_counter;
   int *overflow;           // sticky device word, see EvalParams
+  int *work_list;          // optional [npose * nq]: filled by the launcher's cull pass with the queries whose root boxes come
+  int *work_count;         //   within the threshold; the warps then take their work from this list
 };
 struct RegionParams {
   MeshDev mesh;
