@@ -66,7 +66,7 @@ def build_host_planner_check() -> str:
     for d in ("/usr/local/cuda/lib64", "/usr/local/cuda/targets/x86_64-linux/lib"):
         if os.path.exists(os.path.join(d, "libcudart.so")):
             cudart = d
-    cmd = [ccbin, "-std=c++14", "-O2", "-Wall", "-I", os.path.join(root, "include"), "-I", os.path.join(HERE, "host"),
+    cmd = [ccbin, "-std=c++14", "-O2", "-g", "-rdynamic", "-Wall", "-I", os.path.join(root, "include"), "-I", os.path.join(HERE, "host"),
            os.path.join(HERE, "host", "b200Planner.cpp"), os.path.join(root, "tests", "host", "b200planner_check.cpp"),
            "-o", out, "-L", HERE, "-lb2c", "-Wl,-rpath,$ORIGIN/.."]
     if cudart:

@@ -144,6 +144,8 @@ struct b2c_ctx {
   DevBuf<int> d_coffsets;           // per query: first record, fill cursor
   DevBuf<unsigned char> d_cubtemp;
   std::vector<int> h_soff;
+  DevBuf<int> d_rfirst, d_rkeep, d_rpos, d_roff; DevBuf<double> d_rout;     // vertex lists of a region batch
+  void *h_rout = nullptr; size_t h_rout_cap = 0;                           // pinned staging of the finished lists
   int *h_qoff = nullptr; size_t h_qoff_cap = 0;        // pinned: first record of every (pose, pair) query of a batched contacts call
   int *h_qsmall = nullptr; size_t h_qsmall_cap = 0;    // pinned: chunk starts + pairs in use (contact_digest_kernel)
   DevBuf<int> d_qsmall;
@@ -479,6 +481,8 @@ void b2c_destroy(b2c_ctx *ctx) {
   if (ctx->h_nsurv) cudaFreeHost(ctx->h_nsurv);
   if (ctx->h_dtotals) cudaFreeHost(ctx->h_dtotals);
   if (ctx->h_qoff) cudaFreeHost(ctx->h_qoff);
+  if (ctx->h_rout) cudaFreeHost(ctx->h_rout);
+  ctx->d_rfirst.release(); ctx->d_rkeep.release(); ctx->d_rpos.release(); ctx->d_roff.release(); ctx->d_rout.release();
   if (ctx->h_qsmall) cudaFreeHost(ctx->h_qsmall);
   ctx->d_qsmall.release();
   if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);

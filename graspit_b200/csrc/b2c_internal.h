@@ -237,6 +237,7 @@ struct ContactParams {
   int *overflow;           // sticky device word, see EvalParams
   int *work_list;          // optional [npose * nq]: filled by the launcher's cull pass with the queries whose root boxes come
   int *work_count;         //   within the threshold; the warps then take their work from this list
+  int exhaustive;          // 1: no fp32 triangle-pair gate (every queued pair is enumerated in fp64) -- the check of the gate
 };
 struct RegionParams {
   MeshDev mesh;
@@ -257,6 +258,11 @@ struct RegionBatchParams {
   int *out_count;
 };
 cudaError_t launch_region_batch(const RegionBatchParams &p, cudaStream_t s);
+size_t region_lists_temp_bytes(int nhits);
+cudaError_t launch_region_keep(const int2 *hits, int nhits, int n, const int *mesh_of, const MeshDev *meshes, int *first, int *keep,
+                               int *pos, void *temp, size_t temp_bytes, cudaStream_t s);
+cudaError_t launch_region_write(const int2 *hits, int nhits, int n, const int *mesh_of, const MeshDev *meshes, const double *points,
+                                const int *first, const int *keep, const int *pos, double *out, long long cap, int *offsets, cudaStream_t s);
 // K6b (contact_order.cu): per-candidate visit keys
 struct OrderNode;
 struct OrderParams {

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256, CONTACT_MIN_BLOCKS) contact_kernel(Contac
         bool keep = false;
         if (lane < n) {
           e = leafq[lq - n + lane];
-          keep = !tri_pair_far(ma.tris, mb.tris, (int)((e >> 24) & 0xffffffu), (int)(e & 0xffffffu), xp, far_lim2);
+          keep = p.exhaustive || !tri_pair_far(ma.tris, mb.tris, (int)((e >> 24) & 0xffffffu), (int)(e & 0xffffffu), xp, far_lim2);
         }
         unsigned km = __ballot_sync(FULL, keep);
         if (keep) exactq[xq + __popc(km & lt_mask)] = e;
@@ -345,6 +345,91 @@ cudaError_t launch_region_sort(unsigned long long *pairs, unsigned long long *al
   cudaError_t e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, k, n, 0, 32 + query_bits, s);
   *sorted = k.Current();
   return e;
+}
+
+// ---- vertex lists of a region batch on the device -----------------------------------------------------------------
+// RegionCallback::insertPoint (collisionAlgorithms.h:218-232) keeps the first occurrence of every vertex, compared with
+// exact equality, in the order the flagged triangles are visited; bodyRegion then appends the query point itself
+// (graspitCollision.cpp:495).  With the (triangle, query) pairs sorted by query and triangle: first[q] = the query's first
+// pair; a vertex is kept when no earlier vertex of the same query equals it (equality is transitive, so this is the
+// sequential rule); an exclusive scan of the keep flags gives every kept vertex its place, query q's list being shifted by
+// the q query points appended before it.
+__global__ void region_first_kernel(const int2 *hits, int nhits, int n, int *first) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > nhits) return;
+  const int qprev = k == 0 ? -1 : hits[k - 1].y, qcur = k == nhits ? n : hits[k].y;
+  for (int q = qprev + 1; q <= qcur; q++) first[q] = k;
+}
+constexpr int REGION_STAGE = 384;          // vertices of one query staged in shared memory (a query holds ~70)
+__global__ void __launch_bounds__(256) region_keep_kernel(const int2 *hits, const int *first, int n, const int *mesh_of,
+                                                          const MeshDev *meshes, int *keep) {
+  __shared__ float stage[8][REGION_STAGE][3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * 8 + warp;
+  if (q >= n) return;
+  const int lo = first[q], k = 3 * (first[q + 1] - lo);
+  const Tri *tris = meshes[mesh_of[q]].tris;
+  float (*sv)[3] = stage[warp];
+  for (int j = lane; j < k && j < REGION_STAGE; j += 32) {
+    const float4 v = __ldg(&tris[hits[lo + j / 3].x].v[j % 3]);
+    sv[j][0] = v.x; sv[j][1] = v.y; sv[j][2] = v.z;
+  }
+  __syncwarp();
+  for (int j = lane; j < k; j += 32) {
+    float vx, vy, vz;
+    if (j < REGION_STAGE) { vx = sv[j][0]; vy = sv[j][1]; vz = sv[j][2]; }
+    else { const float4 v = __ldg(&tris[hits[lo + j / 3].x].v[j % 3]); vx = v.x; vy = v.y; vz = v.z; }
+    bool dup = false;
+    const int ns = j < REGION_STAGE ? j : REGION_STAGE;
+    for (int i = 0; i < ns && !dup; i++) dup = sv[i][0] == vx && sv[i][1] == vy && sv[i][2] == vz;
+    for (int i = REGION_STAGE; i < j && !dup; i++) {
+      const float4 u = __ldg(&tris[hits[lo + i / 3].x].v[i % 3]);
+      dup = u.x == vx && u.y == vy && u.z == vz;
+    }
+    keep[3 * (size_t)lo + j] = dup ? 0 : 1;
+  }
+}
+// thread j < 3 nhits: vertex j, written if kept; thread 3 nhits + q: query q's own point and its list's start
+__global__ void region_write_kernel(const int2 *hits, int nhits, const int *first, int n, const int *mesh_of, const MeshDev *meshes,
+                                    const int *keep, const int *pos, const double *points, double *out, long long cap, int *offsets) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nv = 3ll * nhits;
+  if (j < nv) {
+    if (!keep[j]) return;
+    const int2 h = hits[j / 3];
+    const long long at = (long long)pos[j] + h.y;
+    if (at >= cap) return;
+    const float4 v = __ldg(&meshes[mesh_of[h.y]].tris[h.x].v[j % 3]);
+    out[3 * at] = (double)v.x; out[3 * at + 1] = (double)v.y; out[3 * at + 2] = (double)v.z;
+  } else if (j < nv + n) {
+    const int q = (int)(j - nv);
+    offsets[q] = pos[3 * (size_t)first[q]] + q;
+    const long long at = (long long)pos[3 * (size_t)first[q + 1]] + q;
+    if (q == n - 1) offsets[n] = (int)(at + 1);
+    if (at >= cap) return;
+    out[3 * at] = points[3 * (size_t)q]; out[3 * at + 1] = points[3 * (size_t)q + 1]; out[3 * at + 2] = points[3 * (size_t)q + 2];
+  }
+}
+size_t region_lists_temp_bytes(int nhits) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int *)nullptr, (int *)nullptr, 3 * nhits + 1);
+  return bytes;
+}
+// keep / pos: [3 nhits + 1] ints each; first: [n + 1].  After this pos[3 nhits] = the number of kept vertices.
+cudaError_t launch_region_keep(const int2 *hits, int nhits, int n, const int *mesh_of, const MeshDev *meshes, int *first, int *keep,
+                               int *pos, void *temp, size_t temp_bytes, cudaStream_t s) {
+  region_first_kernel<<<(nhits + 1 + 255) / 256, 256, 0, s>>>(hits, nhits, n, first);
+  cudaError_t e = cudaMemsetAsync(keep + 3 * (size_t)nhits, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  region_keep_kernel<<<(n + 7) / 8, 256, 0, s>>>(hits, first, n, mesh_of, meshes, keep);
+  return cub::DeviceScan::ExclusiveSum(temp, temp_bytes, keep, pos, 3 * nhits + 1, s);
+}
+// offsets: [n + 1] (device); out: [cap][3] doubles (device)
+cudaError_t launch_region_write(const int2 *hits, int nhits, int n, const int *mesh_of, const MeshDev *meshes, const double *points,
+                                const int *first, const int *keep, const int *pos, double *out, long long cap, int *offsets, cudaStream_t s) {
+  const long long nt = 3ll * nhits + n;
+  region_write_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(hits, nhits, first, n, mesh_of, meshes, keep, pos, points, out, cap, offsets);
+  return cudaGetLastError();
 }
 
 // Cull pass of a batched call, one thread per (pose, pair) query: only queries whose two root boxes come within the

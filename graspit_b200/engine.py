@@ -460,7 +460,7 @@ class Engine:
         if tot.value > cap:
             return self.body_region_batch(bodies, points, normals, radii, cap=tot.value, flat=flat)
         if flat:
-            return out[:tot.value].copy(), off          # ragged form of the C ABI: points back to back + offsets[n + 1]
+            return out[:tot.value], off                 # ragged form of the C ABI: points back to back + offsets[n + 1]
         return [out[off[i]:off[i + 1]].copy() for i in range(n)]
 
     def get_bounding_volumes(self, body: int, depth: int, cap=1 << 16):

@@ -89,6 +89,7 @@ class BatchedSimAnnPlanner
     BestList mBestList;
     std::string mError;
   public:
+    // ctx is borrowed and must outlive the planner (the destructor releases the annealer in it)
     BatchedSimAnnPlanner(b2c_ctx *ctx, int robot, int object, const transf7 &refTran,
                          const std::vector<SearchVariable> &variables, const SimAnnParams &params,
                          const std::vector<float> &initialStates, unsigned long long seed = 1234,

@@ -12,6 +12,10 @@
 #include <string>
 #include <vector>
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include "b200Planner.h"
 
 extern "C" int cudaGetDeviceCount(int *count);      // libcudart (no CUDA headers needed on the host side)
@@ -157,6 +161,8 @@ static void gpuChecks(const char *scenePath)
 {
   Scene S;
   if (!loadScene(scenePath, &S)) { printf("FAIL cannot load the scene (%s)\n", S.ctx ? b2c_last_error(S.ctx) : "no device"); g_fail++; return; }
+  // (declared before the planner: the context must outlive it -- the planner's destructor releases its annealer there)
+  struct CtxGuard { b2c_ctx *c; ~CtxGuard() { b2c_destroy(c); } } guard{S.ctx};
   std::vector<SearchVariable> vars = axisAngleEigenVariables(S.neg);
   const int K = 4096, nv = (int)vars.size();
   std::mt19937_64 rng(5);
@@ -236,7 +242,6 @@ static void gpuChecks(const char *scenePath)
     CHECK(nlegal >= (int)(0.99 * lg.size()), "%d of %zu closed postures are collision-free", nlegal, lg.size());
     printf("autoGraspBatch: %zu poses, %d moved, %d start in collision, %d coupled, %d legal\n", poses.size(), moved, errors, coupled, nlegal);
   }
-  b2c_destroy(S.ctx);
 }
 
 // One process, several contexts (one per device; on a single-GPU box both on device 0): the chains are split over them,
@@ -286,8 +291,22 @@ static void multiGpuChecks(const char *scenePath)
   b2c_destroy(One.ctx);
 }
 
+// a fault in the harness or the library prints where it happened (the GPU boxes have no debugger)
+static void onFault(int sig)
+{
+  void *frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "b200planner_check: fatal signal, backtrace:\n";
+  if (write(2, msg, sizeof msg - 1) < 0) {}
+  backtrace_symbols_fd(frames, n, 2);
+  (void)sig;
+  _exit(70);                 // (an exit code, not a re-raised signal: the GPU pool backs off after killed commands)
+}
+
 int main(int argc, char **argv)
 {
+  signal(SIGSEGV, onFault);
+  signal(SIGABRT, onFault);
   if (argc < 2) { fprintf(stderr, "usage: %s cpu | gpu scene.txt\n", argv[0]); return 2; }
   cpuChecks();
   if (!strcmp(argv[1], "gpu")) {

@@ -162,6 +162,31 @@ def test_device_visit_keys_equal_host_replay(closed):
         assert np.array_equal(a["contacts"], b["contacts"])
 
 
+def test_fp32_short_cuts_change_nothing(closed):
+    """contact_kernel's two fp32 short cuts -- the root-box cull pass that builds the warps' work list, and the
+    separating-axis gate in front of the fp64 feature enumeration -- may only drop work that would have emitted nothing:
+    with B2C_CONTACT_EXHAUSTIVE=1 (every query a warp, every queued triangle pair enumerated) the candidates themselves
+    (raw, as a set per (pose, pair)) and the processed contacts must be the same, bit for bit."""
+    eng, rid, js = closed["eng"], closed["rid"], closed["js"]
+    big = np.tile(js, (3000 // len(js) + 1, 1))[:3000]
+    out = {}
+    for mode in ("fast", "exhaustive"):
+        if mode == "exhaustive":
+            os.environ["B2C_CONTACT_EXHAUSTIVE"] = "1"
+        else:
+            os.environ.pop("B2C_CONTACT_EXHAUSTIVE", None)
+        try:
+            out[mode] = (eng.contacts_batch(rid, big, THR, input_mode=B2C_INPUT_JOINTS, raw=True),
+                         eng.contacts_batch(rid, big, THR, input_mode=B2C_INPUT_JOINTS))
+        finally:
+            os.environ.pop("B2C_CONTACT_EXHAUSTIVE", None)
+    for i in (0, 1):
+        a, b = out["fast"][i], out["exhaustive"][i]
+        assert len(a["contacts"]) == len(b["contacts"]) > 1000
+        assert np.array_equal(a["pose"], b["pose"]) and np.array_equal(a["pair"], b["pair"])
+        assert np.array_equal(a["contacts"], b["contacts"])
+
+
 def test_region_batch_matches_single_queries_and_reference():
     """neighbourhoods of every contact of a batch of closed human hands (elastic fingertips): the batched bodyRegion returns
     exactly what one b2c_region call per contact returns, which equals the reference's bodyRegion as a set"""
