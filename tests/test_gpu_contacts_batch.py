@@ -228,3 +228,61 @@ def test_region_batch_matches_single_queries_and_reference():
     assert nonempty > 5
     # the last point of every list is the query point itself
     assert all(np.array_equal(g[-1], np.asarray(p, dtype=np.float64)) for g, p in zip(got, points))
+
+
+def test_region_batch_edge_cases(closed):
+    """queries that flag nothing (a radius of a micron away from the surface: the list is the query point alone), queries on
+    different bodies mixed in one call, and a caller buffer smaller than the result (the lists are cut at `cap` points, the
+    offsets and the total still describe the whole result) -- each against the single-query call"""
+    import ctypes as C
+    eng, sb, sc = closed["eng"], closed["sb"], closed["sc"]
+    ids = sorted(sb.body_ids.values())
+    rng = np.random.default_rng(5)
+    bodies, points, normals, radii = [], [], [], []
+    for k in range(60):
+        b = ids[k % len(ids)]
+        tri = np.asarray(sc.bodies[{v: kk for kk, v in sb.body_ids.items()}[b]].tris, dtype=np.float64).reshape(-1, 3, 3)
+        t = tri[rng.integers(len(tri))]
+        n = np.cross(t[1] - t[0], t[2] - t[0]); n /= max(np.linalg.norm(n), 1e-30)
+        far = k % 3 == 0
+        p = t.mean(axis=0) + (500.0 * n if far else 0.0)
+        bodies.append(b); points.append(p); normals.append(-n); radii.append(1.0e-3 if far else 6.0)
+    got = eng.body_region_batch(bodies, points, normals, radii)
+    assert len(got) == 60
+    for i in range(60):
+        one = eng.body_region(bodies[i], points[i], normals[i], radii[i])
+        assert np.array_equal(got[i], one), i
+        if i % 3 == 0:
+            assert len(got[i]) == 1 and np.array_equal(got[i][0], points[i])
+    assert sum(len(g) > 3 for g in got) > 20
+    # a buffer that holds only part of the result
+    total = sum(len(g) for g in got)
+    cap = total // 2
+    b = np.ascontiguousarray(bodies, dtype=np.int32); p = np.ascontiguousarray(points); nn = np.ascontiguousarray(normals)
+    r = np.ascontiguousarray(radii, dtype=np.float64)
+    out = np.full((cap, 3), np.nan); off = np.zeros(61, dtype=np.int32); tot = C.c_int(0)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    eng._ck(eng.L.b2c_region_batch(eng.h, 60, b.ctypes.data_as(C.POINTER(C.c_int)), dp(p), dp(nn), dp(r), dp(out), cap,
+                                   off.ctypes.data_as(C.POINTER(C.c_int)), C.byref(tot)))
+    assert tot.value == total and off[60] == total
+    flat = np.concatenate(got)
+    assert np.array_equal(off[:60], np.cumsum([0] + [len(g) for g in got])[:60])
+    assert np.array_equal(out, flat[:cap])
+
+
+def test_contacts_batch_without_any_contact(closed):
+    """hands far away from everything: no candidates, no groups, all offsets zero (the empty batch goes through the same
+    chunked pipeline)"""
+    eng, rid, js = closed["eng"], closed["rid"], closed["js"]
+    far = np.tile(js[:1], (2500, 1))
+    far[:, 4:7] += np.array([5000.0, 0.0, 0.0])             # translation of the base: 5 m away from the object
+    far[:, 7:] = 0.0                                          # open hand (no self contact)
+    res = eng.contacts_batch(rid, far, THR, input_mode=B2C_INPUT_JOINTS)
+    assert len(res["contacts"]) == 0 and len(res["pose"]) == 0
+    assert res["offsets"].shape == (2501,) and not res["offsets"].any()
+    # ... and a batch where only a few poses touch anything
+    mixed = far.copy(); mixed[::500] = js[:5]
+    res = eng.contacts_batch(rid, mixed, THR, input_mode=B2C_INPUT_JOINTS)
+    one = eng.contacts_batch(rid, js[:5], THR, input_mode=B2C_INPUT_JOINTS)
+    assert len(res["contacts"]) == len(one["contacts"]) > 0
+    assert np.array_equal(res["contacts"], one["contacts"]) and np.array_equal(res["pose"] // 500, one["pose"])
