@@ -21,7 +21,7 @@ engine's collective-free peer exchange (rows stored straight into the peers' HBM
 the best list), `--exchange nccl` keeps the NCCL all-gather as the checked alternative.
 
 Besides the headline line the default run adds sub-records (`--no-sub` skips them).  At N = 1 only: "config3" (allContacts
-for 16 384 closed HumanHand poses), "config4" (allCollisions for 262 144 arm + hand configurations), "autograsp" (65 536
+for 16 384 closed HumanHand poses, with "region_batch": bodyRegion for both sides of every contact on an elastic body), "config4" (allCollisions for 262 144 arm + hand configurations), "autograsp" (65 536
 hands closed in one call) -- one timed call each, host buffers.  At every N, measured like the headline:
     "live"     CONTACT_LIVE annealing steps of the same chains,
     "config5"  BASELINE.json configs[4]: 1 048 576 chains in total (strong scaling: / N per GPU) against the mug
@@ -528,6 +528,28 @@ def secondary_configs(device):
                       "npose": len(js), "seconds": dt, "value": len(js) / dt, "unit": "poses/s", "contacts_total": int(len(res["contacts"])),
                       "contacts_per_pose": float(len(res["contacts"]) / max(1, len(js))), "active_pairs": len(eng.robot_pairs(rid)),
                       "gpu_launches": int(eng.launch_count - l0)}
+    # ... and the neighbourhoods of both sides of every contact on an elastic body (findSoftNeighborhoods -> bodyRegion), one call
+    from graspit_b200 import engine as E
+    pairs = eng.robot_pairs(rid)
+    inv_b = {v: k for k, v in sb.body_ids.items()}
+    y = np.array([[sc.bodies[inv_b[a]].youngs, sc.bodies[inv_b[b]].youngs] for a, b in pairs])
+    soft = y.max(axis=1)[res["pair"]] > 0
+    if soft.any():
+        cs, pq = res["contacts"][soft], res["pair"][soft]
+        pa = np.array(pairs)[pq]
+        rad = np.array([E.soft_neighborhood_radius(*y[q]) for q in pq])
+        qb = np.stack([pa[:, 0], pa[:, 1]], 1).reshape(-1)
+        qp = np.stack([cs[:, 0:3], cs[:, 3:6]], 1).reshape(-1, 3)
+        qn = np.stack([cs[:, 6:9], cs[:, 9:12]], 1).reshape(-1, 3)
+        qr = np.repeat(rad, 2)
+        eng.body_region_batch(qb, qp, qn, qr, flat=True)
+        l0 = eng.launch_count
+        t0 = time.perf_counter()
+        flat, off = eng.body_region_batch(qb, qp, qn, qr, flat=True)
+        dt = time.perf_counter() - t0
+        out["config3"]["region_batch"] = {"metric": "bodyRegion queries/s (both sides of every contact on an elastic body, one b2c_region_batch call, host buffers)",
+                                          "queries": int(len(qb)), "seconds": dt, "value": len(qb) / dt, "unit": "queries/s",
+                                          "points_out": int(len(flat)), "gpu_launches": int(eng.launch_count - l0)}
     eng.close()
     # ---- config 4: Staubli TX60L + Barrett vs obstacles, allCollisions(ALL) for 262 144 arm + hand configurations
     sc = load_pack("staubli_barrett")
