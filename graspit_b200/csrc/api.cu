@@ -537,6 +537,17 @@ int b2c_mesh_create(b2c_ctx *ctx, const float *tri9, int ntri, int *mesh_id) {
   for (int i = 0; i < ntri; i++)
     for (int v = 0; v < 3; v++)
       tris[i].v[v] = make_float4(tri9[9 * (size_t)i + 3 * v], tri9[9 * (size_t)i + 3 * v + 1], tri9[9 * (size_t)i + 3 * v + 2], 0.f);
+  // v[0].w = radius of the triangle about its first vertex, rounded up: region_batch_kernel's gate bounds a triangle's
+  // distance to a point from that one 16-byte load
+  for (int i = 0; i < ntri; i++) {
+    const float *t = tri9 + 9 * (size_t)i;
+    double e1 = 0.0, e2 = 0.0;
+    for (int k = 0; k < 3; k++) {
+      e1 += ((double)t[3 + k] - (double)t[k]) * ((double)t[3 + k] - (double)t[k]);
+      e2 += ((double)t[6 + k] - (double)t[k]) * ((double)t[6 + k] - (double)t[k]);
+    }
+    tris[i].v[0].w = (float)(std::sqrt(std::max(e1, e2)) * 1.00001 + 1.0e-30);
+  }
   CU(cudaMalloc(&m.d_nodes, m.nodes.size() * sizeof(NodeQ)));
   CU(cudaMalloc(&m.d_tris, tris.size() * sizeof(Tri)));
   CU(cudaMemcpy(m.d_nodes, m.nodes.data(), m.nodes.size() * sizeof(NodeQ), cudaMemcpyHostToDevice));

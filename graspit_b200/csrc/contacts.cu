@@ -306,7 +306,8 @@ __global__ void region_kernel(RegionParams p) {
 // as region_kernel; flagged triangles are appended to one list with warp-aggregated atomics.  Brute force over the
 // triangles is deliberate: the bodies that get neighbourhoods are elastic fingertips and small objects (a few thousand
 // triangles), and the test is ~100 fp64 flops.
-// fp32 gate (round 2): |ref - a| - max(|b - a|, |c - a|) is a lower bound of the triangle's distance to ref; with
+// fp32 gate (round 2): |ref - a| - max(|b - a|, |c - a|) (the second term stored with the vertex) is a lower bound of the
+// triangle's distance to ref; with
 // head-room for the fp32 rounding, a triangle beyond the radius by this bound cannot be flagged.  22 of a fingertip's ~3 000
 // triangles are, so the fp64 test runs on a packed queue of the few that pass.
 __device__ __forceinline__ bool region_flag_exact(const RegionBatchParams &p, const MeshDev &m, int t, d3 cn, d3 ref, double r2) {
@@ -336,11 +337,9 @@ __global__ void __launch_bounds__(256) region_batch_kernel(RegionBatchParams p) 
       const int t = t0 + lane;
       bool near = false;
       if (t < m.ntri) {
-        const float4 va = __ldg(&m.tris[t].v[0]), vb = __ldg(&m.tris[t].v[1]), vc = __ldg(&m.tris[t].v[2]);
-        const f3 a = mk<float>(va.x, va.y, va.z);
-        const f3 ra = reff - a, e1 = mk<float>(vb.x, vb.y, vb.z) - a, e2 = mk<float>(vc.x, vc.y, vc.z) - a;
-        const float ext = sqrtf(fmaxf(dot(e1, e1), dot(e2, e2))) * 1.00001f;
-        near = !(sqrtf(dot(ra, ra)) - ext > lim);
+        const float4 va = __ldg(&m.tris[t].v[0]);              // .w: the triangle's radius about this vertex (mesh_create)
+        const f3 ra = reff - mk<float>(va.x, va.y, va.z);
+        near = !(sqrtf(dot(ra, ra)) - va.w > lim);
       }
       const unsigned nm = __ballot_sync(0xffffffffu, near);
       if (near) queue[nq + __popc(nm & lt)] = t;
